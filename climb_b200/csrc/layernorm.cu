@@ -1,0 +1,242 @@
+// LayerNorm forward / backward for the ViLT hot path: layernorm_before / layernorm_after / final
+// layernorm (modeling_vilt.py:505,517,873, eps 1e-12), the text-embedding LayerNorm (:302) and the
+// task-head LayerNorm(1536)+GELU (src/modeling/vilt.py:190-197, eps 1e-5).
+//
+// HBM-bound: one warp owns one row, the row stays in registers (d/128 float4 per lane) between the
+// statistics and the normalisation, so x is read once; all global accesses are 128-bit and
+// coalesced; row statistics use warp shuffles. The backward fuses the residual-gradient add and the
+// bf16 copy that feeds the next tensor-core GEMM, and reduces dgamma/dbeta per CTA before touching
+// global memory with one atomic per column per CTA.
+#include "common.cuh"
+#include "climb_b200.h"
+
+namespace climb {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y_bf16,
+              float* __restrict__ y_f32, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+              int rows, int act) {
+    constexpr int D = NV * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + warp;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+    float4 v[NV];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = xr[lane + 32 * i];
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (act == CLIMB_EPI_GELU) { o.x = gelu_f(o.x); o.y = gelu_f(o.y); o.z = gelu_f(o.z); o.w = gelu_f(o.w); }
+        if (y_f32)
+            reinterpret_cast<float4*>(y_f32 + static_cast<long long>(row) * D)[lane + 32 * i] = o;
+        if (y_bf16) {
+            uint2 p;
+            p.x = pack_bf16(o.x, o.y);
+            p.y = pack_bf16(o.z, o.w);
+            reinterpret_cast<uint2*>(y_bf16 + static_cast<long long>(row) * D)[lane + 32 * i] = p;
+        }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict__ dy_bf16,
+              const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+              const float* __restrict__ beta, const float* __restrict__ mean_in,
+              const float* __restrict__ rstd_in, const float* __restrict__ dres,
+              float* __restrict__ dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int act) {
+    constexpr int D = NV * 128;
+    __shared__ float s_red[kWarpsPerBlock][128];     // one 128-column slab at a time
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+
+    float4 dg[NV], db[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < rows; row += gridDim.x * kWarpsPerBlock) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+        float4 xh[NV], gy[NV];
+        float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 xv = xr[lane + 32 * i];
+            float4 dy;
+            if (dy_f32) {
+                dy = reinterpret_cast<const float4*>(dy_f32 + static_cast<long long>(row) * D)[lane + 32 * i];
+            } else {
+                const uint2 p = reinterpret_cast<const uint2*>(dy_bf16 + static_cast<long long>(row) * D)[lane + 32 * i];
+                const float2 a = unpack_bf16(p.x), b = unpack_bf16(p.y);
+                dy = make_float4(a.x, a.y, b.x, b.y);
+            }
+            const float4 g = __ldg(g4 + lane + 32 * i);
+            xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
+            xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
+            if (act == CLIMB_EPI_GELU) {
+                const float4 b = __ldg(b4 + lane + 32 * i);
+                dy.x *= dgelu_f(xh[i].x * g.x + b.x); dy.y *= dgelu_f(xh[i].y * g.y + b.y);
+                dy.z *= dgelu_f(xh[i].z * g.z + b.z); dy.w *= dgelu_f(xh[i].w * g.w + b.w);
+            }
+            dg[i].x += dy.x * xh[i].x; dg[i].y += dy.y * xh[i].y;
+            dg[i].z += dy.z * xh[i].z; dg[i].w += dy.w * xh[i].w;
+            db[i].x += dy.x; db[i].y += dy.y; db[i].z += dy.z; db[i].w += dy.w;
+            gy[i].x = dy.x * g.x; gy[i].y = dy.y * g.y; gy[i].z = dy.z * g.z; gy[i].w = dy.w * g.w;
+            c1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+            c2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+        }
+        c1 = warp_sum(c1) * (1.0f / D);
+        c2 = warp_sum(c2) * (1.0f / D);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float4 o;
+            o.x = rstd * (gy[i].x - c1 - xh[i].x * c2);
+            o.y = rstd * (gy[i].y - c1 - xh[i].y * c2);
+            o.z = rstd * (gy[i].z - c1 - xh[i].z * c2);
+            o.w = rstd * (gy[i].w - c1 - xh[i].w * c2);
+            if (dres) {
+                const float4 r = reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * ldx)[lane + 32 * i];
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            if (dx_f32)
+                reinterpret_cast<float4*>(dx_f32 + static_cast<long long>(row) * ldx)[lane + 32 * i] = o;
+            if (dx_bf16) {
+                uint2 p;
+                p.x = pack_bf16(o.x, o.y);
+                p.y = pack_bf16(o.z, o.w);
+                reinterpret_cast<uint2*>(dx_bf16 + static_cast<long long>(row) * D)[lane + 32 * i] = p;
+            }
+        }
+    }
+
+    if (dgamma == nullptr && dbeta == nullptr) return;
+    // CTA reduction of the per-warp column partials, one 128-column slab at a time
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        float* out = which == 0 ? dgamma : dbeta;
+        if (out == nullptr) continue;       // uniform across the CTA
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 v = which == 0 ? dg[i] : db[i];
+            __syncthreads();
+            reinterpret_cast<float4*>(s_red[warp])[lane] = v;
+            __syncthreads();
+            if (threadIdx.x < 128) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kWarpsPerBlock; ++w) acc += s_red[w][threadIdx.x];
+                // slab i holds columns (lane + 32 i) * 4 + {0..3} == i*128 + threadIdx.x
+                atomicAdd(out + i * 128 + threadIdx.x, acc);
+            }
+        }
+    }
+}
+
+template <int NV>
+int launch_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+               void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int act,
+               cudaStream_t stream) {
+    const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    ln_fwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+        x, ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, act);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+template <int NV>
+int launch_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long long ldx,
+               const float* gamma, const float* beta, const float* mean, const float* rstd,
+               const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int rows,
+               int act, cudaStream_t stream) {
+    int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int cap = 148 * 4;          // a few CTAs per SM; rows are grid-strided beyond that
+    if (grid > cap) grid = cap;
+    ln_bwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+        dy_f32, static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres,
+        dx_f32, static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows, act);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+                  void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int d, int act,
+                  cudaStream_t stream) {
+    CLIMB_REQUIRE(x && gamma && beta, "layernorm_fwd: null pointer");
+    CLIMB_REQUIRE(rows > 0, "layernorm_fwd: no rows");
+    CLIMB_REQUIRE(d % 128 == 0 && ldx % 4 == 0, "layernorm_fwd: d=%d / ldx=%lld must be multiples of 128 / 4", d, ldx);
+    CLIMB_REQUIRE(act == CLIMB_EPI_NONE || act == CLIMB_EPI_GELU, "layernorm_fwd: act must be NONE or GELU");
+#define ARGS (x, ldx, gamma, beta, eps, y_bf16, y_f32, mean, rstd, rows, act, stream)
+    switch (d / 128) {
+        case 1: return launch_fwd<1> ARGS;
+        case 2: return launch_fwd<2> ARGS;
+        case 3: return launch_fwd<3> ARGS;
+        case 4: return launch_fwd<4> ARGS;
+        case 6: return launch_fwd<6> ARGS;
+        case 8: return launch_fwd<8> ARGS;
+        case 12: return launch_fwd<12> ARGS;
+        default: break;
+    }
+#undef ARGS
+    CLIMB_REQUIRE(false, "layernorm_fwd: unsupported width d=%d (128,256,384,512,768,1024,1536)", d);
+    return -1;
+}
+
+int layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long long ldx,
+                  const float* gamma, const float* beta, const float* mean, const float* rstd,
+                  const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                  int rows, int d, int act, cudaStream_t stream) {
+    CLIMB_REQUIRE((dy_f32 != nullptr) != (dy_bf16 != nullptr), "layernorm_bwd: exactly one of dy_f32 / dy_bf16");
+    CLIMB_REQUIRE(x && gamma && beta && mean && rstd, "layernorm_bwd: null pointer");
+    CLIMB_REQUIRE(rows > 0, "layernorm_bwd: no rows");
+    CLIMB_REQUIRE(d % 128 == 0 && ldx % 4 == 0, "layernorm_bwd: d=%d / ldx=%lld must be multiples of 128 / 4", d, ldx);
+    CLIMB_REQUIRE(act == CLIMB_EPI_NONE || act == CLIMB_EPI_GELU, "layernorm_bwd: act must be NONE or GELU");
+#define ARGS (dy_f32, dy_bf16, x, ldx, gamma, beta, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, act, stream)
+    switch (d / 128) {
+        case 1: return launch_bwd<1> ARGS;
+        case 2: return launch_bwd<2> ARGS;
+        case 3: return launch_bwd<3> ARGS;
+        case 4: return launch_bwd<4> ARGS;
+        case 6: return launch_bwd<6> ARGS;
+        case 8: return launch_bwd<8> ARGS;
+        case 12: return launch_bwd<12> ARGS;
+        default: break;
+    }
+#undef ARGS
+    CLIMB_REQUIRE(false, "layernorm_bwd: unsupported width d=%d (128,256,384,512,768,1024,1536)", d);
+    return -1;
+}
+
+}  // namespace climb

@@ -1,0 +1,249 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (ctypes).
+
+Each kernel is compared with a plain PyTorch fp32 evaluation of the same arithmetic on the same
+(bf16-rounded) inputs. Tolerances are written next to each check: outputs stored as bf16 carry one
+bf16 rounding (2^-9 relative), fp32 outputs only accumulation-order noise.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from climb_b200 import _lib
+    return _lib
+
+
+def _rel_err(got, ref):
+    got = got.float()
+    ref = ref.float()
+    return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+
+def _max_err(got, ref):
+    return (got.float() - ref.float()).abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 128, 128), (256, 256, 256), (300, 768, 768), (948, 2304, 768),
+    (948, 768, 3072), (64, 1536, 768), (64, 3129, 1536), (1000, 72, 200), (130, 3072, 768),
+]
+
+
+@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_kmajor(M, N, K, block_n):
+    L = _lib()
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(N, K, device="cuda").bfloat16()
+    ldc = (N + 7) // 8 * 8
+    out = torch.full((M, ldc), float("nan"), device="cuda", dtype=torch.float32)
+    L.gemm(a, b, out, N=N, block_n=block_n)
+    ref = a.float() @ b.float().t()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out[:, :N]).all()
+    assert _rel_err(out[:, :N], ref) < 1e-5, (_rel_err(out[:, :N], ref), _max_err(out[:, :N], ref))
+    if ldc > N:   # padding columns untouched
+        assert torch.isnan(out[:, N:]).all()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 192), (768, 768, 948), (3072, 768, 500), (200, 136, 72)])
+def test_gemm_mn_major(M, N, K, block_n, a_mn, b_mn):
+    L = _lib()
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = torch.randn(N, K, device="cuda").bfloat16()
+    a_in = a.t().contiguous() if a_mn else a      # [K, M] storage when MN-major
+    b_in = b.t().contiguous() if b_mn else b
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    L.gemm(a_in, b_in, out, a_mn_major=a_mn, b_mn_major=b_mn, block_n=block_n)
+    ref = a.float() @ b.float().t()
+    assert _rel_err(out, ref) < 1e-5, (_rel_err(out, ref), _max_err(out, ref))
+
+
+@pytest.mark.parametrize("split_k", [0, 2, 5])
+def test_gemm_wgrad_splitk_accumulate(split_k):
+    """dW[N_out, K_in] += dY^T X, both operands read in place (MN-major), split over tokens."""
+    L = _lib()
+    torch.manual_seed(3)
+    tokens, n_out, k_in = 237 * 8, 768, 768
+    dy = torch.randn(tokens, n_out, device="cuda").bfloat16()
+    x = torch.randn(tokens, k_in, device="cuda").bfloat16()
+    dw = torch.ones(n_out, k_in, device="cuda", dtype=torch.float32)
+    L.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, accumulate=True, split_k=split_k)
+    ref = 1.0 + dy.float().t() @ x.float()
+    assert _rel_err(dw, ref) < 1e-5, _rel_err(dw, ref)
+
+
+def test_gemm_epilogues():
+    L = _lib()
+    torch.manual_seed(11)
+    M, N, K = 500, 384, 256
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    acc = a.float() @ b.float().t() + bias
+    # bias + residual, fp32 out
+    out = torch.empty(M, N, device="cuda")
+    L.gemm(a, b, out, bias=bias, residual=res)
+    assert _rel_err(out, acc + res) < 1e-5
+    # bias, bf16 out  (one bf16 rounding: 2^-9)
+    outb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, outb, bias=bias)
+    assert _max_err(outb, acc.bfloat16()) <= 2 ** -6 * acc.abs().max().item() * 2 ** -2
+    assert _rel_err(outb, acc) < 4e-3
+    # GELU with pre-activation saved
+    aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, outb, bias=bias, epilogue=L.EPI_GELU, aux=aux)
+    assert _rel_err(aux, acc) < 4e-3
+    assert _rel_err(outb, torch.nn.functional.gelu(acc)) < 4e-3
+    # dGELU: out = acc * gelu'(aux)
+    u = torch.randn(M, N, device="cuda").bfloat16()
+    L.gemm(a, b, outb, epilogue=L.EPI_DGELU, aux=u)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf).sum().backward()
+    assert _rel_err(outb, (acc - bias) * uf.grad) < 4e-3
+    # swish / dswish / relu / drelu / tanh
+    L.gemm(a, b, out, bias=bias, epilogue=L.EPI_SWISH)
+    assert _rel_err(out, torch.nn.functional.silu(acc)) < 1e-5
+    L.gemm(a, b, out, epilogue=L.EPI_DSWISH, aux=u)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.silu(uf).sum().backward()
+    assert _rel_err(out, (acc - bias) * uf.grad) < 1e-5
+    L.gemm(a, b, out, bias=bias, epilogue=L.EPI_RELU)
+    assert _rel_err(out, torch.relu(acc)) < 1e-5
+    L.gemm(a, b, out, epilogue=L.EPI_DRELU, aux=u)
+    assert _rel_err(out, (acc - bias) * (u.float() > 0)) < 1e-5
+    L.gemm(a, b, out, bias=bias, epilogue=L.EPI_TANH)
+    assert _max_err(out, torch.tanh(acc)) < 1e-5
+    # alpha
+    L.gemm(a, b, out, alpha=0.25)
+    assert _rel_err(out, 0.25 * (acc - bias)) < 1e-5
+
+
+def test_gemm_large_persistent():
+    """Config-2 sized forward GEMM (B=64 sequences): many tiles per CTA, both accumulator stages."""
+    L = _lib()
+    torch.manual_seed(5)
+    M, N, K = 64 * 237, 3072, 768
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, out)
+    ref = a.float() @ b.float().t()
+    assert _rel_err(out, ref) < 4e-3
+
+
+def test_gemm_rejects_bad_args():
+    L = _lib()
+    a = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)   # K*2 not a multiple of 16
+    b = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(128, 128, device="cuda")
+    with pytest.raises(L.ClimbError):
+        L.gemm(a, b, out)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def _attn_ref(qkv, key_bias, B, L_, H, scale):
+    q, k, v = qkv.float().view(B, L_, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * scale
+    if key_bias is not None:
+        s = s + key_bias[:, None, None, :]
+    p = torch.softmax(s, dim=-1)
+    ctx = (p @ v).permute(0, 2, 1, 3).reshape(B, L_, H * 64)
+    return ctx, torch.logsumexp(s, dim=-1)
+
+
+@pytest.mark.parametrize("B,L_,H,masked", [(2, 237, 12, False), (3, 237, 12, True), (2, 13, 2, True),
+                                           (1, 64, 1, False), (2, 200, 3, True), (1, 281, 2, True)])
+def test_attention_fwd_bwd(B, L_, H, masked):
+    L = _lib()
+    torch.manual_seed(B * 100 + L_)
+    qkv = torch.randn(B, L_, 3 * H * 64, device="cuda").bfloat16()
+    key_bias = None
+    if masked:
+        lens = torch.randint(max(1, L_ // 2), L_ + 1, (B,), device="cuda")
+        mask = (torch.arange(L_, device="cuda")[None, :] < lens[:, None]).float()
+        key_bias = (1.0 - mask) * -10000.0
+    scale = 1.0 / math.sqrt(64)
+    ctx, lse = L.attention_fwd(qkv, key_bias, B, L_, H, scale)
+    qkv_ref = qkv.float().requires_grad_(True)
+    ctx_ref, lse_ref = _attn_ref(qkv_ref, key_bias, B, L_, H, scale)
+    # ctx is stored in bf16 and P is rounded to bf16 before P.V: 2^-8 relative
+    assert _rel_err(ctx, ctx_ref) < 6e-3, _rel_err(ctx, ctx_ref)
+    assert _max_err(lse, lse_ref) < 2e-3, _max_err(lse, lse_ref)
+    dctx = torch.randn(B, L_, H * 64, device="cuda").bfloat16()
+    dqkv = L.attention_bwd(qkv, key_bias, ctx, dctx, lse, B, L_, H, scale)
+    ctx_ref.backward(dctx.float())
+    ref = qkv_ref.grad.view(B, L_, 3, H * 64)
+    got = dqkv.float().view(B, L_, 3, H * 64)
+    for i, name in enumerate("qkv"):
+        e = _rel_err(got[:, :, i], ref[:, :, i])
+        assert e < 1.5e-2, (name, e)
+
+
+# ------------------------------------------------------------------------------------------------
+# layernorm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,d,eps", [(1000, 768, 1e-12), (37, 128, 1e-12), (64, 1536, 1e-5), (9, 256, 1e-5)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_layernorm_fwd_bwd(rows, d, eps, act):
+    L = _lib()
+    torch.manual_seed(rows + d)
+    x = torch.randn(rows, d, device="cuda") * 2 + 0.5
+    g = torch.randn(d, device="cuda")
+    b = torch.randn(d, device="cuda")
+    yb, yf, mean, rstd = L.layernorm_fwd(x, g, b, eps, out_bf16=True, out_f32=True, act=act)
+    xr = x.clone().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (d,), gr, br, eps)
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    assert _max_err(yf, ref) < 2e-5 * max(1.0, ref.abs().max().item())
+    assert _rel_err(yb, ref) < 4e-3
+    dy = torch.randn(rows, d, device="cuda")
+    dres = torch.randn(rows, d, device="cuda")
+    ref.backward(dy)
+    dx = torch.empty(rows, d, device="cuda")
+    dxb = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    dg = torch.zeros(d, device="cuda")
+    db = torch.zeros(d, device="cuda")
+    L.layernorm_bwd(dy, x, g, b, mean, rstd, dres=dres, dx_f32=dx, dx_bf16=dxb, dgamma=dg, dbeta=db, act=act)
+    assert _rel_err(dx, xr.grad + dres) < 2e-5, _rel_err(dx, xr.grad + dres)
+    assert _rel_err(dxb, xr.grad + dres) < 4e-3
+    assert _rel_err(dg, gr.grad) < 2e-5, _rel_err(dg, gr.grad)
+    assert _rel_err(db, br.grad) < 2e-5
+    # bf16 dy path
+    dx2 = torch.empty(rows, d, device="cuda")
+    L.layernorm_bwd(dy.bfloat16(), x, g, b, mean, rstd, dx_f32=dx2, act=act)
+    xr.grad = None
+    ref2 = torch.nn.functional.layer_norm(xr, (d,), gr, br, eps)
+    if act:
+        ref2 = torch.nn.functional.gelu(ref2)
+    ref2.backward(dy.bfloat16().float())
+    assert _rel_err(dx2, xr.grad) < 2e-5
+
+
+def test_layernorm_strided_cls_rows():
+    L = _lib()
+    torch.manual_seed(0)
+    B, L_, d = 5, 237, 768
+    x = torch.randn(B, L_, d, device="cuda")
+    g = torch.randn(d, device="cuda")
+    b = torch.randn(d, device="cuda")
+    yb, yf, mean, rstd = L.layernorm_fwd(x, g, b, 1e-12, rows=B, ldx=L_ * d, out_f32=True)
+    ref = torch.nn.functional.layer_norm(x[:, 0], (d,), g, b, 1e-12)
+    assert _max_err(yf, ref) < 2e-5 * ref.abs().max().item()

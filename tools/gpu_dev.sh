@@ -1,0 +1,23 @@
+#!/bin/bash
+# Dev loop on the GPU box: every pytest group in its own process (a trapped kernel kills the CUDA
+# context) under its own timeout; logs land in gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+run() {  # name, timeout, args...
+  local name=$1; shift; local to=$1; shift
+  echo "=== $name" | tee -a gpurun_out/summary.txt
+  timeout $to python -m pytest -x -q -m gpu "$@" > gpurun_out/$name.log 2>&1
+  echo "exit=$? $(tail -n 3 gpurun_out/$name.log | tr '\n' ' ')" | tee -a gpurun_out/summary.txt
+}
+: > gpurun_out/summary.txt
+for g in "$@"; do
+  case $g in
+    gemm_k)   run gemm_k 600 tests/test_gpu_kernels.py -k "gemm_kmajor" ;;
+    gemm_mn)  run gemm_mn 600 tests/test_gpu_kernels.py -k "gemm_mn_major" ;;
+    gemm_x)   run gemm_x 600 tests/test_gpu_kernels.py -k "gemm_wgrad or gemm_epilogues or gemm_large or gemm_rejects" ;;
+    attn)     run attn 600 tests/test_gpu_kernels.py -k "attention" ;;
+    ln)       run ln 600 tests/test_gpu_kernels.py -k "layernorm" ;;
+    *)        run "$(echo $g | tr '/:. ' '____')" 900 $g ;;
+  esac
+done
+cat gpurun_out/summary.txt
