@@ -45,6 +45,7 @@ class GemmDesc(Structure):
         ("residual", c_void_p), ("ldr", c_int64),
         ("epilogue", c_int),
         ("aux", c_void_p), ("ldaux", c_int64),
+        ("c2", c_void_p), ("ldc2", c_int64),
         ("alpha", c_float),
         ("accumulate", c_int),
         ("split_k", c_int),
@@ -96,7 +97,7 @@ def stream() -> int:
 # Thin tensor-level wrappers (no autograd here; see climb_b200.ops)
 # -------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=False, b_mn_major=False,
-         bias=None, residual=None, epilogue=EPI_NONE, aux=None, alpha=1.0, accumulate=False,
+         bias=None, residual=None, epilogue=EPI_NONE, aux=None, c2=None, alpha=1.0, accumulate=False,
          split_k=0, block_n=0, M=None, N=None, K=None) -> torch.Tensor:
     """out[M,N] = epi(alpha * A B^T + bias) + residual. A, B bf16 2-D (possibly row-strided views)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -129,6 +130,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
     d.ldaux = aux.stride(0) if aux is not None else 0
     if aux is not None:
         assert aux.dtype == torch.bfloat16
+    d.c2 = ptr(c2)
+    d.ldc2 = c2.stride(0) if c2 is not None else 0
+    if c2 is not None:
+        assert c2.dtype == torch.bfloat16
     d.alpha = alpha
     d.accumulate = int(accumulate)
     d.split_k = split_k

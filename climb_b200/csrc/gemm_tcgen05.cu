@@ -41,6 +41,8 @@ struct GemmDeviceArgs {
     int epilogue;                 // climb_epilogue
     void* aux;                    // bf16 [M, ldaux]
     long long ldaux;
+    void* c2;                     // optional bf16 copy of the final value [M, ldc2]
+    long long ldc2;
     float alpha;
     int accumulate;
     int split_k;
@@ -229,6 +231,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                            ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         const bool vec_aux = p.aux != nullptr && ((p.ldaux * 2) % 16 == 0) &&
                              ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+        const bool vec_c2 = p.c2 != nullptr && ((p.ldc2 * 2) % 16 == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.c2) & 15) == 0);
         const bool vec_res = p.residual != nullptr && ((p.ldr * 4) % 16 == 0) &&
                              ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
         const bool aux_in = (p.epilogue == CLIMB_EPI_DGELU || p.epilogue == CLIMB_EPI_DSWISH ||
@@ -335,6 +339,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (n0 + j < p.N) v[j] += rp[j];
+                        }
+                    }
+                    // ---- optional bf16 copy of the final value (feeds the next GEMM) ----
+                    if (p.c2 != nullptr) {
+                        __nv_bfloat16* c2p = reinterpret_cast<__nv_bfloat16*>(p.c2) +
+                                             static_cast<long long>(row) * p.ldc2 + n0;
+                        if (full && vec_c2) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 u;
+                                u.x = pack_bf16(v[j], v[j + 1]);
+                                u.y = pack_bf16(v[j + 2], v[j + 3]);
+                                u.z = pack_bf16(v[j + 4], v[j + 5]);
+                                u.w = pack_bf16(v[j + 6], v[j + 7]);
+                                *reinterpret_cast<uint4*>(c2p + j) = u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + j < p.N) c2p[j] = __float2bfloat16_rn(v[j]);
                         }
                     }
                     // ---- store ----
@@ -509,6 +533,7 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     const bool aux_needed = (d->epilogue == CLIMB_EPI_DGELU || d->epilogue == CLIMB_EPI_DSWISH ||
                              d->epilogue == CLIMB_EPI_DRELU);
     CLIMB_REQUIRE(!aux_needed || d->aux != nullptr, "gemm: derivative epilogue needs aux");
+    CLIMB_REQUIRE(!(d->accumulate && d->c2 != nullptr), "gemm: accumulate cannot produce a bf16 copy");
     CLIMB_REQUIRE(!(d->accumulate && d->epilogue != CLIMB_EPI_NONE),
                   "gemm: accumulate cannot be combined with a non-linear epilogue");
 
@@ -519,6 +544,7 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     a.C = d->C; a.ldc = d->ldc; a.c_dtype = d->c_dtype;
     a.bias = d->bias; a.residual = d->residual; a.ldr = d->ldr;
     a.epilogue = d->epilogue; a.aux = d->aux; a.ldaux = d->ldaux;
+    a.c2 = d->c2; a.ldc2 = d->ldc2;
     a.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
     a.accumulate = d->accumulate ? 1 : 0;
 

@@ -48,8 +48,9 @@ int climb_version(void);
  *   b_mn_major likewise for B[n*ldb + k] / B[k*ldb + n].
  *   accumulate = 1: C += result with fp32 atomics (gradient accumulation, split-K).
  *   split_k = 0 picks a split automatically (only when accumulate = 1), block_n = 0 picks a tile.
- *   aux: bf16 [M, ldaux]; written with the pre-activation for GELU/SWISH/RELU/NONE when non-null,
- *        read by the D* epilogues.
+ *   aux: bf16 [M, ldaux]; written with the pre-activation (acc*alpha+bias, before the activation
+ *        and the residual) for GELU/SWISH/RELU/TANH/NONE when non-null, read by the D* epilogues.
+ *   c2 : optional bf16 [M, ldc2] copy of the final value, i.e. the operand of the next GEMM.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int M, N, K;
@@ -60,6 +61,7 @@ typedef struct {
     const float* residual; int64_t ldr;
     int epilogue;
     void* aux; int64_t ldaux;
+    void* c2; int64_t ldc2;   /* optional bf16 copy of the final C (after residual) */
     float alpha;          /* 0 is read as 1 */
     int accumulate;
     int split_k;

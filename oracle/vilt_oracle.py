@@ -1,0 +1,406 @@
+"""ORACLE (test infrastructure, not product code): a plain-PyTorch fp32 CPU restatement of the
+reference arithmetic on CLiMB's ViLT hot path. Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this package; nothing under climb_b200/ does.
+
+It is written functionally over a state dict that uses the reference's own parameter names
+(SURVEY.md appendix B), so the same weights drive the reference modules, this oracle and the CUDA
+path. Gradients come from torch autograd over these forward functions, exactly as in the reference.
+
+Parity pin: oracle/make_golden.py runs the UNMODIFIED reference (vendored transformers 4.17 fork +
+src/modeling/vilt.py + src/cl_algorithms) in this container on the same weights / inputs and stores
+its outputs under tests/golden/; tests/test_oracle_golden.py checks this restatement against them
+(and against the live reference whenever /root/reference is mounted).
+
+Scope of the restatement: the fixed-resolution path (all images of a batch share one H x W that is
+a multiple of the patch size and pixel_mask is all ones). There the reference's random patch
+selection (modeling_vilt.py:170-193, torch.multinomial) is a permutation of the patch rows, to
+which every output that CLiMB consumes (pooler_output, logits, loss, gradients) is invariant; the
+oracle keeps raster order.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class ViltDims:
+    """The subset of ViltConfig (configuration_vilt.py:101-124) that shapes the arithmetic."""
+    hidden_size: int = 768
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    intermediate_size: int = 3072
+    image_size: int = 384
+    patch_size: int = 32
+    num_channels: int = 3
+    vocab_size: int = 30522
+    max_position_embeddings: int = 40
+    type_vocab_size: int = 2
+    modality_type_vocab_size: int = 2
+    layer_norm_eps: float = 1e-12
+
+    @property
+    def patch_dim(self) -> int:
+        return self.image_size // self.patch_size
+
+
+# task head specs of src/configs/task_configs.py (num_labels / num_images / model_type only)
+TASK_SPECS: Dict[str, Dict] = {
+    "vqa": dict(num_labels=3129, num_images=1, model_type="classification"),
+    "nlvr2": dict(num_labels=2, num_images=2, model_type="classification"),
+    "snli-ve": dict(num_labels=3, num_images=1, model_type="classification"),
+    "vcr": dict(num_labels=4, num_images=1, model_type="multi-choice", num_choices=4),
+}
+
+ENC = "vilt_encoder.vilt."
+
+
+# -------------------------------------------------------------------------------------------------
+# deterministic synthetic weights (shared by the golden generator, the tests and bench.py)
+# -------------------------------------------------------------------------------------------------
+def param_shapes(dims: ViltDims, tasks: Sequence[str] = (), adapters: Optional[Dict[str, int]] = None,
+                 adapter_sites: Sequence[str] = ("mh", "output"),
+                 task_specs: Dict[str, Dict] = TASK_SPECS) -> "OrderedDict[str, Tuple[int, ...]]":
+    """Names and shapes of a ViltContinualLearner state dict, in the
+    reference's registration order. adapters: {task_key: bottleneck width r}."""
+    d, ff, P = dims.hidden_size, dims.intermediate_size, dims.patch_size
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    e = ENC + "embeddings."
+    s[e + "cls_token"] = (1, 1, d)
+    s[e + "position_embeddings"] = (1, dims.patch_dim ** 2 + 1, d)
+    s[e + "text_embeddings.word_embeddings.weight"] = (dims.vocab_size, d)
+    s[e + "text_embeddings.position_embeddings.weight"] = (dims.max_position_embeddings, d)
+    s[e + "text_embeddings.token_type_embeddings.weight"] = (dims.type_vocab_size, d)
+    s[e + "text_embeddings.LayerNorm.weight"] = (d,)
+    s[e + "text_embeddings.LayerNorm.bias"] = (d,)
+    s[e + "patch_embeddings.projection.weight"] = (d, dims.num_channels, P, P)
+    s[e + "patch_embeddings.projection.bias"] = (d,)
+    n_types = max(dims.modality_type_vocab_size, 3 if "nlvr2" in tasks else 2)
+    s[e + "token_type_embeddings.weight"] = (n_types, d)
+    for i in range(dims.num_hidden_layers):
+        l = f"{ENC}encoder.layer.{i}."
+        for n in ("query", "key", "value"):
+            s[l + f"attention.attention.{n}.weight"] = (d, d)
+            s[l + f"attention.attention.{n}.bias"] = (d,)
+        s[l + "attention.output.dense.weight"] = (d, d)
+        s[l + "attention.output.dense.bias"] = (d,)
+        if adapters and "mh" in adapter_sites:
+            for t, r in adapters.items():
+                a = l + f"attention.output.adapters.{t}."
+                s[a + "adapter_down.0.weight"] = (r, d)
+                s[a + "adapter_down.0.bias"] = (r,)
+                s[a + "adapter_up.weight"] = (d, r)
+                s[a + "adapter_up.bias"] = (d,)
+        s[l + "intermediate.dense.weight"] = (ff, d)
+        s[l + "intermediate.dense.bias"] = (ff,)
+        s[l + "output.dense.weight"] = (d, ff)
+        s[l + "output.dense.bias"] = (d,)
+        if adapters and "output" in adapter_sites:
+            for t, r in adapters.items():
+                a = l + f"output.adapters.{t}."
+                s[a + "adapter_down.0.weight"] = (r, d)
+                s[a + "adapter_down.0.bias"] = (r,)
+                s[a + "adapter_up.weight"] = (d, r)
+                s[a + "adapter_up.bias"] = (d,)
+        s[l + "layernorm_before.weight"] = (d,)
+        s[l + "layernorm_before.bias"] = (d,)
+        s[l + "layernorm_after.weight"] = (d,)
+        s[l + "layernorm_after.bias"] = (d,)
+    s[ENC + "layernorm.weight"] = (d,)
+    s[ENC + "layernorm.bias"] = (d,)
+    s[ENC + "pooler.dense.weight"] = (d, d)
+    s[ENC + "pooler.dense.bias"] = (d,)
+    for t in tasks:
+        spec = task_specs[t]
+        h = f"task_layer.{t}."
+        if spec["model_type"] == "classification":
+            s[h + "0.weight"] = (2 * d, d * spec["num_images"])
+            s[h + "0.bias"] = (2 * d,)
+            s[h + "1.weight"] = (2 * d,)
+            s[h + "1.bias"] = (2 * d,)
+            s[h + "3.weight"] = (spec["num_labels"], 2 * d)
+            s[h + "3.bias"] = (spec["num_labels"],)
+        else:
+            s[h + "1.weight"] = (1, d)
+            s[h + "1.bias"] = (1,)
+    return s
+
+
+def synth_state_dict(dims: ViltDims, tasks: Sequence[str] = (), seed: int = 42,
+                     adapters: Optional[Dict[str, int]] = None,
+                     adapter_sites: Sequence[str] = ("mh", "output")) -> "OrderedDict[str, Tensor]":
+    """Seeded synthetic weights. Same family as the reference's _init_weights (normal(0, 0.02),
+    modeling_vilt.py:597-611) but with non-trivial LayerNorm gains and biases so that every term of
+    the arithmetic is exercised. One torch.Generator per tensor: values do not depend on which other
+    tensors exist."""
+    sd: "OrderedDict[str, Tensor]" = OrderedDict()
+    for idx, (name, shape) in enumerate(param_shapes(dims, tasks, adapters, adapter_sites).items()):
+        g = torch.Generator().manual_seed(seed * 1_000_003 + _stable_hash(name))
+        if name.endswith("LayerNorm.weight") or "layernorm" in name and name.endswith("weight") \
+                or (name.startswith("task_layer") and name.endswith("1.weight") and len(shape) == 1):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith("bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        else:
+            t = 0.02 * torch.randn(shape, generator=g)
+        sd[name] = t.float()
+    return sd
+
+
+def _stable_hash(name: str) -> int:
+    h = 2166136261
+    for ch in name.encode():
+        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+    return h
+
+
+# -------------------------------------------------------------------------------------------------
+# forward pieces
+# -------------------------------------------------------------------------------------------------
+def text_embeddings(sd, input_ids: Optional[Tensor], token_type_ids: Optional[Tensor], dims: ViltDims,
+                    inputs_embeds: Optional[Tensor] = None) -> Tensor:
+    """TextEmbeddings.forward, modeling_vilt.py:272-304 (dropout p = 0 in ViltConfig)."""
+    p = ENC + "embeddings.text_embeddings."
+    if inputs_embeds is None:
+        inputs_embeds = F.embedding(input_ids, sd[p + "word_embeddings.weight"])
+    B, T = inputs_embeds.shape[:2]
+    if token_type_ids is None:
+        token_type_ids = torch.zeros(B, T, dtype=torch.long)
+    emb = inputs_embeds + F.embedding(token_type_ids, sd[p + "token_type_embeddings.weight"])
+    emb = emb + sd[p + "position_embeddings.weight"][:T][None]
+    return F.layer_norm(emb, (dims.hidden_size,), sd[p + "LayerNorm.weight"], sd[p + "LayerNorm.bias"],
+                        dims.layer_norm_eps)
+
+
+def interpolated_position_table(sd, dims: ViltDims, h: int, w: int) -> Tensor:
+    """Rows 1.. of position_embeddings bilinearly resized (align_corners=True) from the
+    patch_dim x patch_dim training grid to h x w, raster order: modeling_vilt.py:130-147."""
+    d = dims.hidden_size
+    pos = sd[ENC + "embeddings.position_embeddings"]
+    spatial = pos[:, 1:, :].transpose(1, 2).reshape(1, d, dims.patch_dim, dims.patch_dim)
+    out = F.interpolate(spatial, size=(h, w), mode="bilinear", align_corners=True)
+    return out.flatten(2).transpose(1, 2)[0]          # [h*w, d]
+
+
+def visual_embed_fixed(sd, pixel_values: Tensor, dims: ViltDims) -> Tensor:
+    """ViltEmbeddings.visual_embed (modeling_vilt.py:121-205) on the fixed-resolution path:
+    conv patchify (:124, :309-328), interpolated position table (:130-147), [cls] prepended and
+    position row 0 added (:195-200). Patch rows stay in raster order (see module docstring)."""
+    e = ENC + "embeddings."
+    x = F.conv2d(pixel_values, sd[e + "patch_embeddings.projection.weight"],
+                 sd[e + "patch_embeddings.projection.bias"], stride=dims.patch_size)
+    B, d, h, w = x.shape
+    x = x.flatten(2).transpose(1, 2)                                   # [B, h*w, d]
+    x = x + interpolated_position_table(sd, dims, h, w)[None]
+    cls = sd[e + "cls_token"].expand(B, -1, -1) + sd[e + "position_embeddings"][:, :1, :]
+    return torch.cat([cls, x], dim=1)
+
+
+def embeddings(sd, dims: ViltDims, input_ids, attention_mask, token_type_ids, pixel_values,
+               image_token_type_idx: int = 1, inputs_embeds=None) -> Tuple[Tensor, Tensor]:
+    """ViltEmbeddings.forward, modeling_vilt.py:207-246: text || image with modality-type rows."""
+    tt = sd[ENC + "embeddings.token_type_embeddings.weight"]
+    text = text_embeddings(sd, input_ids, token_type_ids, dims, inputs_embeds) + tt[0]
+    image = visual_embed_fixed(sd, pixel_values, dims) + tt[image_token_type_idx]
+    masks = torch.cat([attention_mask.to(text.dtype),
+                       torch.ones(image.shape[:2], dtype=text.dtype)], dim=1)
+    return torch.cat([text, image], dim=1), masks
+
+
+_ACTS = {"swish": F.silu, "relu": F.relu, "gelu": F.gelu}
+
+
+def adapter_bottleneck(sd, prefix: str, h: Tensor, non_linearity: str, scaling: float = 1.0) -> Tensor:
+    """Adapter.forward with the Houlsby / Pfeiffer configs as ViLT calls it (residual input = the
+    adapter's own input, "input_tensor" = zeros, no LayerNorm): adapters/modeling.py:120-201,
+    mixins/vilt.py:23-69; h + s * (W_u act(W_d h + b_d) + b_u)."""
+    down = _ACTS[non_linearity](F.linear(h, sd[prefix + "adapter_down.0.weight"], sd[prefix + "adapter_down.0.bias"]))
+    up = F.linear(down, sd[prefix + "adapter_up.weight"], sd[prefix + "adapter_up.bias"])
+    return h + scaling * up
+
+
+@dataclass
+class AdapterSpec:
+    """Active adapter (Stack[name]) and where it sits. houlsby: mh + output, swish;
+    pfeiffer: output only, relu (adapters/configuration.py:259-308)."""
+    name: str
+    non_linearity: str = "swish"
+    sites: Tuple[str, ...] = ("mh", "output")
+    scaling: float = 1.0
+
+
+def vilt_layer(sd, i: int, x: Tensor, ext_mask: Tensor, dims: ViltDims,
+               adapter: Optional[AdapterSpec] = None) -> Tensor:
+    """ViltLayer.forward, modeling_vilt.py:503-525 (pre-LN block)."""
+    l = f"{ENC}encoder.layer.{i}."
+    d, H = dims.hidden_size, dims.num_attention_heads
+    dh = d // H
+    B, L, _ = x.shape
+    h1 = F.layer_norm(x, (d,), sd[l + "layernorm_before.weight"], sd[l + "layernorm_before.bias"], dims.layer_norm_eps)
+
+    def heads(t):                                            # transpose_for_scores, :350-353
+        return t.view(B, L, H, dh).permute(0, 2, 1, 3)
+    q = heads(F.linear(h1, sd[l + "attention.attention.query.weight"], sd[l + "attention.attention.query.bias"]))
+    k = heads(F.linear(h1, sd[l + "attention.attention.key.weight"], sd[l + "attention.attention.key.bias"]))
+    v = heads(F.linear(h1, sd[l + "attention.attention.value.weight"], sd[l + "attention.attention.value.bias"]))
+    scores = q @ k.transpose(-1, -2) / math.sqrt(dh) + ext_mask       # :363-368
+    probs = torch.softmax(scores, dim=-1)                              # :371 (dropout p = 0, :375)
+    ctx = (probs @ v).permute(0, 2, 1, 3).reshape(B, L, d)             # :381-384
+    a = F.linear(ctx, sd[l + "attention.output.dense.weight"], sd[l + "attention.output.dense.bias"])   # :409
+    if adapter is not None and "mh" in adapter.sites:
+        a = adapter_bottleneck(sd, l + f"attention.output.adapters.{adapter.name}.", a, adapter.non_linearity, adapter.scaling)
+    x = a + x                                                          # :514
+    h2 = F.layer_norm(x, (d,), sd[l + "layernorm_after.weight"], sd[l + "layernorm_after.bias"], dims.layer_norm_eps)
+    inter = F.gelu(F.linear(h2, sd[l + "intermediate.dense.weight"], sd[l + "intermediate.dense.bias"]))  # :461-466
+    o = F.linear(inter, sd[l + "output.dense.weight"], sd[l + "output.dense.bias"]) + x                   # :480-484
+    if adapter is not None and "output" in adapter.sites:
+        o = adapter_bottleneck(sd, l + f"output.adapters.{adapter.name}.", o, adapter.non_linearity, adapter.scaling)
+    return o
+
+
+def vilt_forward(sd, dims: ViltDims, input_ids, attention_mask, token_type_ids, pixel_values,
+                 image_token_type_idx: int = 1, inputs_embeds=None,
+                 adapter: Optional[AdapterSpec] = None, return_hidden: bool = False):
+    """ViltModel.forward -> pooler_output, modeling_vilt.py:777-884, 887-899."""
+    x, masks = embeddings(sd, dims, input_ids, attention_mask, token_type_ids, pixel_values,
+                          image_token_type_idx, inputs_embeds)
+    ext = (1.0 - masks)[:, None, None, :] * -10000.0                   # modeling_utils.py:299-311
+    for i in range(dims.num_hidden_layers):
+        x = vilt_layer(sd, i, x, ext, dims, adapter)
+    x = F.layer_norm(x, (dims.hidden_size,), sd[ENC + "layernorm.weight"], sd[ENC + "layernorm.bias"], dims.layer_norm_eps)
+    pooled = torch.tanh(F.linear(x[:, 0], sd[ENC + "pooler.dense.weight"], sd[ENC + "pooler.dense.bias"]))
+    return (pooled, x) if return_hidden else pooled
+
+
+def task_head(sd, task: str, pooled: Tensor, spec: Optional[Dict] = None, train: bool = False) -> Tensor:
+    """Task heads of ViltContinualLearner.add_task_layer, src/modeling/vilt.py:179-203.
+    classification: Linear -> LayerNorm(eps 1e-5) -> GELU -> Linear. multi-choice: Dropout(0.1) ->
+    Linear(d, 1) on [B, choices, d], squeezed (:349). Dropout is identity here (eval / p handled by
+    the caller): the oracle is deterministic."""
+    spec = spec or TASK_SPECS[task]
+    h = f"task_layer.{task}."
+    if spec["model_type"] == "classification":
+        z = F.linear(pooled, sd[h + "0.weight"], sd[h + "0.bias"])
+        z = F.gelu(F.layer_norm(z, (z.shape[-1],), sd[h + "1.weight"], sd[h + "1.bias"], 1e-5))
+        return F.linear(z, sd[h + "3.weight"], sd[h + "3.bias"])
+    return F.linear(pooled, sd[h + "1.weight"], sd[h + "1.bias"]).squeeze()
+
+
+def learner_forward(sd, dims: ViltDims, task: str, batch: Dict[str, Tensor],
+                    adapter: Optional[AdapterSpec] = None, spec: Optional[Dict] = None):
+    """ViltContinualLearner.forward on tensor inputs (src/modeling/vilt.py:218-350):
+    single image (:241-261), NLVR2 two passes with image_token_type_idx 1, 2 (:291-304), VCR four
+    text choices over the same pixels (:334-349). Returns (pooled, logits)."""
+    spec = spec or TASK_SPECS[task]
+    ids, am, tt, px = batch["input_ids"], batch["attention_mask"], batch["token_type_ids"], batch["pixel_values"]
+    if spec["model_type"] == "multi-choice":
+        outs = [vilt_forward(sd, dims, ids[:, c], am[:, c], tt[:, c], px, 1, adapter=adapter)
+                for c in range(spec["num_choices"])]
+        pooled = torch.stack(outs, dim=0).transpose(0, 1)
+    elif spec["num_images"] == 1:
+        pooled = vilt_forward(sd, dims, ids, am, tt, px, 1, adapter=adapter)
+    else:
+        outs = [vilt_forward(sd, dims, ids, am, tt, px[:, i], i + 1, adapter=adapter)
+                for i in range(spec["num_images"])]
+        pooled = torch.cat(outs, dim=-1)
+    return pooled, task_head(sd, task, pooled, spec)
+
+
+def task_loss(task: str, logits: Tensor, target: Tensor) -> Tensor:
+    """VQA: BCEWithLogits(mean) * num_labels on soft scores (train_vqa.py:95,157);
+    others: CrossEntropyLoss (train_nlvr2.py:80,133; train_snli_ve.py; train_vcr.py:83,135)."""
+    if task == "vqa":
+        return F.binary_cross_entropy_with_logits(logits, target) * target.shape[1]
+    return F.cross_entropy(logits, target)
+
+
+# -------------------------------------------------------------------------------------------------
+# EWC (src/cl_algorithms/ewc.py)
+# -------------------------------------------------------------------------------------------------
+def ewc_penalty(params: Dict[str, Tensor], theta_star: Dict[str, Tensor], fisher: Dict[str, Tensor],
+                ewc_loss_weight: float) -> Tensor:
+    """EWC.compute_ewc_loss, ewc.py:75-87: lambda * sum_p sum(F_p * (theta_p - theta*_p)^2) over the
+    encoder's named parameters."""
+    loss = torch.zeros(())
+    for name, p in params.items():
+        loss = loss + (fisher[name] * (p - theta_star[name]) ** 2).sum()
+    return ewc_loss_weight * loss
+
+
+def fisher_from_batch_grads(batch_grads: List[Dict[str, Tensor]], batch_sizes: List[int]) -> Dict[str, Tensor]:
+    """EWC.save_task_parameters, ewc.py:55-71, including its quirk: gradients are never zeroed inside
+    the loop, so batch t contributes (sum_{s<=t} g_s)^2, and the sum is divided by the sample count."""
+    fisher: Dict[str, Tensor] = {}
+    running: Dict[str, Tensor] = {}
+    for g in batch_grads:
+        for n, t in g.items():
+            running[n] = running.get(n, torch.zeros_like(t)) + t
+            fisher[n] = fisher.get(n, torch.zeros_like(t)) + running[n] ** 2
+    total = float(sum(batch_sizes))
+    return {n: t / total for n, t in fisher.items()}
+
+
+# -------------------------------------------------------------------------------------------------
+# optimizer grouping (src/modeling/vilt.py:205-215) and LR schedule (optimization.py:208-220)
+# -------------------------------------------------------------------------------------------------
+def weight_decay_groups(names: Sequence[str]) -> Tuple[List[str], List[str]]:
+    no_decay = ["bias", "LayerNorm.weight"]
+    decay = [n for n in names if not any(nd in n for nd in no_decay)]
+    nodecay = [n for n in names if any(nd in n for nd in no_decay)]
+    return decay, nodecay
+
+
+def linear_warmup_decay(step: int, warmup: int, total: int) -> float:
+    """get_polynomial_decay_schedule_with_warmup(power=1, lr_end=0) multiplier (train_vqa.py:199-205)."""
+    if step < warmup:
+        return step / max(1, warmup)
+    if step > total:
+        return 0.0
+    return 1.0 - (step - warmup) / (total - warmup)
+
+
+# -------------------------------------------------------------------------------------------------
+# synthetic batches
+# -------------------------------------------------------------------------------------------------
+def synth_batch(task: str, B: int, dims: ViltDims, T: int = 40, image_hw: Tuple[int, int] = (448, 448),
+                seed: int = 0, masked: bool = False) -> Dict[str, Tensor]:
+    g = torch.Generator().manual_seed(10_000 + seed)
+    spec = TASK_SPECS[task]
+    n_choices = spec.get("num_choices", 1)
+    lo, hi = min(1000, dims.vocab_size // 2), dims.vocab_size
+    ids = torch.randint(lo, hi, (B, n_choices, T), generator=g)
+    ids[..., 0] = min(101, dims.vocab_size - 2)
+    am = torch.ones(B, n_choices, T, dtype=torch.long)
+    if masked:
+        lens = torch.randint(max(2, T // 5), T + 1, (B, n_choices), generator=g)
+        am = (torch.arange(T)[None, None, :] < lens[..., None]).long()
+        ids = ids * am
+    last = am.sum(-1) - 1
+    ids.scatter_(-1, last[..., None], min(102, dims.vocab_size - 1))
+    tt = torch.zeros(B, n_choices, T, dtype=torch.long)
+    H, W = image_hw
+    n_img = spec["num_images"]
+    px = torch.rand(B, n_img, dims.num_channels, H, W, generator=g) * 2 - 1
+    batch = dict(input_ids=ids, attention_mask=am, token_type_ids=tt, pixel_values=px)
+    if n_choices == 1:
+        for k in ("input_ids", "attention_mask", "token_type_ids"):
+            batch[k] = batch[k][:, 0]
+    if n_img == 1:
+        batch["pixel_values"] = px[:, 0]
+    if task == "vqa":
+        tgt = torch.zeros(B, spec["num_labels"])
+        for b in range(B):
+            k = int(torch.randint(1, 4, (1,), generator=g))
+            idx = torch.randperm(spec["num_labels"], generator=g)[:k]
+            tgt[b, idx] = torch.tensor([0.3, 0.6, 0.9, 1.0])[torch.randint(0, 4, (k,), generator=g)]
+        batch["target"] = tgt
+    else:
+        batch["target"] = torch.randint(0, spec["num_labels"], (B,), generator=g)
+    return batch

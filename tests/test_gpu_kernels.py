@@ -56,7 +56,7 @@ def test_gemm_kmajor(M, N, K, block_n):
 
 @pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
 @pytest.mark.parametrize("block_n", [64, 128, 256])
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 192), (768, 768, 948), (3072, 768, 500), (200, 136, 72)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 192), (768, 768, 952), (3072, 768, 504), (200, 136, 72)])
 def test_gemm_mn_major(M, N, K, block_n, a_mn, b_mn):
     L = _lib()
     torch.manual_seed(M + N + K)
@@ -126,6 +126,12 @@ def test_gemm_epilogues():
     assert _rel_err(out, (acc - bias) * (u.float() > 0)) < 1e-5
     L.gemm(a, b, out, bias=bias, epilogue=L.EPI_TANH)
     assert _max_err(out, torch.tanh(acc)) < 1e-5
+    # bf16 copy of the final value (after residual) next to the fp32 output, pre-residual aux
+    c2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, out, bias=bias, residual=res, c2=c2, aux=aux)
+    assert _rel_err(out, acc + res) < 1e-5
+    assert _rel_err(c2, acc + res) < 4e-3
+    assert _rel_err(aux, acc) < 4e-3
     # alpha
     L.gemm(a, b, out, alpha=0.25)
     assert _rel_err(out, 0.25 * (acc - bias)) < 1e-5

@@ -1,0 +1,110 @@
+"""CPU: the oracle restatement (oracle/vilt_oracle.py) against the golden vectors produced by the
+unmodified reference (oracle/make_golden.py). fp32 vs fp32 on the same machine: the only expected
+differences are summation order and the reference's random patch permutation (~1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vilt_oracle as vo
+from tests.golden_util import (ALL_TASKS, BASE, BASE_HW, TINY, TINY_HW, TINY_T, compare_grads, load,
+                               regen_batch)
+
+
+def _oracle_step(sd, dims, task, batch, adapter=None):
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    pooled, logits = vo.learner_forward(params, dims, task, batch, adapter=adapter)
+    loss = vo.task_loss(task, logits, batch["target"])
+    loss.backward()
+    return pooled, logits, loss, {k: v.grad for k, v in params.items()}
+
+
+@pytest.mark.parametrize("task", ALL_TASKS)
+def test_tiny_tasks_match_reference(task):
+    g = load(f"tiny_{task}")
+    seed = int(g["seed"])
+    batch = regen_batch(g, task, TINY, TINY_T, TINY_HW, 3, seed, True)
+    assert np.array_equal(g["in_pixel_values"], batch["pixel_values"].numpy())
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=seed)
+    pooled, logits, loss, grads = _oracle_step(sd, TINY, task, batch)
+    assert np.allclose(pooled.detach().numpy(), g["pooled"], atol=2e-6)
+    assert np.allclose(logits.detach().numpy(), g["logits"], atol=5e-6)
+    assert abs(loss.item() - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    worst = compare_grads(g, grads, rtol_norm=1e-4, tol_elem=2e-4)
+    print("worst grad", worst)
+
+
+@pytest.mark.parametrize("tag,kind,task,rf", [("tiny_adapter_houlsby_nlvr2", "houlsby", "nlvr2", 4),
+                                               ("tiny_adapter_pfeiffer_vqa", "pfeiffer", "vqa", 2)])
+def test_tiny_adapters_match_reference(tag, kind, task, rf):
+    g = load(tag)
+    seed = int(g["seed"])
+    batch = regen_batch(g, task, TINY, TINY_T, TINY_HW, 3, seed, True)
+    sites = ("mh", "output") if kind == "houlsby" else ("output",)
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=seed, adapters={task: TINY.hidden_size // rf},
+                             adapter_sites=sites)
+    spec = vo.AdapterSpec(task, "swish" if kind == "houlsby" else "relu", sites)
+    pooled, logits, loss, grads = _oracle_step(sd, TINY, task, batch, adapter=spec)
+    assert np.allclose(pooled.detach().numpy(), g["pooled"], atol=2e-6)
+    assert np.allclose(logits.detach().numpy(), g["logits"], atol=5e-6)
+    trainable = set(g["trainable"].tolist())
+    # train_adapter freezes ViltModel only: the adapter + ALL task heads stay trainable
+    assert all((".adapters." in n) or n.startswith("task_layer.") for n in trainable)
+    worst = compare_grads(g, grads, rtol_norm=1e-4, tol_elem=2e-4)
+    print("worst grad", worst)
+
+
+def test_tiny_ewc_matches_reference():
+    g = load("tiny_ewc_snli-ve")
+    seed = int(g["seed"])
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=seed)
+    sizes = g["batch_sizes"].tolist()
+    batch_grads = []
+    for i, b in enumerate(sizes):
+        batch = vo.synth_batch("snli-ve", b, TINY, T=TINY_T, image_hw=TINY_HW, seed=seed + i, masked=True)
+        assert np.array_equal(g[f"b{i}_input_ids"], batch["input_ids"].numpy())
+        _, _, _, grads = _oracle_step(sd, TINY, "snli-ve", batch)
+        batch_grads.append({k[len("vilt_encoder."):]: v for k, v in grads.items()
+                            if k.startswith("vilt_encoder.") and v is not None})
+    fisher = vo.fisher_from_batch_grads(batch_grads, sizes)
+    n_checked = 0
+    fscale = max(float(g[k]) for k in g.files if k.startswith("fisher_norm/"))
+    for key in g.files:
+        if not key.startswith("fisher_norm/"):
+            continue
+        name = key[len("fisher_norm/"):]
+        ref_norm = float(g[key])
+        if ref_norm < 1e-10 * fscale:       # squared rounding noise of an analytically-zero gradient
+            assert fisher[name].norm().item() < 1e-9 * fscale, name
+            n_checked += 1
+            continue
+        assert abs(fisher[name].norm().item() - ref_norm) <= 2e-4 * max(ref_norm, 1e-20), name
+        if "fisher/" + name in g.files:
+            ref = torch.from_numpy(g["fisher/" + name])
+            assert (fisher[name] - ref).abs().max().item() <= 5e-4 * max(ref.abs().max().item(), 1e-20), name
+        n_checked += 1
+    assert n_checked > 30
+    # penalty and its gradient at the perturbed parameters
+    gen = torch.Generator().manual_seed(seed + 99)
+    theta_star = {k[len("vilt_encoder."):]: v for k, v in sd.items() if k.startswith("vilt_encoder.")}
+    theta = {}
+    for n, p in theta_star.items():         # same order as named_parameters() of the reference encoder
+        theta[n] = (p + 0.01 * torch.randn(p.shape, generator=gen)).requires_grad_(True)
+    loss = vo.ewc_penalty(theta, theta_star, fisher, float(g["ewc_loss_weight"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["ewc_loss"])) <= 5e-4 * float(g["ewc_loss"])
+    compare_grads(g, {n: t.grad for n, t in theta.items()}, rtol_norm=5e-4, tol_elem=1e-3)
+
+
+@pytest.mark.parametrize("task,seed,masked", [("vqa", 42, False), ("nlvr2", 43, True)])
+def test_base_config_matches_reference(task, seed, masked):
+    """ViLT-base geometry (BASELINE.json configs[0] shape at B=2): 40 tokens + 14x14 patches."""
+    g = load(f"base_{task}")
+    batch = regen_batch(g, task, BASE, 40, BASE_HW, 2, seed, masked)
+    sd = vo.synth_state_dict(BASE, ALL_TASKS, seed=seed)
+    torch.set_num_threads(8)
+    pooled, logits, loss, grads = _oracle_step(sd, BASE, task, batch)
+    assert np.allclose(pooled.detach().numpy(), g["pooled"], atol=5e-6)
+    assert np.allclose(logits.detach().numpy(), g["logits"], atol=2e-5)
+    assert abs(loss.item() - float(g["loss"])) <= 5e-6 * abs(float(g["loss"]))
+    worst = compare_grads(g, grads, rtol_norm=2e-4, tol_elem=5e-4)
+    print("worst grad", worst)
