@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 import torch
 
@@ -72,6 +72,74 @@ climb_layernorm_fwd = _sig(
 climb_layernorm_bwd = _sig(
     "climb_layernorm_bwd",
     [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P])
+
+
+climb_cast_f32_bf16 = _sig("climb_cast_f32_bf16", [_P, _P, c_int64, _P])
+climb_colsum = _sig("climb_colsum", [_P, c_int, c_int64, c_int, c_int, _P, _P])
+climb_bce_logits_loss = _sig(
+    "climb_bce_logits_loss", [_P, c_int64, _P, c_int, c_int, c_float, c_float, _P, _P, _P, c_int64, _P])
+climb_cross_entropy_loss = _sig(
+    "climb_cross_entropy_loss", [_P, c_int64, _P, c_int, c_int, c_float, _P, _P, _P, c_int64, _P])
+climb_ewc_penalty = _sig(
+    "climb_ewc_penalty", [_P, _P, _P, c_int64, c_float, _P, c_int, _P, _P, c_float, _P, _P])
+climb_fisher_accumulate = _sig("climb_fisher_accumulate", [_P, _P, c_int64, _P])
+climb_scale_inplace = _sig("climb_scale_inplace", [_P, c_int64, c_float, _P])
+climb_adamw_step = _sig(
+    "climb_adamw_step", [_P, _P, _P, _P, _P, c_int, POINTER(c_float), POINTER(c_float), c_int, c_float, c_float,
+                         c_float, c_int, _P])
+
+
+class ViltDimsC(Structure):
+    _fields_ = [("hidden", c_int), ("layers", c_int), ("heads", c_int), ("ffn", c_int),
+                ("patch", c_int), ("channels", c_int), ("pos_grid", c_int), ("n_modality", c_int),
+                ("ln_eps", c_float)]
+
+
+LAYER_FIELDS = ["qkv_w", "qkv_b", "o_w", "o_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+                "ln1_w", "ln1_b", "ln2_w", "ln2_b",
+                "mh_down_w", "mh_down_b", "mh_up_w", "mh_up_b",
+                "out_down_w", "out_down_b", "out_up_w", "out_up_b"]
+
+
+class ViltLayerC(Structure):
+    _fields_ = [(n, c_int64) for n in LAYER_FIELDS] + [("flags", c_int32), ("pad_", c_int32)]
+
+
+PARAM_FIELDS = ["cls_token", "pos_emb", "word_emb", "text_pos_emb", "text_type_emb", "text_ln_w",
+                "text_ln_b", "patch_w", "patch_b", "mod_emb", "final_ln_w", "final_ln_b", "pooler_w",
+                "pooler_b"]
+
+
+class ViltParamsC(Structure):
+    _fields_ = [(n, c_int64) for n in PARAM_FIELDS] + [
+        ("layer", POINTER(ViltLayerC)), ("adapter_r", c_int), ("adapter_act", c_int),
+        ("embed_flags", c_int32), ("tail_flags", c_int32)]
+
+
+class ViltBatchC(Structure):
+    _fields_ = [("B", c_int), ("T", c_int), ("H", c_int), ("W", c_int),
+                ("input_ids", c_void_p), ("inputs_embeds", c_void_p), ("token_type_ids", c_void_p),
+                ("attention_mask", c_void_p), ("pixel_values", c_void_p), ("image_type_idx", c_void_p),
+                ("image_type_idx_scalar", c_int)]
+
+
+class AdamWChunkC(Structure):
+    _fields_ = [("start", c_int64), ("length", c_int32), ("group", c_int32)]
+
+
+TRAIN_BASE, TRAIN_ADAPTER = 1, 2
+
+climb_vilt_forward_workspace_bytes = _sig(
+    "climb_vilt_forward_workspace_bytes", [POINTER(ViltDimsC), POINTER(ViltParamsC), POINTER(ViltBatchC), c_int],
+    c_int64)
+climb_vilt_backward_scratch_bytes = _sig(
+    "climb_vilt_backward_scratch_bytes", [POINTER(ViltDimsC), POINTER(ViltParamsC), POINTER(ViltBatchC)], c_int64)
+climb_vilt_forward = _sig(
+    "climb_vilt_forward", [POINTER(ViltDimsC), POINTER(ViltParamsC), POINTER(ViltBatchC), _P, _P, _P, c_int64,
+                           c_int, _P, _P])
+climb_vilt_backward = _sig(
+    "climb_vilt_backward", [POINTER(ViltDimsC), POINTER(ViltParamsC), POINTER(ViltBatchC), _P, _P, _P, c_int64,
+                            _P, c_int64, _P, _P, _P])
 
 
 def check(rc: int) -> None:
@@ -185,3 +253,17 @@ def layernorm_bwd(dy, x, gamma, beta, mean, rstd, *, rows=None, ldx=None, dres=N
     check(climb_layernorm_bwd(ptr(dy_f32), ptr(dy_b16), ptr(x), ldx, ptr(gamma), ptr(beta), ptr(mean),
                               ptr(rstd), ptr(dres), ptr(dx_f32), ptr(dx_bf16), ptr(dgamma), ptr(dbeta),
                               rows, d, act, stream()))
+
+
+def cast_f32_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    check(climb_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream()))
+
+
+def colsum(src: torch.Tensor, out: torch.Tensor, rows=None, cols=None) -> None:
+    """out[c] += sum_r src[r, c] (src bf16 or fp32, row stride src.stride(0))."""
+    assert src.dim() == 2 and src.stride(1) == 1 and out.dtype == torch.float32
+    rows = src.shape[0] if rows is None else rows
+    cols = src.shape[1] if cols is None else cols
+    dt = {torch.bfloat16: BF16, torch.float32: F32}[src.dtype]
+    check(climb_colsum(ptr(src), dt, src.stride(0), rows, cols, ptr(out), stream()))

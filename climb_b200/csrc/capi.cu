@@ -53,4 +53,59 @@ int climb_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x
                          dgamma, dbeta, rows, d, act, S(stream));
 }
 
+
+int climb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
+    return cast_f32_bf16(src, dst_bf16, n, S(stream));
+}
+int climb_colsum(const void* src, int dtype, int64_t ld, int rows, int cols, float* out, void* stream) {
+    return colsum(src, dtype, ld, rows, cols, out, S(stream));
+}
+int climb_bce_logits_loss(const float* logits, int64_t ld, const float* target, int rows, int cols, float scale,
+                          float grad_scale, float* row_loss, float* loss, float* dlogits, int64_t ldd, void* stream) {
+    return bce_logits_loss(logits, ld, target, rows, cols, scale, grad_scale, row_loss, loss, dlogits, ldd, S(stream));
+}
+int climb_cross_entropy_loss(const float* logits, int64_t ld, const int64_t* target, int rows, int cols,
+                             float grad_scale, float* row_loss, float* loss, float* dlogits, int64_t ldd,
+                             void* stream) {
+    return cross_entropy_loss(logits, ld, reinterpret_cast<const long long*>(target), rows, cols, grad_scale, row_loss,
+                              loss, dlogits, ldd, S(stream));
+}
+int climb_ewc_penalty(const float* theta, const float* theta_star, const float* fisher, int64_t n, float lambda,
+                      float* partials, int n_partials, float* loss, float* grad, float grad_scale,
+                      const float* grad_scale_dev, void* stream) {
+    return ewc_penalty(theta, theta_star, fisher, n, lambda, partials, n_partials, loss, grad, grad_scale,
+                       grad_scale_dev, S(stream));
+}
+int climb_fisher_accumulate(const float* grad, float* fisher, int64_t n, void* stream) {
+    return fisher_accumulate(grad, fisher, n, S(stream));
+}
+int climb_scale_inplace(float* x, int64_t n, float s, void* stream) { return scale_inplace(x, n, s, S(stream)); }
+int climb_adamw_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq,
+                     const climb_adamw_chunk* chunks_dev, int n_chunks, const float* group_lr_host,
+                     const float* group_wd_host, int n_groups, float beta1, float beta2, float eps, int step,
+                     void* stream) {
+    return adamw_step(theta, grad, exp_avg, exp_avg_sq, chunks_dev, n_chunks, group_lr_host, group_wd_host, n_groups,
+                      beta1, beta2, eps, step, S(stream));
+}
+int64_t climb_vilt_forward_workspace_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                                           const climb_vilt_batch* batch, int save_for_backward) {
+    return vilt_forward_workspace_bytes(dims, params, batch, save_for_backward);
+}
+int64_t climb_vilt_backward_scratch_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                                          const climb_vilt_batch* batch) {
+    return vilt_backward_scratch_bytes(dims, params, batch);
+}
+int climb_vilt_forward(const climb_vilt_dims* dims, const climb_vilt_params* params, const climb_vilt_batch* batch,
+                       const float* theta, const void* shadow, void* workspace, int64_t workspace_bytes,
+                       int save_for_backward, float* pooled_out, void* stream) {
+    return vilt_forward(dims, params, batch, theta, shadow, workspace, workspace_bytes, save_for_backward, pooled_out,
+                        S(stream));
+}
+int climb_vilt_backward(const climb_vilt_dims* dims, const climb_vilt_params* params, const climb_vilt_batch* batch,
+                        const float* theta, const void* shadow, const void* workspace, int64_t workspace_bytes,
+                        void* scratch, int64_t scratch_bytes, const float* dpooled, float* grad, void* stream) {
+    return vilt_backward(dims, params, batch, theta, shadow, workspace, workspace_bytes, scratch, scratch_bytes, dpooled,
+                         grad, S(stream));
+}
+
 }  // extern "C"

@@ -1,0 +1,280 @@
+// Embedding kernels of the ViLT hot path (ViltEmbeddings / TextEmbeddings / PatchEmbeddings,
+// modeling_vilt.py:92-328) on the fixed-resolution path (one H x W per batch, pixel_mask all ones):
+//   text : word[ids] (or inputs_embeds) + segment[tt] + position[t]            (:292-301; LN runs in layernorm.cu)
+//   image: im2col of the 32x32/stride-32 conv (:309-328) so that it becomes one tcgen05 GEMM,
+//          bilinear (align_corners) resize of the position table (:130-147), [cls] + pos[0] (:195-200)
+//   both : + modality-type rows and concatenation text || image (:231-246), written straight into the
+//          [B, L, d] fp32 residual stream.
+// Backward kernels reduce the gradient of that stream onto the embedding tables. All HBM-bound:
+// float4 / uint4 accesses, one pass over the data.
+#include "common.cuh"
+#include "climb_b200.h"
+
+namespace climb {
+namespace {
+
+__global__ void text_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ inputs_embeds,
+                                   const long long* __restrict__ tt, const float* __restrict__ word,
+                                   const float* __restrict__ type_emb, const float* __restrict__ pos,
+                                   float* __restrict__ e, int rows, int T, int d4) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(rows) * d4) return;
+    const int r = static_cast<int>(i / d4), c = static_cast<int>(i - static_cast<long long>(r) * d4);
+    const int t = r % T;
+    const float4 w = inputs_embeds ? reinterpret_cast<const float4*>(inputs_embeds)[i]
+                                   : reinterpret_cast<const float4*>(word)[ids[r] * d4 + c];
+    const long long ty = tt ? tt[r] : 0;
+    const float4 s = reinterpret_cast<const float4*>(type_emb)[ty * d4 + c];
+    const float4 p = reinterpret_cast<const float4*>(pos)[static_cast<long long>(t) * d4 + c];
+    reinterpret_cast<float4*>(e)[i] = make_float4(w.x + s.x + p.x, w.y + s.y + p.y, w.z + s.z + p.z, w.w + s.w + p.w);
+}
+
+// pixel fp32 [B, C, H, W] -> bf16 [B*hp*wp, C*P*P], k = (c, ky, kx) as in the conv weight [d, C, P, P]
+__global__ void im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ out, int B, int C,
+                              int H, int W, int P, int hp, int wp) {
+    const int K = C * P * P;
+    const int k8 = K / 8;
+    const long long total = static_cast<long long>(B) * hp * wp * k8;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long m = i / k8;
+    const int k0 = static_cast<int>(i - m * k8) * 8;
+    const int c = k0 / (P * P), rem = k0 - c * P * P, ky = rem / P, kx = rem - ky * P;
+    const int b = static_cast<int>(m / (hp * wp)), pr = static_cast<int>(m - static_cast<long long>(b) * hp * wp);
+    const int py = pr / wp, pxi = pr - py * wp;
+    const float* src = px + ((static_cast<long long>(b) * C + c) * H + (py * P + ky)) * W + pxi * P + kx;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b4 = *reinterpret_cast<const float4*>(src + 4);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w);
+    o.z = pack_bf16(b4.x, b4.y); o.w = pack_bf16(b4.z, b4.w);
+    *reinterpret_cast<uint4*>(out + m * K + k0) = o;
+}
+
+struct Taps { int i00, i01, i10, i11; float w00, w01, w10, w11; };
+
+// torch's bilinear / align_corners=True source index (UpSample.h area_pixel_compute_source_index)
+__device__ __forceinline__ Taps bilinear_taps(int py, int pxi, int hp, int wp, int G) {
+    const float sy = hp > 1 ? static_cast<float>(G - 1) / static_cast<float>(hp - 1) : 0.0f;
+    const float sx = wp > 1 ? static_cast<float>(G - 1) / static_cast<float>(wp - 1) : 0.0f;
+    const float fy = sy * py, fx = sx * pxi;
+    const int y0 = min(static_cast<int>(fy), G - 1), x0 = min(static_cast<int>(fx), G - 1);
+    const int y1 = min(y0 + 1, G - 1), x1 = min(x0 + 1, G - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    Taps t;
+    t.i00 = y0 * G + x0; t.i01 = y0 * G + x1; t.i10 = y1 * G + x0; t.i11 = y1 * G + x1;
+    t.w00 = (1.0f - ly) * (1.0f - lx); t.w01 = (1.0f - ly) * lx; t.w10 = ly * (1.0f - lx); t.w11 = ly * lx;
+    return t;
+}
+
+// pos_emb [1 + G*G, d] -> table [hp*wp, d]
+__global__ void pos_interp_kernel(const float* __restrict__ pos_emb, float* __restrict__ table, int hp, int wp,
+                                  int G, int d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hp * wp * d) return;
+    const int p = i / d, c = i - p * d;
+    const Taps t = bilinear_taps(p / wp, p % wp, hp, wp, G);
+    const float* g = pos_emb + d;      // skip row 0 (the [cls] position)
+    table[i] = t.w00 * g[t.i00 * d + c] + t.w01 * g[t.i01 * d + c] + t.w10 * g[t.i10 * d + c] + t.w11 * g[t.i11 * d + c];
+}
+
+// x[b, l, :] for l < T: text_ln[b*T+l] + mod[0]; l == T: cls + pos[0] + mod[idx_b]; l > T: patch + table + mod[idx_b]
+__global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const float* __restrict__ patch,
+                                      const float* __restrict__ table, const float* __restrict__ cls,
+                                      const float* __restrict__ pos_emb, const float* __restrict__ mod,
+                                      const int* __restrict__ type_idx, int type_idx_scalar,
+                                      float* __restrict__ x, int B, int T, int Np, int d4) {
+    const int L = T + 1 + Np;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * L * d4) return;
+    const long long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    const int b = static_cast<int>(row / L), l = static_cast<int>(row - static_cast<long long>(b) * L);
+    float4 v, m;
+    if (l < T) {
+        v = reinterpret_cast<const float4*>(text_ln)[(static_cast<long long>(b) * T + l) * d4 + c];
+        m = reinterpret_cast<const float4*>(mod)[c];
+    } else {
+        const int idx = type_idx ? type_idx[b] : type_idx_scalar;
+        m = reinterpret_cast<const float4*>(mod)[static_cast<long long>(idx) * d4 + c];
+        if (l == T) {
+            const float4 a = reinterpret_cast<const float4*>(cls)[c];
+            const float4 p0 = reinterpret_cast<const float4*>(pos_emb)[c];
+            v = make_float4(a.x + p0.x, a.y + p0.y, a.z + p0.z, a.w + p0.w);
+        } else {
+            const int p = l - T - 1;
+            const float4 a = reinterpret_cast<const float4*>(patch)[(static_cast<long long>(b) * Np + p) * d4 + c];
+            const float4 t = reinterpret_cast<const float4*>(table)[static_cast<long long>(p) * d4 + c];
+            v = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+        }
+    }
+    reinterpret_cast<float4*>(x)[i] = make_float4(v.x + m.x, v.y + m.y, v.z + m.z, v.w + m.w);
+}
+
+// dx [B, L, d] -> dy_text fp32 [B*T, d] (input of the text LayerNorm backward) and
+//                 dpatch bf16 [B*Np, d] (A operand of the patch-projection wgrad)
+__global__ void embed_split_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dy_text,
+                                       __nv_bfloat16* __restrict__ dpatch, int B, int T, int Np, int d4) {
+    const int L = T + 1 + Np;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * L * d4) return;
+    const long long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    const int b = static_cast<int>(row / L), l = static_cast<int>(row - static_cast<long long>(b) * L);
+    if (l == T) return;
+    const float4 v = reinterpret_cast<const float4*>(dx)[i];
+    if (l < T) {
+        if (dy_text) reinterpret_cast<float4*>(dy_text)[(static_cast<long long>(b) * T + l) * d4 + c] = v;
+    } else if (dpatch) {
+        uint2 o;
+        o.x = pack_bf16(v.x, v.y);
+        o.y = pack_bf16(v.z, v.w);
+        reinterpret_cast<uint2*>(dpatch)[(static_cast<long long>(b) * Np + (l - T - 1)) * d4 + c] = o;
+    }
+}
+
+// S[k][l, c] = sum over the sequences b whose image type index is k+1 of dx[b, l, c]  (k = 0, 1).
+// Text rows (l < T) all go to S[0]. One thread per (l, float4 column), sequential over b: fixed
+// summation order, coalesced across the warp.
+__global__ void embed_reduce_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ type_idx,
+                                        int type_idx_scalar, float* __restrict__ S, int B, int T, int L, int d4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * d4) return;
+    const int l = i / d4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int b = 0; b < B; ++b) {
+        const float4 v = reinterpret_cast<const float4*>(dx)[static_cast<long long>(b) * L * d4 + i];
+        const int idx = (l < T) ? 1 : (type_idx ? type_idx[b] : type_idx_scalar);
+        if (idx == 2) { a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w; }
+        else          { a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w; }
+    }
+    reinterpret_cast<float4*>(S)[i] = a0;
+    reinterpret_cast<float4*>(S)[static_cast<long long>(L) * d4 + i] = a1;
+}
+
+// one thread per column: folds S onto cls_token, position_embeddings (row 0 + the transposed
+// bilinear taps), the modality-type table and the patch-projection bias
+__global__ void embed_finalize_bwd_kernel(const float* __restrict__ S, float* __restrict__ d_cls,
+                                          float* __restrict__ d_pos, float* __restrict__ d_mod,
+                                          float* __restrict__ d_patch_bias, int n_mod, int T, int hp, int wp,
+                                          int G, int d) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    const int Np = hp * wp, L = T + 1 + Np;
+    const float* S0 = S;
+    const float* S1 = S + static_cast<long long>(L) * d;
+    float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, pb = 0.0f;
+    for (int l = 0; l < T; ++l) m0 += S0[l * d + c];
+    for (int l = T; l < L; ++l) { m1 += S0[l * d + c]; m2 += S1[l * d + c]; }
+    if (d_mod) {
+        d_mod[c] += m0;
+        d_mod[d + c] += m1;
+        if (n_mod > 2) d_mod[2 * d + c] += m2;
+    }
+    const float cls_g = S0[T * d + c] + S1[T * d + c];
+    if (d_cls) d_cls[c] += cls_g;
+    if (d_pos) d_pos[c] += cls_g;
+    for (int p = 0; p < Np; ++p) {
+        const float g = S0[(T + 1 + p) * d + c] + S1[(T + 1 + p) * d + c];
+        pb += g;
+        if (d_pos) {
+            const Taps t = bilinear_taps(p / wp, p % wp, hp, wp, G);
+            float* dp = d_pos + d;
+            dp[t.i00 * d + c] += t.w00 * g;
+            dp[t.i01 * d + c] += t.w01 * g;
+            dp[t.i10 * d + c] += t.w10 * g;
+            dp[t.i11 * d + c] += t.w11 * g;
+        }
+    }
+    if (d_patch_bias) d_patch_bias[c] += pb;
+}
+
+// de [B*T, d] -> word / segment / position embedding gradients (dense tables, atomics on collisions)
+__global__ void text_scatter_bwd_kernel(const float* __restrict__ de, const long long* __restrict__ ids,
+                                        const long long* __restrict__ tt, float* __restrict__ d_word,
+                                        float* __restrict__ d_type, float* __restrict__ d_pos, int rows, int T, int d) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(rows) * d) return;
+    const int r = static_cast<int>(i / d), c = static_cast<int>(i - static_cast<long long>(r) * d);
+    const float g = de[i];
+    if (d_word && ids) atomicAdd(d_word + ids[r] * d + c, g);
+    if (d_type) atomicAdd(d_type + (tt ? tt[r] : 0) * d + c, g);
+    if (d_pos) atomicAdd(d_pos + static_cast<long long>(r % T) * d + c, g);
+}
+
+inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+}  // namespace
+
+int text_gather(const long long* ids, const float* inputs_embeds, const long long* tt, const float* word,
+                const float* type_emb, const float* pos, float* e, int rows, int T, int d, cudaStream_t stream) {
+    CLIMB_REQUIRE((ids != nullptr) != (inputs_embeds != nullptr), "text_gather: exactly one of input_ids / inputs_embeds");
+    CLIMB_REQUIRE(type_emb && pos && e && rows > 0 && d % 4 == 0, "text_gather: bad arguments");
+    CLIMB_REQUIRE(ids == nullptr || word != nullptr, "text_gather: word table missing");
+    text_gather_kernel<<<blocks_for(static_cast<long long>(rows) * (d / 4), 256), 256, 0, stream>>>(
+        ids, inputs_embeds, tt, word, type_emb, pos, e, rows, T, d / 4);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int im2col(const float* px, void* out, int B, int C, int H, int W, int P, cudaStream_t stream) {
+    CLIMB_REQUIRE(px && out && B > 0, "im2col: bad arguments");
+    CLIMB_REQUIRE(P % 8 == 0 && H % P == 0 && W % P == 0,
+                  "im2col: fixed-resolution path needs H, W multiples of the patch size (%d x %d, P=%d)", H, W, P);
+    CLIMB_REQUIRE((reinterpret_cast<uintptr_t>(px) & 15) == 0 && W % 4 == 0, "im2col: pixel rows must be 16-byte aligned");
+    const int hp = H / P, wp = W / P;
+    const long long total = static_cast<long long>(B) * hp * wp * (C * P * P / 8);
+    im2col_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, static_cast<__nv_bfloat16*>(out), B, C, H, W, P, hp, wp);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int pos_interp(const float* pos_emb, float* table, int hp, int wp, int G, int d, cudaStream_t stream) {
+    CLIMB_REQUIRE(pos_emb && table && hp > 0 && wp > 0 && G > 0, "pos_interp: bad arguments");
+    pos_interp_kernel<<<blocks_for(static_cast<long long>(hp) * wp * d, 256), 256, 0, stream>>>(pos_emb, table, hp, wp, G, d);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int embed_assemble(const float* text_ln, const float* patch, const float* table, const float* cls,
+                   const float* pos_emb, const float* mod, const int* type_idx, int type_idx_scalar, float* x,
+                   int B, int T, int Np, int d, cudaStream_t stream) {
+    CLIMB_REQUIRE(text_ln && patch && table && cls && pos_emb && mod && x && d % 4 == 0, "embed_assemble: bad arguments");
+    const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
+    embed_assemble_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, table, cls, pos_emb, mod,
+                                                                     type_idx, type_idx_scalar, x, B, T, Np, d / 4);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T, int Np, int d, cudaStream_t stream) {
+    CLIMB_REQUIRE(dx && d % 4 == 0, "embed_split_bwd: bad arguments");
+    const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
+    embed_split_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(dx, dy_text, static_cast<__nv_bfloat16*>(dpatch), B, T, Np, d / 4);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, float* S, float* d_cls,
+                     float* d_pos, float* d_mod, float* d_patch_bias, int n_mod, int B, int T, int hp, int wp,
+                     int G, int d, cudaStream_t stream) {
+    CLIMB_REQUIRE(dx && S && d % 4 == 0, "embed_reduce_bwd: bad arguments");
+    const int L = T + 1 + hp * wp;
+    embed_reduce_bwd_kernel<<<blocks_for(static_cast<long long>(L) * (d / 4), 128), 128, 0, stream>>>(
+        dx, type_idx, type_idx_scalar, S, B, T, L, d / 4);
+    CLIMB_LAUNCH_OK();
+    embed_finalize_bwd_kernel<<<blocks_for(d, 128), 128, 0, stream>>>(S, d_cls, d_pos, d_mod, d_patch_bias, n_mod, T, hp, wp, G, d);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int text_scatter_bwd(const float* de, const long long* ids, const long long* tt, float* d_word, float* d_type,
+                     float* d_pos, int rows, int T, int d, cudaStream_t stream) {
+    CLIMB_REQUIRE(de && rows > 0, "text_scatter_bwd: bad arguments");
+    text_scatter_bwd_kernel<<<blocks_for(static_cast<long long>(rows) * d, 256), 256, 0, stream>>>(
+        de, ids, tt, d_word, d_type, d_pos, rows, T, d);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace climb

@@ -21,4 +21,54 @@ int layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long
                   const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
                   int rows, int d, int act, cudaStream_t stream);
 
+
+// elementwise.cu
+int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+int colsum(const void* src, int dtype, long long ld, int rows, int cols, float* out, cudaStream_t stream);
+int key_bias(const long long* mask, float* out, int B, int T, int L, cudaStream_t stream);
+int tanh_bwd(const float* dy, const float* y, void* out_bf16, long long n, cudaStream_t stream);
+int bce_logits_loss(const float* logits, long long ld, const float* target, int rows, int cols, float scale,
+                    float grad_scale, float* row_loss, float* loss, float* dlogits, long long ldd,
+                    cudaStream_t stream);
+int cross_entropy_loss(const float* logits, long long ld, const long long* target, int rows, int cols,
+                       float grad_scale, float* row_loss, float* loss, float* dlogits, long long ldd,
+                       cudaStream_t stream);
+
+// embed.cu
+int text_gather(const long long* ids, const float* inputs_embeds, const long long* tt, const float* word,
+                const float* type_emb, const float* pos, float* e, int rows, int T, int d, cudaStream_t stream);
+int im2col(const float* px, void* out, int B, int C, int H, int W, int P, cudaStream_t stream);
+int pos_interp(const float* pos_emb, float* table, int hp, int wp, int G, int d, cudaStream_t stream);
+int embed_assemble(const float* text_ln, const float* patch, const float* table, const float* cls,
+                   const float* pos_emb, const float* mod, const int* type_idx, int type_idx_scalar, float* x,
+                   int B, int T, int Np, int d, cudaStream_t stream);
+int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T, int Np, int d, cudaStream_t stream);
+int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, float* S, float* d_cls,
+                     float* d_pos, float* d_mod, float* d_patch_bias, int n_mod, int B, int T, int hp, int wp,
+                     int G, int d, cudaStream_t stream);
+int text_scatter_bwd(const float* de, const long long* ids, const long long* tt, float* d_word, float* d_type,
+                     float* d_pos, int rows, int T, int d, cudaStream_t stream);
+
+// optim.cu
+int ewc_penalty(const float* theta, const float* theta_star, const float* fisher, long long n, float lambda,
+                float* partials, int n_partials, float* loss, float* grad, float grad_scale,
+                const float* grad_scale_dev, cudaStream_t stream);
+int fisher_accumulate(const float* grad, float* fisher, long long n, cudaStream_t stream);
+int scale_inplace(float* x, long long n, float s, cudaStream_t stream);
+int adamw_step(float* theta, const float* grad, float* m, float* v, const climb_adamw_chunk* chunks_dev,
+               int n_chunks, const float* group_lr, const float* group_wd, int n_groups, float beta1, float beta2,
+               float eps, int step, cudaStream_t stream);
+
+// engine.cu
+long long vilt_forward_workspace_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                                       const climb_vilt_batch* batch, int save);
+long long vilt_backward_scratch_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                                      const climb_vilt_batch* batch);
+int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const climb_vilt_batch* bt,
+                 const float* theta, const void* shadow, void* workspace, long long workspace_bytes, int save,
+                 float* pooled_out, cudaStream_t s);
+int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const climb_vilt_batch* bt,
+                  const float* theta, const void* shadow, const void* workspace, long long workspace_bytes,
+                  void* scratch, long long scratch_bytes, const float* dpooled, float* grad, cudaStream_t s);
+
 }  // namespace climb

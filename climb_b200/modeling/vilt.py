@@ -1,0 +1,269 @@
+"""B200 drop-ins for CLiMB's ViLT wrappers (src/modeling/vilt.py): same class surface, same
+registry signatures, same state-dict keys -- the encoder arithmetic runs in libclimb_b200.so.
+
+    ViltEncoderWrapper      -> B200ViltEncoderWrapper      (vilt.py:30-144)
+    ViltContinualLearner    -> B200ViltContinualLearner    (vilt.py:147-367)
+    load_vilt_encoder       -> load_vilt_encoder           (vilt.py:481-514)
+    create_vilt_continual_learner_model                    (vilt.py:516-546)
+    convert_batch_to_vilt_input_dict / convert_seq_batch_to_vilt_input_dict (vilt.py:548-567)
+
+Differences that are deliberate:
+  * NLVR2's two passes and VCR's four passes (vilt.py:291-304, 334-347) are batched into ONE encoder
+    call over 2B / 4B sequences -- numerically the same rows, no cross-row op exists in the encoder;
+  * `forward_tensors(task_key, encodings)` takes the processor's output directly (the synthetic
+    benchmark and the tests feed tensors; the PIL / tokenizer path of process_inputs still works
+    when a processor is supplied).
+"""
+from __future__ import annotations
+
+import itertools
+import logging
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..optim import ArenaAdamW
+from .continual_learner import ContinualLearner, EncoderWrapper
+from .vilt_model import B200ViltConfig, B200ViltModel
+
+logger = logging.getLogger(__name__)
+
+
+class B200ViltEncoderWrapper(EncoderWrapper):
+    def __init__(self, processor, vilt: B200ViltModel, device: torch.device):
+        super().__init__()
+        self.processor = processor
+        self.vilt = vilt
+        self.device = device
+        self.max_text_length = self.vilt.config.max_position_embeddings
+        self.encoder_dim = self.vilt.config.hidden_size
+
+    def reset_processor(self, max_text_length: int, img_size: tuple):
+        self.max_text_length = max_text_length
+        if self.processor is not None:
+            self.processor.feature_extractor.size = img_size
+
+    def reallocate_text_image(self, pretrained_pos_emb: torch.Tensor, max_len: int, img_size: int):
+        """vilt.py:57-81: tile the text position table so longer language inputs fit."""
+        cfg = self.vilt.config
+        assert max_len % cfg.max_position_embeddings == 0
+        self.reset_processor(max_len, img_size)
+        extended = torch.cat([pretrained_pos_emb for _ in range(0, max_len, cfg.max_position_embeddings)], 0)
+        te = self.vilt.embeddings.text_embeddings
+        te.position_embeddings = nn.Embedding(max_len, cfg.hidden_size).from_pretrained(extended, freeze=False)
+        te.register_buffer("position_ids", torch.arange(max_len).expand((1, -1)))
+
+    def process_inputs(self, images: List, texts: List[str]) -> Dict:
+        if self.processor is None:
+            raise RuntimeError("this encoder was built without a ViltProcessor: call forward_tensors() / pass "
+                               "encodings, or construct it with processor=ViltProcessor.from_pretrained(...)")
+        encodings = self.processor(images=images, text=texts, max_length=self.max_text_length,
+                                   padding=True, truncation=True, return_tensors='pt').to(self.device)
+        return encodings
+
+    def expand_modality_type_embeddings(self, type_vocab_size=3):
+        """vilt.py:98-109: third modality row (second NLVR2 image) initialised from row 1."""
+        self.vilt.config.modality_type_vocab_size = type_vocab_size
+        old = self.vilt.embeddings.token_type_embeddings.weight.data
+        new = nn.Embedding(type_vocab_size, self.encoder_dim).to(old.device)
+        new.weight.data[0, :] = old[0, :]
+        new.weight.data[1, :] = old[1, :]
+        new.weight.data[2, :] = old[1, :]
+        self.vilt.embeddings.token_type_embeddings = new
+
+    def forward(self, **encodings) -> torch.FloatTensor:
+        return self.vilt(**encodings).pooler_output
+
+    def freeze_all_weights(self):
+        for p in self.vilt.parameters():
+            p.requires_grad = False
+
+    def freeze_bottom_k_layers(self, k: int):
+        assert k < len(self.vilt.encoder.layer)
+        for p in self.vilt.embeddings.parameters():
+            p.requires_grad = False
+        for i in range(k):
+            for p in self.vilt.encoder.layer[i].parameters():
+                p.requires_grad = False
+
+
+class ClassifierHead(nn.Sequential):
+    """nn.Sequential(Linear, LayerNorm, GELU, Linear) of vilt.py:190-197 -- same child indices, hence the
+    same state-dict keys (task_layer.<task>.{0,1,3}.*) -- evaluated by the CUDA kernels."""
+
+    def __init__(self, in_dim: int, hidden: int, num_labels: int):
+        super().__init__(nn.Linear(in_dim, hidden), nn.LayerNorm(hidden), nn.GELU(), nn.Linear(hidden, num_labels))
+
+    def forward(self, x):
+        z = ops.linear(x, self[0].weight, self[0].bias)
+        z = ops.layernorm_gelu(z, self[1].weight, self[1].bias, self[1].eps, gelu=True)
+        return ops.linear(z, self[3].weight, self[3].bias)
+
+
+class MultiChoiceHead(nn.Sequential):
+    """nn.Sequential(Dropout(0.1), Linear(d, 1)) of vilt.py:199-202."""
+
+    def __init__(self, in_dim: int):
+        super().__init__(nn.Dropout(0.1), nn.Linear(in_dim, 1))
+
+    def forward(self, x):
+        x = self[0](x)
+        return ops.linear(x, self[1].weight, self[1].bias)
+
+
+class B200ViltContinualLearner(ContinualLearner):
+    def __init__(self, ordered_cl_tasks: List[str], encoder: B200ViltEncoderWrapper, encoder_dim: int, task_configs: Dict):
+        super().__init__()
+        self.encoder_dim = encoder_dim
+        self.vilt_encoder = encoder
+        self.ordered_cl_tasks = ordered_cl_tasks
+        self.task_configs = task_configs
+        self.task_layer_dict = {}
+        for task_key in ordered_cl_tasks:
+            self.add_task_layer(task_key, task_configs[task_key])
+        self.task_layer = nn.ModuleDict(self.task_layer_dict)
+        if 'nlvr2' in ordered_cl_tasks:
+            self.vilt_encoder.expand_modality_type_embeddings()
+
+    def add_task_layer(self, task_key: str, task_config: Dict):
+        num_labels = task_config['num_labels']
+        if task_config['model_type'] == 'classification':
+            num_images = task_config['num_images']
+            self.task_layer_dict[task_key] = ClassifierHead(self.encoder_dim * num_images, self.encoder_dim * 2, num_labels)
+        elif task_config['model_type'] == 'multi-choice':
+            self.task_layer_dict[task_key] = MultiChoiceHead(self.encoder_dim)
+
+    def create_optimizer(self, hparams):
+        """vilt.py:205-215, including its grouping quirk: only names containing 'bias' or
+        'LayerNorm.weight' skip weight decay. Returns a torch Optimizer whose
+        step() is one fused kernel per parameter arena."""
+        no_decay = ['bias', 'LayerNorm.weight']
+        groups = [
+            {'params': [p for n, p in self.named_parameters() if not any(nd in n for nd in no_decay)],
+             'weight_decay': hparams['weight_decay']},
+            {'params': [p for n, p in self.named_parameters() if any(nd in n for nd in no_decay)],
+             'weight_decay': 0.0}]
+        return ArenaAdamW(groups, lr=hparams['lr'], eps=hparams['adam_epsilon'], betas=(0.9, 0.98),
+                          arenas=[self.vilt_encoder.vilt._arena])
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, task_key: str, images: List, texts: List[str]):
+        task_config = self.task_configs[task_key]
+        if task_config['model_type'] == 'multi-choice':
+            texts = list(itertools.chain(*texts))
+        elif task_config.get('num_images', 1) > 1:
+            images = list(itertools.chain(*images))
+        encodings = self.vilt_encoder.process_inputs(images, texts)
+        return self.forward_tensors(task_key, encodings)
+
+    def forward_tensors(self, task_key: str, encodings: Dict):
+        """encodings as ViltProcessor lays them out: NLVR2 pixel_values [bs*2, 3, H, W] (the two images of a
+        sample adjacent), VCR input_ids [bs*4, T] (the four choices adjacent)."""
+        task_config = self.task_configs[task_key]
+        if task_config['model_type'] == 'multi-choice':
+            return self.forward_multi_choice(task_key, encodings, task_config['num_choices'])
+        if task_config['num_images'] == 1:
+            return self.forward_single_image(task_key, encodings)
+        return self.forward_multi_images(task_key, encodings, task_config['num_images'])
+
+    @staticmethod
+    def _enc(encodings, key, default=None):
+        try:
+            return encodings[key]
+        except (KeyError, TypeError):
+            return getattr(encodings, key, default)
+
+    def forward_single_image(self, task_key, encodings):
+        pooled = self.vilt_encoder(**{k: encodings[k] for k in ('input_ids', 'attention_mask', 'token_type_ids',
+                                                                'pixel_values', 'pixel_mask') if k in encodings})
+        return pooled, self.task_layer[task_key](pooled)
+
+    def forward_multi_images(self, task_key, encodings, num_images=2):
+        """vilt.py:263-307, batched: sequence (b, i) = text b with image i and image_token_type_idx i + 1."""
+        ids, am, tt = encodings['input_ids'], encodings['attention_mask'], encodings['token_type_ids']
+        bs = len(ids)
+        px = encodings['pixel_values']
+        rep = lambda t: t.repeat_interleave(num_images, dim=0)
+        type_idx = (torch.arange(num_images, device=px.device, dtype=torch.int32) + 1).repeat(bs)
+        pooled = self.vilt_encoder(input_ids=rep(ids), attention_mask=rep(am), token_type_ids=rep(tt),
+                                   pixel_values=px, pixel_mask=encodings.get('pixel_mask') if hasattr(encodings, 'get') else None,
+                                   image_token_type_idx=type_idx)
+        pooled = pooled.view(bs, num_images * pooled.shape[-1])       # == torch.cat(pooler_outputs, dim=-1)
+        return pooled, self.task_layer[task_key](pooled)
+
+    def forward_multi_choice(self, task_key, encodings, num_choices):
+        """vilt.py:309-350, batched: sequence (b, c) = image b with text choice c."""
+        px = encodings['pixel_values']
+        bs = px.shape[0]
+        pooled = self.vilt_encoder(input_ids=encodings['input_ids'], attention_mask=encodings['attention_mask'],
+                                   token_type_ids=encodings['token_type_ids'],
+                                   pixel_values=px.repeat_interleave(num_choices, dim=0),
+                                   pixel_mask=None)
+        pooled = pooled.view(bs, num_choices, -1)                     # == stack(dim=0).transpose(0, 1)
+        logits = self.task_layer[task_key](pooled).squeeze()
+        return pooled, logits
+
+    def get_encoder(self):
+        return self.vilt_encoder
+
+    # ---- adapter passthrough (vilt.py:356-367) --------------------------------------------------
+    def add_adapter(self, task_key: str, config: Dict):
+        self.vilt_encoder.vilt.add_adapter(task_key, config)
+
+    def train_adapter(self, task_key: str):
+        self.vilt_encoder.vilt.train_adapter(task_key)
+
+    def set_active_adapters(self, task_key: str):
+        self.vilt_encoder.vilt.set_active_adapters(task_key)
+
+    def get_active_adapters(self):
+        return self.vilt_encoder.vilt.active_adapters
+
+
+def load_vilt_encoder(pretrained_vilt_name, device, processor=None, config=None, state_dict=None) -> B200ViltEncoderWrapper:
+    """load_vilt_encoder of vilt.py:481-514. `pretrained_vilt_name` may be
+      * a B200ViltConfig / transformers ViltConfig / dict (random init, as ViltModel(config)),
+      * a path to a torch checkpoint holding a ViltModel or CLiMB encoder state dict,
+      * a hub name -- resolved through transformers.ViltModel.from_pretrained when that is importable
+        and the weights are cached (no network is assumed)."""
+    import os
+    if config is None and not isinstance(pretrained_vilt_name, str):
+        config = pretrained_vilt_name
+    if isinstance(pretrained_vilt_name, str) and os.path.isfile(pretrained_vilt_name):
+        state_dict = torch.load(pretrained_vilt_name, map_location="cpu")
+    elif isinstance(pretrained_vilt_name, str) and state_dict is None:
+        from transformers import ViltModel, ViltProcessor      # stock or vendored transformers
+        hf = ViltModel.from_pretrained(pretrained_vilt_name)
+        config, state_dict = hf.config, hf.state_dict()
+        if processor is None:
+            processor = ViltProcessor.from_pretrained(pretrained_vilt_name)
+    vilt = B200ViltModel(config)
+    if state_dict is not None:
+        sd = {k[len("vilt."):] if k.startswith("vilt.") else k: v for k, v in state_dict.items()}
+        missing, unexpected = vilt.load_state_dict(sd, strict=False)
+        if unexpected:
+            raise RuntimeError(f"unexpected keys in ViLT checkpoint: {unexpected[:5]} ...")
+        logger.info("loaded ViLT weights (%d missing keys)", len(missing))
+    enc = B200ViltEncoderWrapper(processor, vilt, device)
+    enc.to(device)
+    return enc
+
+
+def create_vilt_continual_learner_model(model_name_or_path, ordered_cl_tasks, model_config, task_configs, device,
+                                        processor=None):
+    """create_vilt_continual_learner_model of vilt.py:516-546 (same positional signature)."""
+    encoder = load_vilt_encoder(model_name_or_path, device, processor=processor)
+    model = B200ViltContinualLearner(ordered_cl_tasks=ordered_cl_tasks, encoder=encoder,
+                                     encoder_dim=model_config['encoder_dim'], task_configs=task_configs)
+    model.to(device)
+    return model
+
+
+def convert_batch_to_vilt_input_dict(batch: Dict):
+    return {'images': batch['images'], 'texts': batch['raw_texts']}
+
+
+def convert_seq_batch_to_vilt_input_dict(batch: List, mean_image):
+    return {'images': [mean_image], 'texts': list(batch[0])}

@@ -1,0 +1,118 @@
+"""ArenaAdamW: torch.optim.AdamW semantics (what ViltContinualLearner.create_optimizer builds,
+src/modeling/vilt.py:205-215) executed as ONE CUDA kernel per flat parameter arena.
+
+It is a real torch.optim.Optimizer -- param_groups, lr schedulers (the trainers wrap it in
+get_polynomial_decay_schedule_with_warmup, train_vqa.py:199-205) and zero_grad keep working -- but
+step() does not loop over ~230 tensors: parameters that live in a ParamArena are updated by
+climb_adamw_step over (theta, grad, exp_avg, exp_avg_sq) arenas with a chunk -> param-group table;
+parameters outside any arena (the task heads) go through the same kernel on their own storage.
+
+Reference semantics kept: a parameter whose .grad is None is skipped entirely (no moment update, no
+weight decay) -- that is what makes ER's fresh-optimizer replay step (experience_replay.py:53-67)
+and the unused task heads behave as in the reference. Bias correction uses one step counter per
+arena / per loose parameter, counting the steps in which it actually had a gradient (torch keeps the
+counter per parameter; the two agree whenever a tensor's gradient is present from its first step on,
+which holds for every CLiMB algorithm because each task builds a fresh optimizer).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+
+_CHUNK = 1 << 16
+
+
+def _upload_chunks(chunks, device) -> torch.Tensor:
+    arr = (_lib.AdamWChunkC * len(chunks))()
+    for i, (s, l, g) in enumerate(chunks):
+        arr[i].start, arr[i].length, arr[i].group = s, l, g
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+
+class ArenaAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, arenas: Optional[List] = None):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        if len(self.param_groups) > 8:
+            raise _lib.ClimbError("ArenaAdamW supports up to 8 param groups")
+        self.arenas = list(arenas or [])
+        self._arena_state: Dict[int, Dict] = {}
+        self._table_cache = None
+
+    def _arena_of(self, p: torch.Tensor):
+        for a in self.arenas:
+            if a.theta is None:
+                continue
+            base = a.theta.data_ptr()
+            if base <= p.data_ptr() < base + 4 * a.size:
+                return a
+        return None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        beta1, beta2 = self.param_groups[0]["betas"]
+        eps = self.param_groups[0]["eps"]
+        n_groups = len(self.param_groups)
+        lr_arr = (ctypes.c_float * n_groups)(*[float(g["lr"]) for g in self.param_groups])
+        wd_arr = (ctypes.c_float * n_groups)(*[float(g["weight_decay"]) for g in self.param_groups])
+        in_arena, loose, sig = [], [], []
+        for gi, g in enumerate(self.param_groups):
+            if tuple(g["betas"]) != (beta1, beta2) or g["eps"] != eps:
+                raise _lib.ClimbError("ArenaAdamW needs the same betas / eps in every param group")
+            for p in g["params"]:
+                grad = p.grad
+                if grad is None:
+                    continue
+                a = self._arena_of(p)
+                if a is not None and grad.data_ptr() == a.grad.data_ptr() + (p.data_ptr() - a.theta.data_ptr()):
+                    in_arena.append((a, p, gi))
+                    sig.append((p.data_ptr(), gi))
+                else:
+                    loose.append((p, gi))
+        stream = _lib.stream()
+        sig = tuple(sig)
+        if self._table_cache is None or self._table_cache[0] != sig:
+            per_arena: Dict[int, List] = {}
+            for a, p, gi in in_arena:
+                start = (p.data_ptr() - a.theta.data_ptr()) // 4
+                n = p.numel()
+                lst = per_arena.setdefault(id(a), [a, []])[1]
+                for o in range(0, n, _CHUNK):
+                    lst.append((start + o, min(_CHUNK, n - o), gi))
+            self._table_cache = (sig, {aid: (a, _upload_chunks(ch, a.theta.device), len(ch))
+                                       for aid, (a, ch) in per_arena.items()})
+        for aid, (a, table, n_chunks) in self._table_cache[1].items():
+            st = self._arena_state.get(aid)
+            if st is None or st["theta_ptr"] != a.theta.data_ptr():
+                st = dict(exp_avg=torch.zeros_like(a.theta), exp_avg_sq=torch.zeros_like(a.theta),
+                          theta_ptr=a.theta.data_ptr(), step=0)
+                self._arena_state[aid] = st
+            st["step"] += 1
+            _lib.check(_lib.climb_adamw_step(_lib.ptr(a.theta), _lib.ptr(a.grad), _lib.ptr(st["exp_avg"]),
+                                             _lib.ptr(st["exp_avg_sq"]), _lib.ptr(table), n_chunks, lr_arr, wd_arr,
+                                             n_groups, beta1, beta2, eps, st["step"], stream))
+            a.shadow_dirty = True
+        for p, gi in loose:
+            if not (p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32 and p.is_cuda):
+                raise _lib.ClimbError("ArenaAdamW handles contiguous fp32 CUDA parameters")
+            st = self.state[p]
+            if not st or st.get("group") != gi:
+                n = p.numel()
+                chunks = [(o, min(_CHUNK, n - o), gi) for o in range(0, n, _CHUNK)]
+                st.setdefault("exp_avg", torch.zeros_like(p, memory_format=torch.contiguous_format))
+                st.setdefault("exp_avg_sq", torch.zeros_like(p, memory_format=torch.contiguous_format))
+                st.setdefault("step", 0)
+                st["table"], st["n_chunks"], st["group"] = _upload_chunks(chunks, p.device), len(chunks), gi
+            st["step"] += 1
+            _lib.check(_lib.climb_adamw_step(_lib.ptr(p), _lib.ptr(p.grad), _lib.ptr(st["exp_avg"]),
+                                             _lib.ptr(st["exp_avg_sq"]), _lib.ptr(st["table"]), st["n_chunks"],
+                                             lr_arr, wd_arr, n_groups, beta1, beta2, eps, st["step"], stream))
+        return loss

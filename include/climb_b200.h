@@ -103,6 +103,126 @@ int climb_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x
                         const float* dres, float* dx_f32, void* dx_bf16,
                         float* dgamma, float* dbeta, int rows, int d, int act, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Streaming helpers
+ * ------------------------------------------------------------------------------------------- */
+/* bf16 shadow of the fp32 master parameters (tensor-core operands); n elements, 16-byte aligned */
+int climb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* out[c] += sum_r src[r*ld + c]  (bias gradients); dtype = CLIMB_BF16 / CLIMB_F32 */
+int climb_colsum(const void* src, int dtype, int64_t ld, int rows, int cols, float* out, void* stream);
+
+/* Trainer losses with fused gradient (train_vqa.py:95,157: BCEWithLogits(mean) * num_labels;
+ * train_nlvr2.py:80,133 / train_snli_ve.py / train_vcr.py:83,135: CrossEntropy(mean)).
+ * row_loss: [rows] scratch; loss: 1 float; dlogits (nullable) = grad_scale * dloss/dlogits. */
+int climb_bce_logits_loss(const float* logits, int64_t ld, const float* target, int rows, int cols,
+                          float scale, float grad_scale, float* row_loss, float* loss,
+                          float* dlogits, int64_t ldd, void* stream);
+int climb_cross_entropy_loss(const float* logits, int64_t ld, const int64_t* target, int rows, int cols,
+                             float grad_scale, float* row_loss, float* loss,
+                             float* dlogits, int64_t ldd, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * EWC (src/cl_algorithms/ewc.py) on device-resident flat arenas of n floats
+ *   climb_ewc_penalty : *loss = lambda * sum F (theta - theta*)^2 ; if grad != NULL also
+ *                       grad += grad_scale * (*grad_scale_dev) * 2 lambda F (theta - theta*)  (ewc.py:75-87)
+ *                       (grad_scale_dev: optional device scalar = the upstream gradient, read without a sync)
+ *                       partials: scratch of n_partials floats (>= 1184 is always enough)
+ *   climb_fisher_accumulate : fisher += grad^2                                    (ewc.py:61-64)
+ *   climb_scale_inplace     : x *= s   (the division by the sample count, ewc.py:70-71)
+ * ------------------------------------------------------------------------------------------- */
+int climb_ewc_penalty(const float* theta, const float* theta_star, const float* fisher, int64_t n,
+                      float lambda, float* partials, int n_partials, float* loss,
+                      float* grad, float grad_scale, const float* grad_scale_dev, void* stream);
+int climb_fisher_accumulate(const float* grad, float* fisher, int64_t n, void* stream);
+int climb_scale_inplace(float* x, int64_t n, float s, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * AdamW over the flat arena (torch.optim.AdamW semantics; src/modeling/vilt.py:205-215).
+ * chunks: DEVICE array; every chunk lies inside one parameter tensor and names that tensor's param
+ * group (the reference has two: decayed / not decayed); the groups' current lr / weight decay are
+ * HOST arrays passed by value each step, so an lr scheduler never forces a table rebuild.
+ * ------------------------------------------------------------------------------------------- */
+#define CLIMB_ADAMW_MAX_GROUPS 8
+typedef struct {
+    int64_t start;
+    int32_t length;
+    int32_t group;       /* index into group_lr / group_wd */
+} climb_adamw_chunk;
+int climb_adamw_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq,
+                     const climb_adamw_chunk* chunks_dev, int n_chunks,
+                     const float* group_lr_host, const float* group_wd_host, int n_groups,
+                     float beta1, float beta2, float eps, int step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-encoder engine: ViltModel.forward -> pooler_output and its backward
+ * (modeling_vilt.py:777-899 with ViltEmbeddings :92-328, 12 x ViltLayer :503-525, final LayerNorm,
+ * ViltPooler; adapters per adapters/mixins/vilt.py:23-125). One C call launches every kernel of
+ * the pass on `stream`.
+ *
+ * Parameters live in ONE flat fp32 arena `theta`; `shadow` is its bf16 copy (climb_cast_f32_bf16)
+ * and `grad` the fp32 gradient arena, all three with the same element offsets (below, -1 = absent).
+ * query/key/value weights (and biases) must be contiguous in that order: qkv_w points at query.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int hidden, layers, heads, ffn;
+    int patch, channels, pos_grid;      /* pos_grid = image_size / patch_size of the position table */
+    int n_modality;                     /* rows of token_type_embeddings (2, or 3 with NLVR2) */
+    float ln_eps;
+} climb_vilt_dims;
+
+typedef struct {
+    int64_t qkv_w, qkv_b, o_w, o_b, fc1_w, fc1_b, fc2_w, fc2_b;
+    int64_t ln1_w, ln1_b, ln2_w, ln2_b;
+    int64_t mh_down_w, mh_down_b, mh_up_w, mh_up_b;        /* attention.output.adapters.<task> */
+    int64_t out_down_w, out_down_b, out_up_w, out_up_b;    /* output.adapters.<task> */
+    int32_t flags;                                         /* CLIMB_TRAIN_* bits, backward only */
+    int32_t pad_;
+} climb_vilt_layer;
+
+#define CLIMB_TRAIN_BASE 1      /* base weights of this layer / of the embeddings need gradients */
+#define CLIMB_TRAIN_ADAPTER 2   /* the active adapter of this layer needs gradients */
+
+typedef struct {
+    int64_t cls_token, pos_emb, word_emb, text_pos_emb, text_type_emb, text_ln_w, text_ln_b;
+    int64_t patch_w, patch_b, mod_emb, final_ln_w, final_ln_b, pooler_w, pooler_b;
+    const climb_vilt_layer* layer;      /* HOST array [dims.layers] */
+    int adapter_r;                      /* bottleneck width of the active adapter, 0 = none */
+    int adapter_act;                    /* CLIMB_EPI_SWISH (houlsby) or CLIMB_EPI_RELU (pfeiffer) */
+    int32_t embed_flags;                /* CLIMB_TRAIN_BASE if the embeddings need gradients */
+    int32_t tail_flags;                 /* CLIMB_TRAIN_BASE if final LayerNorm + pooler need gradients */
+} climb_vilt_params;
+
+typedef struct {
+    int B, T, H, W;                     /* sequences, text tokens, image height / width (pixels) */
+    const int64_t* input_ids;           /* [B, T] or NULL when inputs_embeds is given */
+    const float* inputs_embeds;         /* [B, T, hidden] (ViLT-BERT) or NULL */
+    const int64_t* token_type_ids;      /* [B, T] or NULL (= zeros) */
+    const int64_t* attention_mask;      /* [B, T] or NULL (= ones) */
+    const float* pixel_values;          /* [B, C, H, W] */
+    const int32_t* image_type_idx;      /* [B] or NULL -> image_type_idx_scalar for every sequence */
+    int image_type_idx_scalar;
+} climb_vilt_batch;
+
+/* bytes of the activation workspace a forward needs (save_for_backward = 1 keeps every layer's
+ * activations; 0 recycles one layer's worth) and of the scratch a backward needs */
+int64_t climb_vilt_forward_workspace_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                                           const climb_vilt_batch* batch, int save_for_backward);
+int64_t climb_vilt_backward_scratch_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                                          const climb_vilt_batch* batch);
+
+int climb_vilt_forward(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                       const climb_vilt_batch* batch, const float* theta, const void* shadow,
+                       void* workspace, int64_t workspace_bytes, int save_for_backward,
+                       float* pooled_out /* [B, hidden] */, void* stream);
+
+/* grad arena += d(pooled . dpooled)/d(theta) for every parameter whose flag asks for it.
+ * `workspace` is the one the matching forward (save_for_backward = 1) filled. */
+int climb_vilt_backward(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                        const climb_vilt_batch* batch, const float* theta, const void* shadow,
+                        const void* workspace, int64_t workspace_bytes,
+                        void* scratch, int64_t scratch_bytes,
+                        const float* dpooled /* [B, hidden] */, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,174 @@
+"""CPU tests of the host side: C-ABI surface, parameter tree / checkpoint compatibility, the flat
+arena, optimizer grouping, adapter bookkeeping. No kernel runs here (there is no GPU in the build
+container); compute parity lives in the -m gpu tests."""
+import copy
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import vilt_oracle as vo
+from tests.golden_util import ALL_TASKS, TINY
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _learner(dims=TINY, tasks=ALL_TASKS):
+    from climb_b200.modeling import B200ViltConfig, B200ViltContinualLearner, B200ViltEncoderWrapper, B200ViltModel
+    cfg = B200ViltConfig(hidden_size=dims.hidden_size, num_hidden_layers=dims.num_hidden_layers,
+                         num_attention_heads=dims.num_attention_heads, intermediate_size=dims.intermediate_size,
+                         image_size=dims.image_size, patch_size=dims.patch_size, vocab_size=dims.vocab_size,
+                         max_position_embeddings=dims.max_position_embeddings)
+    enc = B200ViltEncoderWrapper(None, B200ViltModel(cfg), torch.device("cpu"))
+    return B200ViltContinualLearner(list(tasks), enc, dims.hidden_size, vo.TASK_SPECS)
+
+
+def test_library_exports_every_declared_symbol():
+    from climb_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "climb_b200.h")).read()
+    declared = set(re.findall(r"\b(climb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 19
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), f"{name} declared in include/climb_b200.h but not exported"
+    assert _lib.climb_version() >= 100
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors of the C structs: field counts / sizes that would silently corrupt calls."""
+    from climb_b200 import _lib
+    assert ctypes.sizeof(_lib.ViltLayerC) == 20 * 8 + 8
+    assert ctypes.sizeof(_lib.AdamWChunkC) == 16
+    assert ctypes.sizeof(_lib.ViltDimsC) == 9 * 4
+    assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from climb_b200 import _lib
+    with pytest.raises(_lib.ClimbError):
+        _lib.ptr(torch.zeros(4))
+    learner = _learner()
+    batch = vo.synth_batch("vqa", 2, TINY, T=8, image_hw=(32, 32))
+    with pytest.raises(_lib.ClimbError):
+        learner.forward_tensors("vqa", {k: v for k, v in batch.items() if k != "target"})
+
+
+def test_state_dict_is_key_and_shape_compatible_with_the_reference():
+    learner = _learner()
+    shapes = vo.param_shapes(TINY, ALL_TASKS)
+    sd = learner.state_dict()
+    ours = {k: tuple(v.shape) for k, v in sd.items() if "position_ids" not in k}
+    assert ours == dict(shapes)
+    assert "vilt_encoder.vilt.embeddings.text_embeddings.position_ids" in sd
+    # registration order = the reference's named_parameters() order (EWC / optimizers iterate it)
+    assert [n for n, _ in learner.named_parameters()] == list(shapes.keys())
+    base = vo.param_shapes(vo.ViltDims(), ALL_TASKS)
+    assert sum(int(torch.tensor(s).prod()) for s in base.values()) == 121_145_919      # SURVEY.md 8c (includes the third modality row)
+
+
+def test_adapter_parameter_names_and_freezing():
+    learner = _learner()
+    learner.add_adapter("nlvr2", "houlsby")
+    learner.add_adapter("vqa", {"reduction_factor": 4, "non_linearity": "relu", "mh_adapter": False, "output_adapter": True})
+    names = [n for n, _ in learner.named_parameters()]
+    exp = vo.param_shapes(TINY, ALL_TASKS, adapters={"nlvr2": 8})
+    assert set(n for n in exp if ".adapters.nlvr2." in n) <= set(names)
+    assert not any(".attention.output.adapters.vqa." in n for n in names)       # pfeiffer-style: output only
+    learner.train_adapter("nlvr2")
+    assert learner.get_active_adapters() == "nlvr2"
+    for n, p in learner.named_parameters():
+        expect = (".adapters.nlvr2." in n) or n.startswith("task_layer.")
+        assert p.requires_grad == expect, n
+    with pytest.raises(NotImplementedError):
+        learner.add_adapter("snli-ve", {"reduction_factor": 16, "phm_layer": True})
+    with pytest.raises(ValueError):
+        learner.set_active_adapters("missing")
+
+
+def test_arena_views_qkv_contiguity_and_rebinding():
+    learner = _learner()
+    vilt = learner.vilt_encoder.vilt
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=5)
+    learner.load_state_dict(sd, strict=False)
+    arena = vilt._arena
+    assert arena.sync(allow_cpu=True) is True
+    assert arena.sync(allow_cpu=True) is False
+    off = arena.offsets
+    d = TINY.hidden_size
+    q = "encoder.layer.1.attention.attention."
+    assert off[q + "key.weight"] == off[q + "query.weight"] + d * d
+    assert off[q + "value.weight"] == off[q + "key.weight"] + d * d
+    assert off[q + "key.bias"] == off[q + "query.bias"] + d
+    assert all(o % 64 == 0 for o in off.values())
+    # parameters are views: the fused [3d, d] weight is readable straight from theta
+    fused = arena.theta[off[q + "query.weight"]: off[q + "query.weight"] + 3 * d * d].view(3 * d, d)
+    assert torch.equal(fused[d:2 * d], sd["vilt_encoder.vilt." + q + "key.weight"])
+    # in-place edits through torch land in the arena and are noticed (shadow refresh trigger)
+    v0 = arena._version_sum
+    with torch.no_grad():
+        vilt.pooler.dense.bias.add_(1.0)
+    arena.sync(allow_cpu=True)
+    assert arena._version_sum != v0
+    assert torch.equal(arena.theta[off["pooler.dense.bias"]: off["pooler.dense.bias"] + d], vilt.pooler.dense.bias)
+    # load_state_dict copies in place: still views
+    learner.load_state_dict(vo.synth_state_dict(TINY, ALL_TASKS, seed=6), strict=False)
+    assert arena.sync(allow_cpu=True) is False
+    # replacing a module (expand / reallocate) forces a rebuild
+    learner.vilt_encoder.reallocate_text_image(vilt.embeddings.text_embeddings.position_embeddings.weight.data.clone(), 16, 32)
+    assert arena.sync(allow_cpu=True) is True
+    assert vilt.embeddings.text_embeddings.position_embeddings.weight.shape[0] == 16
+
+
+def test_deepcopy_gives_an_independent_model():
+    """train_vqa.py:210,242 deep-copies the learner for best-model tracking."""
+    learner = _learner()
+    learner.vilt_encoder.vilt._arena.sync(allow_cpu=True)
+    clone = copy.deepcopy(learner)
+    a, b = learner.vilt_encoder.vilt, clone.vilt_encoder.vilt
+    assert b._arena is not a._arena and b._arena.owner is b
+    b._arena.sync(allow_cpu=True)
+    with torch.no_grad():
+        a.pooler.dense.weight.zero_()
+    assert b.pooler.dense.weight.abs().sum() > 0
+    assert set(clone.state_dict().keys()) == set(learner.state_dict().keys())
+
+
+def test_static_tables_flags_follow_requires_grad():
+    from climb_b200 import _lib
+    learner = _learner()
+    vilt = learner.vilt_encoder.vilt
+    vilt._arena.sync(allow_cpu=True)
+    st = vilt._static_tables()
+    assert st["dims"].pos_grid == 2 and st["dims"].n_modality == 3
+    assert all(st["layers"][i].flags == _lib.TRAIN_BASE for i in range(TINY.num_hidden_layers))
+    assert st["params"].embed_flags == _lib.TRAIN_BASE and st["params"].adapter_r == 0
+    learner.vilt_encoder.freeze_bottom_k_layers(1)
+    st = vilt._static_tables()
+    assert st["layers"][0].flags == 0 and st["layers"][1].flags == _lib.TRAIN_BASE and st["params"].embed_flags == 0
+    learner.add_adapter("vqa", "houlsby")
+    learner.train_adapter("vqa")
+    vilt._arena.sync(allow_cpu=True)
+    st = vilt._static_tables()
+    assert st["params"].adapter_r == 8 and st["params"].adapter_act == _lib.EPI_SWISH
+    assert all(st["layers"][i].flags == _lib.TRAIN_ADAPTER for i in range(TINY.num_hidden_layers))
+    assert st["params"].tail_flags == 0
+    assert all(".adapters.vqa." in n for n, _ in st["trainable"])
+
+
+def test_optimizer_groups_reproduce_the_reference_quirk():
+    """Only names containing 'bias' or 'LayerNorm.weight' skip weight decay (src/modeling/vilt.py:209-213):
+    layernorm_before/after.weight ARE decayed."""
+    learner = _learner()
+    opt = learner.create_optimizer({"lr": 1e-4, "weight_decay": 1e-2, "adam_epsilon": 1e-8})
+    names = {id(p): n for n, p in learner.named_parameters()}
+    decay = [names[id(p)] for p in opt.param_groups[0]["params"]]
+    nodecay = [names[id(p)] for p in opt.param_groups[1]["params"]]
+    exp_decay, exp_nodecay = vo.weight_decay_groups(list(names.values()))
+    assert decay == exp_decay and nodecay == exp_nodecay
+    assert "vilt_encoder.vilt.encoder.layer.0.layernorm_before.weight" in decay
+    assert "vilt_encoder.vilt.embeddings.text_embeddings.LayerNorm.weight" in nodecay
+    assert opt.param_groups[0]["weight_decay"] == 1e-2 and opt.param_groups[1]["weight_decay"] == 0.0
+    assert opt.defaults["betas"] == (0.9, 0.98)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: vo.linear_warmup_decay(s, 10, 100))
+    assert isinstance(opt, torch.optim.Optimizer) and sched is not None

@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out
 run() {  # name, timeout, args...
   local name=$1; shift; local to=$1; shift
   echo "=== $name" | tee -a gpurun_out/summary.txt
-  timeout $to python -m pytest -x -q -m gpu "$@" > gpurun_out/$name.log 2>&1
+  timeout $to python -m pytest -q -m gpu "$@" > gpurun_out/$name.log 2>&1
   echo "exit=$? $(tail -n 3 gpurun_out/$name.log | tr '\n' ' ')" | tee -a gpurun_out/summary.txt
 }
 : > gpurun_out/summary.txt
@@ -17,6 +17,8 @@ for g in "$@"; do
     gemm_x)   run gemm_x 600 tests/test_gpu_kernels.py -k "gemm_wgrad or gemm_epilogues or gemm_large or gemm_rejects" ;;
     attn)     run attn 600 tests/test_gpu_kernels.py -k "attention" ;;
     ln)       run ln 600 tests/test_gpu_kernels.py -k "layernorm" ;;
+    parity)   run parity 900 tests/test_gpu_parity.py -s ;;
+    perf)     echo "=== perf" | tee -a gpurun_out/summary.txt; timeout 600 python tools/perf_kernels.py > gpurun_out/perf.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; tail -n 12 gpurun_out/perf.log | tee -a gpurun_out/summary.txt ;;
     *)        run "$(echo $g | tr '/:. ' '____')" 900 $g ;;
   esac
 done
