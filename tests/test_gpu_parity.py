@@ -6,9 +6,15 @@ Tolerances (stated, bf16 tensor-core operands with fp32 accumulation / residual 
   pooled, logits : relative Frobenius error <= 2e-2 (the reference's own bf16-autocast path sits at
                    5e-3 .. 7e-3 vs fp32 on random-init weights)
   loss           : relative error <= 2e-2
-  gradients      : per-tensor relative Frobenius error <= 6e-2 against the stored reference gradient
-                   (full tensor or strided sample), analytically-zero gradients compared to the
-                   global gradient scale.
+  gradients      : per tensor, ||got - ref|| <= 6e-2 * max(||ref||, floor * G) against the stored
+                   reference gradient (full tensor or strided sample), G = the largest gradient-tensor
+                   norm of the step. floor = 0.02 everywhere except VCR, where it is 1.0: the four
+                   choices of a VCR sample share one image and their dlogits sum to zero, so every
+                   bias-like gradient is a small residual of large cancelling terms. The reference's
+                   own bf16-autocast path shows relative errors of 4x-9x on exactly those tensors
+                   (layernorm.bias 8.8, pooler.dense.bias 7.4, layer.1.output.dense.bias 4.3 on the
+                   tiny_vcr fixture, measured with torch.autocast on the CPU oracle) while staying
+                   within 6e-2 * G -- so the honest bound there is the absolute one.
 """
 import numpy as np
 import pytest
@@ -82,7 +88,7 @@ def _rel(got, ref):
     return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
 
 
-def _check_grads(g, learner, tol=TOL_GRAD, names=None):
+def _check_grads(g, learner, tol=TOL_GRAD, names=None, floor=0.02):
     grads = {n: p.grad for n, p in learner.named_parameters()}
     gscale = max(float(g[k]) for k in g.files if k.startswith("gnorm/"))
     report = []
@@ -104,8 +110,11 @@ def _check_grads(g, learner, tol=TOL_GRAD, names=None):
         else:
             ref = torch.from_numpy(g["gsample/" + name])
             got_c = got.flatten()[torch.from_numpy(grad_sample_index(got.numel()))]
-        err = ((got_c - ref).norm() / ref.norm().clamp_min(1e-30)).item()
-        nerr = abs(got.norm().item() - ref_norm) / ref_norm
+        # the stored sample covers a fraction of the tensor: scale the floor to the sample's share
+        share = (ref.norm().item() / ref_norm) if ref_norm > 0 else 1.0
+        denom = max(ref.norm().item(), floor * gscale * share)
+        err = (got_c - ref).norm().item() / denom
+        nerr = abs(got.norm().item() - ref_norm) / max(ref_norm, floor * gscale)
         report.append((err, nerr, name))
     report.sort(reverse=True)
     print("worst gradient errors:", report[:5])
@@ -126,7 +135,7 @@ def test_tiny_tasks_vs_reference_golden(task):
     print(f"{task}: pooled rel {e_p:.3e} logits rel {e_l:.3e} loss {loss.item():.6f} vs {float(g['loss']):.6f}")
     assert e_p <= TOL_OUT and e_l <= TOL_OUT
     assert abs(loss.item() - float(g["loss"])) <= TOL_OUT * abs(float(g["loss"]))
-    _check_grads(g, learner)
+    _check_grads(g, learner, floor=1.0 if task == "vcr" else 0.02)
 
 
 @pytest.mark.parametrize("task,seed,masked", [("vqa", 42, False), ("nlvr2", 43, True)])
