@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native ViLT hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                      # our arm, 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W        # N ranks, one per GPU
+    python bench.py --impl reference --steps 3 --warmup 1                # reference arithmetic on host cores
+
+A "step" is one upstream-CL training step of CLiMB's sequential-FT VQA task on one synthetic batch
+per GPU (BASELINE.json configs[1]): forward (B sequences of 40 text tokens + 197 image patches,
+ViLT-base) -> BCEWithLogits x 3129 -> backward -> AdamW step (train_vqa.py:135-174), through the
+public API of this repo (B200ViltContinualLearner + ArenaAdamW). One JSON line goes to stdout.
+
+  value      samples/s over all GPUs, inputs already resident in HBM
+  e2e        the same step fed from PINNED HOST buffers: the H2D copy of every step's inputs (prefetched
+             on a copy stream, as a data loader would) and a D2H read of every step's loss are inside
+             the timed region
+  roofline   tcgen05 GEMM kernel: algorithmic FLOPs (2MNK per launch) / device time of those launches,
+             measured with CUDA events on the launch stream inside this process (climb_profile_*),
+             against the measured sustained bf16 peak of MEASURED_PEAKS.json; plus the attention
+             kernels against the measured HBM copy bandwidth
+  cpu_baseline  oracle/ (the CPU restatement of the reference arithmetic, pinned to the reference by
+             tests/golden) timed on this box's host cores on BASELINE config 1 (B=4) -- a reported
+             baseline, not the target
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_TEXT, IMG, N_LABELS = 40, 448, 3129
+FLOPS_PER_SAMPLE_STEP = 128.88e9        # BASELINE.md section 3 (algorithmic, full-FT step)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")   # B200_PROFILING.md
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 <= ts <= t1 + 0.2:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:          # region shorter than one sample: take what we have
+            sm = [float(l.split(",")[1]) for _, l in self.lines[-2:] if l.count(",") >= 8] or [0.0]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference arithmetic on host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps: int, warmup: int, batch: int = 4):
+    """BASELINE config 1: ViLT-base, seeded random init, VQA head, B=4 synthetic batch, fp32, all host
+    threads; one fwd + loss + bwd + AdamW step per iteration. Returns (samples/s, cores, seconds/step)."""
+    from oracle import vilt_oracle as vo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dims = vo.ViltDims()
+    sd = vo.synth_state_dict(dims, ["vqa"], seed=42)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-2)
+    b = vo.synth_batch("vqa", batch, dims, T=T_TEXT, image_hw=(IMG, IMG), seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, logits = vo.learner_forward(params, dims, "vqa", b)
+        loss = vo.task_loss("vqa", logits, b["target"])
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return batch / sec, cores, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    # each step is a bounded sample (B=4) of the workload; cap the run at a few minutes
+    steps = min(steps, 8)
+    warmup = min(warmup, 2)
+    sps, cores, sec = cpu_reference_steps(steps, warmup)
+    line = {
+        "impl": "reference", "metric": "ViLT upstream-CL training throughput", "value": sps, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViLT-base sequential-FT VQAv2-shaped synthetic step (fwd+loss+bwd+AdamW), "
+                               "40 text tokens + 14x14 patches + cls = 237 tokens", "sample_batch": 4},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of B=4 (BASELINE config 1) through oracle/vilt_oracle.py, "
+                                   "the CPU restatement pinned to the reference by tests/golden; the reference itself "
+                                   "is Python under /root/reference, which does not exist on the GPU box"},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def make_host_batch(B: int, seed: int, pin: bool):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1000, 30000, (B, T_TEXT), generator=g)
+    ids[:, 0], ids[:, -1] = 101, 102
+    batch = {
+        "input_ids": ids,
+        "attention_mask": torch.ones(B, T_TEXT, dtype=torch.int64),
+        "token_type_ids": torch.zeros(B, T_TEXT, dtype=torch.int64),
+        "pixel_values": torch.rand(B, 3, IMG, IMG, generator=g) * 2 - 1,
+    }
+    tgt = torch.zeros(B, N_LABELS)
+    for b in range(B):
+        k = int(torch.randint(1, 4, (1,), generator=g))
+        idx = torch.randperm(N_LABELS, generator=g)[:k]
+        tgt[b, idx] = torch.tensor([0.3, 0.6, 0.9, 1.0])[torch.randint(0, 4, (k,), generator=g)]
+    batch["target"] = tgt
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    return batch
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from climb_b200 import _lib, ops
+    from climb_b200 import distributed as cdist
+    from climb_b200.modeling import B200ViltConfig, B200ViltContinualLearner, B200ViltEncoderWrapper, B200ViltModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: climb_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+
+    B = args.batch
+    tasks = ["vqa", "nlvr2", "snli-ve", "vcr"]
+    task_specs = {"vqa": dict(num_labels=N_LABELS, num_images=1, model_type="classification"),
+                  "nlvr2": dict(num_labels=2, num_images=2, model_type="classification"),
+                  "snli-ve": dict(num_labels=3, num_images=1, model_type="classification"),
+                  "vcr": dict(num_labels=4, num_images=1, model_type="multi-choice", num_choices=4)}
+    torch.manual_seed(42)                       # same weights on every rank (train_upstream..py:103)
+    learner = B200ViltContinualLearner(tasks, B200ViltEncoderWrapper(None, B200ViltModel(B200ViltConfig()), dev), 768,
+                                       task_specs).to(dev)
+    learner.train()
+    if world > 1:
+        cdist.attach(learner)                   # gradient all-reduce over NCCL after every backward
+    opt = learner.create_optimizer({"lr": 1e-4, "weight_decay": 1e-2, "adam_epsilon": 1e-8})
+    total_steps = args.warmup * 2 + args.steps * 2 + 8
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: min(1.0, (s + 1) / 10.0) * max(0.0, 1.0 - s / (10.0 * total_steps)))
+
+    n_batches = 4
+    host = [make_host_batch(B, 1000 * rank + i, pin=True) for i in range(n_batches)]
+    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def step(batch):
+        enc = {k: batch[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values")}
+        _, logits = learner.forward_tensors("vqa", enc)
+        loss = ops.vqa_loss(logits, batch["target"])
+        loss.backward()
+        opt.step()
+        sched.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for i in range(args.warmup):
+        step(resident[i % n_batches])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.climb_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        step(resident[i % n_batches])
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _lib.climb_launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: pinned host inputs, H2D prefetch on a copy stream, per-step D2H loss read ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    slots = [None, None]
+    slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    slot_free = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot_free[s])           # the step that last used this slot has finished
+            slots[s] = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
+            slot_ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            slot_free[s].record(main_stream)
+        upload(0)
+        losses = []
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                upload(i + 1)
+            main_stream.wait_event(slot_ready[s])
+            loss = step(slots[s])
+            slot_free[s].record(main_stream)
+            if i >= 1:                                     # read the PREVIOUS step's loss: no pipeline bubble
+                loss_ev[(i - 1) % 2].synchronize()
+                losses.append(float(loss_host[(i - 1) % 2]))
+            loss_host[s].copy_(loss.detach(), non_blocking=True)
+            loss_ev[s].record(main_stream)
+        loss_ev[(n - 1) % 2].synchronize()
+        losses.append(float(loss_host[(n - 1) % 2]))
+        return losses
+
+    e2e_loop(max(2, min(args.warmup, 3)))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # ---- per-kernel device time for the roofline (events on the launch stream) -------------------
+    roofline, attn_roof = None, None
+    if rank == 0:
+        peaks = load_peaks()
+        torch.cuda.synchronize()
+        _lib.check(_lib.climb_profile_begin())
+        for i in range(2):
+            step(resident[i % n_batches])
+        prof = _lib.profile_end()
+        g_ms, g_flops, g_n = prof["gemm"]
+        achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(achieved, 1),
+                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4),
+                    "traffic": traffic, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+                    "launches_per_step": g_n // 2, "gemm_ms_per_step": round(g_ms / 2, 3),
+                    "gemm_share_of_step": round((g_ms / 2) / (ms_total / args.steps), 3)}
+        af_ms, af_b, af_n = prof["attn_fwd"]
+        ab_ms, ab_b, ab_n = prof["attn_bwd"]
+        attn_roof = {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm"],
+                     "fwd": {"achieved": round(af_b / (af_ms * 1e-3) / 1e9, 1) if af_ms else 0.0, "ms_per_step": round(af_ms / 2, 3)},
+                     "bwd": {"achieved": round(ab_b / (ab_ms * 1e-3) / 1e9, 1) if ab_ms else 0.0, "ms_per_step": round(ab_ms / 2, 3)}}
+        attn_roof["fwd"]["frac"] = round(attn_roof["fwd"]["achieved"] / peaks["hbm"], 4)
+        attn_roof["bwd"]["frac"] = round(attn_roof["bwd"]["achieved"] / peaks["hbm"], 4)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, cores, sec = cpu_reference_steps(steps=5, warmup=1)
+        cpu_baseline = {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port",
+                        "sample": "5 steps (median) of B=4 fwd+loss+bwd+AdamW, BASELINE config 1, oracle/vilt_oracle.py fp32"}
+
+    if rank == 0:
+        peaks = load_peaks()
+        line = {
+            "metric": "ViLT upstream-CL training throughput", "value": round(value, 1), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "ViLT-base sequential-FT VQAv2-shaped synthetic step (fwd+BCEx3129+bwd+AdamW), "
+                                   "BASELINE.json configs[1]", "batch_per_gpu": B, "global_batch": B * world,
+                       "text_tokens": T_TEXT, "image": f"{IMG}x{IMG} -> 14x14 patches + cls", "seq_len": 237,
+                       "layers": 12, "hidden": 768, "parallelism": f"dp{world}",
+                       "l2": "activation working set ~5 GB per step >> 126 MB L2; 4 rotating input batches"},
+            "samples_per_s_per_gpu": round(value / world, 1),
+            "model_tflops_per_gpu": round(value / world * FLOPS_PER_SAMPLE_STEP / 1e12, 1),
+            "step_frac_of_tensor_roofline": round(value / world * FLOPS_PER_SAMPLE_STEP / 1e12 / peaks["tf_sustained"], 4),
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes * world,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": round(e2e_ms / args.steps, 3),
+                    "last_loss": round(losses[-1], 4)},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "attention_roofline": attn_roof, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU (the shipped scripts use 64)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

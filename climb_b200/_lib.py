@@ -63,6 +63,9 @@ def _sig(name, argtypes, restype=c_int):
 _P = c_void_p
 climb_last_error = _sig("climb_last_error", [], c_char_p)
 climb_version = _sig("climb_version", [])
+climb_launch_count = _sig("climb_launch_count", [], ctypes.c_uint64)
+climb_profile_begin = _sig("climb_profile_begin", [])
+climb_profile_end = _sig("climb_profile_end", [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int])
 climb_gemm_bf16 = _sig("climb_gemm_bf16", [POINTER(GemmDesc), _P])
 climb_attention_fwd = _sig("climb_attention_fwd", [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P])
 climb_attention_bwd = _sig(
@@ -267,3 +270,13 @@ def colsum(src: torch.Tensor, out: torch.Tensor, rows=None, cols=None) -> None:
     cols = src.shape[1] if cols is None else cols
     dt = {torch.bfloat16: BF16, torch.float32: F32}[src.dtype]
     check(climb_colsum(ptr(src), dt, src.stride(0), rows, cols, ptr(out), stream()))
+
+
+def profile_end():
+    """-> {category: (ms, work, launches)} for gemm / attn_fwd / attn_bwd."""
+    ms = (ctypes.c_double * 4)()
+    work = (ctypes.c_double * 4)()
+    n = (c_int64 * 4)()
+    check(climb_profile_end(ms, work, n, 4))
+    names = ["gemm", "attn_fwd", "attn_bwd", "other"]
+    return {names[i]: (ms[i], work[i], n[i]) for i in range(4)}

@@ -455,6 +455,8 @@ int attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse,
         smem_set = smem;
     }
     dim3 grid((L + 63) / 64, H, B);
+    // algorithmic bytes: Q, K, V read + O written (bf16) + LSE (fp32)  
+    ProfScope prof(PROF_ATTN_FWD, static_cast<double>(B) * (4.0 * L * H * kDh * 2 + static_cast<double>(L) * H * 4), stream);
     attn_fwd_kernel<<<grid, 128, smem, stream>>>(
         static_cast<const __nv_bfloat16*>(qkv), key_bias, static_cast<__nv_bfloat16*>(ctx), lse, L, H,
         Lpad, scale * kLog2e);
@@ -480,6 +482,8 @@ int attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const
         CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv));
         set_dkv = smem_dkv;
     }
+    // algorithmic bytes: Q, K, V, O, dO read + dQ, dK, dV written (bf16) + LSE, delta (fp32)
+    ProfScope prof(PROF_ATTN_BWD, static_cast<double>(B) * (8.0 * L * H * kDh * 2 + 2.0 * L * H * 4), stream);
     const long long groups = static_cast<long long>(B) * L * H;
     const int threads = 256;
     const long long blocks = (groups * 8 + threads - 1) / threads;

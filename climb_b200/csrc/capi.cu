@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstring>
+#include <vector>
 
 namespace climb {
 
@@ -17,6 +18,29 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+unsigned long long g_launch_count = 0;
+
+// ---- profiler ----------------------------------------------------------------------------------
+namespace {
+struct ProfRecord { cudaEvent_t a, b; int category; double work; };
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof;
+}  // namespace
+
+ProfScope::ProfScope(int category, double work, cudaStream_t s) : idx(-1), stream(s) {
+    if (!g_prof_on) return;
+    ProfRecord r;
+    r.category = category;
+    r.work = work;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+    idx = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].b, stream);
+}
+
 }  // namespace climb
 
 using namespace climb;
@@ -27,6 +51,32 @@ extern "C" {
 
 const char* climb_last_error(void) { return g_last_error; }
 int climb_version(void) { return 100; }
+uint64_t climb_launch_count(void) { return g_launch_count; }
+
+int climb_profile_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+    return 0;
+}
+int climb_profile_end(double* ms, double* work, int64_t* launches, int n_categories) {
+    g_prof_on = false;
+    CLIMB_REQUIRE(ms && work && launches && n_categories >= PROF_NUM, "climb_profile_end: need %d categories", PROF_NUM);
+    CLIMB_CUDA_OK(cudaDeviceSynchronize());
+    for (int i = 0; i < n_categories; ++i) { ms[i] = 0.0; work[i] = 0.0; launches[i] = 0; }
+    for (auto& r : g_prof) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            ms[r.category] += t;
+            work[r.category] += r.work;
+            launches[r.category] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return 0;
+}
 
 int climb_gemm_bf16(const climb_gemm_desc* desc, void* stream) { return gemm_bf16(desc, S(stream)); }
 

@@ -20,6 +20,18 @@ namespace climb {
 // ---------------------------------------------------------------------------------------------
 void set_last_error(const char* fmt, ...);
 
+// launch accounting (climb_launch_count) and the optional per-category device-time profiler
+// (climb_profile_begin / climb_profile_end): a Scope brackets one launcher with two events on the
+// launch stream when profiling is on and costs one branch when it is off.
+extern unsigned long long g_launch_count;
+enum ProfCategory { PROF_GEMM = 0, PROF_ATTN_FWD = 1, PROF_ATTN_BWD = 2, PROF_OTHER = 3, PROF_NUM = 4 };
+struct ProfScope {
+    int idx;
+    cudaStream_t stream;
+    ProfScope(int category, double work, cudaStream_t s);
+    ~ProfScope();
+};
+
 #define CLIMB_CUDA_OK(expr)                                                                  \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \
@@ -40,6 +52,7 @@ void set_last_error(const char* fmt, ...);
 
 #define CLIMB_LAUNCH_OK()                                                                    \
     do {                                                                                     \
+        ++::climb::g_launch_count;                                                           \
         cudaError_t _e = cudaGetLastError();                                                 \
         if (_e != cudaSuccess) {                                                             \
             ::climb::set_last_error("kernel launch failed: %s (%s:%d)",                      \

@@ -517,6 +517,7 @@ int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
     }
     const int total = a.m_tiles * a.n_tiles * a.split_k;
     const int grid = total < num_sms() ? total : num_sms();
+    ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
     gemm_bf16_tcgen05_kernel<BLOCK_N><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, a);
     CLIMB_LAUNCH_OK();
     return 0;

@@ -1,0 +1,121 @@
+"""Data-parallel gradient synchronisation for the B200 ViLT path (the reference is
+single-process, so this layer is new). One process per GPU, torch.distributed over NCCL/NVLink.
+
+The path shards on BATCH only: every rank runs the same task on its own rows of the step's batch, the
+encoder has no cross-row operation, and the single exchange per step is the gradient all-reduce
+(average). Because all encoder gradients live in ONE flat arena (climb_b200/arena.py) the exchange is a
+handful of large all-reduces over contiguous spans of that buffer instead of ~230 per-tensor calls:
+
+  * spans = maximal runs of trainable parameters in arena order (full fine-tuning: one 446 MB span;
+    adapters: 2 small spans per layer), cut into buckets of at most `bucket_mb`;
+  * task-head gradients (ordinary autograd tensors outside the arena) are reduced from
+    post-accumulate-grad hooks as soon as autograd produces them, i.e. while the encoder backward
+    is still running.
+
+EWC's penalty / Fisher and the optimizer are purely local (replicated parameters): no communication.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def trainable_spans(offsets, numels, names_in_order: Sequence[str], trainable: set, align: int = 64) -> List[Tuple[int, int]]:
+    """Maximal contiguous [start, end) element ranges of the arena covered by trainable parameters
+    (alignment padding between two trainable neighbours is bridged)."""
+    spans: List[Tuple[int, int]] = []
+    for n in names_in_order:
+        if n not in trainable:
+            continue
+        s, e = offsets[n], offsets[n] + numels[n]
+        if spans and s - spans[-1][1] < align:
+            spans[-1] = (spans[-1][0], e)
+        else:
+            spans.append((s, e))
+    return spans
+
+
+def bucketize(spans: Sequence[Tuple[int, int]], bucket_elems: int) -> List[Tuple[int, int]]:
+    out = []
+    for s, e in spans:
+        while e - s > bucket_elems:
+            out.append((s, s + bucket_elems))
+            s += bucket_elems
+        if e > s:
+            out.append((s, e))
+    return out
+
+
+def allreduce_mean_(flat: torch.Tensor, buckets: Sequence[Tuple[int, int]], group=None) -> None:
+    """In-place average of the listed ranges of `flat` over the process group. Buckets are issued
+    back to front: the backward pass fills the arena from the last layer to the first."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    works = []
+    for s, e in reversed(list(buckets)):
+        view = flat[s:e]
+        if flat.is_cuda:
+            works.append(dist.all_reduce(view, op=dist.ReduceOp.AVG, group=group, async_op=True))
+        else:   # gloo (CPU tests) has no AVG
+            works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    if not flat.is_cuda:
+        for s, e in buckets:
+            flat[s:e].div_(world)
+
+
+class GradSync:
+    def __init__(self, learner, bucket_mb: float = 64.0, group=None):
+        self.learner = learner
+        self.group = group
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self._cache = None
+        self._hooks = []
+        vilt = learner.get_encoder().vilt
+        vilt.grad_sync = self._sync_arena
+        for n, p in learner.named_parameters():
+            if not n.startswith(("vilt_encoder.", "viltbert_encoder.")):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._sync_loose))
+
+    def _sync_loose(self, p: torch.Tensor) -> None:
+        if p.grad is not None:
+            dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
+
+    def _sync_arena(self, arena) -> None:
+        items = arena.named_items()
+        key = (id(arena.theta), tuple(p.requires_grad for _, p in items))
+        if self._cache is None or self._cache[0] != key:
+            names = [n for n, _ in items]
+            trainable = {n for n, p in items if p.requires_grad}
+            spans = trainable_spans(arena.offsets, arena.numels, names, trainable)
+            self._cache = (key, bucketize(spans, self.bucket_elems))
+        allreduce_mean_(arena.grad, self._cache[1], self.group)
+
+    def detach(self):
+        self.learner.get_encoder().vilt.grad_sync = None
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def attach(learner, bucket_mb: float = 64.0, group=None) -> GradSync:
+    """Make every backward of `learner` end with its gradients averaged over the ranks. Parameters must
+    already be identical on all ranks (same seed / same checkpoint), as in any data-parallel run."""
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    return GradSync(learner, bucket_mb, group)
+
+
+def shard_batch(batch: dict, rank: int, world: int, group_size: int = 1) -> dict:
+    """Rows of the step's batch owned by `rank`: contiguous slices, keeping NLVR2 image pairs / VCR
+    four-choice tuples (group_size rows) together. Tensors and lists are both sliced."""
+    def cut(v):
+        n = len(v) // group_size
+        per = (n + world - 1) // world
+        lo, hi = min(n, rank * per) * group_size, min(n, (rank + 1) * per) * group_size
+        return v[lo:hi]
+    return {k: (cut(v) if hasattr(v, "__len__") and not isinstance(v, str) else v) for k, v in batch.items()}

@@ -266,15 +266,21 @@ class B200ViltModel(nn.Module):
             m.bias.data.zero_()
             m.weight.data.fill_(1.0)
 
-    # -- arena order: q,k,v weights (and biases) adjacent so that one [3d, d] GEMM reads them -------
+    # -- arena order: network order (embeddings, layer 0 .. layer L-1, tail) so that the backward pass
+    #    fills the gradient arena back to front; inside a layer q,k,v weights (and biases) are adjacent
+    #    so that one [3d, d] GEMM reads them ----------------------------------------------------------
     def _arena_items(self) -> List[Tuple[str, nn.Parameter]]:
         named = dict(self.named_parameters())
-        order: List[str] = []
+        order: List[str] = [n for n in named if n.startswith("embeddings.")]
         for i in range(len(self.encoder.layer)):
-            a = f"encoder.layer.{i}.attention.attention."
-            order += [a + "query.weight", a + "key.weight", a + "value.weight"]
+            pre = f"encoder.layer.{i}."
+            a = pre + "attention.attention."
+            qkv = [a + "query.weight", a + "key.weight", a + "value.weight"]
             if self.config.qkv_bias:
-                order += [a + "query.bias", a + "key.bias", a + "value.bias"]
+                qkv += [a + "query.bias", a + "key.bias", a + "value.bias"]
+            order += qkv
+            skip = set(qkv)
+            order += [n for n in named if n.startswith(pre) and n not in skip]
         seen = set(order)
         order += [n for n in named if n not in seen]
         return [(n, named[n]) for n in order]

@@ -39,6 +39,17 @@ typedef enum {
 const char* climb_last_error(void);
 int climb_version(void);
 
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t climb_launch_count(void);
+
+/* Device-time profiler used by bench.py's roofline: between begin and end every GEMM / attention
+ * launcher is bracketed by two CUDA events ON ITS LAUNCH STREAM. climb_profile_end synchronises and
+ * returns per category (0 = tcgen05 GEMM, 1 = attention fwd, 2 = attention bwd [3 kernels], 3 = unused)
+ * the summed device milliseconds, the summed algorithmic work (GEMM: FLOPs = 2 M N K; attention:
+ * algorithmic HBM bytes of SURVEY.md 8d) and the number of launches. Arrays of >= 4 entries. */
+int climb_profile_begin(void);
+int climb_profile_end(double* ms, double* work, int64_t* launches, int n_categories);
+
 /* ---------------------------------------------------------------------------------------------
  * GEMM: C[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T + bias[n]) + residual[m,n]
  * Replaces every nn.Linear / Conv2d-as-GEMM of the path (modeling_vilt.py:309-328,356-360,
