@@ -88,7 +88,7 @@ climb_ewc_penalty = _sig(
 climb_fisher_accumulate = _sig("climb_fisher_accumulate", [_P, _P, c_int64, _P])
 climb_scale_inplace = _sig("climb_scale_inplace", [_P, c_int64, c_float, _P])
 climb_adamw_step = _sig(
-    "climb_adamw_step", [_P, _P, _P, _P, _P, c_int, POINTER(c_float), POINTER(c_float), c_int, c_float, c_float,
+    "climb_adamw_step", [_P, _P, _P, _P, _P, _P, c_int, POINTER(c_float), POINTER(c_float), c_int, c_float, c_float,
                          c_float, c_int, _P])
 
 

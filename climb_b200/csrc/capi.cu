@@ -130,11 +130,11 @@ int climb_fisher_accumulate(const float* grad, float* fisher, int64_t n, void* s
     return fisher_accumulate(grad, fisher, n, S(stream));
 }
 int climb_scale_inplace(float* x, int64_t n, float s, void* stream) { return scale_inplace(x, n, s, S(stream)); }
-int climb_adamw_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq,
+int climb_adamw_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                      const climb_adamw_chunk* chunks_dev, int n_chunks, const float* group_lr_host,
                      const float* group_wd_host, int n_groups, float beta1, float beta2, float eps, int step,
                      void* stream) {
-    return adamw_step(theta, grad, exp_avg, exp_avg_sq, chunks_dev, n_chunks, group_lr_host, group_wd_host, n_groups,
+    return adamw_step(theta, grad, exp_avg, exp_avg_sq, shadow_bf16, chunks_dev, n_chunks, group_lr_host, group_wd_host, n_groups,
                       beta1, beta2, eps, step, S(stream));
 }
 int64_t climb_vilt_forward_workspace_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,

@@ -55,7 +55,7 @@ int ewc_penalty(const float* theta, const float* theta_star, const float* fisher
                 const float* grad_scale_dev, cudaStream_t stream);
 int fisher_accumulate(const float* grad, float* fisher, long long n, cudaStream_t stream);
 int scale_inplace(float* x, long long n, float s, cudaStream_t stream);
-int adamw_step(float* theta, const float* grad, float* m, float* v, const climb_adamw_chunk* chunks_dev,
+int adamw_step(float* theta, const float* grad, float* m, float* v, void* shadow_bf16, const climb_adamw_chunk* chunks_dev,
                int n_chunks, const float* group_lr, const float* group_wd, int n_groups, float beta1, float beta2,
                float eps, int step, cudaStream_t stream);
 

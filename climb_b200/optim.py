@@ -96,10 +96,15 @@ class ArenaAdamW(torch.optim.Optimizer):
                           theta_ptr=a.theta.data_ptr(), step=0)
                 self._arena_state[aid] = st
             st["step"] += 1
+            # the kernel also refreshes the bf16 shadow of everything it updates; parameters it skipped
+            # (grad None) did not change, so the shadow stays coherent if it was coherent before
+            coherent = a.shadow is not None and not a.shadow_dirty and a._shadow_version == a._version_sum
             _lib.check(_lib.climb_adamw_step(_lib.ptr(a.theta), _lib.ptr(a.grad), _lib.ptr(st["exp_avg"]),
-                                             _lib.ptr(st["exp_avg_sq"]), _lib.ptr(table), n_chunks, lr_arr, wd_arr,
+                                             _lib.ptr(st["exp_avg_sq"]), _lib.ptr(a.shadow) if coherent else None,
+                                             _lib.ptr(table), n_chunks, lr_arr, wd_arr,
                                              n_groups, beta1, beta2, eps, st["step"], stream))
-            a.shadow_dirty = True
+            if not coherent:
+                a.shadow_dirty = True
         for p, gi in loose:
             if not (p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32 and p.is_cuda):
                 raise _lib.ClimbError("ArenaAdamW handles contiguous fp32 CUDA parameters")
@@ -113,6 +118,6 @@ class ArenaAdamW(torch.optim.Optimizer):
                 st["table"], st["n_chunks"], st["group"] = _upload_chunks(chunks, p.device), len(chunks), gi
             st["step"] += 1
             _lib.check(_lib.climb_adamw_step(_lib.ptr(p), _lib.ptr(p.grad), _lib.ptr(st["exp_avg"]),
-                                             _lib.ptr(st["exp_avg_sq"]), _lib.ptr(st["table"]), st["n_chunks"],
+                                             _lib.ptr(st["exp_avg_sq"]), None, _lib.ptr(st["table"]), st["n_chunks"],
                                              lr_arr, wd_arr, n_groups, beta1, beta2, eps, st["step"], stream))
         return loss

@@ -160,6 +160,7 @@ typedef struct {
     int32_t group;       /* index into group_lr / group_wd */
 } climb_adamw_chunk;
 int climb_adamw_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq,
+                     void* shadow_bf16 /* nullable: bf16 copy of the updated theta, same offsets */,
                      const climb_adamw_chunk* chunks_dev, int n_chunks,
                      const float* group_lr_host, const float* group_wd_host, int n_groups,
                      float beta1, float beta2, float eps, int step, void* stream);

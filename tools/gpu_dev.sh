@@ -18,7 +18,12 @@ for g in "$@"; do
     attn)     run attn 600 tests/test_gpu_kernels.py -k "attention" ;;
     ln)       run ln 600 tests/test_gpu_kernels.py -k "layernorm" ;;
     parity)   run parity 900 tests/test_gpu_parity.py -s ;;
+    cl)       run cl 900 tests/test_gpu_cl.py -s ;;
     perf)     echo "=== perf" | tee -a gpurun_out/summary.txt; timeout 600 python tools/perf_kernels.py > gpurun_out/perf.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; tail -n 12 gpurun_out/perf.log | tee -a gpurun_out/summary.txt ;;
+    smoke)    echo "=== smoke" | tee -a gpurun_out/summary.txt; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "exit=$? $(tail -n 2 gpurun_out/smoke.log | tr '\n' ' ')" | tee -a gpurun_out/summary.txt ;;
+    bench)    echo "=== bench" | tee -a gpurun_out/summary.txt; timeout 900 python bench.py --steps ${BENCH_STEPS:-10} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "exit=$?" | tee -a gpurun_out/summary.txt; tail -n 5 gpurun_out/bench.err | tee -a gpurun_out/summary.txt; cat gpurun_out/bench.json | tee -a gpurun_out/summary.txt ;;
+    benchref) echo "=== benchref" | tee -a gpurun_out/summary.txt; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit=$?" | tee -a gpurun_out/summary.txt; cat gpurun_out/bench_ref.json | tee -a gpurun_out/summary.txt ;;
+    launches) echo "=== launches" | tee -a gpurun_out/summary.txt; timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/one_step.py > gpurun_out/launches.log 2>&1; echo "exit=$? rows=$(wc -l < gpurun_out/launches.csv)" | tee -a gpurun_out/summary.txt ;;
     *)        run "$(echo $g | tr '/:. ' '____')" 900 $g ;;
   esac
 done
