@@ -28,7 +28,7 @@ constexpr int kBlockK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
 constexpr int kAccStages = 2;
-constexpr int kEpiScratchBytes = 4096;   // per epilogue warp: 32 rows x 128 B
+constexpr int kEpiHalfBytes = 4096;      // one staging block of an epilogue warp: 32 rows x 128 B
 
 struct GemmDeviceArgs {
     int M, N, K;
@@ -48,6 +48,8 @@ struct GemmDeviceArgs {
     int accumulate;
     int split_k;
     int m_tiles, n_tiles, k_blocks_per_split, k_blocks_total;
+    int num_stages;               // smem ring depth (runtime: deeper when the epilogue needs no input prefetch)
+    int scratch_bytes;            // per epilogue warp: 4096 (staging only) or 8192 (+ prefetch half)
 };
 
 template <int BLOCK_N>
@@ -55,11 +57,17 @@ struct SmemLayout {
     static constexpr int kABytes = kBlockM * kBlockK * 2;
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int kMaxStages = 8;
     static constexpr int kBarrierBytes = 1024;
-    static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + kNumEpiWarps * kEpiScratchBytes +
-                                  1024 /*align slack*/;
-    static_assert(kTotal <= 227 * 1024, "shared memory budget");
+    // ring depth: as deep as the 227 KB allow next to the epilogue scratch
+    static constexpr int stages_for(int scratch_per_warp) {
+        int s = (227 * 1024 - 1024 - kBarrierBytes - kNumEpiWarps * scratch_per_warp) / kStageBytes;
+        return s > kMaxStages ? kMaxStages : s;
+    }
+    static constexpr int total_for(int scratch_per_warp) {
+        return stages_for(scratch_per_warp) * kStageBytes + kBarrierBytes + kNumEpiWarps * scratch_per_warp + 1024;
+    }
+    static_assert(stages_for(8192) >= 3, "shared memory budget");
 };
 
 // UMMA shared-memory descriptor, 128B swizzle (layout type 2), sm_100 version bit.
@@ -197,12 +205,38 @@ __device__ __forceinline__ void load_rows(uint8_t* scratch, uint32_t* pk, const 
     }
 }
 
+// Asynchronous (cp.async, no registers) version of load_rows' first half: the rows of the NEXT chunk
+// are put in flight while the current chunk is being processed; finish with prefetch_take().
+template <int NCH>
+__device__ __forceinline__ void prefetch_rows(uint8_t* buf, const uint8_t* gbase, long long ld_bytes,
+                                              int rows_valid, int lane) {
+    const uint32_t sb = smem_u32(buf);
+#pragma unroll
+    for (int it = 0; it < NCH; ++it) {
+        const int q = it * 32 + lane;
+        const int rr = q / NCH, j = q % NCH;
+        const bool ok = rr < rows_valid;
+        cp_async_16(sb + swz128(q * 16), gbase + (ok ? rr * ld_bytes : 0) + j * 16, ok);
+    }
+    cp_async_commit();
+}
+template <int NCH>
+__device__ __forceinline__ void prefetch_take(const uint8_t* buf, uint32_t* pk, int lane) {
+    cp_async_wait<0>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const uint4 val = *reinterpret_cast<const uint4*>(buf + swz128((lane * NCH + j) * 16));
+        pk[4 * j] = val.x; pk[4 * j + 1] = val.y; pk[4 * j + 2] = val.z; pk[4 * j + 3] = val.w;
+    }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b, const GemmDeviceArgs p) {
     using L = SmemLayout<BLOCK_N>;
-    constexpr int kStages = L::kStages;
+    const int kStages = p.num_stages;
     constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;   // 512 / 256 / 128: powers of two >= 32
 
     extern __shared__ uint8_t smem_raw[];
@@ -210,8 +244,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                ~static_cast<uintptr_t>(1023));
     uint8_t* bar_base = smem + kStages * L::kStageBytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* acc_full = empty_bar + kStages;
+    uint64_t* empty_bar = full_bar + L::kMaxStages;
+    uint64_t* acc_full = empty_bar + L::kMaxStages;
     uint64_t* acc_empty = acc_full + kAccStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
 
@@ -328,7 +362,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int ew = warp - 2;                  // 0..7
         const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are ours
         const int col_half = ew >> 2;             // two warps share a lane group: even/odd chunks
-        uint8_t* scratch = smem + kStages * L::kStageBytes + L::kBarrierBytes + ew * kEpiScratchBytes;
+        uint8_t* scratch_base = smem + kStages * L::kStageBytes + L::kBarrierBytes + ew * p.scratch_bytes;
+        int buf = 0;                              // which half of the warp's scratch the current chunk uses
+        int pf_tile = -1, pf_c = -1;              // chunk whose epilogue input is in flight in the other half
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool c_f32 = p.c_dtype == CLIMB_F32;
@@ -341,6 +377,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const bool aux_in = (p.epilogue == CLIMB_EPI_DGELU || p.epilogue == CLIMB_EPI_DSWISH ||
                              p.epilogue == CLIMB_EPI_DRELU);
         const bool aux_out = (p.aux != nullptr) && !aux_in;   // pre-activation copy (bf16)
+        // The one epilogue INPUT stream worth prefetching: the bf16 aux tensor of the derivative
+        // epilogues (dGELU reads the saved pre-activation), else the fp32 residual.
+        const int pf_kind = (!all_fast || p.scratch_bytes < 2 * kEpiHalfBytes) ? 0
+                            : (aux_in ? 1 : (p.residual != nullptr ? 2 : 0));
+        // issue the loads of chunk (t, cc) into scratch half `b`; returns false if that chunk does not
+        // exist or is not on the fast path (then it will be loaded synchronously, or not at all)
+        auto prefetch = [&](int t, int cc, int b) -> bool {
+            if (pf_kind == 0 || t >= total_tiles) return false;
+            const int sp = t / tiles_mn;
+            if (sp != 0 && pf_kind == 2) return false;
+            const int mn2 = t - sp * tiles_mn;
+            const int mb = mn2 / p.n_tiles, nb = mn2 - mb * p.n_tiles;
+            const int nn0 = nb * BLOCK_N + cc * 32;
+            if (cc >= BLOCK_N / 32 || nn0 + 32 > p.N) return false;
+            const int r0 = mb * kBlockM + lane_grp * 32;
+            const int rv = min(32, max(0, p.M - r0));
+            uint8_t* dstb = scratch_base + b * kEpiHalfBytes;
+            if (pf_kind == 1)
+                prefetch_rows<4>(dstb, reinterpret_cast<const uint8_t*>(p.aux) + (static_cast<long long>(r0) * p.ldaux + nn0) * 2,
+                                 p.ldaux * 2, rv, lane);
+            else
+                prefetch_rows<8>(dstb, reinterpret_cast<const uint8_t*>(p.residual) + (static_cast<long long>(r0) * p.ldr + nn0) * 4,
+                                 p.ldr * 4, rv, lane);
+            return true;
+        };
+        if (prefetch(blockIdx.x, col_half, buf ^ 1)) { pf_tile = blockIdx.x; pf_c = col_half; }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int split = tile / tiles_mn;
             const int mn = tile - split * tiles_mn;
@@ -360,15 +422,45 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int c = col_half; c < BLOCK_N / 32; c += 2) {
                 const int n0 = n_blk * BLOCK_N + c * 32;
                 if (n0 >= p.N) break;                      // warp-uniform
+                const bool full = (n0 + 32 <= p.N);
+                // epilogue input of THIS chunk: already in flight (prefetched) or fetched now
+                uint32_t pin[32];
+                const bool have_pf = (pf_tile == tile && pf_c == c);
+                if (have_pf) buf ^= 1;            // prefetches always target the half the previous chunk did not use
+                uint8_t* scratch = scratch_base + buf * kEpiHalfBytes;
+                if (full && all_fast) {
+                    if (have_pf) {
+                        if (pf_kind == 1) prefetch_take<4>(scratch, pin, lane);
+                        else prefetch_take<8>(scratch, pin, lane);
+                    } else if (aux_in) {
+                        cp_async_wait<0>();
+                        load_rows<4>(scratch, pin, reinterpret_cast<const uint8_t*>(p.aux) +
+                                                       (static_cast<long long>(row0) * p.ldaux + n0) * 2,
+                                     p.ldaux * 2, rows_valid, lane);
+                    } else if (add_res) {
+                        cp_async_wait<0>();
+                        load_rows<8>(scratch, pin, reinterpret_cast<const uint8_t*>(p.residual) +
+                                                       (static_cast<long long>(row0) * p.ldr + n0) * 4,
+                                     p.ldr * 4, rows_valid, lane);
+                    }
+                    // next chunk of this warp: same tile two chunks on, else the first chunk of its next tile
+                    int nt = tile, nc = c + 2;
+                    if (nc >= BLOCK_N / 32 || n_blk * BLOCK_N + nc * 32 >= p.N) { nt = tile + gridDim.x; nc = col_half; }
+                    if (prefetch(nt, nc, buf ^ 1)) { pf_tile = nt; pf_c = nc; } else { pf_tile = -1; }
+                }
                 float v[32];
                 {
                     uint32_t r[32];
                     tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), r);
                     tmem_ld_wait();
+                    if (p.alpha == 1.0f) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                    }
                 }
-                const bool full = (n0 + 32 <= p.N);
                 if (full && all_fast) {
                     // ------------------------------ fast path ------------------------------------
                     if (add_bias) {
@@ -380,10 +472,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                     uint32_t pk[32];
                     if (aux_in) {
-                        load_rows<4>(scratch, pk, reinterpret_cast<const uint8_t*>(p.aux) +
-                                                       (static_cast<long long>(row0) * p.ldaux + n0) * 2,
-                                     p.ldaux * 2, rows_valid, lane);
-                        dact_chunk(p.epilogue, v, pk);
+                        dact_chunk(p.epilogue, v, pin);
                     } else {
                         if (aux_out) {
 #pragma unroll
@@ -395,11 +484,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         act_chunk(p.epilogue, v);
                     }
                     if (add_res) {
-                        load_rows<8>(scratch, pk, reinterpret_cast<const uint8_t*>(p.residual) +
-                                                       (static_cast<long long>(row0) * p.ldr + n0) * 4,
-                                     p.ldr * 4, rows_valid, lane);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(pk[j]);
+                        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(pin[j]);
                     }
                     if (p.c2 != nullptr) {
 #pragma unroll
@@ -572,13 +658,18 @@ int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
     a.k_blocks_total = (d->K + kBlockK - 1) / kBlockK;
     int split = d->split_k;
     if (split <= 0) {
-        // auto: only worth it when the output grid cannot fill the machine and K is deep
+        // auto split-K (accumulating fp32 outputs only): choose the split whose tile count fills
+        // whole waves of the machine best, e.g. 108 tiles x 4 = 432 = 2.92 waves instead of 0.73
         split = 1;
         const int tiles = a.m_tiles * a.n_tiles;
-        if (d->accumulate && d->c_dtype == CLIMB_F32 && tiles < num_sms() && a.k_blocks_total >= 8) {
-            split = num_sms() / tiles;
-            if (split > a.k_blocks_total / 4) split = a.k_blocks_total / 4;
-            if (split < 1) split = 1;
+        if (d->accumulate && d->c_dtype == CLIMB_F32 && a.k_blocks_total >= 16) {
+            double best = 0.0;
+            for (int s = 1; s <= 16 && a.k_blocks_total / s >= 8; ++s) {
+                const long long t = 1LL * tiles * s;
+                const long long waves = (t + num_sms() - 1) / num_sms();
+                const double fill = static_cast<double>(t) / (waves * num_sms());
+                if (fill > best + 0.03) { best = fill; split = s; }
+            }
         }
     }
     if (split > a.k_blocks_total) split = a.k_blocks_total;
@@ -591,13 +682,20 @@ int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
     static bool attr_set = false;
     if (!attr_set) {
         CLIMB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
+    // epilogues that read a tensor (derivative activations, residual) get a second scratch half for
+    // the cp.async prefetch of the next chunk's input and pay one ring stage for it
+    const bool epi_input = d->residual != nullptr || d->epilogue == CLIMB_EPI_DGELU ||
+                           d->epilogue == CLIMB_EPI_DSWISH || d->epilogue == CLIMB_EPI_DRELU;
+    a.scratch_bytes = epi_input ? 2 * kEpiHalfBytes : kEpiHalfBytes;
+    a.num_stages = L::stages_for(a.scratch_bytes);
+    const int smem_bytes = L::total_for(a.scratch_bytes);
     const int total = a.m_tiles * a.n_tiles * a.split_k;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
-    gemm_bf16_tcgen05_kernel<BLOCK_N><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, a);
+    gemm_bf16_tcgen05_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, a);
     CLIMB_LAUNCH_OK();
     return 0;
 }
