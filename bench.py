@@ -192,7 +192,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
     B = args.batch
@@ -309,14 +310,16 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
     # ---- per-kernel device time for the roofline (events on the launch stream) -------------------
+    # (every rank runs the two extra steps -- they contain the gradient all-reduce -- rank 0 reports)
     roofline, attn_roof = None, None
+    barrier()
+    _lib.check(_lib.climb_profile_begin())
+    for i in range(2):
+        step(resident[i % n_batches])
+    prof = _lib.profile_end()
+    barrier()
     if rank == 0:
         peaks = load_peaks()
-        torch.cuda.synchronize()
-        _lib.check(_lib.climb_profile_begin())
-        for i in range(2):
-            step(resident[i % n_batches])
-        prof = _lib.profile_end()
         g_ms, g_flops, g_n = prof["gemm"]
         achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         traffic = None
