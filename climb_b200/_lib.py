@@ -131,6 +131,7 @@ class AdamWChunkC(Structure):
 
 
 TRAIN_BASE, TRAIN_ADAPTER = 1, 2
+BWD_TAIL, BWD_EMBED = 1, 2
 
 climb_vilt_forward_workspace_bytes = _sig(
     "climb_vilt_forward_workspace_bytes", [POINTER(ViltDimsC), POINTER(ViltParamsC), POINTER(ViltBatchC), c_int],
@@ -142,7 +143,7 @@ climb_vilt_forward = _sig(
                            c_int, _P, _P])
 climb_vilt_backward = _sig(
     "climb_vilt_backward", [POINTER(ViltDimsC), POINTER(ViltParamsC), POINTER(ViltBatchC), _P, _P, _P, c_int64,
-                            _P, c_int64, _P, _P, _P])
+                            _P, c_int64, _P, _P, c_int, c_int, c_int, _P])
 
 
 def check(rc: int) -> None:

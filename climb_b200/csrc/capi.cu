@@ -153,9 +153,10 @@ int climb_vilt_forward(const climb_vilt_dims* dims, const climb_vilt_params* par
 }
 int climb_vilt_backward(const climb_vilt_dims* dims, const climb_vilt_params* params, const climb_vilt_batch* batch,
                         const float* theta, const void* shadow, const void* workspace, int64_t workspace_bytes,
-                        void* scratch, int64_t scratch_bytes, const float* dpooled, float* grad, void* stream) {
+                        void* scratch, int64_t scratch_bytes, const float* dpooled, float* grad, int first_layer,
+                        int last_layer, int parts, void* stream) {
     return vilt_backward(dims, params, batch, theta, shadow, workspace, workspace_bytes, scratch, scratch_bytes, dpooled,
-                         grad, S(stream));
+                         grad, first_layer, last_layer, parts, S(stream));
 }
 
 }  // extern "C"

@@ -152,8 +152,9 @@ __global__ void embed_reduce_bwd_kernel(const float* __restrict__ dx, const int*
     reinterpret_cast<float4*>(S)[static_cast<long long>(L) * d4 + i] = a1;
 }
 
-// one thread per column: folds S onto cls_token, position_embeddings (row 0 + the transposed
-// bilinear taps), the modality-type table and the patch-projection bias
+// Folds S onto cls_token, position_embeddings (row 0 + the transposed bilinear taps), the
+// modality-type table and the patch-projection bias. grid.x covers the columns, grid.y slices the
+// L rows; every CTA reduces its slice and finishes with one atomic per column and target.
 __global__ void embed_finalize_bwd_kernel(const float* __restrict__ S, float* __restrict__ d_cls,
                                           float* __restrict__ d_pos, float* __restrict__ d_mod,
                                           float* __restrict__ d_patch_bias, int n_mod, int T, int hp, int wp,
@@ -161,32 +162,41 @@ __global__ void embed_finalize_bwd_kernel(const float* __restrict__ S, float* __
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d) return;
     const int Np = hp * wp, L = T + 1 + Np;
+    const int per = (L + gridDim.y - 1) / gridDim.y;
+    const int l0 = blockIdx.y * per, l1 = min(L, l0 + per);
     const float* S0 = S;
     const float* S1 = S + static_cast<long long>(L) * d;
     float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, pb = 0.0f;
-    for (int l = 0; l < T; ++l) m0 += S0[l * d + c];
-    for (int l = T; l < L; ++l) { m1 += S0[l * d + c]; m2 += S1[l * d + c]; }
-    if (d_mod) {
-        d_mod[c] += m0;
-        d_mod[d + c] += m1;
-        if (n_mod > 2) d_mod[2 * d + c] += m2;
-    }
-    const float cls_g = S0[T * d + c] + S1[T * d + c];
-    if (d_cls) d_cls[c] += cls_g;
-    if (d_pos) d_pos[c] += cls_g;
-    for (int p = 0; p < Np; ++p) {
-        const float g = S0[(T + 1 + p) * d + c] + S1[(T + 1 + p) * d + c];
+    for (int l = l0; l < l1; ++l) {
+        const float a = S0[l * d + c], b = S1[l * d + c];
+        if (l < T) { m0 += a; continue; }
+        m1 += a;
+        m2 += b;
+        const float g = a + b;
+        if (l == T) {
+            if (d_cls) atomicAdd(d_cls + c, g);
+            if (d_pos) atomicAdd(d_pos + c, g);
+            continue;
+        }
         pb += g;
         if (d_pos) {
+            const int p = l - T - 1;
             const Taps t = bilinear_taps(p / wp, p % wp, hp, wp, G);
             float* dp = d_pos + d;
-            dp[t.i00 * d + c] += t.w00 * g;
-            dp[t.i01 * d + c] += t.w01 * g;
-            dp[t.i10 * d + c] += t.w10 * g;
-            dp[t.i11 * d + c] += t.w11 * g;
+            atomicAdd(dp + t.i00 * d + c, t.w00 * g);
+            atomicAdd(dp + t.i01 * d + c, t.w01 * g);
+            atomicAdd(dp + t.i10 * d + c, t.w10 * g);
+            atomicAdd(dp + t.i11 * d + c, t.w11 * g);
         }
     }
-    if (d_patch_bias) d_patch_bias[c] += pb;
+    if (d_mod) {
+        if (m0 != 0.0f) atomicAdd(d_mod + c, m0);
+        if (l1 > T) {
+            atomicAdd(d_mod + d + c, m1);
+            if (n_mod > 2) atomicAdd(d_mod + 2 * d + c, m2);
+        }
+    }
+    if (d_patch_bias && l1 > T + 1) atomicAdd(d_patch_bias + c, pb);
 }
 
 // de [B*T, d] -> word / segment / position embedding gradients (dense tables, atomics on collisions)
@@ -263,7 +273,7 @@ int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, 
     embed_reduce_bwd_kernel<<<blocks_for(static_cast<long long>(L) * (d / 4), 128), 128, 0, stream>>>(
         dx, type_idx, type_idx_scalar, S, B, T, L, d / 4);
     CLIMB_LAUNCH_OK();
-    embed_finalize_bwd_kernel<<<blocks_for(d, 128), 128, 0, stream>>>(S, d_cls, d_pos, d_mod, d_patch_bias, n_mod, T, hp, wp, G, d);
+    embed_finalize_bwd_kernel<<<dim3(blocks_for(d, 128), 32), 128, 0, stream>>>(S, d_cls, d_pos, d_mod, d_patch_bias, n_mod, T, hp, wp, G, d);
     CLIMB_LAUNCH_OK();
     return 0;
 }

@@ -364,7 +364,8 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
 
 int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const climb_vilt_batch* bt,
                   const float* theta, const void* shadow, const void* workspace, long long workspace_bytes,
-                  void* scratch, long long scratch_bytes, const float* dpooled, float* grad, cudaStream_t s) {
+                  void* scratch, long long scratch_bytes, const float* dpooled, float* grad, int first_layer,
+                  int last_layer, int parts, cudaStream_t s) {
     Plan P;
     TRY(fill_plan(P, dm, pr, bt, const_cast<void*>(workspace), 1));
     CLIMB_REQUIRE(theta && shadow && workspace && scratch && dpooled && grad, "vilt_backward: null buffer");
@@ -383,7 +384,14 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             if (pr->layer[l].flags & (CLIMB_TRAIN_BASE | CLIMB_TRAIN_ADAPTER)) { lowest = l; break; }
     const bool tail = (pr->tail_flags & CLIMB_TRAIN_BASE) != 0;
     if (lowest == P.layers && !tail) return 0;      // nothing inside the encoder is trainable
+    CLIMB_REQUIRE(first_layer < P.layers && last_layer >= 0 && (first_layer >= last_layer || first_layer < 0),
+                  "vilt_backward: bad layer range [%d, %d]", first_layer, last_layer);
 
+    // The gradient of the residual stream lives in S.dxa / S.dxa_h at every layer boundary, so the pass
+    // can be issued in several calls (top layers first) with gradient all-reduces launched in between.
+    float* dx = S.dxa;  bf16* dx_h = S.dxa_h;      // gradient w.r.t. the current layer's output
+    float* dn = S.dxb;  bf16* dn_h = S.dxb_h;      // scratch for the next one
+    if (parts & CLIMB_BWD_TAIL) {
     // ---- pooler + final LayerNorm ----
     TRY(tanh_bwd(dpooled, P.pooled, S.dpool, static_cast<long long>(P.B) * d, s));
     if (tail) {
@@ -405,10 +413,10 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
                       tail ? G(grad, pr->final_ln_w) : nullptr, tail ? G(grad, pr->final_ln_b) : nullptr, P.B, d,
                       CLIMB_EPI_NONE, s));
     TRY(cast_f32_bf16(S.dxa, S.dxa_h, static_cast<long long>(M) * d, s));
+    }   // CLIMB_BWD_TAIL
+    if (lowest == P.layers) return 0;
 
-    float* dx = S.dxa;  bf16* dx_h = S.dxa_h;      // gradient w.r.t. the current layer's output
-    float* dn = S.dxb;  bf16* dn_h = S.dxb_h;      // scratch for the next one
-    for (int li = P.layers - 1; li >= lowest; --li) {
+    for (int li = first_layer; li >= last_layer && li >= lowest; --li) {
         const climb_vilt_layer& w = pr->layer[li];
         const LayerAct& a = P.act[li];
         const bool base = (w.flags & CLIMB_TRAIN_BASE) != 0;
@@ -472,7 +480,7 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
     }
 
     // ---- embeddings ----
-    if (pr->embed_flags & CLIMB_TRAIN_BASE) {
+    if ((parts & CLIMB_BWD_EMBED) && (pr->embed_flags & CLIMB_TRAIN_BASE)) {
         TRY(embed_split_bwd(dx, S.dy_text, S.dpatch, P.B, P.T, P.Np, d, s));
         TRY(embed_reduce_bwd(dx, bt->image_type_idx, bt->image_type_idx_scalar, S.S, G(grad, pr->cls_token),
                              G(grad, pr->pos_emb), G(grad, pr->mod_emb), G(grad, pr->patch_b), dm->n_modality, P.B, P.T,

@@ -69,6 +69,7 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
                  float* pooled_out, cudaStream_t s);
 int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const climb_vilt_batch* bt,
                   const float* theta, const void* shadow, const void* workspace, long long workspace_bytes,
-                  void* scratch, long long scratch_bytes, const float* dpooled, float* grad, cudaStream_t s);
+                  void* scratch, long long scratch_bytes, const float* dpooled, float* grad, int first_layer,
+                  int last_layer, int parts, cudaStream_t s);
 
 }  // namespace climb

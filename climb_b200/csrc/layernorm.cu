@@ -68,7 +68,7 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
 }
 
 template <int NV>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict__ dy_bf16,
               const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
               const float* __restrict__ beta, const float* __restrict__ mean_in,
@@ -81,50 +81,63 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict_
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 
+    // Only the column accumulators stay in registers across the row: x and dy are read twice (the second
+    // read hits L1/L2 -- a row is 4.5 KB) so that two CTAs fit per SM and more loads are in flight.
     float4 dg[NV], db[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    auto load_dy = [&](int row, int i, const float4& xh, const float4& g) -> float4 {
+        float4 dy;
+        if (dy_f32) {
+            dy = reinterpret_cast<const float4*>(dy_f32 + static_cast<long long>(row) * D)[lane + 32 * i];
+        } else {
+            const uint2 p = reinterpret_cast<const uint2*>(dy_bf16 + static_cast<long long>(row) * D)[lane + 32 * i];
+            const float2 a = unpack_bf16(p.x), b = unpack_bf16(p.y);
+            dy = make_float4(a.x, a.y, b.x, b.y);
+        }
+        if (act == CLIMB_EPI_GELU) {
+            const float4 b = __ldg(b4 + lane + 32 * i);
+            dy.x *= dgelu_f(xh.x * g.x + b.x); dy.y *= dgelu_f(xh.y * g.y + b.y);
+            dy.z *= dgelu_f(xh.z * g.z + b.z); dy.w *= dgelu_f(xh.w * g.w + b.w);
+        }
+        return dy;
+    };
+
     for (int row = blockIdx.x * kWarpsPerBlock + warp; row < rows; row += gridDim.x * kWarpsPerBlock) {
         const float mean = mean_in[row], rstd = rstd_in[row];
         const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
-        float4 xh[NV], gy[NV];
         float c1 = 0.0f, c2 = 0.0f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const float4 xv = xr[lane + 32 * i];
-            float4 dy;
-            if (dy_f32) {
-                dy = reinterpret_cast<const float4*>(dy_f32 + static_cast<long long>(row) * D)[lane + 32 * i];
-            } else {
-                const uint2 p = reinterpret_cast<const uint2*>(dy_bf16 + static_cast<long long>(row) * D)[lane + 32 * i];
-                const float2 a = unpack_bf16(p.x), b = unpack_bf16(p.y);
-                dy = make_float4(a.x, a.y, b.x, b.y);
-            }
             const float4 g = __ldg(g4 + lane + 32 * i);
-            xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
-            xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
-            if (act == CLIMB_EPI_GELU) {
-                const float4 b = __ldg(b4 + lane + 32 * i);
-                dy.x *= dgelu_f(xh[i].x * g.x + b.x); dy.y *= dgelu_f(xh[i].y * g.y + b.y);
-                dy.z *= dgelu_f(xh[i].z * g.z + b.z); dy.w *= dgelu_f(xh[i].w * g.w + b.w);
-            }
-            dg[i].x += dy.x * xh[i].x; dg[i].y += dy.y * xh[i].y;
-            dg[i].z += dy.z * xh[i].z; dg[i].w += dy.w * xh[i].w;
+            float4 xh;
+            xh.x = (xv.x - mean) * rstd; xh.y = (xv.y - mean) * rstd;
+            xh.z = (xv.z - mean) * rstd; xh.w = (xv.w - mean) * rstd;
+            const float4 dy = load_dy(row, i, xh, g);
+            dg[i].x += dy.x * xh.x; dg[i].y += dy.y * xh.y; dg[i].z += dy.z * xh.z; dg[i].w += dy.w * xh.w;
             db[i].x += dy.x; db[i].y += dy.y; db[i].z += dy.z; db[i].w += dy.w;
-            gy[i].x = dy.x * g.x; gy[i].y = dy.y * g.y; gy[i].z = dy.z * g.z; gy[i].w = dy.w * g.w;
-            c1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
-            c2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+            const float gx = dy.x * g.x, gy = dy.y * g.y, gz = dy.z * g.z, gw = dy.w * g.w;
+            c1 += (gx + gy) + (gz + gw);
+            c2 += (gx * xh.x + gy * xh.y) + (gz * xh.z + gw * xh.w);
         }
         c1 = warp_sum(c1) * (1.0f / D);
         c2 = warp_sum(c2) * (1.0f / D);
+        if (dx_f32 == nullptr && dx_bf16 == nullptr) continue;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
+            const float4 xv = xr[lane + 32 * i];
+            const float4 g = __ldg(g4 + lane + 32 * i);
+            float4 xh;
+            xh.x = (xv.x - mean) * rstd; xh.y = (xv.y - mean) * rstd;
+            xh.z = (xv.z - mean) * rstd; xh.w = (xv.w - mean) * rstd;
+            const float4 dy = load_dy(row, i, xh, g);
             float4 o;
-            o.x = rstd * (gy[i].x - c1 - xh[i].x * c2);
-            o.y = rstd * (gy[i].y - c1 - xh[i].y * c2);
-            o.z = rstd * (gy[i].z - c1 - xh[i].z * c2);
-            o.w = rstd * (gy[i].w - c1 - xh[i].w * c2);
+            o.x = rstd * (dy.x * g.x - c1 - xh.x * c2);
+            o.y = rstd * (dy.y * g.y - c1 - xh.y * c2);
+            o.z = rstd * (dy.z * g.z - c1 - xh.z * c2);
+            o.w = rstd * (dy.w * g.w - c1 - xh.w * c2);
             if (dres) {
                 const float4 r = reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * ldx)[lane + 32 * i];
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -180,7 +193,7 @@ int launch_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long lo
                const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int rows,
                int act, cudaStream_t stream) {
     int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int cap = 148 * 4;          // a few CTAs per SM; rows are grid-strided beyond that
+    const int cap = 148 * 4;          // two resident CTAs per SM, two rounds; rows are grid-strided beyond that
     if (grid > cap) grid = cap;
     ln_bwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
         dy_f32, static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres,

@@ -69,14 +69,20 @@ def allreduce_mean_(flat: torch.Tensor, buckets: Sequence[Tuple[int, int]], grou
 
 
 class GradSync:
-    def __init__(self, learner, bucket_mb: float = 64.0, group=None):
+    """Callable hook object stored on B200ViltModel.grad_sync. With layers_per_chunk > 0 the model issues
+    its backward in chunks of that many layers and calls begin / reduce_range / finish so that each
+    chunk's gradient span is all-reduced while the layers below it are still computing."""
+
+    def __init__(self, learner, bucket_mb: float = 64.0, group=None, layers_per_chunk: int = 3):
         self.learner = learner
         self.group = group
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.layers_per_chunk = layers_per_chunk
         self._cache = None
         self._hooks = []
+        self._works = []
         vilt = learner.get_encoder().vilt
-        vilt.grad_sync = self._sync_arena
+        vilt.grad_sync = self
         for n, p in learner.named_parameters():
             if not n.startswith(("vilt_encoder.", "viltbert_encoder.")):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._sync_loose))
@@ -85,14 +91,46 @@ class GradSync:
         if p.grad is not None:
             dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
 
-    def _sync_arena(self, arena) -> None:
+    # ---- overlapped path -------------------------------------------------------------------------
+    def _spans(self, arena):
         items = arena.named_items()
         key = (id(arena.theta), tuple(p.requires_grad for _, p in items))
         if self._cache is None or self._cache[0] != key:
             names = [n for n, _ in items]
             trainable = {n for n, p in items if p.requires_grad}
             spans = trainable_spans(arena.offsets, arena.numels, names, trainable)
-            self._cache = (key, bucketize(spans, self.bucket_elems))
+            self._cache = (key, bucketize(spans, self.bucket_elems), spans)
+        return self._cache[2]
+
+    def begin(self, arena) -> None:
+        self._works = []
+
+    def reduce_range(self, arena, lo: int, hi: int) -> None:
+        """All-reduce (mean) the trainable spans inside [lo, hi) of the gradient arena, asynchronously:
+        NCCL's stream waits for the kernels enqueued so far, not for the ones that follow."""
+        if dist.get_world_size(self.group) == 1:
+            return
+        for s, e in self._spans(arena):
+            s2, e2 = max(s, lo), min(e, hi)
+            if e2 > s2:
+                for bs, be in bucketize([(s2, e2)], self.bucket_elems):
+                    self._works.append(dist.all_reduce(arena.grad[bs:be], op=dist.ReduceOp.AVG, group=self.group,
+                                                       async_op=True))
+
+    def finish(self, arena) -> None:
+        for w in self._works:
+            w.wait()            # stream-level wait: the optimizer kernels queue behind the reductions
+        self._works = []
+
+    # ---- one-shot path (layers_per_chunk = 0) ------------------------------------------------------
+    def __call__(self, arena) -> None:
+        items = arena.named_items()
+        key = (id(arena.theta), tuple(p.requires_grad for _, p in items))
+        if self._cache is None or self._cache[0] != key:
+            names = [n for n, _ in items]
+            trainable = {n for n, p in items if p.requires_grad}
+            spans = trainable_spans(arena.offsets, arena.numels, names, trainable)
+            self._cache = (key, bucketize(spans, self.bucket_elems), spans)
         allreduce_mean_(arena.grad, self._cache[1], self.group)
 
     def detach(self):
@@ -102,12 +140,12 @@ class GradSync:
         self._hooks = []
 
 
-def attach(learner, bucket_mb: float = 64.0, group=None) -> GradSync:
+def attach(learner, bucket_mb: float = 64.0, group=None, layers_per_chunk: int = 3) -> GradSync:
     """Make every backward of `learner` end with its gradients averaged over the ranks. Parameters must
     already be identical on all ranks (same seed / same checkpoint), as in any data-parallel run."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
-    return GradSync(learner, bucket_mb, group)
+    return GradSync(learner, bucket_mb, group, layers_per_chunk)
 
 
 def shard_batch(batch: dict, rank: int, world: int, group_size: int = 1) -> dict:

@@ -547,14 +547,40 @@ class B200ViltModel(nn.Module):
         if self._scratch is None or self._scratch.numel() < nbytes or self._scratch.device != arena.theta.device:
             self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=arena.theta.device)
         arena.prepare_grads(call.trainable)
-        _lib.check(_lib.climb_vilt_backward(ctypes.byref(call.dims), ctypes.byref(call.params), ctypes.byref(call.batch),
-                                            _lib.ptr(arena.theta), _lib.ptr(arena.shadow), _lib.ptr(call.workspace),
-                                            call.ws_bytes, _lib.ptr(self._scratch), self._scratch.numel(),
-                                            _lib.ptr(dpooled), _lib.ptr(arena.grad), _lib.stream()))
-        arena.publish_grads(call.trainable)
+        n_layers = call.dims.layers
+
+        def run(first, last, parts):
+            _lib.check(_lib.climb_vilt_backward(ctypes.byref(call.dims), ctypes.byref(call.params), ctypes.byref(call.batch),
+                                                _lib.ptr(arena.theta), _lib.ptr(arena.shadow), _lib.ptr(call.workspace),
+                                                call.ws_bytes, _lib.ptr(self._scratch), self._scratch.numel(),
+                                                _lib.ptr(dpooled), _lib.ptr(arena.grad), first, last, parts, _lib.stream()))
+
+        sync = self.grad_sync
+        chunk = getattr(sync, "layers_per_chunk", 0) if sync is not None else 0
+        if sync is None or chunk <= 0 or chunk >= n_layers:
+            run(n_layers - 1, 0, _lib.BWD_TAIL | _lib.BWD_EMBED)
+            arena.publish_grads(call.trainable)
+            if sync is not None:
+                sync(arena)
+        else:
+            # data parallel: issue the backward top-down in chunks of layers; after each chunk the
+            # gradient span it completed (arena order = network order) is all-reduced on NCCL's stream
+            # while the next chunk computes
+            off = arena.offsets
+            hi_elem = arena.size
+            first = n_layers - 1
+            sync.begin(arena)
+            while first >= 0:
+                last = max(0, first - chunk + 1)
+                parts = (_lib.BWD_TAIL if first == n_layers - 1 else 0) | (_lib.BWD_EMBED if last == 0 else 0)
+                run(first, last, parts)
+                lo_elem = 0 if last == 0 else off[f"encoder.layer.{last}.attention.attention.query.weight"]
+                sync.reduce_range(arena, lo_elem, hi_elem)
+                hi_elem = lo_elem
+                first = last - 1
+            arena.publish_grads(call.trainable)
+            sync.finish(arena)
         call.workspace = None
-        if self.grad_sync is not None:
-            self.grad_sync(arena)
 
     # scratch is a cache, not state
     def __deepcopy__(self, memo):

@@ -228,12 +228,21 @@ int climb_vilt_forward(const climb_vilt_dims* dims, const climb_vilt_params* par
                        float* pooled_out /* [B, hidden] */, void* stream);
 
 /* grad arena += d(pooled . dpooled)/d(theta) for every parameter whose flag asks for it.
- * `workspace` is the one the matching forward (save_for_backward = 1) filled. */
+ * `workspace` is the one the matching forward (save_for_backward = 1) filled.
+ * The pass may be issued in several calls over the same scratch, top of the network first, so that the
+ * data-parallel gradient all-reduce of the layers already done overlaps the rest of the backward:
+ *   parts & CLIMB_BWD_TAIL  : pooler + final LayerNorm (must be in the first call)
+ *   layers first_layer .. last_layer (descending, inclusive)
+ *   parts & CLIMB_BWD_EMBED : embeddings (must be in the last call)
+ * One call with first_layer = layers-1, last_layer = 0, parts = TAIL|EMBED does everything. */
+#define CLIMB_BWD_TAIL 1
+#define CLIMB_BWD_EMBED 2
 int climb_vilt_backward(const climb_vilt_dims* dims, const climb_vilt_params* params,
                         const climb_vilt_batch* batch, const float* theta, const void* shadow,
                         const void* workspace, int64_t workspace_bytes,
                         void* scratch, int64_t scratch_bytes,
-                        const float* dpooled /* [B, hidden] */, float* grad, void* stream);
+                        const float* dpooled /* [B, hidden] */, float* grad,
+                        int first_layer, int last_layer, int parts, void* stream);
 
 #ifdef __cplusplus
 }
