@@ -11,7 +11,9 @@
 //               tensor cores already in A-fragment layout for dV += P^T dO and dK += dS^T Q.
 // Tensor path: mma.sync m16n8k16 bf16 (fp32 accumulate) fed by ldmatrix from XOR-swizzled smem.
 #include "common.cuh"
-#include "climb_b200.h"
+#include "internal.h"
+
+#include <cstdlib>
 
 namespace climb {
 namespace {
@@ -440,12 +442,28 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restri
 
 int round_up(int a, int m) { return (a + m - 1) / m * m; }
 
+// L <= 256 runs on the tcgen05 / TMEM kernels of attention_tc.cu; longer sequences (CLiMB's
+// language-only variants with stretched text) keep the mma.sync kernels of this file.
+// CLIMB_ATTN_LEGACY=1 forces the latter (A/B measurements only).
+bool use_tc(int L) {
+    static int legacy = -1;
+    if (legacy < 0) {
+        const char* e = std::getenv("CLIMB_ATTN_LEGACY");
+        legacy = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return L <= 256 && legacy == 0;
+}
+
 }  // namespace
 
 int attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H,
                   float scale, cudaStream_t stream) {
     CLIMB_REQUIRE(qkv && ctx && lse, "attention_fwd: null pointer");
     CLIMB_REQUIRE(B > 0 && L > 0 && H > 0, "attention_fwd: empty problem B=%d L=%d H=%d", B, L, H);
+    if (use_tc(L)) {
+        ProfScope prof(PROF_ATTN_FWD, static_cast<double>(B) * (4.0 * L * H * kDh * 2 + static_cast<double>(L) * H * 4), stream);
+        return attention_tc_fwd(qkv, key_bias, ctx, lse, B, L, H, scale, stream);
+    }
     const int Lpad = round_up(L, 64);
     const int smem = 64 * kRowBytes + 2 * Lpad * kRowBytes + Lpad * 4;
     CLIMB_REQUIRE(smem <= 227 * 1024, "attention_fwd: L=%d does not fit one CTA's shared memory", L);
@@ -469,6 +487,10 @@ int attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const
                   cudaStream_t stream) {
     CLIMB_REQUIRE(qkv && ctx && dctx && lse && delta && dqkv, "attention_bwd: null pointer");
     CLIMB_REQUIRE(B > 0 && L > 0 && H > 0, "attention_bwd: empty problem B=%d L=%d H=%d", B, L, H);
+    if (use_tc(L)) {
+        ProfScope prof(PROF_ATTN_BWD, static_cast<double>(B) * (8.0 * L * H * kDh * 2 + 2.0 * L * H * 4), stream);
+        return attention_tc_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, B, L, H, scale, stream);
+    }
     const int Lpad = round_up(L, 64);
     const int smem_dq = 2 * 64 * kRowBytes + 2 * Lpad * kRowBytes + Lpad * 4;
     const int smem_dkv = 2 * 64 * kRowBytes + 2 * Lpad * kRowBytes + 2 * Lpad * 4;

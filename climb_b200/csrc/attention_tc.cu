@@ -1,0 +1,479 @@
+// tcgen05 / TMEM fused attention for the ViLT hot path (ViltSelfAttention, modeling_vilt.py:355-388)
+// when a whole head fits one key tile (L <= 256 keys, dh = 64): CLiMB's 40 text + 197 image tokens.
+//
+//   forward  (CTA = 128 query rows of one (b, h); 2 CTAs / SM):
+//     TMA (3-D map over [B, L, 3*H*64]: rows past L are zero-filled, so no padding buffer exists)
+//       -> Q [128 x 64], K [256 x 64], V [256 x 64] in 128B-swizzled smem
+//     S = Q K^T            one 128 x 256 x 64 UMMA chain, accumulator = 256 TMEM columns
+//     softmax              thread = row (TMEM lane): two passes over the row held in TMEM, additive key
+//                          mask, exp2; P is written as bf16 straight into the K-major A-operand layout
+//     O = P V              128 x 64 x 256 UMMA chain (V read in place as an MN-major B operand),
+//                          accumulator aliases S's first 64 columns
+//   backward (CTA = one (b, h); K, V, Q, dO resident; 512 TMEM columns):
+//     for key tile j, query tile i:  S = Q_i K_j^T, dP = dO_i V_j^T          (two 128x128x64 chains)
+//                                    P = exp2(S*c + mask - lse_i), dS = P * (dP - delta_i)   (thread = row)
+//                                    dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j
+//     P / dS are stored once in smem and read BOTH as K-major A (for dQ) and, in place, as MN-major A
+//     (for the transposed products): no transpose is ever materialised. No atomics; deterministic.
+//
+// Row reductions need no shuffles here: a softmax thread owns a whole row (the TMEM lane), which is the
+// tcgen05 counterpart of the warp-shuffle row reductions of the general-L kernels in attention.cu.
+#include "common.cuh"
+#include "internal.h"
+
+#include <cuda.h>
+
+namespace climb {
+namespace {
+
+constexpr int kDh = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kRowB = 128;              // bytes per 64-element bf16 row
+
+__device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t granule) {      // offset inside a [rows x 128 B] tile
+    return row * kRowB + ((granule ^ (row & 7u)) << 4);
+}
+
+// 32 fp32 (thread = row) -> bf16 -> 4 granules of the row at column chunk c32 (32 columns) of a
+// [128 rows x 64 cols]-chunked K-major tile (16 KB per 64-column chunk)
+__device__ __forceinline__ void store_row_chunk_bf16(uint8_t* tile, int row, int c32, const float (&v)[32]) {
+    uint8_t* chunk = tile + (c32 >> 1) * (128 * kRowB);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        u.x = pack_bf16(v[8 * g], v[8 * g + 1]);
+        u.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+        u.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]);
+        u.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+        *reinterpret_cast<uint4*>(chunk + swz(row, (c32 & 1) * 4 + g)) = u;
+    }
+}
+
+// a warp's 32 rows x 64 bf16 (thread = row, 32 packed words) -> global rows, coalesced through a 4 KB
+// swizzled staging block
+__device__ __forceinline__ void store_rows_64(uint8_t* stage, const uint32_t (&pk)[32], __nv_bfloat16* gdst,
+                                              long long ld_elems, int rows_valid, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<uint4*>(stage + swz(lane, g)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int q = it * 32 + lane;
+        const int rr = q >> 3, g = q & 7;
+        if (rr < rows_valid) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + swz(rr, g));
+            *reinterpret_cast<uint4*>(gdst + rr * ld_elems + g * 8) = val;
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct FwdSmem {
+    static constexpr int kP = 0;                 // P [128 x 256] bf16 = 64 KB, aliases Q (16 KB) + K (32 KB)
+    static constexpr int kQ = 0;
+    static constexpr int kK = 16 * 1024;
+    static constexpr int kV = 64 * 1024;         // 32 KB; reused as output staging after O = P V
+    static constexpr int kBias = 96 * 1024;      // 256 floats
+    static constexpr int kBar = 97 * 1024;
+    static constexpr int kTotal = 97 * 1024 + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(160, 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                   const float* __restrict__ key_bias, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
+                   int L, int H, float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    float* sBias = reinterpret_cast<float*>(sm + FwdSmem::kBias);
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(sm + FwdSmem::kBar);
+    uint64_t* bar_s = bar_load + 1;
+    uint64_t* bar_p = bar_load + 2;
+    uint64_t* bar_o = bar_load + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_q);
+            tma_prefetch_desc(&map_kv);
+            mbar_init(bar_load, 1);
+            mbar_init(bar_s, 1);
+            mbar_init(bar_p, 128);
+            mbar_init(bar_o, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    } else {
+        for (int j = threadIdx.x; j < 256; j += 128)
+            sBias[j] = j < L ? (key_bias ? key_bias[static_cast<long long>(b) * L + j] * kLog2e : 0.0f) : -INFINITY;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_load, (128 + 256 + 256) * kRowB);
+            tma_load_3d(&map_q, bar_load, sm + FwdSmem::kQ, h * kDh, q0, b);
+            tma_load_3d(&map_kv, bar_load, sm + FwdSmem::kK, (H + h) * kDh, 0, b);
+            tma_load_3d(&map_kv, bar_load, sm + FwdSmem::kV, (2 * H + h) * kDh, 0, b);
+            mbar_wait(bar_load, 0);
+            tc_fence_after();
+            const uint32_t sQ = smem_u32(sm + FwdSmem::kQ), sK = smem_u32(sm + FwdSmem::kK);
+            const uint32_t idesc_s = umma_instr_desc(128, 256, 0, 0);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(tmem, umma_smem_desc(sQ + kk * 32, 16, 1024), umma_smem_desc(sK + kk * 32, 16, 1024), idesc_s,
+                          kk > 0 ? 1u : 0u);
+            umma_commit(bar_s);
+            mbar_wait(bar_p, 0);
+            tc_fence_after();
+            const uint32_t sP = smem_u32(sm + FwdSmem::kP), sV = smem_u32(sm + FwdSmem::kV);
+            const uint32_t idesc_o = umma_instr_desc(128, 64, 0, 1);
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                umma_bf16(tmem, umma_smem_desc(sP + (k >> 2) * (128 * kRowB) + (k & 3) * 32, 16, 1024),
+                          umma_smem_desc(sV + k * (16 * kRowB), 256 * kRowB, 1024), idesc_o, k > 0 ? 1u : 0u);
+            umma_commit(bar_o);
+        }
+        __syncwarp();
+    } else {
+        const int row = warp * 32 + lane;
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        mbar_wait(bar_s, 0);
+        tc_fence_after();
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), scale_log2, sBias[c * 32 + j]));
+        }
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + c * 32, r);
+            tmem_ld_wait();
+            float p[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                p[j] = exp2f(fmaf(__uint_as_float(r[j]), scale_log2, sBias[c * 32 + j]) - m);
+                sum += p[j];
+            }
+            store_row_chunk_bf16(sm + FwdSmem::kP, row, c, p);     // Q / K are dead: S = Q K^T has retired
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        mbar_wait(bar_o, 0);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                pk[c * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+        }
+        const int qrow0 = q0 + warp * 32;
+        const int rows_valid = min(32, max(0, L - qrow0));
+        store_rows_64(sm + FwdSmem::kV + warp * 4096, pk,
+                      ctx + (static_cast<long long>(b) * L + qrow0) * (H * kDh) + h * kDh, static_cast<long long>(H) * kDh,
+                      rows_valid, lane);
+        if (q0 + row < L) lse[(static_cast<long long>(b) * H + h) * L + q0 + row] = (m + log2f(sum)) * kLn2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct BwdSmem {
+    static constexpr int kQ = 0;                 // [256 x 64] bf16, 32 KB each
+    static constexpr int kDO = 32 * 1024;
+    static constexpr int kK = 64 * 1024;
+    static constexpr int kV = 96 * 1024;
+    static constexpr int kP = 128 * 1024;        // [128 x 128] bf16 = two 16 KB chunks of 64 columns
+    static constexpr int kDS = 160 * 1024;
+    static constexpr int kLse = 192 * 1024;      // 256 floats each
+    static constexpr int kDelta = 193 * 1024;
+    static constexpr int kBias = 194 * 1024;
+    static constexpr int kBar = 195 * 1024;
+    static constexpr int kTotal = 195 * 1024 + 128 + 1024;
+};
+// TMEM columns
+constexpr uint32_t kTS = 0, kTdP = 128, kTdV = 256, kTdK = 320, kTdQ = 384;
+
+__global__ void __launch_bounds__(160, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                   const float* __restrict__ key_bias, const __nv_bfloat16* __restrict__ ctx,
+                   const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
+                   __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale_log2, float scale) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    float* sLse = reinterpret_cast<float*>(sm + BwdSmem::kLse);
+    float* sDelta = reinterpret_cast<float*>(sm + BwdSmem::kDelta);
+    float* sBias = reinterpret_cast<float*>(sm + BwdSmem::kBias);
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(sm + BwdSmem::kBar);
+    uint64_t* bar_a = bar_load + 1;      // S, dP of a block are in TMEM
+    uint64_t* bar_p = bar_load + 2;      // P, dS of a block are in smem (128 arrivals)
+    uint64_t* bar_b = bar_load + 3;      // dV / dK / dQ chains of a block have retired
+    uint64_t* bar_kv = bar_load + 4;     // dV_j, dK_j have been read out of TMEM (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const long long ld = 3LL * H * kDh, ldo = static_cast<long long>(H) * kDh;
+    const int n_jt = (L + 127) / 128;            // key / query tiles that contain real rows (1 or 2)
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_qkv);
+            tma_prefetch_desc(&map_do);
+            mbar_init(bar_load, 1);
+            mbar_init(bar_a, 1);
+            mbar_init(bar_p, 128);
+            mbar_init(bar_b, 1);
+            mbar_init(bar_kv, 128);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    } else {
+        // per-row scalars: lse (log2 domain; +inf past L makes P = 0 there), delta = rowsum(dO * O), key mask
+        const long long stat = (static_cast<long long>(b) * H + h) * L;
+        for (int r = threadIdx.x; r < 256; r += 128) {
+            float dl = 0.0f;
+            if (r < L) {
+                const __nv_bfloat16* o = ctx + (static_cast<long long>(b) * L + r) * ldo + h * kDh;
+                const __nv_bfloat16* g = dctx + (static_cast<long long>(b) * L + r) * ldo + h * kDh;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(o + k * 8);
+                    const uint4 d = *reinterpret_cast<const uint4*>(g + k * 8);
+                    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 x = unpack_bf16(av[e]), y = unpack_bf16(dv[e]);
+                        dl = fmaf(x.x, y.x, dl);
+                        dl = fmaf(x.y, y.y, dl);
+                    }
+                }
+            }
+            sDelta[r] = dl;
+            sLse[r] = r < L ? lse[stat + r] * kLog2e : INFINITY;
+            sBias[r] = r < L ? (key_bias ? key_bias[static_cast<long long>(b) * L + r] * kLog2e : 0.0f) : -INFINITY;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int n_blocks = n_jt * n_jt;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_load, 4 * 256 * kRowB);
+            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kQ, h * kDh, 0, b);
+            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kK, (H + h) * kDh, 0, b);
+            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kV, (2 * H + h) * kDh, 0, b);
+            tma_load_3d(&map_do, bar_load, sm + BwdSmem::kDO, h * kDh, 0, b);
+            mbar_wait(bar_load, 0);
+            tc_fence_after();
+            const uint32_t sQ = smem_u32(sm + BwdSmem::kQ), sDO = smem_u32(sm + BwdSmem::kDO);
+            const uint32_t sK = smem_u32(sm + BwdSmem::kK), sV = smem_u32(sm + BwdSmem::kV);
+            const uint32_t sP = smem_u32(sm + BwdSmem::kP), sDS = smem_u32(sm + BwdSmem::kDS);
+            const uint32_t id_a = umma_instr_desc(128, 128, 0, 0);     // S / dP: both operands K-major
+            const uint32_t id_t = umma_instr_desc(128, 64, 1, 1);      // dV / dK: A = P^T / dS^T in place, B MN-major
+            const uint32_t id_q = umma_instr_desc(128, 64, 0, 1);      // dQ: A = dS K-major, B = K MN-major
+            const uint32_t tile = 128 * kRowB;                          // 16 KB: 128 rows of a [rows x 64] tile
+            for (int n = 0; n < n_blocks; ++n) {
+                const int j = n / n_jt, i = n - j * n_jt;
+                // phase A
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + kTS, umma_smem_desc(sQ + i * tile + kk * 32, 16, 1024),
+                              umma_smem_desc(sK + j * tile + kk * 32, 16, 1024), id_a, kk > 0 ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + kTdP, umma_smem_desc(sDO + i * tile + kk * 32, 16, 1024),
+                              umma_smem_desc(sV + j * tile + kk * 32, 16, 1024), id_a, kk > 0 ? 1u : 0u);
+                umma_commit(bar_a);
+                mbar_wait(bar_p, n & 1);
+                tc_fence_after();
+                if (i == 0 && j > 0) {                  // previous key tile's dV / dK must have been read out
+                    mbar_wait(bar_kv, (j - 1) & 1);
+                    tc_fence_after();
+                }
+                // phase B: k runs over the 128 query rows (dV, dK) or the 128 keys (dQ), 16 per UMMA
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tmem + kTdV, umma_smem_desc(sP + k * (16 * kRowB), tile, 1024),
+                              umma_smem_desc(sDO + i * tile + k * (16 * kRowB), tile, 1024), id_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tmem + kTdK, umma_smem_desc(sDS + k * (16 * kRowB), tile, 1024),
+                              umma_smem_desc(sQ + i * tile + k * (16 * kRowB), tile, 1024), id_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tmem + kTdQ + i * 64, umma_smem_desc(sDS + (k >> 2) * tile + (k & 3) * 32, 16, 1024),
+                              umma_smem_desc(sK + j * tile + k * (16 * kRowB), tile, 1024), id_q, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(bar_b);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int row = warp * 32 + lane;
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        uint8_t* stage = sm + BwdSmem::kP + warp * 4096;       // output staging (P is free whenever we use it)
+        for (int n = 0; n < n_blocks; ++n) {
+            const int j = n / n_jt, i = n - j * n_jt;
+            mbar_wait(bar_a, n & 1);
+            tc_fence_after();
+            if (n > 0) mbar_wait(bar_b, (n - 1) & 1);           // previous block's chains no longer read P / dS
+            const float lse_r = sLse[i * 128 + row], dl_r = sDelta[i * 128 + row];
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t rs[32], rd[32];
+                tmem_ld_32x32(t_row + kTS + c * 32, rs);
+                tmem_ld_32x32(t_row + kTdP + c * 32, rd);
+                tmem_ld_wait();
+                float p[32], ds[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float pe = exp2f(fmaf(__uint_as_float(rs[e]), scale_log2, sBias[j * 128 + c * 32 + e]) - lse_r);
+                    p[e] = pe;
+                    ds[e] = pe * (__uint_as_float(rd[e]) - dl_r);
+                }
+                store_row_chunk_bf16(sm + BwdSmem::kP, row, c, p);
+                store_row_chunk_bf16(sm + BwdSmem::kDS, row, c, ds);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_p);
+            if (i == n_jt - 1) {
+                // dV_j, dK_j are complete once this block's chains retire
+                mbar_wait(bar_b, n & 1);
+                tc_fence_after();
+                const int key0 = j * 128 + warp * 32;
+                const int rows_valid = min(32, max(0, L - key0));
+                __nv_bfloat16* dst = dqkv + (static_cast<long long>(b) * L + key0) * ld + h * kDh;
+                uint32_t pk[32];
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {          // 0: dK (scaled), 1: dV
+                    const uint32_t col = which == 0 ? kTdK : kTdV;
+                    const float sc = which == 0 ? scale : 1.0f;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_row + col + c * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            pk[c * 16 + e] = pack_bf16(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
+                    }
+                    store_rows_64(stage, pk, dst + (which == 0 ? H * kDh : 2 * H * kDh), ld, rows_valid, lane);
+                }
+                tc_fence_before();
+                mbar_arrive(bar_kv);
+            }
+        }
+        // dQ tiles: complete after the last block (its bar_b wait happened above)
+        for (int i = 0; i < n_jt; ++i) {
+            const int q0 = i * 128 + warp * 32;
+            const int rows_valid = min(32, max(0, L - q0));
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + kTdQ + i * 64 + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    pk[c * 16 + e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
+            }
+            store_rows_64(stage, pk, dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh, ld, rows_valid, lane);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+int make_map3(CUtensorMap* map, const void* ptr, int B, int L, long long row_elems, int box_rows) {
+    const long long dims[3] = {row_elems, L, B};
+    const long long strides[2] = {row_elems, static_cast<long long>(L) * row_elems};
+    const int box[3] = {64, box_rows, 1};
+    return encode_tmap_bf16(map, ptr, 3, dims, strides, box);
+}
+
+}  // namespace
+
+int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H, float scale,
+                     cudaStream_t stream) {
+    CLIMB_REQUIRE(L <= 256, "attention_tc_fwd: L=%d > 256", L);
+    CUtensorMap mq, mkv;
+    int rc = make_map3(&mq, qkv, B, L, 3LL * H * kDh, 128);
+    if (rc) return rc;
+    rc = make_map3(&mkv, qkv, B, L, 3LL * H * kDh, 256);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal));
+        attr = true;
+    }
+    dim3 grid((L + 127) / 128, H, B);
+    attn_tc_fwd_kernel<<<grid, 160, FwdSmem::kTotal, stream>>>(mq, mkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, L,
+                                                               H, scale * kLog2e);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
+                     void* dqkv, int B, int L, int H, float scale, cudaStream_t stream) {
+    CLIMB_REQUIRE(L <= 256, "attention_tc_bwd: L=%d > 256", L);
+    CUtensorMap mqkv, mdo;
+    int rc = make_map3(&mqkv, qkv, B, L, 3LL * H * kDh, 256);
+    if (rc) return rc;
+    rc = make_map3(&mdo, dctx, B, L, static_cast<long long>(H) * kDh, 256);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal));
+        attr = true;
+    }
+    dim3 grid(H, B);
+    attn_tc_bwd_kernel<<<grid, 160, BwdSmem::kTotal, stream>>>(
+        mqkv, mdo, key_bias, static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx), lse,
+        static_cast<__nv_bfloat16*>(dqkv), L, H, scale * kLog2e, scale);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace climb

@@ -191,9 +191,45 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, void* smem_dst,
+                                            int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------------
+// UMMA shared-memory descriptor, 128B swizzle (layout type 2), sm_100 version bit.
+//   K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused.
+//   MN-major: 64-element (128 B) runs along MN, one row per k; 8 k-rows per 1024 B atom (SBO);
+//             the next 64-wide MN chunk starts LBO bytes later.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;     // descriptor version (Blackwell)
+    d |= 2ull << 61;     // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, M x N tile, per-operand major bits
+__device__ __forceinline__ uint32_t umma_instr_desc(int umma_m, int umma_n, int a_mn, int b_mn) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // D format = F32
+    d |= 1u << 7;                       // A format = BF16
+    d |= 1u << 10;                      // B format = BF16
+    d |= static_cast<uint32_t>(a_mn & 1) << 15;
+    d |= static_cast<uint32_t>(b_mn & 1) << 16;
+    d |= static_cast<uint32_t>(umma_n >> 3) << 17;
+    d |= static_cast<uint32_t>(umma_m >> 4) << 24;
+    return d;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(smem_dst)),

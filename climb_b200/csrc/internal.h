@@ -22,6 +22,16 @@ int layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long
                   int rows, int d, int act, cudaStream_t stream);
 
 
+// tma_host.cu
+int encode_tmap_bf16(void* map_out, const void* ptr, int rank, const long long* dims, const long long* strides_elems,
+                     const int* box);
+
+// attention_tc.cu (tcgen05 / TMEM attention for L <= 256; attention.cu keeps the general-L kernels)
+int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H, float scale,
+                     cudaStream_t stream);
+int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
+                     void* dqkv, int B, int L, int H, float scale, cudaStream_t stream);
+
 // elementwise.cu
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
 int colsum(const void* src, int dtype, long long ld, int rows, int cols, float* out, cudaStream_t stream);

@@ -173,7 +173,8 @@ def _attn_ref(qkv, key_bias, B, L_, H, scale):
 
 
 @pytest.mark.parametrize("B,L_,H,masked", [(2, 237, 12, False), (3, 237, 12, True), (2, 13, 2, True),
-                                           (1, 64, 1, False), (2, 200, 3, True), (1, 281, 2, True)])
+                                           (1, 64, 1, False), (2, 200, 3, True), (1, 281, 2, True),
+                                           (2, 256, 2, True), (2, 128, 1, False), (3, 129, 2, True), (5, 1, 1, False)])
 def test_attention_fwd_bwd(B, L_, H, masked):
     L = _lib()
     torch.manual_seed(B * 100 + L_)
