@@ -71,6 +71,27 @@ __device__ __forceinline__ void store_rows_64(uint8_t* stage, const uint32_t (&p
     __syncwarp();
 }
 
+// same for 32 bf16 columns per row (64 B): two rows share one 128 B staging line
+__device__ __forceinline__ void store_rows_32(uint8_t* stage, const uint32_t (&pk)[16], __nv_bfloat16* gdst,
+                                              long long ld_elems, int rows_valid, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(stage + swz(lane >> 1, (lane & 1) * 4 + g)) =
+            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int q = it * 32 + lane;
+        const int rr = q >> 2, g = q & 3;
+        if (rr < rows_valid) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + swz(rr >> 1, (rr & 1) * 4 + g));
+            *reinterpret_cast<uint4*>(gdst + rr * ld_elems + g * 8) = val;
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -80,11 +101,20 @@ struct FwdSmem {
     static constexpr int kK = 16 * 1024;
     static constexpr int kV = 64 * 1024;         // 32 KB; reused as output staging after O = P V
     static constexpr int kBias = 96 * 1024;      // 256 floats
-    static constexpr int kBar = 97 * 1024;
-    static constexpr int kTotal = 97 * 1024 + 128 + 1024;
+    static constexpr int kXchg = 97 * 1024;      // row max / row sum exchange between the two column halves: 2 x 256 floats
+    static constexpr int kBar = 99 * 1024;
+    static constexpr int kTotal = 99 * 1024 + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(160, 2)
+constexpr int kSoftmaxThreads = 256;             // 8 warps: warp w and w + 4 share TMEM lanes 32*(w%4).., split the columns
+constexpr int kCtlWarp = 8;
+constexpr int kThreads = kSoftmaxThreads + 32;
+
+__device__ __forceinline__ void softmax_bar_sync() {      // named barrier 1: the softmax warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxThreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                    const float* __restrict__ key_bias, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
                    int L, int H, float scale_log2) {
@@ -100,13 +130,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
 
-    if (warp == 4) {
+    float* sXmax = reinterpret_cast<float*>(sm + FwdSmem::kXchg);       // [2][128]
+    float* sXsum = sXmax + 256;                                          // [2][128]
+    if (warp == kCtlWarp) {
         if (lane == 0) {
             tma_prefetch_desc(&map_q);
             tma_prefetch_desc(&map_kv);
             mbar_init(bar_load, 1);
             mbar_init(bar_s, 1);
-            mbar_init(bar_p, 128);
+            mbar_init(bar_p, kSoftmaxThreads);
             mbar_init(bar_o, 1);
             fence_barrier_init();
         }
@@ -114,15 +146,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     } else {
-        for (int j = threadIdx.x; j < 256; j += 128)
-            sBias[j] = j < L ? (key_bias ? key_bias[static_cast<long long>(b) * L + j] * kLog2e : 0.0f) : -INFINITY;
+        const int j = threadIdx.x;
+        sBias[j] = j < L ? (key_bias ? key_bias[static_cast<long long>(b) * L + j] * kLog2e : 0.0f) : -INFINITY;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == kCtlWarp) {
         if (lane == 0) {
             mbar_arrive_expect_tx(bar_load, (128 + 256 + 256) * kRowB);
             tma_load_3d(&map_q, bar_load, sm + FwdSmem::kQ, h * kDh, q0, b);
@@ -149,22 +181,26 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         __syncwarp();
     } else {
-        const int row = warp * 32 + lane;
-        const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const int lg = warp & 3, half = warp >> 2;          // TMEM lane group, column half
+        const int row = lg * 32 + lane;
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16);
         mbar_wait(bar_s, 0);
         tc_fence_after();
         float m = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = half * 4; c < half * 4 + 4; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(t_row + c * 32, r);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), scale_log2, sBias[c * 32 + j]));
         }
+        sXmax[half * 128 + row] = m;
+        softmax_bar_sync();
+        m = fmaxf(m, sXmax[(half ^ 1) * 128 + row]);       // key 0 is always valid: m is finite
         float sum = 0.0f;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = half * 4; c < half * 4 + 4; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(t_row + c * 32, r);
             tmem_ld_wait();
@@ -176,32 +212,35 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             }
             store_row_chunk_bf16(sm + FwdSmem::kP, row, c, p);     // Q / K are dead: S = Q K^T has retired
         }
+        sXsum[half * 128 + row] = sum;
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_p);
+        softmax_bar_sync();
+        sum += sXsum[(half ^ 1) * 128 + row];
         mbar_wait(bar_o, 0);
         tc_fence_after();
         const float inv = 1.0f / sum;
-        uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        // O epilogue: this warp converts 32 of the row's 64 output columns
+        uint32_t pk[16];
+        {
             uint32_t r[32];
-            tmem_ld_32x32(t_row + c * 32, r);
+            tmem_ld_32x32(t_row + half * 32, r);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                pk[c * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+                pk[j] = pack_bf16(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
         }
-        const int qrow0 = q0 + warp * 32;
+        const int qrow0 = q0 + lg * 32;
         const int rows_valid = min(32, max(0, L - qrow0));
-        store_rows_64(sm + FwdSmem::kV + warp * 4096, pk,
-                      ctx + (static_cast<long long>(b) * L + qrow0) * (H * kDh) + h * kDh, static_cast<long long>(H) * kDh,
-                      rows_valid, lane);
-        if (q0 + row < L) lse[(static_cast<long long>(b) * H + h) * L + q0 + row] = (m + log2f(sum)) * kLn2;
+        store_rows_32(sm + FwdSmem::kV + warp * 2048, pk,
+                      ctx + (static_cast<long long>(b) * L + qrow0) * (H * kDh) + h * kDh + half * 32,
+                      static_cast<long long>(H) * kDh, rows_valid, lane);
+        if (half == 0 && q0 + row < L) lse[(static_cast<long long>(b) * H + h) * L + q0 + row] = (m + log2f(sum)) * kLn2;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kCtlWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, 256);
     }
@@ -226,7 +265,7 @@ struct BwdSmem {
 // TMEM columns
 constexpr uint32_t kTS = 0, kTdP = 128, kTdV = 256, kTdK = 320, kTdQ = 384;
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                    const float* __restrict__ key_bias, const __nv_bfloat16* __restrict__ ctx,
                    const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
@@ -248,15 +287,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const long long ld = 3LL * H * kDh, ldo = static_cast<long long>(H) * kDh;
     const int n_jt = (L + 127) / 128;            // key / query tiles that contain real rows (1 or 2)
 
-    if (warp == 4) {
+    if (warp == kCtlWarp) {
         if (lane == 0) {
             tma_prefetch_desc(&map_qkv);
             tma_prefetch_desc(&map_do);
             mbar_init(bar_load, 1);
             mbar_init(bar_a, 1);
-            mbar_init(bar_p, 128);
+            mbar_init(bar_p, kSoftmaxThreads);
             mbar_init(bar_b, 1);
-            mbar_init(bar_kv, 128);
+            mbar_init(bar_kv, kSoftmaxThreads);
             fence_barrier_init();
         }
         __syncwarp();
@@ -265,7 +304,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     } else {
         // per-row scalars: lse (log2 domain; +inf past L makes P = 0 there), delta = rowsum(dO * O), key mask
         const long long stat = (static_cast<long long>(b) * H + h) * L;
-        for (int r = threadIdx.x; r < 256; r += 128) {
+        {
+            const int r = threadIdx.x;          // 256 softmax threads: one row each
             float dl = 0.0f;
             if (r < L) {
                 const __nv_bfloat16* o = ctx + (static_cast<long long>(b) * L + r) * ldo + h * kDh;
@@ -294,7 +334,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const uint32_t tmem = *tmem_slot;
     const int n_blocks = n_jt * n_jt;
 
-    if (warp == 4) {
+    if (warp == kCtlWarp) {
         if (lane == 0) {
             mbar_arrive_expect_tx(bar_load, 4 * 256 * kRowB);
             tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kQ, h * kDh, 0, b);
@@ -346,9 +386,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
         __syncwarp();
     } else {
-        const int row = warp * 32 + lane;
-        const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-        uint8_t* stage = sm + BwdSmem::kP + warp * 4096;       // output staging (P is free whenever we use it)
+        const int lg = warp & 3, half = warp >> 2;          // TMEM lane group, column half
+        const int row = lg * 32 + lane;
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16);
+        uint8_t* stage = sm + BwdSmem::kP + warp * 2048;        // output staging (P is free whenever we use it)
         for (int n = 0; n < n_blocks; ++n) {
             const int j = n / n_jt, i = n - j * n_jt;
             mbar_wait(bar_a, n & 1);
@@ -356,7 +397,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             if (n > 0) mbar_wait(bar_b, (n - 1) & 1);           // previous block's chains no longer read P / dS
             const float lse_r = sLse[i * 128 + row], dl_r = sDelta[i * 128 + row];
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = half * 2; c < half * 2 + 2; ++c) {
                 uint32_t rs[32], rd[32];
                 tmem_ld_32x32(t_row + kTS + c * 32, rs);
                 tmem_ld_32x32(t_row + kTdP + c * 32, rd);
@@ -375,27 +416,23 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             tc_fence_before();
             mbar_arrive(bar_p);
             if (i == n_jt - 1) {
-                // dV_j, dK_j are complete once this block's chains retire
+                // dV_j, dK_j are complete once this block's chains retire; each warp converts 32 of the 64 columns
                 mbar_wait(bar_b, n & 1);
                 tc_fence_after();
-                const int key0 = j * 128 + warp * 32;
+                const int key0 = j * 128 + lg * 32;
                 const int rows_valid = min(32, max(0, L - key0));
-                __nv_bfloat16* dst = dqkv + (static_cast<long long>(b) * L + key0) * ld + h * kDh;
-                uint32_t pk[32];
+                __nv_bfloat16* dst = dqkv + (static_cast<long long>(b) * L + key0) * ld + h * kDh + half * 32;
 #pragma unroll
                 for (int which = 0; which < 2; ++which) {          // 0: dK (scaled), 1: dV
                     const uint32_t col = which == 0 ? kTdK : kTdV;
                     const float sc = which == 0 ? scale : 1.0f;
+                    uint32_t r[32], pk[16];
+                    tmem_ld_32x32(t_row + col + half * 32, r);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(t_row + col + c * 32, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            pk[c * 16 + e] = pack_bf16(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
-                    }
-                    store_rows_64(stage, pk, dst + (which == 0 ? H * kDh : 2 * H * kDh), ld, rows_valid, lane);
+                    for (int e = 0; e < 16; ++e)
+                        pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
+                    store_rows_32(stage, pk, dst + (which == 0 ? H * kDh : 2 * H * kDh), ld, rows_valid, lane);
                 }
                 tc_fence_before();
                 mbar_arrive(bar_kv);
@@ -403,24 +440,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
         // dQ tiles: complete after the last block (its bar_b wait happened above)
         for (int i = 0; i < n_jt; ++i) {
-            const int q0 = i * 128 + warp * 32;
+            const int q0 = i * 128 + lg * 32;
             const int rows_valid = min(32, max(0, L - q0));
-            uint32_t pk[32];
+            uint32_t r[32], pk[16];
+            tmem_ld_32x32(t_row + kTdQ + i * 64 + half * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + kTdQ + i * 64 + c * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    pk[c * 16 + e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
-            }
-            store_rows_64(stage, pk, dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh, ld, rows_valid, lane);
+            for (int e = 0; e < 16; ++e)
+                pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
+            store_rows_32(stage, pk, dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32, ld, rows_valid, lane);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kCtlWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
@@ -449,7 +482,7 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
         attr = true;
     }
     dim3 grid((L + 127) / 128, H, B);
-    attn_tc_fwd_kernel<<<grid, 160, FwdSmem::kTotal, stream>>>(mq, mkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, L,
+    attn_tc_fwd_kernel<<<grid, kThreads, FwdSmem::kTotal, stream>>>(mq, mkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, L,
                                                                H, scale * kLog2e);
     CLIMB_LAUNCH_OK();
     return 0;
@@ -469,7 +502,7 @@ int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, co
         attr = true;
     }
     dim3 grid(H, B);
-    attn_tc_bwd_kernel<<<grid, 160, BwdSmem::kTotal, stream>>>(
+    attn_tc_bwd_kernel<<<grid, kThreads, BwdSmem::kTotal, stream>>>(
         mqkv, mdo, key_bias, static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx), lse,
         static_cast<__nv_bfloat16*>(dqkv), L, H, scale * kLog2e, scale);
     CLIMB_LAUNCH_OK();

@@ -196,7 +196,11 @@ def test_attention_fwd_bwd(B, L_, H, masked):
     ctx_ref.backward(dctx.float())
     ref = qkv_ref.grad.view(B, L_, 3, H * 64)
     got = dqkv.float().view(B, L_, 3, H * 64)
+    gscale = ref.norm().item()
     for i, name in enumerate("qkv"):
+        if ref[:, :, i].norm().item() < 1e-6 * gscale:      # analytically zero (e.g. dq, dk when L == 1)
+            assert got[:, :, i].norm().item() < 1e-3 * gscale, name
+            continue
         e = _rel_err(got[:, :, i], ref[:, :, i])
         assert e < 1.5e-2, (name, e)
 
