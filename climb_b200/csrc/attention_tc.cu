@@ -141,6 +141,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_init(bar_p, kSoftmaxThreads);
             mbar_init(bar_o, 1);
             fence_barrier_init();
+            // loads go out before anything else so that they overlap TMEM allocation and the prologue
+            mbar_arrive_expect_tx(bar_load, (128 + 256 + 256) * kRowB);
+            tma_load_3d(&map_q, bar_load, sm + FwdSmem::kQ, h * kDh, q0, b);
+            tma_load_3d(&map_kv, bar_load, sm + FwdSmem::kK, (H + h) * kDh, 0, b);
+            tma_load_3d(&map_kv, bar_load, sm + FwdSmem::kV, (2 * H + h) * kDh, 0, b);
         }
         __syncwarp();
         tmem_alloc(tmem_slot, 256);
@@ -156,10 +161,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
     if (warp == kCtlWarp) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(bar_load, (128 + 256 + 256) * kRowB);
-            tma_load_3d(&map_q, bar_load, sm + FwdSmem::kQ, h * kDh, q0, b);
-            tma_load_3d(&map_kv, bar_load, sm + FwdSmem::kK, (H + h) * kDh, 0, b);
-            tma_load_3d(&map_kv, bar_load, sm + FwdSmem::kV, (2 * H + h) * kDh, 0, b);
             mbar_wait(bar_load, 0);
             tc_fence_after();
             const uint32_t sQ = smem_u32(sm + FwdSmem::kQ), sK = smem_u32(sm + FwdSmem::kK);
@@ -297,35 +298,46 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             mbar_init(bar_b, 1);
             mbar_init(bar_kv, kSoftmaxThreads);
             fence_barrier_init();
+            // loads go out first: they overlap TMEM allocation and the delta prologue of the other warps
+            mbar_arrive_expect_tx(bar_load, 4 * 256 * kRowB);
+            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kQ, h * kDh, 0, b);
+            tma_load_3d(&map_do, bar_load, sm + BwdSmem::kDO, h * kDh, 0, b);
+            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kK, (H + h) * kDh, 0, b);
+            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kV, (2 * H + h) * kDh, 0, b);
         }
         __syncwarp();
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     } else {
-        // per-row scalars: lse (log2 domain; +inf past L makes P = 0 there), delta = rowsum(dO * O), key mask
+        // per-row scalars: lse (log2 domain; +inf past L makes P = 0 there), key mask, and
+        // delta = rowsum(dO * O) with coalesced loads: 8 lanes x 16 B cover one 128 B row, 4 rows per warp access
         const long long stat = (static_cast<long long>(b) * H + h) * L;
         {
-            const int r = threadIdx.x;          // 256 softmax threads: one row each
-            float dl = 0.0f;
-            if (r < L) {
-                const __nv_bfloat16* o = ctx + (static_cast<long long>(b) * L + r) * ldo + h * kDh;
-                const __nv_bfloat16* g = dctx + (static_cast<long long>(b) * L + r) * ldo + h * kDh;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(o + k * 8);
-                    const uint4 d = *reinterpret_cast<const uint4*>(g + k * 8);
-                    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 x = unpack_bf16(av[e]), y = unpack_bf16(dv[e]);
-                        dl = fmaf(x.x, y.x, dl);
-                        dl = fmaf(x.y, y.y, dl);
-                    }
-                }
-            }
-            sDelta[r] = dl;
+            const int r = threadIdx.x;
             sLse[r] = r < L ? lse[stat + r] * kLog2e : INFINITY;
             sBias[r] = r < L ? (key_bias ? key_bias[static_cast<long long>(b) * L + r] * kLog2e : 0.0f) : -INFINITY;
+        }
+        const int sub = lane & 7, rsel = lane >> 3;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = warp * 32 + it * 4 + rsel;
+            float dl = 0.0f;
+            if (r < L) {
+                const long long off = (static_cast<long long>(b) * L + r) * ldo + h * kDh + sub * 8;
+                const uint4 a = *reinterpret_cast<const uint4*>(ctx + off);
+                const uint4 d = *reinterpret_cast<const uint4*>(dctx + off);
+                const uint32_t av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 x = unpack_bf16(av[e]), y = unpack_bf16(dv[e]);
+                    dl = fmaf(x.x, y.x, dl);
+                    dl = fmaf(x.y, y.y, dl);
+                }
+            }
+            dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+            if (sub == 0) sDelta[r] = dl;
         }
     }
     tc_fence_before();
@@ -336,11 +348,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 
     if (warp == kCtlWarp) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(bar_load, 4 * 256 * kRowB);
-            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kQ, h * kDh, 0, b);
-            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kK, (H + h) * kDh, 0, b);
-            tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kV, (2 * H + h) * kDh, 0, b);
-            tma_load_3d(&map_do, bar_load, sm + BwdSmem::kDO, h * kDh, 0, b);
             mbar_wait(bar_load, 0);
             tc_fence_after();
             const uint32_t sQ = smem_u32(sm + BwdSmem::kQ), sDO = smem_u32(sm + BwdSmem::kDO);
