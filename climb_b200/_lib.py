@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libclimb_b200.so")
 
 BF16, F32 = 0, 1
-EPI_NONE, EPI_GELU, EPI_DGELU, EPI_SWISH, EPI_DSWISH, EPI_RELU, EPI_DRELU, EPI_TANH = range(8)
+EPI_NONE, EPI_GELU, EPI_DGELU, EPI_SWISH, EPI_DSWISH, EPI_RELU, EPI_DRELU, EPI_TANH, EPI_GELU_SAVE_GRAD, EPI_MUL_AUX = range(10)
 
 
 class ClimbError(RuntimeError):
@@ -46,6 +46,7 @@ class GemmDesc(Structure):
         ("epilogue", c_int),
         ("aux", c_void_p), ("ldaux", c_int64),
         ("c2", c_void_p), ("ldc2", c_int64),
+        ("colsum", c_void_p),
         ("alpha", c_float),
         ("accumulate", c_int),
         ("split_k", c_int),
@@ -69,7 +70,7 @@ climb_profile_end = _sig("climb_profile_end", [POINTER(ctypes.c_double), POINTER
 climb_gemm_bf16 = _sig("climb_gemm_bf16", [POINTER(GemmDesc), _P])
 climb_attention_fwd = _sig("climb_attention_fwd", [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P])
 climb_attention_bwd = _sig(
-    "climb_attention_bwd", [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P])
+    "climb_attention_bwd", [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P])
 climb_layernorm_fwd = _sig(
     "climb_layernorm_fwd", [_P, c_int64, _P, _P, c_float, _P, _P, _P, _P, c_int, c_int, c_int, _P])
 climb_layernorm_bwd = _sig(
@@ -169,7 +170,7 @@ def stream() -> int:
 # Thin tensor-level wrappers (no autograd here; see climb_b200.ops)
 # -------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=False, b_mn_major=False,
-         bias=None, residual=None, epilogue=EPI_NONE, aux=None, c2=None, alpha=1.0, accumulate=False,
+         bias=None, residual=None, epilogue=EPI_NONE, aux=None, c2=None, colsum=None, alpha=1.0, accumulate=False,
          split_k=0, block_n=0, M=None, N=None, K=None) -> torch.Tensor:
     """out[M,N] = epi(alpha * A B^T + bias) + residual. A, B bf16 2-D (possibly row-strided views)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -206,6 +207,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
     d.ldc2 = c2.stride(0) if c2 is not None else 0
     if c2 is not None:
         assert c2.dtype == torch.bfloat16
+    d.colsum = ptr(colsum)
     d.alpha = alpha
     d.accumulate = int(accumulate)
     d.split_k = split_k
@@ -221,11 +223,11 @@ def attention_fwd(qkv, key_bias, B, L, H, scale):
     return ctx, lse
 
 
-def attention_bwd(qkv, key_bias, ctx, dctx, lse, B, L, H, scale):
+def attention_bwd(qkv, key_bias, ctx, dctx, lse, B, L, H, scale, colsum=None):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
     check(climb_attention_bwd(ptr(qkv), ptr(key_bias), ptr(ctx), ptr(dctx), ptr(lse), ptr(delta),
-                              ptr(dqkv), B, L, H, scale, stream()))
+                              ptr(dqkv), ptr(colsum), B, L, H, scale, stream()))
     return dqkv
 
 

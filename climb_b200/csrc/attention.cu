@@ -483,13 +483,13 @@ int attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse,
 }
 
 int attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx,
-                  const float* lse, float* delta, void* dqkv, int B, int L, int H, float scale,
+                  const float* lse, float* delta, void* dqkv, float* dqkv_colsum, int B, int L, int H, float scale,
                   cudaStream_t stream) {
     CLIMB_REQUIRE(qkv && ctx && dctx && lse && delta && dqkv, "attention_bwd: null pointer");
     CLIMB_REQUIRE(B > 0 && L > 0 && H > 0, "attention_bwd: empty problem B=%d L=%d H=%d", B, L, H);
     if (use_tc(L)) {
         ProfScope prof(PROF_ATTN_BWD, static_cast<double>(B) * (8.0 * L * H * kDh * 2 + 2.0 * L * H * 4), stream);
-        return attention_tc_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, B, L, H, scale, stream);
+        return attention_tc_bwd(qkv, key_bias, ctx, dctx, lse, dqkv, dqkv_colsum, B, L, H, scale, stream);
     }
     const int Lpad = round_up(L, 64);
     const int smem_dq = 2 * 64 * kRowBytes + 2 * Lpad * kRowBytes + Lpad * 4;
@@ -521,6 +521,8 @@ int attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const
         static_cast<const __nv_bfloat16*>(qkv), key_bias, static_cast<const __nv_bfloat16*>(dctx), lse,
         delta, static_cast<__nv_bfloat16*>(dqkv), L, H, Lpad, scale * kLog2e, scale);
     CLIMB_LAUNCH_OK();
+    if (dqkv_colsum != nullptr)
+        return colsum(dqkv, CLIMB_BF16, 3LL * H * kDh, B * L, 3 * H * kDh, dqkv_colsum, stream);
     return 0;
 }
 

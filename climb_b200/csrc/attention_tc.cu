@@ -92,6 +92,17 @@ __device__ __forceinline__ void store_rows_32(uint8_t* stage, const uint32_t (&p
     __syncwarp();
 }
 
+// column sums of the 32 x 32 block that store_rows_32 just staged: lane l owns column l
+__device__ __forceinline__ void staged_colsum_32(const uint8_t* stage, int rows_valid, int lane, float* dst) {
+    float cs = 0.0f;
+    for (int rr = 0; rr < rows_valid; ++rr) {
+        const uint16_t h16 = *reinterpret_cast<const uint16_t*>(stage + swz(rr >> 1, (rr & 1) * 4 + (lane >> 3)) + (lane & 7) * 2);
+        cs += __uint_as_float(static_cast<uint32_t>(h16) << 16);
+    }
+    atomicAdd(dst + lane, cs);
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -270,7 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                    const float* __restrict__ key_bias, const __nv_bfloat16* __restrict__ ctx,
                    const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
-                   __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale_log2, float scale) {
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int L, int H, float scale_log2,
+                   float scale) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     float* sLse = reinterpret_cast<float*>(sm + BwdSmem::kLse);
@@ -440,6 +452,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                     for (int e = 0; e < 16; ++e)
                         pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
                     store_rows_32(stage, pk, dst + (which == 0 ? H * kDh : 2 * H * kDh), ld, rows_valid, lane);
+                    if (colsum) staged_colsum_32(stage, rows_valid, lane, colsum + (which == 0 ? H : 2 * H) * kDh + h * kDh + half * 32);
                 }
                 tc_fence_before();
                 mbar_arrive(bar_kv);
@@ -456,6 +469,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             for (int e = 0; e < 16; ++e)
                 pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
             store_rows_32(stage, pk, dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32, ld, rows_valid, lane);
+            if (colsum) staged_colsum_32(stage, rows_valid, lane, colsum + h * kDh + half * 32);
         }
     }
     tc_fence_before();
@@ -496,7 +510,7 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
 }
 
 int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
-                     void* dqkv, int B, int L, int H, float scale, cudaStream_t stream) {
+                     void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream) {
     CLIMB_REQUIRE(L <= 256, "attention_tc_bwd: L=%d > 256", L);
     CUtensorMap mqkv, mdo;
     int rc = make_map3(&mqkv, qkv, B, L, 3LL * H * kDh, 256);
@@ -511,7 +525,7 @@ int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, co
     dim3 grid(H, B);
     attn_tc_bwd_kernel<<<grid, kThreads, BwdSmem::kTotal, stream>>>(
         mqkv, mdo, key_bias, static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx), lse,
-        static_cast<__nv_bfloat16*>(dqkv), L, H, scale * kLog2e, scale);
+        static_cast<__nv_bfloat16*>(dqkv), colsum, L, H, scale * kLog2e, scale);
     CLIMB_LAUNCH_OK();
     return 0;
 }

@@ -85,9 +85,9 @@ int climb_attention_fwd(const void* qkv, const float* key_bias, void* ctx, float
     return attention_fwd(qkv, key_bias, ctx, lse, B, L, H, scale, S(stream));
 }
 int climb_attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx,
-                        const float* lse, float* delta, void* dqkv, int B, int L, int H, float scale,
-                        void* stream) {
-    return attention_bwd(qkv, key_bias, ctx, dctx, lse, delta, dqkv, B, L, H, scale, S(stream));
+                        const float* lse, float* delta, void* dqkv, float* dqkv_colsum, int B, int L, int H,
+                        float scale, void* stream) {
+    return attention_bwd(qkv, key_bias, ctx, dctx, lse, delta, dqkv, dqkv_colsum, B, L, H, scale, S(stream));
 }
 
 int climb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,

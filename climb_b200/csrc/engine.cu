@@ -44,8 +44,8 @@ struct LayerAct {
     float* x1;          // after the attention block
     bf16* h2;
     float *mean2, *rstd2;
-    bf16* u;            // pre-GELU
-    bf16* inter;        // GELU(u)
+    bf16* u;            // gelu'(pre-activation), saved by the FC1 epilogue for the backward
+    bf16* inter;        // GELU(pre-activation)
     // adapters
     bf16* mh_in;        // O-proj output (adapter input), [M, d]
     bf16* mh_pre;       // [M, r] pre-activation
@@ -167,7 +167,7 @@ int run_linear(const Lin& l, cudaStream_t s) {
 
 // dX[M, K] = epi(dY[M, N] * W[N, K]) (+ residual); W read in place (MN-major B operand)
 int run_dgrad(int M, int N, int K, const bf16* dY, const bf16* W, void* dX, int c_dtype, int epi, const bf16* aux,
-              long long ldaux, const float* residual, bf16* c2, cudaStream_t s) {
+              long long ldaux, const float* residual, bf16* c2, cudaStream_t s, float* colsum_out = nullptr) {
     climb_gemm_desc g;
     std::memset(&g, 0, sizeof(g));
     g.M = M; g.N = K; g.K = N;
@@ -177,6 +177,7 @@ int run_dgrad(int M, int N, int K, const bf16* dY, const bf16* W, void* dX, int 
     g.epilogue = epi; g.aux = const_cast<bf16*>(aux); g.ldaux = ldaux;
     g.residual = residual; g.ldr = K;
     g.c2 = c2; g.ldc2 = K;
+    g.colsum = colsum_out;
     g.alpha = 1.0f;
     return gemm_bf16(&g, s);
 }
@@ -331,7 +332,7 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
                           d, CLIMB_EPI_NONE, s));
         {
             Lin l{M, P.ff, d, a.h2, d, H(shadow, w.fc1_w)};
-            l.bias = F(theta, w.fc1_b); l.C = a.inter; l.epi = CLIMB_EPI_GELU; l.aux = a.u;
+            l.bias = F(theta, w.fc1_b); l.C = a.inter; l.epi = CLIMB_EPI_GELU_SAVE_GRAD; l.aux = a.u;   // u <- gelu'(pre)
             TRY(run_linear(l, s));
         }
         {
@@ -437,12 +438,15 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             TRY(run_dgrad(M, r, d, S.dz, H(shadow, w.out_down_w), dx, CLIMB_F32, CLIMB_EPI_NONE, nullptr, 0, dx, dx_h, s));
         }
         // ---- FFN: y = FC2(GELU(FC1(LN2(x1)))) + x1 ----
-        TRY(run_dgrad(M, d, ff, dx_h, H(shadow, w.fc2_w), S.du, CLIMB_BF16, CLIMB_EPI_DGELU, a.u, ff, nullptr, nullptr, s));
+        // du = (dx W2) * gelu'(pre); the FC1 bias gradient (column sums of du) is reduced in the same epilogue
+        const bool fuse_db1 = base && (ff % 32 == 0);
+        TRY(run_dgrad(M, d, ff, dx_h, H(shadow, w.fc2_w), S.du, CLIMB_BF16, CLIMB_EPI_MUL_AUX, a.u, ff, nullptr, nullptr, s,
+                      fuse_db1 ? G(grad, w.fc1_b) : nullptr));
         if (base) {
             TRY(run_wgrad(M, d, ff, dx_h, d, a.inter, ff, G(grad, w.fc2_w), s));
             TRY(colsum(dx_h, CLIMB_BF16, d, M, d, G(grad, w.fc2_b), s));
             TRY(run_wgrad(M, ff, d, S.du, ff, a.h2, d, G(grad, w.fc1_w), s));
-            TRY(colsum(S.du, CLIMB_BF16, ff, M, ff, G(grad, w.fc1_b), s));
+            if (!fuse_db1) TRY(colsum(S.du, CLIMB_BF16, ff, M, ff, G(grad, w.fc1_b), s));
         }
         TRY(run_dgrad(M, ff, d, S.du, H(shadow, w.fc1_w), S.dh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, nullptr, nullptr, s));
         // dx1 = dx + LN2'(dh2)
@@ -467,11 +471,10 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             TRY(run_wgrad(M, d, d, dho, d, a.ctx, d, G(grad, w.o_w), s));
             TRY(colsum(dho, CLIMB_BF16, d, M, d, G(grad, w.o_b), s));
         }
-        TRY(attention_bwd(a.qkv, P.key_bias, a.ctx, S.dh, a.lse, S.delta, S.dqkv, P.B, P.L, P.heads, 0.125f, s));
-        if (base) {
-            TRY(run_wgrad(M, 3 * d, d, S.dqkv, 3 * d, a.h1, d, G(grad, w.qkv_w), s));
-            TRY(colsum(S.dqkv, CLIMB_BF16, 3 * d, M, 3 * d, G(grad, w.qkv_b), s));
-        }
+        // the q/k/v bias gradient (column sums of dqkv) comes out of the attention backward's epilogue
+        TRY(attention_bwd(a.qkv, P.key_bias, a.ctx, S.dh, a.lse, S.delta, S.dqkv, base ? G(grad, w.qkv_b) : nullptr, P.B,
+                          P.L, P.heads, 0.125f, s));
+        if (base) TRY(run_wgrad(M, 3 * d, d, S.dqkv, 3 * d, a.h1, d, G(grad, w.qkv_w), s));
         TRY(run_dgrad(M, 3 * d, d, S.dqkv, H(shadow, w.qkv_w), S.dh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, nullptr, nullptr, s));  // dh1
         // dx_in = dx1 + LN1'(dh1)   (written over the old dx buffers)
         TRY(layernorm_bwd(nullptr, S.dh, a.x_in, d, F(theta, w.ln1_w), F(theta, w.ln1_b), a.mean1, a.rstd1, dn, dx, dx_h,

@@ -44,6 +44,7 @@ struct GemmDeviceArgs {
     long long ldaux;
     void* c2;                     // optional bf16 copy of the final value [M, ldc2]
     long long ldc2;
+    float* colsum;                // optional [N] += column sums of the (bf16) C tile
     float alpha;
     int accumulate;
     int split_k;
@@ -146,7 +147,29 @@ __device__ __forceinline__ void dact_chunk(int epi, float (&v)[32], const uint32
                 v[2 * j + 1] = a.y > 0.0f ? v[2 * j + 1] : 0.0f;
             }
             break;
+        case CLIMB_EPI_MUL_AUX:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 a = unpack_bf16(aux_pk[j]);
+                v[2 * j] *= a.x;
+                v[2 * j + 1] *= a.y;
+            }
+            break;
         default: break;
+    }
+}
+
+// v <- gelu(v), g <- packed bf16 gelu'(v): Phi and the Gaussian density are shared between the two
+__device__ __forceinline__ void gelu_and_grad_chunk(float (&v)[32], uint32_t (&g)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float c0, e0, c1, e1;
+        const float x0 = v[2 * j], x1 = v[2 * j + 1];
+        phi_pdf(x0, c0, e0);
+        phi_pdf(x1, c1, e1);
+        v[2 * j] = x0 * c0;
+        v[2 * j + 1] = x1 * c1;
+        g[j] = pack_bf16(fmaf(x0 * 0.39894228040143267794f, e0, c0), fmaf(x1 * 0.39894228040143267794f, e1, c1));
     }
 }
 
@@ -231,7 +254,9 @@ __device__ __forceinline__ void prefetch_take(const uint8_t* buf, uint32_t* pk, 
     }
 }
 
-template <int BLOCK_N>
+// HAS_INPUT: the epilogue reads a tensor (derivative aux / residual); only those instantiations carry
+// the input registers and the prefetch machinery.
+template <int BLOCK_N, bool HAS_INPUT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b, const GemmDeviceArgs p) {
@@ -375,11 +400,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const bool fast_bias = p.bias == nullptr || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         const bool all_fast = fast_c && fast_aux && fast_c2 && fast_res && fast_bias;
         const bool aux_in = (p.epilogue == CLIMB_EPI_DGELU || p.epilogue == CLIMB_EPI_DSWISH ||
-                             p.epilogue == CLIMB_EPI_DRELU);
-        const bool aux_out = (p.aux != nullptr) && !aux_in;   // pre-activation copy (bf16)
+                             p.epilogue == CLIMB_EPI_DRELU || p.epilogue == CLIMB_EPI_MUL_AUX);
+        const bool save_grad = p.epilogue == CLIMB_EPI_GELU_SAVE_GRAD;
+        const bool aux_out = (p.aux != nullptr) && !aux_in && !save_grad;   // pre-activation copy (bf16)
         // The one epilogue INPUT stream worth prefetching: the bf16 aux tensor of the derivative
         // epilogues (dGELU reads the saved pre-activation), else the fp32 residual.
-        const int pf_kind = (!all_fast || p.scratch_bytes < 2 * kEpiHalfBytes) ? 0
+        const int pf_kind = (!HAS_INPUT || !all_fast || p.scratch_bytes < 2 * kEpiHalfBytes) ? 0
                             : (aux_in ? 1 : (p.residual != nullptr ? 2 : 0));
         // issue the loads of chunk (t, cc) into scratch half `b`; returns false if that chunk does not
         // exist or is not on the fast path (then it will be loaded synchronously, or not at all)
@@ -424,11 +450,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (n0 >= p.N) break;                      // warp-uniform
                 const bool full = (n0 + 32 <= p.N);
                 // epilogue input of THIS chunk: already in flight (prefetched) or fetched now
-                uint32_t pin[32];
-                const bool have_pf = (pf_tile == tile && pf_c == c);
+                uint32_t pin[HAS_INPUT ? 32 : 1];
+                const bool have_pf = HAS_INPUT && (pf_tile == tile && pf_c == c);
                 if (have_pf) buf ^= 1;            // prefetches always target the half the previous chunk did not use
                 uint8_t* scratch = scratch_base + buf * kEpiHalfBytes;
-                if (full && all_fast) {
+                if (HAS_INPUT && full && all_fast) {
                     if (have_pf) {
                         if (pf_kind == 1) prefetch_take<4>(scratch, pin, lane);
                         else prefetch_take<8>(scratch, pin, lane);
@@ -471,8 +497,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         }
                     }
                     uint32_t pk[32];
-                    if (aux_in) {
+                    if (HAS_INPUT && aux_in) {
                         dact_chunk(p.epilogue, v, pin);
+                    } else if (save_grad) {
+                        uint32_t gpk[16];
+                        gelu_and_grad_chunk(v, gpk);
+                        store_rows<4>(scratch, gpk, reinterpret_cast<uint8_t*>(p.aux) +
+                                                        (static_cast<long long>(row0) * p.ldaux + n0) * 2,
+                                      p.ldaux * 2, rows_valid, lane, false);
                     } else {
                         if (aux_out) {
 #pragma unroll
@@ -483,7 +515,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         }
                         act_chunk(p.epilogue, v);
                     }
-                    if (add_res) {
+                    if (HAS_INPUT && add_res) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(pin[j]);
                     }
@@ -506,6 +538,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         store_rows<4>(scratch, pk, reinterpret_cast<uint8_t*>(p.C) +
                                                        (static_cast<long long>(row0) * p.ldc + n0) * 2,
                                       p.ldc * 2, rows_valid, lane, false);
+                        if (p.colsum != nullptr) {
+                            // the chunk is still staged in scratch: lane l sums column l over the warp's rows
+                            __syncwarp();
+                            float cs = 0.0f;
+                            for (int rr = 0; rr < rows_valid; ++rr) {
+                                const uint16_t h16 = *reinterpret_cast<const uint16_t*>(
+                                    scratch + swz128((rr * 4 + (lane >> 3)) * 16) + (lane & 7) * 2);
+                                cs += __uint_as_float(static_cast<uint32_t>(h16) << 16);
+                            }
+                            atomicAdd(p.colsum + n0 + lane, cs);
+                        }
                     }
                     continue;
                 }
@@ -530,6 +573,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             apk[j] = pack_bf16(lo, hi);
                         }
                         dact_chunk(p.epilogue, v, apk);
+                    } else if (save_grad) {
+                        uint32_t gpk[16];
+                        gelu_and_grad_chunk(v, gpk);
+                        if (row_ok) {
+                            __nv_bfloat16* auxp = reinterpret_cast<__nv_bfloat16*>(p.aux) +
+                                                  static_cast<long long>(row) * p.ldaux + n0;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 gg = unpack_bf16(gpk[j]);
+                                if (2 * j < ncols) auxp[2 * j] = __float2bfloat16_rn(gg.x);
+                                if (2 * j + 1 < ncols) auxp[2 * j + 1] = __float2bfloat16_rn(gg.y);
+                            }
+                        }
                     } else {
                         if (aux_out && row_ok) {
                             __nv_bfloat16* auxp = reinterpret_cast<__nv_bfloat16*>(p.aux) +
@@ -641,8 +697,8 @@ int num_sms() {
     return n;
 }
 
-template <int BLOCK_N>
-int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream) {
+template <int BLOCK_N, bool HAS_INPUT>
+int launch_gemm_t(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N>;
     CUtensorMap ta, tb;
     int rc;
@@ -681,23 +737,29 @@ int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
 
     static bool attr_set = false;
     if (!attr_set) {
-        CLIMB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N>,
+        CLIMB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, HAS_INPUT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     // epilogues that read a tensor (derivative activations, residual) get a second scratch half for
     // the cp.async prefetch of the next chunk's input and pay one ring stage for it
-    const bool epi_input = d->residual != nullptr || d->epilogue == CLIMB_EPI_DGELU ||
-                           d->epilogue == CLIMB_EPI_DSWISH || d->epilogue == CLIMB_EPI_DRELU;
-    a.scratch_bytes = epi_input ? 2 * kEpiHalfBytes : kEpiHalfBytes;
+    a.scratch_bytes = HAS_INPUT ? 2 * kEpiHalfBytes : kEpiHalfBytes;
     a.num_stages = L::stages_for(a.scratch_bytes);
     const int smem_bytes = L::total_for(a.scratch_bytes);
     const int total = a.m_tiles * a.n_tiles * a.split_k;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
-    gemm_bf16_tcgen05_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, a);
+    gemm_bf16_tcgen05_kernel<BLOCK_N, HAS_INPUT><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, a);
     CLIMB_LAUNCH_OK();
     return 0;
+}
+
+template <int BLOCK_N>
+int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream) {
+    const bool epi_input = d->residual != nullptr || d->epilogue == CLIMB_EPI_DGELU ||
+                           d->epilogue == CLIMB_EPI_DSWISH || d->epilogue == CLIMB_EPI_DRELU ||
+                           d->epilogue == CLIMB_EPI_MUL_AUX;
+    return epi_input ? launch_gemm_t<BLOCK_N, true>(d, a, stream) : launch_gemm_t<BLOCK_N, false>(d, a, stream);
 }
 
 }  // namespace
@@ -709,7 +771,18 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     CLIMB_REQUIRE(d->c_dtype == CLIMB_F32 || d->c_dtype == CLIMB_BF16, "gemm: bad c_dtype");
     CLIMB_REQUIRE(!(d->accumulate && d->c_dtype != CLIMB_F32), "gemm: accumulate needs fp32 C");
     const bool aux_needed = (d->epilogue == CLIMB_EPI_DGELU || d->epilogue == CLIMB_EPI_DSWISH ||
-                             d->epilogue == CLIMB_EPI_DRELU);
+                             d->epilogue == CLIMB_EPI_DRELU || d->epilogue == CLIMB_EPI_MUL_AUX ||
+                             d->epilogue == CLIMB_EPI_GELU_SAVE_GRAD);
+    if (d->colsum != nullptr) {
+        CLIMB_REQUIRE(d->c_dtype == CLIMB_BF16 && d->N % 32 == 0 && (d->ldc * 2) % 16 == 0 &&
+                          (reinterpret_cast<uintptr_t>(d->C) & 15) == 0 && !d->accumulate,
+                      "gemm: fused colsum needs a bf16 C with N %% 32 == 0 and 16-byte aligned rows");
+        // every other epilogue tensor must be on the aligned fast path too
+        CLIMB_REQUIRE((d->aux == nullptr || ((d->ldaux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)) &&
+                          (d->c2 == nullptr) && (d->residual == nullptr) &&
+                          (d->bias == nullptr || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0),
+                      "gemm: fused colsum needs aligned aux / bias and no residual / c2");
+    }
     CLIMB_REQUIRE(!aux_needed || d->aux != nullptr, "gemm: derivative epilogue needs aux");
     CLIMB_REQUIRE(!(d->accumulate && d->c2 != nullptr), "gemm: accumulate cannot produce a bf16 copy");
     CLIMB_REQUIRE(!(d->accumulate && d->epilogue != CLIMB_EPI_NONE),
@@ -723,6 +796,7 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     a.bias = d->bias; a.residual = d->residual; a.ldr = d->ldr;
     a.epilogue = d->epilogue; a.aux = d->aux; a.ldaux = d->ldaux;
     a.c2 = d->c2; a.ldc2 = d->ldc2;
+    a.colsum = d->colsum;
     a.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
     a.accumulate = d->accumulate ? 1 : 0;
 

@@ -10,7 +10,7 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream);
 int attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H,
                   float scale, cudaStream_t stream);
 int attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx,
-                  const float* lse, float* delta, void* dqkv, int B, int L, int H, float scale,
+                  const float* lse, float* delta, void* dqkv, float* dqkv_colsum, int B, int L, int H, float scale,
                   cudaStream_t stream);
 
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
@@ -30,7 +30,7 @@ int encode_tmap_bf16(void* map_out, const void* ptr, int rank, const long long* 
 int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H, float scale,
                      cudaStream_t stream);
 int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
-                     void* dqkv, int B, int L, int H, float scale, cudaStream_t stream);
+                     void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream);
 
 // elementwise.cu
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);

@@ -33,7 +33,9 @@ typedef enum {
     CLIMB_EPI_DSWISH = 4,
     CLIMB_EPI_RELU = 5,   /* Pfeiffer adapter non-linearity */
     CLIMB_EPI_DRELU = 6,
-    CLIMB_EPI_TANH = 7    /* ViltPooler (modeling_vilt.py:887-899) */
+    CLIMB_EPI_TANH = 7,   /* ViltPooler (modeling_vilt.py:887-899) */
+    CLIMB_EPI_GELU_SAVE_GRAD = 8, /* C = gelu(pre), aux <- gelu'(pre): the backward then needs no erf at all */
+    CLIMB_EPI_MUL_AUX = 9         /* C = acc * aux (backward of GELU_SAVE_GRAD) */
 } climb_epilogue;
 
 const char* climb_last_error(void);
@@ -73,6 +75,8 @@ typedef struct {
     int epilogue;
     void* aux; int64_t ldaux;
     void* c2; int64_t ldc2;   /* optional bf16 copy of the final C (after residual) */
+    float* colsum;            /* optional [N]: colsum[n] += sum_m C[m, n] (bias gradient of the layer that
+                                 produced this dY), bf16 C, N % 32 == 0 and 16-byte aligned rows only */
     float alpha;          /* 0 is read as 1 */
     int accumulate;
     int split_k;
@@ -86,12 +90,14 @@ int climb_gemm_bf16(const climb_gemm_desc* desc, void* stream);
  *   ctx = softmax(Q K^T / 8 + key_bias) V, key_bias = (1 - mask) * -10000 (modeling_utils.py:299-311)
  * qkv  bf16 [B, L, 3*H*64] (q | k | v, head-major inside each third)
  * ctx  bf16 [B, L, H*64];  lse fp32 [B, H, L] (natural-log-sum-exp, saved for backward)
- * backward: dqkv bf16 [B, L, 3*H*64] from dctx bf16 [B, L, H*64]; delta fp32 [B, H, L] scratch.
+ * backward: dqkv bf16 [B, L, 3*H*64] from dctx bf16 [B, L, H*64]; delta fp32 [B, H, L] scratch;
+ *           dqkv_colsum (nullable, fp32 [3*H*64]) += column sums of dqkv = the q/k/v bias gradients.
+ * L <= 256 runs on tcgen05 / TMEM kernels (attention_tc.cu), longer sequences on mma.sync kernels.
  * ------------------------------------------------------------------------------------------- */
 int climb_attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse,
                         int B, int L, int H, float scale, void* stream);
 int climb_attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx,
-                        const float* lse, float* delta, void* dqkv,
+                        const float* lse, float* delta, void* dqkv, float* dqkv_colsum,
                         int B, int L, int H, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

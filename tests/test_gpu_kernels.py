@@ -132,6 +132,18 @@ def test_gemm_epilogues():
     assert _rel_err(out, acc + res) < 1e-5
     assert _rel_err(c2, acc + res) < 4e-3
     assert _rel_err(aux, acc) < 4e-3
+    # GELU with the derivative saved, then the multiply-by-aux backward epilogue with fused column sums
+    gaux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, outb, bias=bias, epilogue=L.EPI_GELU_SAVE_GRAD, aux=gaux)
+    accg = acc.clone().requires_grad_(True)
+    torch.nn.functional.gelu(accg).sum().backward()
+    assert _rel_err(outb, torch.nn.functional.gelu(acc)) < 4e-3
+    assert _rel_err(gaux, accg.grad) < 4e-3
+    cs = torch.ones(N, device="cuda")
+    L.gemm(a, b, outb, epilogue=L.EPI_MUL_AUX, aux=gaux, colsum=cs)
+    ref_mul = (acc - bias) * gaux.float()
+    assert _rel_err(outb, ref_mul) < 4e-3
+    assert _rel_err(cs, 1.0 + outb.float().sum(0)) < 1e-4
     # alpha
     L.gemm(a, b, out, alpha=0.25)
     assert _rel_err(out, 0.25 * (acc - bias)) < 1e-5
@@ -192,7 +204,10 @@ def test_attention_fwd_bwd(B, L_, H, masked):
     assert _rel_err(ctx, ctx_ref) < 6e-3, _rel_err(ctx, ctx_ref)
     assert _max_err(lse, lse_ref) < 2e-3, _max_err(lse, lse_ref)
     dctx = torch.randn(B, L_, H * 64, device="cuda").bfloat16()
-    dqkv = L.attention_bwd(qkv, key_bias, ctx, dctx, lse, B, L_, H, scale)
+    cs = torch.zeros(3 * H * 64, device="cuda")
+    dqkv = L.attention_bwd(qkv, key_bias, ctx, dctx, lse, B, L_, H, scale, colsum=cs)
+    cs_ref = dqkv.float().sum((0, 1))
+    assert (cs - cs_ref).abs().max().item() <= 2e-3 * max(1.0, cs_ref.abs().max().item())
     ctx_ref.backward(dctx.float())
     ref = qkv_ref.grad.view(B, L_, 3, H * 64)
     got = dqkv.float().view(B, L_, 3, H * 64)
