@@ -94,17 +94,29 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 // Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated with Abramowitz-Stegun 7.1.26
 //   erfc(a) = (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-a^2),  t = 1 / (1 + p a),  |error| <= 1.5e-7
 // on a = |x| / sqrt 2, using erfc directly for x < 0 so that the tail suffers no cancellation.
-// ~15 instructions (2 MUFU) per element instead of erff's ~30: the GEMM epilogues that apply it are
-// issue-bound otherwise. exp(-a^2) is shared with the Gaussian density of the derivative.
+// The GEMM epilogues that apply it are issue-bound, so every instruction counts. exp(-a^2) is shared
+// with the Gaussian density of the derivative.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 19 instructions per (gelu, gelu') pair: the single-instruction MUFU forms (no denormal fix-up code),
+// 0.5 and 1/sqrt 2 folded into the constants, exp(-x^2/2) = 2^(-(x sqrt(log2 e / 2))^2).
 __device__ __forceinline__ void phi_pdf(float x, float& cdf, float& pdf_times_sqrt2pi) {
-    const float a = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = __expf(-a * a);                   // = exp(-x^2 / 2)
-    const float half_erfc = 0.5f * poly * t * e;      // 0.5 * erfc(|x| / sqrt 2)
+    const float t = rcp_ftz(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+    float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    const float s = x * 0.84932180028801904272f;
+    const float e = ex2_ftz(-(s * s));                 // = exp(-x^2 / 2)
+    const float half_erfc = (poly * t) * e;            // 0.5 * erfc(|x| / sqrt 2)
     cdf = x >= 0.0f ? 1.0f - half_erfc : half_erfc;
     pdf_times_sqrt2pi = e;
 }
@@ -161,8 +173,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if CLIMB_SPIN_GUARD
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    long long t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); ++spins) {
+        if ((spins & 255u) != 0) continue;              // keep the polling loop to two instructions
+        if (t0 == 0) t0 = clock64();
         if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz: a lost arrive, not a slow one
             printf("climb_b200: mbarrier wait timed out (block %d thread %d parity %u)\n",
                    blockIdx.x, threadIdx.x, parity);

@@ -438,10 +438,12 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             TRY(run_dgrad(M, r, d, S.dz, H(shadow, w.out_down_w), dx, CLIMB_F32, CLIMB_EPI_NONE, nullptr, 0, dx, dx_h, s));
         }
         // ---- FFN: y = FC2(GELU(FC1(LN2(x1)))) + x1 ----
-        // du = (dx W2) * gelu'(pre); the FC1 bias gradient (column sums of du) is reduced in the same epilogue
-        const bool fuse_db1 = base && (ff % 32 == 0);
+        // du = (dx W2) * gelu'(pre). The FC1 bias gradient (column sums of du) is a separate streaming pass:
+        // fused into this K = 768 epilogue it cost 57 us per launch (ncu: a third of the kernel's instructions),
+        // the standalone kernel reads du once more for ~20 us.
+        const bool fuse_db1 = false;
         TRY(run_dgrad(M, d, ff, dx_h, H(shadow, w.fc2_w), S.du, CLIMB_BF16, CLIMB_EPI_MUL_AUX, a.u, ff, nullptr, nullptr, s,
-                      fuse_db1 ? G(grad, w.fc1_b) : nullptr));
+                      nullptr));
         if (base) {
             TRY(run_wgrad(M, d, ff, dx_h, d, a.inter, ff, G(grad, w.fc2_w), s));
             TRY(colsum(dx_h, CLIMB_BF16, d, M, d, G(grad, w.fc2_b), s));

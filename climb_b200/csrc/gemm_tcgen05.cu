@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "climb_b200.h"
 
+#include <cstdlib>
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through the runtime)
 
 namespace climb {
@@ -254,6 +255,90 @@ __device__ __forceinline__ void prefetch_take(const uint8_t* buf, uint32_t* pk, 
     }
 }
 
+
+// ================================ TMA producer (one thread) ================================
+template <int BLOCK_N>
+__device__ __forceinline__ void producer_loop(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmDeviceArgs& p,
+                                              uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, int kStages) {
+    using L = SmemLayout<BLOCK_N>;
+    const int tiles_mn = p.m_tiles * p.n_tiles;
+    const int total_tiles = tiles_mn * p.split_k;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int mn = tile - split * tiles_mn;
+        const int m_blk = mn / p.n_tiles;
+        const int n_blk = mn - m_blk * p.n_tiles;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            if (!p.a_mn_major) {
+                tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kBlockK, m_blk * kBlockM);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kBlockM / 64; ++j)
+                    tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (kBlockK * 128), m_blk * kBlockM + j * 64, kb * kBlockK);
+            }
+            if (!p.b_mn_major) {
+                tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kBlockK, n_blk * BLOCK_N);
+            } else {
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                    tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (kBlockK * 128), n_blk * BLOCK_N + j * 64, kb * kBlockK);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+    }
+}
+
+// ================================ MMA issuer (one thread) ==================================
+template <int BLOCK_N>
+__device__ __forceinline__ void mma_loop(const GemmDeviceArgs& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                         uint64_t* acc_full, uint64_t* acc_empty, uint32_t tmem_base, int kStages) {
+    using L = SmemLayout<BLOCK_N>;
+    const int tiles_mn = p.m_tiles * p.n_tiles;
+    const int total_tiles = tiles_mn * p.split_k;
+    const uint32_t idesc = make_instr_desc(kBlockM, BLOCK_N, p.a_mn_major, p.b_mn_major);
+    // per-operand descriptor constants
+    const uint32_t a_lbo = p.a_mn_major ? kBlockK * 128 : 16;
+    const uint32_t b_lbo = p.b_mn_major ? kBlockK * 128 : 16;
+    const uint32_t a_kstep = p.a_mn_major ? 16 * 128 : 32;   // bytes per UMMA_K = 16
+    const uint32_t b_kstep = p.b_mn_major ? 16 * 128 : 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                const uint64_t da = make_smem_desc(sa + kk * a_kstep, a_lbo, 1024);
+                const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, 1024);
+                umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);       // frees the smem slot when MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&acc_full[acc]);              // accumulator complete -> epilogue
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+}
+
 // HAS_INPUT: the epilogue reads a tensor (derivative aux / residual); only those instantiations carry
 // the input registers and the prefetch machinery.
 template <int BLOCK_N, bool HAS_INPUT>
@@ -303,80 +388,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int total_tiles = tiles_mn * p.split_k;
 
     if (warp == 0) {
-        // ================================ TMA producer =====================================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int split = tile / tiles_mn;
-                const int mn = tile - split * tiles_mn;
-                const int m_blk = mn / p.n_tiles;
-                const int n_blk = mn - m_blk * p.n_tiles;
-                const int kb0 = split * p.k_blocks_per_split;
-                const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t* sa = smem + stage * L::kStageBytes;
-                    uint8_t* sb = sa + L::kABytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-                    if (!p.a_mn_major) {
-                        tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kBlockK, m_blk * kBlockM);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < kBlockM / 64; ++j)
-                            tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (kBlockK * 128),
-                                        m_blk * kBlockM + j * 64, kb * kBlockK);
-                    }
-                    if (!p.b_mn_major) {
-                        tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kBlockK, n_blk * BLOCK_N);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < BLOCK_N / 64; ++j)
-                            tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (kBlockK * 128),
-                                        n_blk * BLOCK_N + j * 64, kb * kBlockK);
-                    }
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
+        if (lane == 0) producer_loop<BLOCK_N>(tmap_a, tmap_b, p, smem, full_bar, empty_bar, kStages);
     } else if (warp == 1) {
-        // ================================ MMA issuer =======================================
-        if (lane == 0) {
-            const uint32_t idesc = make_instr_desc(kBlockM, BLOCK_N, p.a_mn_major, p.b_mn_major);
-            // per-operand descriptor constants
-            const uint32_t a_lbo = p.a_mn_major ? kBlockK * 128 : 16;
-            const uint32_t b_lbo = p.b_mn_major ? kBlockK * 128 : 16;
-            const uint32_t a_kstep = p.a_mn_major ? 16 * 128 : 32;   // bytes per UMMA_K = 16
-            const uint32_t b_kstep = p.b_mn_major ? 16 * 128 : 32;
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int split = tile / tiles_mn;
-                const int kb0 = split * p.k_blocks_per_split;
-                const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
-                mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sb = sa + L::kABytes;
-#pragma unroll
-                    for (int kk = 0; kk < kBlockK / 16; ++kk) {
-                        const uint64_t da = make_smem_desc(sa + kk * a_kstep, a_lbo, 1024);
-                        const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&empty_bar[stage]);       // frees the smem slot when MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                }
-                umma_commit(&acc_full[acc]);              // accumulator complete -> epilogue
-                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
-            }
-        }
+        if (lane == 0) mma_loop<BLOCK_N>(p, smem, full_bar, empty_bar, acc_full, acc_empty, tmem_base, kStages);
     } else {
         // ================================ epilogue =========================================
         // A thread owns one accumulator row (TMEM lane) and walks it in 32-column chunks. Global
@@ -643,6 +657,269 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fast path: the hot Linears of the ViLT step (N a multiple of 256, aligned operands, no split-K).
+// Same producer / MMA warps and ring as above; the epilogue is specialised per KIND at compile time
+// and runs on SIXTEEN warps (four per TMEM lane group, each owning two of the tile's eight 32-column
+// chunks), because with K = 768 a 128 x 256 tile leaves only ~10k cycles to drain 32k accumulators
+// and the math-heavy epilogues are latency-bound on eight warps (ncu: IPC 0.4, stall_wait / long_sb).
+//   FK_BF16       C(bf16) = acc + bias                               QKV, every plain dgrad
+//   FK_GELU_SAVE  C(bf16) = gelu(acc + bias), aux(bf16) = gelu'(..)   FC1 forward
+//   FK_MUL_AUX    C(bf16) = acc * aux(bf16)                           FC2 dgrad (du = dinter * gelu')
+//   FK_RES_F32    C(f32)  = acc + bias + residual(f32)                O-proj / FC2 forward
+// The unit of global I/O is 32 rows x 64 B (32 bf16 or 16 fp32 columns): written by thread = row into a
+// 2 KB swizzled staging block, read back as 16 B per lane over consecutive addresses. Epilogue INPUTS
+// (aux / residual) are fetched one chunk ahead straight into registers in that coalesced mapping and
+// transposed through the same staging block when consumed: 64 KB of loads in flight per SM without
+// spending shared memory, so all kinds keep the 4-stage operand ring.
+// ------------------------------------------------------------------------------------------
+enum FastKind { FK_BF16 = 0, FK_GELU_SAVE = 1, FK_MUL_AUX = 2, FK_RES_F32 = 3 };
+constexpr int kFastEpiWarps = 16;
+constexpr int kFastThreads = 64 + kFastEpiWarps * 32;
+constexpr int kFastBlockN = 256;
+constexpr int kFastStages = 4;
+constexpr int kFastUnitBytes = 2048;
+constexpr int kFastSmemBytes = kFastStages * SmemLayout<kFastBlockN>::kStageBytes + SmemLayout<kFastBlockN>::kBarrierBytes +
+                               kFastEpiWarps * kFastUnitBytes + 1024;
+static_assert(kFastSmemBytes <= 227 * 1024, "fast GEMM shared memory budget");
+
+// tcgen05.wait::ld that also "produces" the loaded registers, so that no use of them can be scheduled above
+// the wait when other work sits between the load and the wait
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_regs16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+// thread = row registers (16 words = 64 B per row) -> global, coalesced. g_lane already points at this lane's
+// granule of row (lane >> 2); rows advance by 8 per iteration.
+__device__ __forceinline__ void store_unit(uint8_t* stg, const uint32_t (&w)[16], uint8_t* g_lane, long long step8_bytes,
+                                           int rows_valid, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(stg + swz128((lane * 4 + g) * 16)) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+    __syncwarp();
+    const int rsub = lane >> 2;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + swz128((it * 32 + lane) * 16));
+        if (it * 8 + rsub < rows_valid) *reinterpret_cast<uint4*>(g_lane + it * step8_bytes) = val;
+    }
+}
+// coalesced registers (4 granules per lane, rows lane>>2 + 8 it) -> thread = row registers
+__device__ __forceinline__ void transpose_unit_in(uint8_t* stg, const uint4 (&pf)[4], uint32_t (&w)[16], int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(stg + swz128((it * 32 + lane) * 16)) = pf[it];
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + swz128((lane * 4 + g) * 16));
+        w[4 * g] = val.x; w[4 * g + 1] = val.y; w[4 * g + 2] = val.z; w[4 * g + 3] = val.w;
+    }
+}
+__device__ __forceinline__ void load_unit(uint4 (&pf)[4], const uint8_t* g_lane, long long step8_bytes, int rows_valid, int lane) {
+    const int rsub = lane >> 2;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        pf[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (it * 8 + rsub < rows_valid) pf[it] = __ldg(reinterpret_cast<const uint4*>(g_lane + it * step8_bytes));
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kFastThreads, 1)
+gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmDeviceArgs p) {
+    constexpr int BLOCK_N = kFastBlockN;
+    using L = SmemLayout<BLOCK_N>;
+    constexpr int kStages = kFastStages;
+    constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* bar_base = smem + kStages * L::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* empty_bar = full_bar + L::kMaxStages;
+    uint64_t* acc_full = empty_bar + L::kMaxStages;
+    uint64_t* acc_empty = acc_full + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], kFastEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) producer_loop<BLOCK_N>(tmap_a, tmap_b, p, smem, full_bar, empty_bar, kStages);
+    } else if (warp == 1) {
+        if (lane == 0) mma_loop<BLOCK_N>(p, smem, full_bar, empty_bar, acc_full, acc_empty, tmem_base, kStages);
+    } else {
+        constexpr bool kF32 = KIND == FK_RES_F32;
+        constexpr bool kHasIn = KIND == FK_MUL_AUX || KIND == FK_RES_F32;
+        constexpr int kUnits = kF32 ? 2 : 1;              // 64 B units per 32-column chunk
+        constexpr int kColGroups = kFastEpiWarps / 4;
+        const int ew = warp - 2;
+        const int lane_grp = warp & 3;                    // TMEM lanes [32 * lane_grp, +32) are this warp's
+        const int cg = ew >> 2;                           // chunks cg, cg + 4 of every tile
+        uint8_t* stg = smem + kStages * L::kStageBytes + L::kBarrierBytes + ew * kFastUnitBytes;
+        const int total_tiles = p.m_tiles * p.n_tiles;
+        const int rsub = lane >> 2, gj = lane & 3;
+        // byte pitches: output rows / input rows, and 8 rows at a time for the coalesced mapping
+        const long long c_pitch = p.ldc * (kF32 ? 4 : 2);
+        const long long in_pitch = kF32 ? p.ldr * 4 : p.ldaux * 2;
+        const uint8_t* in_base = kF32 ? reinterpret_cast<const uint8_t*>(p.residual) : reinterpret_cast<const uint8_t*>(p.aux);
+
+        uint4 pf[kHasIn ? kUnits : 1][4];
+        // fetch the input of chunk cc of tile t (coalesced mapping) into pf
+        auto prefetch = [&](int t, int cc, int h) {
+            const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
+            const int r0 = mb * kBlockM + lane_grp * 32;
+            const int rv = min(32, max(0, p.M - r0));
+            const uint8_t* g = in_base + (static_cast<long long>(r0) + rsub) * in_pitch +
+                               static_cast<long long>(nb * BLOCK_N + cc * 32) * (kF32 ? 4 : 2) + gj * 16;
+            load_unit(pf[h], g + h * 64, 8 * in_pitch, rv, lane);
+        };
+        if (kHasIn && static_cast<int>(blockIdx.x) < total_tiles) {
+#pragma unroll
+            for (int h = 0; h < kUnits; ++h) prefetch(blockIdx.x, cg, h);
+        }
+
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_blk = tile / p.n_tiles;
+            const int n_blk = tile - m_blk * p.n_tiles;
+            const int row0 = m_blk * kBlockM + lane_grp * 32;
+            const int rows_valid = min(32, max(0, p.M - row0));
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = cg; c < BLOCK_N / 32; c += kColGroups) {
+                const int n0 = n_blk * BLOCK_N + c * 32;
+                int nt = tile, nc = c + kColGroups;           // this warp's next chunk
+                if (nc >= BLOCK_N / 32) { nt = tile + gridDim.x; nc = cg; }
+                uint8_t* c_lane = reinterpret_cast<uint8_t*>(p.C) + (static_cast<long long>(row0) + rsub) * c_pitch +
+                                  static_cast<long long>(n0) * (kF32 ? 4 : 2) + gj * 16;
+                if constexpr (KIND == FK_RES_F32) {
+                    // two 16-column halves, each with its own in-flight residual unit
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t r[16], res[16];
+                        tmem_ld_32x16(t_row + static_cast<uint32_t>(c * 32 + h * 16), r);
+                        transpose_unit_in(stg, pf[h], res, lane);
+                        if (nt < total_tiles) prefetch(nt, nc, h);
+                        tmem_ld_wait_regs16(r);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + h * 16 + j));
+                            r[j] = __float_as_uint(__uint_as_float(r[j]) + b4.x + __uint_as_float(res[j]));
+                            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y + __uint_as_float(res[j + 1]));
+                            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z + __uint_as_float(res[j + 2]));
+                            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w + __uint_as_float(res[j + 3]));
+                        }
+                        store_unit(stg, r, c_lane + h * 64, 8 * c_pitch, rows_valid, lane);
+                    }
+                } else {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), r);
+                    uint32_t ain[16];
+                    if constexpr (KIND == FK_MUL_AUX) {
+                        transpose_unit_in(stg, pf[0], ain, lane);
+                        if (nt < total_tiles) prefetch(nt, nc, 0);
+                    }
+                    tmem_ld_wait_regs(r);
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (KIND != FK_MUL_AUX && p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    uint32_t pk[16];
+                    if constexpr (KIND == FK_MUL_AUX) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 a = unpack_bf16(ain[j]);
+                            pk[j] = pack_bf16(v[2 * j] * a.x, v[2 * j + 1] * a.y);
+                        }
+                    } else if constexpr (KIND == FK_GELU_SAVE) {
+                        uint32_t gpk[16];
+                        gelu_and_grad_chunk(v, gpk);
+                        uint8_t* a_lane = reinterpret_cast<uint8_t*>(p.aux) + (static_cast<long long>(row0) + rsub) * (p.ldaux * 2) +
+                                          static_cast<long long>(n0) * 2 + gj * 16;
+                        store_unit(stg, gpk, a_lane, 8 * p.ldaux * 2, rows_valid, lane);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                    }
+                    store_unit(stg, pk, c_lane, 8 * c_pitch, rows_valid, lane);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
@@ -754,6 +1031,63 @@ int launch_gemm_t(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stre
     return 0;
 }
 
+
+template <int KIND>
+int launch_fast(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream) {
+    CUtensorMap ta, tb;
+    int rc;
+    if (!d->a_mn_major) rc = make_tmap_2d(&ta, d->A, d->K, d->M, d->lda, kBlockK, kBlockM);
+    else                rc = make_tmap_2d(&ta, d->A, d->M, d->K, d->lda, 64, kBlockK);
+    if (rc) return rc;
+    if (!d->b_mn_major) rc = make_tmap_2d(&tb, d->B, d->K, d->N, d->ldb, kBlockK, kFastBlockN);
+    else                rc = make_tmap_2d(&tb, d->B, d->N, d->K, d->ldb, 64, kBlockK);
+    if (rc) return rc;
+    a.m_tiles = (d->M + kBlockM - 1) / kBlockM;
+    a.n_tiles = d->N / kFastBlockN;
+    a.k_blocks_total = (d->K + kBlockK - 1) / kBlockK;
+    a.k_blocks_per_split = a.k_blocks_total;
+    a.split_k = 1;
+    a.num_stages = kFastStages;
+    a.scratch_bytes = kFastUnitBytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CLIMB_CUDA_OK(cudaFuncSetAttribute(gemm_fast_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmemBytes));
+        attr_set = true;
+    }
+    const int total = a.m_tiles * a.n_tiles;
+    const int grid = total < num_sms() ? total : num_sms();
+    ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
+    gemm_fast_kernel<KIND><<<grid, kFastThreads, kFastSmemBytes, stream>>>(ta, tb, a);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+inline bool aligned16(const void* p, long long pitch_bytes) {
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && pitch_bytes % 16 == 0;
+}
+
+// which specialised kernel (if any) covers this problem; -1 = the generic kernel
+int fast_kind(const climb_gemm_desc* d) {
+    if (d->block_n != 0 && d->block_n != kFastBlockN) return -1;
+    if (d->N % kFastBlockN != 0 || d->accumulate || d->split_k > 1 || d->c2 != nullptr || d->colsum != nullptr) return -1;
+    if (d->alpha != 0.0f && d->alpha != 1.0f) return -1;
+    const long long tiles = 1LL * ((d->M + kBlockM - 1) / kBlockM) * (d->N / kFastBlockN);
+    if (tiles < num_sms()) return -1;                     // small problems: the generic kernel's narrower tiles
+    if (d->bias != nullptr && (reinterpret_cast<uintptr_t>(d->bias) & 15) != 0) return -1;
+    if (d->c_dtype == CLIMB_BF16) {
+        if (!aligned16(d->C, d->ldc * 2) || d->residual != nullptr) return -1;
+        if (d->epilogue == CLIMB_EPI_NONE && d->aux == nullptr) return FK_BF16;
+        if (d->aux == nullptr || !aligned16(d->aux, d->ldaux * 2)) return -1;
+        if (d->epilogue == CLIMB_EPI_GELU_SAVE_GRAD) return FK_GELU_SAVE;
+        if (d->epilogue == CLIMB_EPI_MUL_AUX && d->bias == nullptr) return FK_MUL_AUX;
+        return -1;
+    }
+    if (d->c_dtype == CLIMB_F32 && d->epilogue == CLIMB_EPI_NONE && d->aux == nullptr && d->residual != nullptr &&
+        aligned16(d->C, d->ldc * 4) && aligned16(d->residual, d->ldr * 4))
+        return FK_RES_F32;
+    return -1;
+}
+
 template <int BLOCK_N>
 int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream) {
     const bool epi_input = d->residual != nullptr || d->epilogue == CLIMB_EPI_DGELU ||
@@ -763,6 +1097,9 @@ int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
 }
 
 }  // namespace
+
+// dev switch (CLIMB_GEMM_GENERIC=1): route everything through the generic kernel, for A/B timing
+static const bool g_disable_fast = [] { const char* e = getenv("CLIMB_GEMM_GENERIC"); return e && e[0] == '1'; }();
 
 int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     CLIMB_REQUIRE(d != nullptr, "null gemm descriptor");
@@ -800,6 +1137,15 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     a.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
     a.accumulate = d->accumulate ? 1 : 0;
 
+    if (!g_disable_fast) {
+        switch (fast_kind(d)) {
+            case FK_BF16: return launch_fast<FK_BF16>(d, a, stream);
+            case FK_GELU_SAVE: return launch_fast<FK_GELU_SAVE>(d, a, stream);
+            case FK_MUL_AUX: return launch_fast<FK_MUL_AUX>(d, a, stream);
+            case FK_RES_F32: return launch_fast<FK_RES_F32>(d, a, stream);
+            default: break;
+        }
+    }
     int bn = d->block_n;
     if (bn == 0) {
         // Tile heuristic. 128x256 halves the shared-memory operand traffic per FLOP of 128x128 (B300

@@ -84,6 +84,51 @@ def test_gemm_wgrad_splitk_accumulate(split_k):
     assert _rel_err(dw, ref) < 1e-5, _rel_err(dw, ref)
 
 
+@pytest.mark.parametrize("M,K", [(2500, 768), (15168, 768), (2400, 200), (2433, 3072)])
+def test_gemm_fast_kinds(M, K):
+    """The specialised 16-epilogue-warp kernels (N % 256 == 0, >= 148 tiles): bf16 + bias, GELU with saved
+    derivative, multiply-by-aux, fp32 + bias + residual; ragged last row tile, ragged K."""
+    L = _lib()
+    torch.manual_seed(M + K)
+    N = 2304
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    acc = a.float() @ b.float().t()
+    # FK_BF16 (with and without bias); padding rows / columns of a wider buffer stay untouched
+    buf = torch.full((M + 3, N + 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, buf[:M], N=N, bias=bias)
+    assert _rel_err(buf[:M, :N], acc + bias) < 4e-3
+    assert torch.isnan(buf[M:]).all() and torch.isnan(buf[:M, N:]).all()
+    outb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, outb)
+    assert _rel_err(outb, acc) < 4e-3
+    # B operand MN-major (dgrad form)
+    L.gemm(a, b.t().contiguous(), outb, b_mn_major=True)
+    assert _rel_err(outb, acc) < 4e-3
+    # FK_GELU_SAVE
+    aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, outb, bias=bias, epilogue=L.EPI_GELU_SAVE_GRAD, aux=aux)
+    pre = (acc + bias).requires_grad_(True)
+    y = torch.nn.functional.gelu(pre)
+    y.sum().backward()
+    assert _rel_err(outb, y.detach()) < 4e-3
+    assert _rel_err(aux, pre.grad) < 4e-3
+    assert _max_err(outb, y.detach()) < 2 ** -7 * max(1.0, y.abs().max().item())
+    # FK_MUL_AUX
+    u = torch.randn(M, N, device="cuda").bfloat16()
+    L.gemm(a, b, outb, epilogue=L.EPI_MUL_AUX, aux=u)
+    assert _rel_err(outb, acc * u.float()) < 4e-3
+    # FK_RES_F32, also in place (C == residual)
+    res = torch.randn(M, N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    L.gemm(a, b, out, bias=bias, residual=res)
+    assert _rel_err(out, acc + bias + res) < 1e-5
+    inplace = res.clone()
+    L.gemm(a, b, inplace, residual=inplace)
+    assert _rel_err(inplace, acc + res) < 1e-5
+
+
 def test_gemm_epilogues():
     L = _lib()
     torch.manual_seed(11)

@@ -19,7 +19,9 @@ for g in "$@"; do
     ln)       run ln 600 tests/test_gpu_kernels.py -k "layernorm" ;;
     parity)   run parity 900 tests/test_gpu_parity.py -s ;;
     cl)       run cl 900 tests/test_gpu_cl.py -s ;;
-    perf)     echo "=== perf" | tee -a gpurun_out/summary.txt; timeout 600 python tools/perf_kernels.py > gpurun_out/perf.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; tail -n 12 gpurun_out/perf.log | tee -a gpurun_out/summary.txt ;;
+    perf)     echo "=== perf" | tee -a gpurun_out/summary.txt; timeout 600 python tools/perf_kernels.py > gpurun_out/perf.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; cat gpurun_out/perf.log | tee -a gpurun_out/summary.txt ;;
+    perfgen)  echo "=== perf (generic GEMM kernel only)" | tee -a gpurun_out/summary.txt; CLIMB_GEMM_GENERIC=1 timeout 600 python tools/perf_kernels.py > gpurun_out/perf_generic.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; head -n 12 gpurun_out/perf_generic.log | tee -a gpurun_out/summary.txt ;;
+    gemm_fast) run gemm_fast 600 tests/test_gpu_kernels.py -k "gemm_fast" ;;
     smoke)    echo "=== smoke" | tee -a gpurun_out/summary.txt; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "exit=$? $(tail -n 2 gpurun_out/smoke.log | tr '\n' ' ')" | tee -a gpurun_out/summary.txt ;;
     bench)    echo "=== bench" | tee -a gpurun_out/summary.txt; timeout 900 python bench.py --steps ${BENCH_STEPS:-10} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "exit=$?" | tee -a gpurun_out/summary.txt; tail -n 5 gpurun_out/bench.err | tee -a gpurun_out/summary.txt; cat gpurun_out/bench.json | tee -a gpurun_out/summary.txt ;;
     benchref) echo "=== benchref" | tee -a gpurun_out/summary.txt; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit=$?" | tee -a gpurun_out/summary.txt; cat gpurun_out/bench_ref.json | tee -a gpurun_out/summary.txt ;;
