@@ -130,7 +130,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                    const float* __restrict__ key_bias, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
                    int L, int H, float scale_log2) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     float* sBias = reinterpret_cast<float*>(sm + FwdSmem::kBias);
     uint64_t* bar_load = reinterpret_cast<uint64_t*>(sm + FwdSmem::kBar);
     uint64_t* bar_s = bar_load + 1;
@@ -284,7 +284,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int L, int H, float scale_log2,
                    float scale) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     float* sLse = reinterpret_cast<float*>(sm + BwdSmem::kLse);
     float* sDelta = reinterpret_cast<float*>(sm + BwdSmem::kDelta);
     float* sBias = reinterpret_cast<float*>(sm + BwdSmem::kBias);

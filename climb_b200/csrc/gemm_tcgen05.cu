@@ -350,8 +350,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;   // 512 / 256 / 128: powers of two >= 32
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* bar_base = smem + kStages * L::kStageBytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty_bar = full_bar + L::kMaxStages;
@@ -760,7 +759,7 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t* bar_base = smem + kStages * L::kStageBytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty_bar = full_bar + L::kMaxStages;

@@ -28,6 +28,8 @@ for g in "$@"; do
     launches) echo "=== launches" | tee -a gpurun_out/summary.txt; timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/one_step.py > gpurun_out/launches.log 2>&1; echo "exit=$? rows=$(wc -l < gpurun_out/launches.csv)" | tee -a gpurun_out/summary.txt ;;
     ncu_gemm) echo "=== ncu_gemm" | tee -a gpurun_out/summary.txt; WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_bf16_tcgen05 -s 40 -c 4 -f -o gpurun_out/prof_gemm python tools/one_step.py > gpurun_out/ncu_gemm.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt ;;
     ncu_gemm_bwd) echo "=== ncu_gemm_bwd" | tee -a gpurun_out/summary.txt; WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_bf16_tcgen05 -s ${NCU_SKIP:-62} -c ${NCU_COUNT:-8} -f -o gpurun_out/prof_gemm_bwd python tools/one_step.py > gpurun_out/ncu_gemm_bwd.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt ;;
+    ncu_fast) echo "=== ncu_fast" | tee -a gpurun_out/summary.txt; WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_fast -s ${NCU_SKIP:-20} -c ${NCU_COUNT:-4} -f -o gpurun_out/prof_fast python tools/one_step.py > gpurun_out/ncu_fast.log 2>&1
+              WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_fast -s ${NCU_SKIP2:-62} -c ${NCU_COUNT2:-5} -f -o gpurun_out/prof_fast_bwd python tools/one_step.py >> gpurun_out/ncu_fast.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt ;;
     ncu_attn) echo "=== ncu_attn" | tee -a gpurun_out/summary.txt
               WARM=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_tc_fwd -s 4 -c 2 -f -o gpurun_out/prof_attn_fwd python tools/one_step.py > gpurun_out/ncu_attn.log 2>&1
               WARM=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_tc_bwd -s 4 -c 2 -f -o gpurun_out/prof_attn_bwd python tools/one_step.py >> gpurun_out/ncu_attn.log 2>&1
