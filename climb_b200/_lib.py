@@ -69,6 +69,8 @@ climb_profile_begin = _sig("climb_profile_begin", [])
 climb_profile_end = _sig("climb_profile_end", [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int])
 climb_gemm_bf16 = _sig("climb_gemm_bf16", [POINTER(GemmDesc), _P])
 climb_attention_fwd = _sig("climb_attention_fwd", [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P])
+climb_attention_fwd_dropout = _sig("climb_attention_fwd_dropout",
+                                   [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, ctypes.c_uint64, _P])
 climb_attention_bwd = _sig(
     "climb_attention_bwd", [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P])
 climb_layernorm_fwd = _sig(
@@ -147,6 +149,36 @@ climb_vilt_backward = _sig(
                             _P, c_int64, _P, _P, c_int, c_int, c_int, _P])
 
 
+# ---- frozen BERT text encoder (ViLT-BERT) -----------------------------------------------------------
+class BertDimsC(Structure):
+    _fields_ = [("hidden", c_int), ("layers", c_int), ("heads", c_int), ("ffn", c_int), ("ln_eps", c_float)]
+
+
+BERT_LAYER_FIELDS = ["qkv_w", "qkv_b", "o_w", "o_b", "attn_ln_w", "attn_ln_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+                     "out_ln_w", "out_ln_b"]
+
+
+class BertLayerC(Structure):
+    _fields_ = [(n, c_int64) for n in BERT_LAYER_FIELDS]
+
+
+class BertParamsC(Structure):
+    _fields_ = [(n, c_int64) for n in ("word_emb", "pos_emb", "type_emb", "emb_ln_w", "emb_ln_b")] + [
+        ("layer", POINTER(BertLayerC))]
+
+
+class BertBatchC(Structure):
+    _fields_ = [("B", c_int), ("T", c_int), ("input_ids", c_void_p), ("token_type_ids", c_void_p),
+                ("attention_mask", c_void_p)]
+
+
+climb_bert_forward_workspace_bytes = _sig("climb_bert_forward_workspace_bytes", [POINTER(BertDimsC), POINTER(BertBatchC)],
+                                          c_int64)
+climb_bert_forward = _sig("climb_bert_forward", [POINTER(BertDimsC), POINTER(BertParamsC), POINTER(BertBatchC), _P, _P, _P,
+                                                 c_int64, c_float, c_float, ctypes.c_uint64, _P, _P])
+climb_dropout_add = _sig("climb_dropout_add", [_P, _P, _P, c_int64, c_float, ctypes.c_uint64, _P])
+
+
 def check(rc: int) -> None:
     if rc != 0:
         msg = climb_last_error()
@@ -216,9 +248,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
     return out
 
 
-def attention_fwd(qkv, key_bias, B, L, H, scale):
+def attention_fwd(qkv, key_bias, B, L, H, scale, p_drop=0.0, seed=0):
     ctx = torch.empty(B, L, H * 64, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(B, H, L, dtype=torch.float32, device=qkv.device)
+    if p_drop > 0.0:
+        check(climb_attention_fwd_dropout(ptr(qkv), ptr(key_bias), ptr(ctx), ptr(lse), B, L, H, scale, p_drop, seed, stream()))
+        return ctx, lse
     check(climb_attention_fwd(ptr(qkv), ptr(key_bias), ptr(ctx), ptr(lse), B, L, H, scale, stream()))
     return ctx, lse
 

@@ -33,13 +33,14 @@ def _round_up(n: int, a: int) -> int:
 
 
 class ParamArena:
-    def __init__(self, owner: nn.Module, lister: str, with_shadow: bool = True):
+    def __init__(self, owner: nn.Module, lister: str, with_shadow: bool = True, with_grad: bool = True):
         """owner.<lister>() returns the (name, parameter) list in arena order. The arena keeps a
         reference to its owner (not a closure) so that copy.deepcopy(model) -- which the trainers do
         for best-model tracking, train_vqa.py:210,242 -- yields an independent arena."""
         self.owner = owner
         self.lister = lister
         self.with_shadow = with_shadow
+        self.with_grad = with_grad          # False: forward-only parameters (ViLT-BERT's frozen BERT), no gradient arena
         self.theta: Optional[torch.Tensor] = None
         self.shadow: Optional[torch.Tensor] = None
         self.grad: Optional[torch.Tensor] = None
@@ -55,7 +56,7 @@ class ParamArena:
 
     def __deepcopy__(self, memo):
         import copy
-        return ParamArena(copy.deepcopy(self.owner, memo), self.lister, self.with_shadow)
+        return ParamArena(copy.deepcopy(self.owner, memo), self.lister, self.with_shadow, self.with_grad)
 
     def _named_params(self):
         return getattr(self.owner, self.lister)()
@@ -104,9 +105,9 @@ class ParamArena:
                 p.data = view
         self.theta, self.offsets, self.numels, self.size = theta, offsets, numels, size
         self.shadow = torch.zeros(size, dtype=torch.bfloat16, device=device) if self.with_shadow else None
-        self.grad = torch.zeros(size, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(size, dtype=torch.float32, device=device) if self.with_grad else None
         self._grad_views = {}
-        for name, p in items:
+        for name, p in (items if self.with_grad else []):
             gv = self.grad[offsets[name]: offsets[name] + p.numel()].view(p.shape)
             self._grad_views[name] = gv
             if name in old_grads:           # carry accumulated gradients over (e.g. after .to())

@@ -128,7 +128,7 @@ __device__ __forceinline__ void softmax_bar_sync() {      // named barrier 1: th
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                    const float* __restrict__ key_bias, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
-                   int L, int H, float scale_log2) {
+                   int L, int H, float scale_log2, uint32_t drop_thresh, float inv_keep, unsigned long long seed) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     float* sBias = reinterpret_cast<float*>(sm + FwdSmem::kBias);
@@ -221,6 +221,19 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int j = 0; j < 32; ++j) {
                 p[j] = exp2f(fmaf(__uint_as_float(r[j]), scale_log2, sBias[c * 32 + j]) - m);
                 sum += p[j];
+            }
+            if (drop_thresh != 0u) {
+                // dropout on the probabilities (modeling_bert.py:341-345): the normaliser keeps every term, the
+                // P V product sees the kept ones scaled by 1/(1-p). Counter = (b, h, query, key / 4).
+                const unsigned long long base = ((static_cast<unsigned long long>(b) * H + h) * L + (q0 + row)) * 64ull + c * 8;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const uint4 rnd = philox4x32(seed, base + g);
+                    p[4 * g] *= dropout_scale(rnd.x, drop_thresh, inv_keep);
+                    p[4 * g + 1] *= dropout_scale(rnd.y, drop_thresh, inv_keep);
+                    p[4 * g + 2] *= dropout_scale(rnd.z, drop_thresh, inv_keep);
+                    p[4 * g + 3] *= dropout_scale(rnd.w, drop_thresh, inv_keep);
+                }
             }
             store_row_chunk_bf16(sm + FwdSmem::kP, row, c, p);     // Q / K are dead: S = Q K^T has retired
         }
@@ -490,8 +503,9 @@ int make_map3(CUtensorMap* map, const void* ptr, int B, int L, long long row_ele
 }  // namespace
 
 int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H, float scale,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, float p_drop, unsigned long long seed) {
     CLIMB_REQUIRE(L <= 256, "attention_tc_fwd: L=%d > 256", L);
+    CLIMB_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "attention_tc_fwd: dropout p=%f outside [0, 1)", p_drop);
     CUtensorMap mq, mkv;
     int rc = make_map3(&mq, qkv, B, L, 3LL * H * kDh, 128);
     if (rc) return rc;
@@ -504,7 +518,8 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
     }
     dim3 grid((L + 127) / 128, H, B);
     attn_tc_fwd_kernel<<<grid, kThreads, FwdSmem::kTotal, stream>>>(mq, mkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, L,
-                                                               H, scale * kLog2e);
+                                                               H, scale * kLog2e, p_drop > 0.0f ? dropout_threshold(p_drop) : 0u,
+                                                               1.0f / (1.0f - p_drop), seed);
     CLIMB_LAUNCH_OK();
     return 0;
 }

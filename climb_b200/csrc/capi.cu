@@ -84,6 +84,11 @@ int climb_attention_fwd(const void* qkv, const float* key_bias, void* ctx, float
                         int H, float scale, void* stream) {
     return attention_fwd(qkv, key_bias, ctx, lse, B, L, H, scale, S(stream));
 }
+int climb_attention_fwd_dropout(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H,
+                                float scale, float p, uint64_t seed, void* stream) {
+    CLIMB_REQUIRE(qkv && ctx && lse && B > 0 && L > 0 && H > 0, "attention_fwd_dropout: bad arguments");
+    return attention_tc_fwd(qkv, key_bias, ctx, lse, B, L, H, scale, S(stream), p, seed);
+}
 int climb_attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx,
                         const float* lse, float* delta, void* dqkv, float* dqkv_colsum, int B, int L, int H,
                         float scale, void* stream) {
@@ -157,6 +162,19 @@ int climb_vilt_backward(const climb_vilt_dims* dims, const climb_vilt_params* pa
                         int last_layer, int parts, void* stream) {
     return vilt_backward(dims, params, batch, theta, shadow, workspace, workspace_bytes, scratch, scratch_bytes, dpooled,
                          grad, first_layer, last_layer, parts, S(stream));
+}
+
+int64_t climb_bert_forward_workspace_bytes(const climb_bert_dims* dims, const climb_bert_batch* batch) {
+    return bert_forward_workspace_bytes(dims, batch);
+}
+int climb_bert_forward(const climb_bert_dims* dims, const climb_bert_params* params, const climb_bert_batch* batch,
+                       const float* theta, const void* shadow, void* workspace, int64_t workspace_bytes,
+                       float hidden_dropout, float attn_dropout, uint64_t seed, float* last_hidden_state, void* stream) {
+    return bert_forward(dims, params, batch, theta, shadow, workspace, workspace_bytes, hidden_dropout, attn_dropout, seed,
+                        last_hidden_state, S(stream));
+}
+int climb_dropout_add(const float* x, const float* res, float* y, int64_t n, float p, uint64_t seed, void* stream) {
+    return dropout_add(x, res, y, n, p, seed, S(stream));
 }
 
 }  // extern "C"

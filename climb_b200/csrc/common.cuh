@@ -138,6 +138,32 @@ __device__ __forceinline__ float dswish_f(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Counter-based random numbers (Philox4x32-10): dropout masks are a pure function of (seed, element
+// index), so a backward pass -- or a test -- can regenerate them without storing anything.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(unsigned long long seed, unsigned long long counter) {
+    uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+    uint4 c = make_uint4(static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32), 0x636c696du, 0x62323030u);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+// keep-scale of one element: 0 if dropped, 1/(1-p) if kept; r = 32 random bits, thresh = p * 2^32
+__device__ __forceinline__ float dropout_scale(uint32_t r, uint32_t thresh, float inv_keep) {
+    return r >= thresh ? inv_keep : 0.0f;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+    const double t = static_cast<double>(p) * 4294967296.0;
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

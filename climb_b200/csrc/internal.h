@@ -28,7 +28,7 @@ int encode_tmap_bf16(void* map_out, const void* ptr, int rank, const long long* 
 
 // attention_tc.cu (tcgen05 / TMEM attention for L <= 256; attention.cu keeps the general-L kernels)
 int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H, float scale,
-                     cudaStream_t stream);
+                     cudaStream_t stream, float p_drop = 0.0f, unsigned long long seed = 0);
 int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
                      void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream);
 
@@ -68,6 +68,13 @@ int scale_inplace(float* x, long long n, float s, cudaStream_t stream);
 int adamw_step(float* theta, const float* grad, float* m, float* v, void* shadow_bf16, const climb_adamw_chunk* chunks_dev,
                int n_chunks, const float* group_lr, const float* group_wd, int n_groups, float beta1, float beta2,
                float eps, int step, cudaStream_t stream);
+
+// bert_engine.cu
+long long bert_forward_workspace_bytes(const climb_bert_dims* dims, const climb_bert_batch* batch);
+int bert_forward(const climb_bert_dims* dm, const climb_bert_params* pr, const climb_bert_batch* bt, const float* theta,
+                 const void* shadow, void* workspace, long long workspace_bytes, float hidden_dropout, float attn_dropout,
+                 unsigned long long seed, float* out, cudaStream_t s);
+int dropout_add(const float* x, const float* res, float* y, long long n, float p, unsigned long long seed, cudaStream_t s);
 
 // engine.cu
 long long vilt_forward_workspace_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,

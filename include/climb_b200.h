@@ -96,6 +96,10 @@ int climb_gemm_bf16(const climb_gemm_desc* desc, void* stream);
  * ------------------------------------------------------------------------------------------- */
 int climb_attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse,
                         int B, int L, int H, float scale, void* stream);
+/* forward with dropout on the attention probabilities (BertSelfAttention, modeling_bert.py:341-345):
+ * ctx = dropout(softmax(..), p) V; L <= 256. The mask is a pure function of (seed, b, h, query, key). */
+int climb_attention_fwd_dropout(const void* qkv, const float* key_bias, void* ctx, float* lse,
+                                int B, int L, int H, float scale, float p, uint64_t seed, void* stream);
 int climb_attention_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx,
                         const float* lse, float* delta, void* dqkv, float* dqkv_colsum,
                         int B, int L, int H, float scale, void* stream);
@@ -249,6 +253,49 @@ int climb_vilt_backward(const climb_vilt_dims* dims, const climb_vilt_params* pa
                         void* scratch, int64_t scratch_bytes,
                         const float* dpooled /* [B, hidden] */, float* grad,
                         int first_layer, int last_layer, int parts, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Frozen BERT text encoder of ViLT-BERT (src/modeling/viltbert.py:115-120 get_bert_outputs:
+ * BertModel(...).last_hidden_state under torch.no_grad(), fed to ViltModel as inputs_embeds :135-151).
+ * Post-LN encoder of adapter-transformers' modeling_bert.py: BertEmbeddings (:171-228), BertSelfAttention
+ * (:231-360), BertSelfOutput (:362-376), BertIntermediate (:430-442), BertOutput (:445-459).
+ * Forward only (the reference never differentiates through it). Offsets index the BERT parameter
+ * arena (theta fp32 / shadow bf16); q, k, v weights (and biases) of a layer are adjacent.
+ * hidden_dropout / attn_dropout > 0 reproduce the reference's train-mode behaviour (its BertModel keeps
+ * hidden_dropout_prob = attention_probs_dropout_prob = 0.1 active inside no_grad when the learner is in
+ * train mode) with a counter-based generator keyed by `seed`; 0 = eval mode = deterministic.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int hidden, layers, heads, ffn;
+    float ln_eps;
+} climb_bert_dims;
+
+typedef struct {
+    int64_t qkv_w, qkv_b, o_w, o_b, attn_ln_w, attn_ln_b, fc1_w, fc1_b, fc2_w, fc2_b, out_ln_w, out_ln_b;
+} climb_bert_layer;
+
+typedef struct {
+    int64_t word_emb, pos_emb, type_emb, emb_ln_w, emb_ln_b;
+    const climb_bert_layer* layer;      /* HOST array [dims.layers] */
+} climb_bert_params;
+
+typedef struct {
+    int B, T;
+    const int64_t* input_ids;           /* [B, T] */
+    const int64_t* token_type_ids;      /* [B, T] or NULL (= zeros) */
+    const int64_t* attention_mask;      /* [B, T] or NULL (= ones) */
+} climb_bert_batch;
+
+int64_t climb_bert_forward_workspace_bytes(const climb_bert_dims* dims, const climb_bert_batch* batch);
+int climb_bert_forward(const climb_bert_dims* dims, const climb_bert_params* params, const climb_bert_batch* batch,
+                       const float* theta, const void* shadow, void* workspace, int64_t workspace_bytes,
+                       float hidden_dropout, float attn_dropout, uint64_t seed,
+                       float* last_hidden_state /* [B, T, hidden] */, void* stream);
+
+/* y = dropout(x, p) (inverted scaling 1/(1-p)) + res (res may be NULL); x, res, y fp32 [n], y may alias x.
+ * Element i of stream `seed` is kept iff philox(seed, i) >= p: the mask is a pure function of (seed, i). */
+int climb_dropout_add(const float* x, const float* res, float* y, int64_t n, float p, uint64_t seed, void* stream);
 
 #ifdef __cplusplus
 }

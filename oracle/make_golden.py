@@ -14,7 +14,9 @@ What is exercised in the reference (no restatement on this side of the compariso
   * ViltModel (modeling_vilt.py) incl. visual_embed with its multinomial patch permutation;
   * the trainers' loss expressions (train_vqa.py:95,157; train_nlvr2.py:80,133) and autograd;
   * adapter-transformers' add_adapter / train_adapter / Stack forward for Houlsby and Pfeiffer;
-  * EWC.compute_ewc_loss and EWC.save_task_parameters (src/cl_algorithms/ewc.py:28-87).
+  * EWC.compute_ewc_loss and EWC.save_task_parameters (src/cl_algorithms/ewc.py:28-87);
+  * ViltBertContinualLearner / ViltBertEncoderWrapper (src/modeling/viltbert.py) with the vendored
+    BertModel (dropouts set to 0), and BertModel alone at bert-base geometry.
 """
 from __future__ import annotations
 
@@ -31,7 +33,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shim  # noqa: E402
-from oracle.vilt_oracle import (TASK_SPECS, ViltDims, synth_batch, synth_state_dict)  # noqa: E402
+from oracle.vilt_oracle import (TASK_SPECS, BertDims, ViltDims, bert_param_shapes, synth_batch, synth_bert_state_dict,  # noqa: E402
+                                synth_state_dict, synth_viltbert_state_dict)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
@@ -238,13 +241,111 @@ def run_ewc(seed, tag):
     print(f"{tag}: task={key} ewc_loss={loss.item():.6f}")
 
 
+TINY_BERT = BertDims(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=200,
+                     max_position_embeddings=16)
+
+
+def build_reference_viltbert(dims: ViltDims, bdims: BertDims, tasks, sd):
+    """ViltBertContinualLearner over ViltBertEncoderWrapper(processor, ViltModel, BertModel) (viltbert.py:31-57,
+    171-201). BertConfig dropouts are set to 0 so that the fixture is deterministic in train mode (the
+    reference leaves BERT's 0.1 dropouts live inside no_grad: a documented quirk, not a parity target)."""
+    from transformers import BertConfig, BertModel, ViltConfig, ViltModel
+    from modeling.viltbert import ViltBertContinualLearner, ViltBertEncoderWrapper
+    from configs.task_configs import task_configs
+    cfg = ViltConfig(hidden_size=dims.hidden_size, num_hidden_layers=dims.num_hidden_layers,
+                     num_attention_heads=dims.num_attention_heads, intermediate_size=dims.intermediate_size,
+                     image_size=dims.image_size, patch_size=dims.patch_size, vocab_size=dims.vocab_size,
+                     max_position_embeddings=dims.max_position_embeddings)
+    bcfg = BertConfig(hidden_size=bdims.hidden_size, num_hidden_layers=bdims.num_hidden_layers,
+                      num_attention_heads=bdims.num_attention_heads, intermediate_size=bdims.intermediate_size,
+                      vocab_size=bdims.vocab_size, max_position_embeddings=bdims.max_position_embeddings,
+                      type_vocab_size=bdims.type_vocab_size, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    enc = ViltBertEncoderWrapper(ref_shim.StubProcessor(), ViltModel(cfg), BertModel(bcfg), torch.device("cpu"))
+    learner = ViltBertContinualLearner(list(tasks), enc, dims.hidden_size, task_configs)
+    missing, unexpected = learner.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("position_ids" in m for m in missing), missing
+    return learner
+
+
+def run_viltbert(task, B, seed, tag, masked=True):
+    """ViLT-BERT (BASELINE.json config 5's encoder) on the tiny geometry: forward_single_image /
+    forward_multi_images / forward_multi_choice of viltbert.py:231-345, loss, backward."""
+    dims, bdims = TINY, TINY_BERT
+    sd = synth_viltbert_state_dict(dims, bdims, ALL_TASKS, seed=seed)
+    learner = build_reference_viltbert(dims, bdims, ALL_TASKS, sd)
+    learner.train()
+    learner.task_layer["vcr"][0].eval()
+    batch = synth_batch(task, B, dims, T=TINY_T, image_hw=TINY_HW, seed=seed, masked=masked)
+    enc_inputs = reference_inputs(task, batch)
+    learner.viltbert_encoder.process_inputs = lambda images, texts: dict(enc_inputs)
+    n = batch["pixel_values"].shape[0]
+    spec = TASK_SPECS[task]
+    images = [[None] * spec["num_images"]] * n if spec["num_images"] > 1 else [None] * n
+    texts = [[None] * spec["num_choices"]] * n if spec["model_type"] == "multi-choice" else [None] * n
+    torch.manual_seed(seed)
+    pooled, logits = learner(task_key=task, images=images, texts=texts)
+    if task == "vqa":
+        loss = torch.nn.BCEWithLogitsLoss(reduction="mean")(logits, batch["target"]) * batch["target"].shape[1]
+    else:
+        loss = torch.nn.CrossEntropyLoss()(logits, batch["target"])
+    loss.backward()
+    with torch.no_grad():           # the frozen BERT's features for the first text of every sample
+        ids = batch["input_ids"] if batch["input_ids"].dim() == 2 else batch["input_ids"][:, 0]
+        am = batch["attention_mask"] if batch["attention_mask"].dim() == 2 else batch["attention_mask"][:, 0]
+        tt = batch["token_type_ids"] if batch["token_type_ids"].dim() == 2 else batch["token_type_ids"][:, 0]
+        feats = learner.viltbert_encoder.get_bert_outputs(input_ids=ids, attention_mask=am, token_type_ids=tt)
+    out = dict(batch_arrays(batch), pooled=pooled.detach().numpy(), logits=logits.detach().numpy(), bert_hidden=feats.numpy(),
+               loss=np.float32(loss.item()), seed=np.int64(seed), task=task, B=np.int64(B), T=np.int64(TINY_T),
+               hw=np.array(TINY_HW), masked=np.int64(masked))
+    no_grad = []
+    for n_, p in learner.named_parameters():
+        if p.grad is None:
+            no_grad.append(n_)
+        else:
+            store_grad(out, n_, p.grad, True)
+    out["no_grad"] = np.array(no_grad)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"{tag}.npz"), **out)
+    print(f"{tag}: loss={loss.item():.6f} params without grad={len(no_grad)}")
+
+
+def run_bert_base(seed, tag):
+    """bert-base-uncased geometry (random init, eval mode): last_hidden_state of the unmodified BertModel on
+    a masked (B=2, T=40) batch, stored as a strided sample + norm."""
+    from transformers import BertConfig, BertModel
+    bdims = BertDims()
+    sd = synth_bert_state_dict(bdims, seed=seed, prefix="")
+    model = BertModel(BertConfig())
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in m for m in missing), (missing, unexpected)
+    model.eval()
+    batch = synth_batch("snli-ve", 2, ViltDims(), T=40, image_hw=(32, 32), seed=seed, masked=True)
+    with torch.no_grad():
+        h = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"],
+                  token_type_ids=batch["token_type_ids"]).last_hidden_state
+    out = {"in_input_ids": batch["input_ids"].numpy(), "in_attention_mask": batch["attention_mask"].numpy(),
+           "in_token_type_ids": batch["token_type_ids"].numpy(), "seed": np.int64(seed),
+           "hidden_norm": np.float32(h.norm().item()), "hidden_cls": h[:, 0].numpy(),
+           "hidden_sample": h.flatten().numpy()[grad_sample_index(h.numel())].copy()}
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"{tag}.npz"), **out)
+    print(f"{tag}: |h|={h.norm().item():.4f}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-base", action="store_true")
+    ap.add_argument("--only-viltbert", action="store_true", help="regenerate the ViLT-BERT fixtures only")
     a = ap.parse_args()
     ref_shim.install()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    run_viltbert("vcr", 3, 400, "tiny_viltbert_vcr")
+    run_viltbert("nlvr2", 3, 401, "tiny_viltbert_nlvr2")
+    run_viltbert("vqa", 3, 402, "tiny_viltbert_vqa")
+    if not a.skip_base:
+        run_bert_base(42, "base_bert_hidden")
+    if a.only_viltbert:
+        return
     for i, task in enumerate(ALL_TASKS):
         run_task(TINY, TINY_HW, TINY_T, task, B=3, seed=100 + i, tag=f"tiny_{task}", masked=True, full_grads=True)
     run_adapter("houlsby", "nlvr2", 4, 200, "tiny_adapter_houlsby_nlvr2")

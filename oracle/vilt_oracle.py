@@ -404,3 +404,134 @@ def synth_batch(task: str, B: int, dims: ViltDims, T: int = 40, image_hw: Tuple[
     else:
         batch["target"] = torch.randint(0, spec["num_labels"], (B,), generator=g)
     return batch
+
+
+# -------------------------------------------------------------------------------------------------
+# ViLT-BERT (src/modeling/viltbert.py): frozen BertModel -> inputs_embeds of ViltModel
+# -------------------------------------------------------------------------------------------------
+@dataclass
+class BertDims:
+    """The subset of BertConfig that shapes the arithmetic (defaults = bert-base-uncased)."""
+    hidden_size: int = 768
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    intermediate_size: int = 3072
+    vocab_size: int = 30522
+    max_position_embeddings: int = 512
+    type_vocab_size: int = 2
+    layer_norm_eps: float = 1e-12
+
+
+VB_ENC = "viltbert_encoder.vilt."
+VB_BERT = "viltbert_encoder.bert."
+
+
+def bert_param_shapes(b: BertDims, prefix: str = VB_BERT) -> "OrderedDict[str, Tuple[int, ...]]":
+    """Names / shapes of adapter-transformers' BertModel (modeling_bert.py:171-192, 231-262, 362-370, 430-453,
+    646-650), registration order."""
+    d, ff = b.hidden_size, b.intermediate_size
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    e = prefix + "embeddings."
+    s[e + "word_embeddings.weight"] = (b.vocab_size, d)
+    s[e + "position_embeddings.weight"] = (b.max_position_embeddings, d)
+    s[e + "token_type_embeddings.weight"] = (b.type_vocab_size, d)
+    s[e + "LayerNorm.weight"] = (d,)
+    s[e + "LayerNorm.bias"] = (d,)
+    for i in range(b.num_hidden_layers):
+        l = f"{prefix}encoder.layer.{i}."
+        for n in ("query", "key", "value"):
+            s[l + f"attention.self.{n}.weight"] = (d, d)
+            s[l + f"attention.self.{n}.bias"] = (d,)
+        s[l + "attention.output.dense.weight"] = (d, d)
+        s[l + "attention.output.dense.bias"] = (d,)
+        s[l + "attention.output.LayerNorm.weight"] = (d,)
+        s[l + "attention.output.LayerNorm.bias"] = (d,)
+        s[l + "intermediate.dense.weight"] = (ff, d)
+        s[l + "intermediate.dense.bias"] = (ff,)
+        s[l + "output.dense.weight"] = (d, ff)
+        s[l + "output.dense.bias"] = (d,)
+        s[l + "output.LayerNorm.weight"] = (d,)
+        s[l + "output.LayerNorm.bias"] = (d,)
+    s[prefix + "pooler.dense.weight"] = (d, d)
+    s[prefix + "pooler.dense.bias"] = (d,)
+    return s
+
+
+def synth_bert_state_dict(b: BertDims, seed: int = 42, prefix: str = VB_BERT) -> "OrderedDict[str, Tensor]":
+    sd: "OrderedDict[str, Tensor]" = OrderedDict()
+    for name, shape in bert_param_shapes(b, prefix).items():
+        g = torch.Generator().manual_seed(seed * 1_000_003 + _stable_hash(name))
+        if name.endswith("LayerNorm.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            t = 0.02 * torch.randn(shape, generator=g)
+        sd[name] = t.float()
+    return sd
+
+
+def synth_viltbert_state_dict(dims: ViltDims, b: BertDims, tasks: Sequence[str] = (), seed: int = 42):
+    """ViltBertContinualLearner state dict: the ViLT learner's tensors under `viltbert_encoder.vilt.` (same
+    values as synth_state_dict: the generator is keyed by the ViLT-learner name) + BERT + task heads."""
+    sd: "OrderedDict[str, Tensor]" = OrderedDict()
+    for k, v in synth_state_dict(dims, tasks, seed).items():
+        sd[VB_ENC + k[len(ENC):] if k.startswith(ENC) else k] = v
+    sd.update(synth_bert_state_dict(b, seed))
+    return sd
+
+
+def bert_forward(sd, b: BertDims, input_ids: Tensor, attention_mask: Optional[Tensor], token_type_ids: Optional[Tensor],
+                 prefix: str = VB_BERT) -> Tensor:
+    """BertModel.forward -> last_hidden_state in eval mode (dropout off): modeling_bert.py:918-1054;
+    BertEmbeddings :194-228, BertSelfAttention :265-360, BertSelfOutput :372-376 (post-LN),
+    BertIntermediate :439-442, BertOutput :455-459."""
+    d, H = b.hidden_size, b.num_attention_heads
+    dh = d // H
+    B, T = input_ids.shape
+    e = prefix + "embeddings."
+    if token_type_ids is None:
+        token_type_ids = torch.zeros(B, T, dtype=torch.long)
+    x = F.embedding(input_ids, sd[e + "word_embeddings.weight"]) + F.embedding(token_type_ids, sd[e + "token_type_embeddings.weight"])
+    x = x + sd[e + "position_embeddings.weight"][:T][None]
+    x = F.layer_norm(x, (d,), sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], b.layer_norm_eps)
+    if attention_mask is None:
+        attention_mask = torch.ones(B, T, dtype=torch.long)
+    ext = (1.0 - attention_mask.to(x.dtype))[:, None, None, :] * -10000.0          # modeling_utils.py:299-311
+    for i in range(b.num_hidden_layers):
+        l = f"{prefix}encoder.layer.{i}."
+        heads = lambda t: t.view(B, T, H, dh).permute(0, 2, 1, 3)
+        q = heads(F.linear(x, sd[l + "attention.self.query.weight"], sd[l + "attention.self.query.bias"]))
+        k = heads(F.linear(x, sd[l + "attention.self.key.weight"], sd[l + "attention.self.key.bias"]))
+        v = heads(F.linear(x, sd[l + "attention.self.value.weight"], sd[l + "attention.self.value.bias"]))
+        probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh) + ext, dim=-1)
+        ctx = (probs @ v).permute(0, 2, 1, 3).reshape(B, T, d)
+        a = F.linear(ctx, sd[l + "attention.output.dense.weight"], sd[l + "attention.output.dense.bias"])
+        x = F.layer_norm(a + x, (d,), sd[l + "attention.output.LayerNorm.weight"], sd[l + "attention.output.LayerNorm.bias"],
+                         b.layer_norm_eps)
+        inter = F.gelu(F.linear(x, sd[l + "intermediate.dense.weight"], sd[l + "intermediate.dense.bias"]))
+        o = F.linear(inter, sd[l + "output.dense.weight"], sd[l + "output.dense.bias"])
+        x = F.layer_norm(o + x, (d,), sd[l + "output.LayerNorm.weight"], sd[l + "output.LayerNorm.bias"], b.layer_norm_eps)
+    return x
+
+
+def viltbert_learner_forward(sd, dims: ViltDims, b: BertDims, task: str, batch: Dict[str, Tensor], spec: Optional[Dict] = None):
+    """ViltBertContinualLearner.forward on tensor inputs (src/modeling/viltbert.py:231-345): every encoder pass
+    first runs the frozen BERT under no_grad (:115-120, :145) and feeds its last_hidden_state to ViltModel as
+    inputs_embeds with input_ids = None (:146-149). Returns (pooled, logits)."""
+    spec = spec or TASK_SPECS[task]
+    vsd = {(ENC + k[len(VB_ENC):] if k.startswith(VB_ENC) else k): v for k, v in sd.items()}      # same tensors, ViLT names
+    ids, am, tt, px = batch["input_ids"], batch["attention_mask"], batch["token_type_ids"], batch["pixel_values"]
+
+    def enc(ids_, am_, tt_, px_, idx):
+        with torch.no_grad():
+            feats = bert_forward(sd, b, ids_, am_, tt_)
+        return vilt_forward(vsd, dims, None, am_, tt_, px_, idx, inputs_embeds=feats)
+
+    if spec["model_type"] == "multi-choice":
+        outs = [enc(ids[:, c], am[:, c], tt[:, c], px, 1) for c in range(spec["num_choices"])]
+        pooled = torch.stack(outs, dim=0).transpose(0, 1)
+    elif spec["num_images"] == 1:
+        pooled = enc(ids, am, tt, px, 1)
+    else:
+        outs = [enc(ids, am, tt, px[:, i], i + 1) for i in range(spec["num_images"])]
+        pooled = torch.cat(outs, dim=-1)
+    return pooled, task_head(vsd, task, pooled, spec)

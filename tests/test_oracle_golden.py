@@ -108,3 +108,53 @@ def test_base_config_matches_reference(task, seed, masked):
     assert abs(loss.item() - float(g["loss"])) <= 5e-6 * abs(float(g["loss"]))
     worst = compare_grads(g, grads, rtol_norm=2e-4, tol_elem=5e-4)
     print("worst grad", worst)
+
+
+TINY_BERT = vo.BertDims(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=200,
+                        max_position_embeddings=16)
+
+
+@pytest.mark.parametrize("task,seed", [("vcr", 400), ("nlvr2", 401), ("vqa", 402)])
+def test_tiny_viltbert_matches_reference(task, seed):
+    """ViLT-BERT (src/modeling/viltbert.py): frozen BERT features -> ViltModel(inputs_embeds=...)."""
+    g = load(f"tiny_viltbert_{task}")
+    batch = regen_batch(g, task, TINY, TINY_T, TINY_HW, 3, seed, True)
+    sd = vo.synth_viltbert_state_dict(TINY, TINY_BERT, ALL_TASKS, seed=seed)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    pooled, logits = vo.viltbert_learner_forward(params, TINY, TINY_BERT, task, batch)
+    loss = vo.task_loss(task, logits, batch["target"])
+    loss.backward()
+    assert np.allclose(pooled.detach().numpy(), g["pooled"], atol=2e-6)
+    assert np.allclose(logits.detach().numpy(), g["logits"], atol=5e-6)
+    assert abs(loss.item() - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    ids = batch["input_ids"] if batch["input_ids"].dim() == 2 else batch["input_ids"][:, 0]
+    am = batch["attention_mask"] if batch["attention_mask"].dim() == 2 else batch["attention_mask"][:, 0]
+    tt = batch["token_type_ids"] if batch["token_type_ids"].dim() == 2 else batch["token_type_ids"][:, 0]
+    with torch.no_grad():
+        feats = vo.bert_forward(sd, TINY_BERT, ids, am, tt)
+    assert np.allclose(feats.numpy(), g["bert_hidden"], atol=5e-6)
+    grads = {k: v.grad for k, v in params.items()}
+    # what the reference leaves without a gradient: all of BERT (no_grad), ViLT's word table (inputs_embeds path),
+    # the heads of the other tasks
+    no_grad = set(g["no_grad"].tolist())
+    assert all(n.startswith("viltbert_encoder.bert.") or n.endswith("text_embeddings.word_embeddings.weight")
+               or n.startswith("task_layer.") for n in no_grad)
+    for n in no_grad:
+        assert grads[n] is None, n
+    # VCR's near-uniform logits give gradients ~1e-5 of the weights' scale: fp32 summation order shows at 3e-4
+    worst = compare_grads(g, grads, rtol_norm=2e-4, tol_elem=5e-4)
+    print("worst grad", worst)
+
+
+def test_bert_base_matches_reference():
+    """bert-base geometry, eval mode: last_hidden_state of the vendored BertModel (random init)."""
+    from tests.golden_util import grad_sample_index
+    g = load("base_bert_hidden")
+    bd = vo.BertDims()
+    sd = vo.synth_bert_state_dict(bd, seed=int(g["seed"]), prefix="")
+    ids, am, tt = (torch.from_numpy(g[k]) for k in ("in_input_ids", "in_attention_mask", "in_token_type_ids"))
+    with torch.no_grad():
+        h = vo.bert_forward(sd, bd, ids, am, tt, prefix="")
+    assert abs(h.norm().item() - float(g["hidden_norm"])) <= 1e-5 * float(g["hidden_norm"])
+    assert np.allclose(h[:, 0].numpy(), g["hidden_cls"], atol=2e-5)
+    assert np.allclose(h.flatten().numpy()[grad_sample_index(h.numel())], g["hidden_sample"], atol=2e-5)
