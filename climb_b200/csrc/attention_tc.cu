@@ -205,7 +205,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tmem_ld_32x32(t_row + c * 32, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(r[j]), scale_log2, sBias[c * 32 + j]));
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sBias + c * 32 + j);
+                m = fmaxf(m, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), scale_log2, b4.x), fmaf(__uint_as_float(r[j + 1]), scale_log2, b4.y)),
+                                   fmaxf(fmaf(__uint_as_float(r[j + 2]), scale_log2, b4.z), fmaf(__uint_as_float(r[j + 3]), scale_log2, b4.w))));
+            }
         }
         sXmax[half * 128 + row] = m;
         softmax_bar_sync();
@@ -218,9 +222,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tmem_ld_wait();
             float p[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                p[j] = exp2f(fmaf(__uint_as_float(r[j]), scale_log2, sBias[c * 32 + j]) - m);
-                sum += p[j];
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sBias + c * 32 + j);
+                p[j] = ex2_ftz(fmaf(__uint_as_float(r[j]), scale_log2, b4.x - m));
+                p[j + 1] = ex2_ftz(fmaf(__uint_as_float(r[j + 1]), scale_log2, b4.y - m));
+                p[j + 2] = ex2_ftz(fmaf(__uint_as_float(r[j + 2]), scale_log2, b4.z - m));
+                p[j + 3] = ex2_ftz(fmaf(__uint_as_float(r[j + 3]), scale_log2, b4.w - m));
+                sum += (p[j] + p[j + 1]) + (p[j + 2] + p[j + 3]);
             }
             if (drop_thresh != 0u) {
                 // dropout on the probabilities (modeling_bert.py:341-345): the normaliser keeps every term, the
@@ -284,28 +292,57 @@ struct BwdSmem {
     static constexpr int kLse = 192 * 1024;      // 256 floats each
     static constexpr int kDelta = 193 * 1024;
     static constexpr int kBias = 194 * 1024;
-    static constexpr int kBar = 195 * 1024;
-    static constexpr int kTotal = 195 * 1024 + 128 + 1024;
+    static constexpr int kColV = 195 * 1024;     // 64 floats: column sums of dO (= of dV, see below)
+    static constexpr int kBar = 195 * 1024 + 256;
+    static constexpr int kStage = 196 * 1024;    // 8 x 2 KB output staging (its own region: a warp that runs ahead into
+                                                 // the next block rewrites P while slower warps still stage dK / dV)
+    static constexpr int kTotal = 196 * 1024 + 8 * 2048 + 1024;
 };
 // TMEM columns
 constexpr uint32_t kTS = 0, kTdP = 128, kTdV = 256, kTdK = 320, kTdQ = 384;
 
-__global__ void __launch_bounds__(kThreads, 1)
+// 16 elementwise warps (four per TMEM lane group, one 32-key chunk of the 128-key block each): the P / dS
+// phase sits between the two MMA phases of every block and nothing else can run meanwhile, so its latency
+// is the kernel's; the first 8 of them also drain the dK / dV / dQ accumulators.
+constexpr int kBwdEwWarps = 16;
+constexpr int kBwdEwThreads = kBwdEwWarps * 32;
+constexpr int kBwdOutThreads = 256;
+constexpr int kBwdCtlWarp = kBwdEwWarps;
+constexpr int kBwdThreads = kBwdEwThreads + 32;
+
+__device__ __forceinline__ void tmem_ld_32x16_a(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// Bias gradients of the q / k / v projections = column sums of dQ / dK / dV over all tokens:
+//   dV:  sum_keys dV = sum_q dO (sum_keys P) = sum_q dO     (softmax rows sum to one) -> reduced from the dO rows
+//        that the delta prologue reads anyway;
+//   dK:  sum_keys dK = scale * sum_q (sum_keys dS) Q = 0     (sum_keys dS = delta - delta): the key bias shifts
+//        every score of a row equally -- nothing is added (the reference's value is fp32 rounding noise);
+//   dQ:  no shortcut: column sums of the staged dQ tiles.
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                    const float* __restrict__ key_bias, const __nv_bfloat16* __restrict__ ctx,
                    const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int L, int H, float scale_log2,
                    float scale) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     float* sLse = reinterpret_cast<float*>(sm + BwdSmem::kLse);
     float* sDelta = reinterpret_cast<float*>(sm + BwdSmem::kDelta);
     float* sBias = reinterpret_cast<float*>(sm + BwdSmem::kBias);
+    float* sColV = reinterpret_cast<float*>(sm + BwdSmem::kColV);
     uint64_t* bar_load = reinterpret_cast<uint64_t*>(sm + BwdSmem::kBar);
     uint64_t* bar_a = bar_load + 1;      // S, dP of a block are in TMEM
-    uint64_t* bar_p = bar_load + 2;      // P, dS of a block are in smem (128 arrivals)
+    uint64_t* bar_p = bar_load + 2;      // P, dS of a block are in smem (kBwdEwThreads arrivals)
     uint64_t* bar_b = bar_load + 3;      // dV / dK / dQ chains of a block have retired
-    uint64_t* bar_kv = bar_load + 4;     // dV_j, dK_j have been read out of TMEM (128 arrivals)
+    uint64_t* bar_kv = bar_load + 4;     // dV_j, dK_j have been read out of TMEM (kBwdOutThreads arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -313,15 +350,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const long long ld = 3LL * H * kDh, ldo = static_cast<long long>(H) * kDh;
     const int n_jt = (L + 127) / 128;            // key / query tiles that contain real rows (1 or 2)
 
-    if (warp == kCtlWarp) {
+    float cv_keep[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cv_keep[e] = 0.0f;
+    if (warp == kBwdCtlWarp) {
         if (lane == 0) {
             tma_prefetch_desc(&map_qkv);
             tma_prefetch_desc(&map_do);
             mbar_init(bar_load, 1);
             mbar_init(bar_a, 1);
-            mbar_init(bar_p, kSoftmaxThreads);
+            mbar_init(bar_p, kBwdEwThreads);
             mbar_init(bar_b, 1);
-            mbar_init(bar_kv, kSoftmaxThreads);
+            mbar_init(bar_kv, kBwdOutThreads);
             fence_barrier_init();
             // loads go out first: they overlap TMEM allocation and the delta prologue of the other warps
             mbar_arrive_expect_tx(bar_load, 4 * 256 * kRowB);
@@ -330,6 +370,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kK, (H + h) * kDh, 0, b);
             tma_load_3d(&map_qkv, bar_load, sm + BwdSmem::kV, (2 * H + h) * kDh, 0, b);
         }
+        if (lane < 16) reinterpret_cast<float4*>(sColV)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
@@ -337,15 +378,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         // per-row scalars: lse (log2 domain; +inf past L makes P = 0 there), key mask, and
         // delta = rowsum(dO * O) with coalesced loads: 8 lanes x 16 B cover one 128 B row, 4 rows per warp access
         const long long stat = (static_cast<long long>(b) * H + h) * L;
-        {
+        if (threadIdx.x < 256) {
             const int r = threadIdx.x;
             sLse[r] = r < L ? lse[stat + r] * kLog2e : INFINITY;
             sBias[r] = r < L ? (key_bias ? key_bias[static_cast<long long>(b) * L + r] * kLog2e : 0.0f) : -INFINITY;
         }
         const int sub = lane & 7, rsel = lane >> 3;
+        float cv[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int r = warp * 32 + it * 4 + rsel;
+        for (int e = 0; e < 8; ++e) cv[e] = 0.0f;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int r = warp * 16 + it * 4 + rsel;
             float dl = 0.0f;
             if (r < L) {
                 const long long off = (static_cast<long long>(b) * L + r) * ldo + h * kDh + sub * 8;
@@ -357,6 +401,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                     const float2 x = unpack_bf16(av[e]), y = unpack_bf16(dv[e]);
                     dl = fmaf(x.x, y.x, dl);
                     dl = fmaf(x.y, y.y, dl);
+                    cv[2 * e] += y.x;
+                    cv[2 * e + 1] += y.y;
                 }
             }
             dl += __shfl_xor_sync(0xffffffffu, dl, 1);
@@ -364,14 +410,31 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             dl += __shfl_xor_sync(0xffffffffu, dl, 4);
             if (sub == 0) sDelta[r] = dl;
         }
+        if (colsum != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 8);
+                cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 16);
+                cv_keep[e] = cv[e];
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (warp != kBwdCtlWarp && colsum != nullptr) {
+        // v-bias gradient: warp partials (lanes 0..7 hold 8 columns each) -> CTA sums in smem -> 64 global atomics
+        if (lane < 8) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(sColV + lane * 8 + e, cv_keep[e]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kBwdEwThreads) : "memory");
+        if (threadIdx.x < 64) atomicAdd(colsum + 2 * H * kDh + h * kDh + threadIdx.x, sColV[threadIdx.x]);
+    }
     const uint32_t tmem = *tmem_slot;
     const int n_blocks = n_jt * n_jt;
 
-    if (warp == kCtlWarp) {
+    if (warp == kBwdCtlWarp) {
         if (lane == 0) {
             mbar_wait(bar_load, 0);
             tc_fence_after();
@@ -418,36 +481,52 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
         __syncwarp();
     } else {
-        const int lg = warp & 3, half = warp >> 2;          // TMEM lane group, column half
+        const int lg = warp & 3, quarter = warp >> 2;       // TMEM lane group, 32-key chunk of the block
         const int row = lg * 32 + lane;
         const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16);
-        uint8_t* stage = sm + BwdSmem::kP + warp * 2048;        // output staging (P is free whenever we use it)
+        const bool out_warp = warp < 8;                     // drains accumulators: lane group lg, column half (warp >> 2)
+        const int half = quarter & 1;
+        uint8_t* stage = sm + BwdSmem::kStage + (warp & 7) * 2048;
         for (int n = 0; n < n_blocks; ++n) {
             const int j = n / n_jt, i = n - j * n_jt;
             mbar_wait(bar_a, n & 1);
             tc_fence_after();
             if (n > 0) mbar_wait(bar_b, (n - 1) & 1);           // previous block's chains no longer read P / dS
             const float lse_r = sLse[i * 128 + row], dl_r = sDelta[i * 128 + row];
-#pragma unroll 1
-            for (int c = half * 2; c < half * 2 + 2; ++c) {
-                uint32_t rs[32], rd[32];
-                tmem_ld_32x32(t_row + kTS + c * 32, rs);
-                tmem_ld_32x32(t_row + kTdP + c * 32, rd);
-                tmem_ld_wait();
-                float p[32], ds[32];
+            const int c = quarter;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float pe = exp2f(fmaf(__uint_as_float(rs[e]), scale_log2, sBias[j * 128 + c * 32 + e]) - lse_r);
-                    p[e] = pe;
-                    ds[e] = pe * (__uint_as_float(rd[e]) - dl_r);
+            for (int hh = 0; hh < 2; ++hh) {                    // two 16-key halves: 32 accumulator registers live
+                uint32_t rs[16], rd[16];
+                tmem_ld_32x16_a(t_row + kTS + c * 32 + hh * 16, rs);
+                tmem_ld_32x16_a(t_row + kTdP + c * 32 + hh * 16, rd);
+                float bias[16];
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sBias + j * 128 + c * 32 + hh * 16 + e);
+                    bias[e] = b4.x - lse_r; bias[e + 1] = b4.y - lse_r; bias[e + 2] = b4.z - lse_r; bias[e + 3] = b4.w - lse_r;
                 }
-                store_row_chunk_bf16(sm + BwdSmem::kP, row, c, p);
-                store_row_chunk_bf16(sm + BwdSmem::kDS, row, c, ds);
+                tmem_ld_wait();
+                uint32_t pp[8], dd[8];
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    const float p0 = ex2_ftz(fmaf(__uint_as_float(rs[e]), scale_log2, bias[e]));
+                    const float p1 = ex2_ftz(fmaf(__uint_as_float(rs[e + 1]), scale_log2, bias[e + 1]));
+                    pp[e >> 1] = pack_bf16(p0, p1);
+                    dd[e >> 1] = pack_bf16(p0 * (__uint_as_float(rd[e]) - dl_r), p1 * (__uint_as_float(rd[e + 1]) - dl_r));
+                }
+                // 16 columns = granules (c & 1) * 4 + hh * 2 + {0, 1} of the row in 64-column chunk (c >> 1)
+                uint8_t* pc = sm + BwdSmem::kP + (c >> 1) * (128 * kRowB);
+                uint8_t* dc = sm + BwdSmem::kDS + (c >> 1) * (128 * kRowB);
+                const int g0 = (c & 1) * 4 + hh * 2;
+                *reinterpret_cast<uint4*>(pc + swz(row, g0)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+                *reinterpret_cast<uint4*>(pc + swz(row, g0 + 1)) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
+                *reinterpret_cast<uint4*>(dc + swz(row, g0)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+                *reinterpret_cast<uint4*>(dc + swz(row, g0 + 1)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
             }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar_p);
-            if (i == n_jt - 1) {
+            if (i == n_jt - 1 && out_warp) {
                 // dV_j, dK_j are complete once this block's chains retire; each warp converts 32 of the 64 columns
                 mbar_wait(bar_b, n & 1);
                 tc_fence_after();
@@ -465,29 +544,32 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                     for (int e = 0; e < 16; ++e)
                         pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
                     store_rows_32(stage, pk, dst + (which == 0 ? H * kDh : 2 * H * kDh), ld, rows_valid, lane);
-                    if (colsum) staged_colsum_32(stage, rows_valid, lane, colsum + (which == 0 ? H : 2 * H) * kDh + h * kDh + half * 32);
                 }
                 tc_fence_before();
                 mbar_arrive(bar_kv);
             }
         }
-        // dQ tiles: complete after the last block (its bar_b wait happened above)
-        for (int i = 0; i < n_jt; ++i) {
-            const int q0 = i * 128 + lg * 32;
-            const int rows_valid = min(32, max(0, L - q0));
-            uint32_t r[32], pk[16];
-            tmem_ld_32x32(t_row + kTdQ + i * 64 + half * 32, r);
-            tmem_ld_wait();
+        // dQ tiles: complete after the last block
+        if (out_warp) {
+            mbar_wait(bar_b, (n_blocks - 1) & 1);
+            tc_fence_after();
+            for (int i = 0; i < n_jt; ++i) {
+                const int q0 = i * 128 + lg * 32;
+                const int rows_valid = min(32, max(0, L - q0));
+                uint32_t r[32], pk[16];
+                tmem_ld_32x32(t_row + kTdQ + i * 64 + half * 32, r);
+                tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-                pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
-            store_rows_32(stage, pk, dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32, ld, rows_valid, lane);
-            if (colsum) staged_colsum_32(stage, rows_valid, lane, colsum + h * kDh + half * 32);
+                for (int e = 0; e < 16; ++e)
+                    pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
+                store_rows_32(stage, pk, dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32, ld, rows_valid, lane);
+                if (colsum) staged_colsum_32(stage, rows_valid, lane, colsum + h * kDh + half * 32);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kCtlWarp) {
+    if (warp == kBwdCtlWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
@@ -538,7 +620,7 @@ int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, co
         attr = true;
     }
     dim3 grid(H, B);
-    attn_tc_bwd_kernel<<<grid, kThreads, BwdSmem::kTotal, stream>>>(
+    attn_tc_bwd_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(
         mqkv, mdo, key_bias, static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx), lse,
         static_cast<__nv_bfloat16*>(dqkv), colsum, L, H, scale * kLog2e, scale);
     CLIMB_LAUNCH_OK();
