@@ -80,6 +80,9 @@ climb_layernorm_bwd = _sig(
     [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P])
 
 
+climb_layernorm_bwd_colsum = _sig(
+    "climb_layernorm_bwd_colsum",
+    [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P])
 climb_cast_f32_bf16 = _sig("climb_cast_f32_bf16", [_P, _P, c_int64, _P])
 climb_colsum = _sig("climb_colsum", [_P, c_int, c_int64, c_int, c_int, _P, _P])
 climb_bce_logits_loss = _sig(
@@ -283,7 +286,7 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows=None, ldx=None, out_bf16=True, ou
 
 
 def layernorm_bwd(dy, x, gamma, beta, mean, rstd, *, rows=None, ldx=None, dres=None, dx_f32=None,
-                  dx_bf16=None, dgamma=None, dbeta=None, act=EPI_NONE):
+                  dx_bf16=None, dgamma=None, dbeta=None, act=EPI_NONE, dx_colsum=None):
     d = gamma.numel()
     if rows is None:
         rows = mean.numel()
@@ -291,6 +294,11 @@ def layernorm_bwd(dy, x, gamma, beta, mean, rstd, *, rows=None, ldx=None, dres=N
         ldx = d
     dy_f32 = dy if dy.dtype == torch.float32 else None
     dy_b16 = dy if dy.dtype == torch.bfloat16 else None
+    if dx_colsum is not None:
+        check(climb_layernorm_bwd_colsum(ptr(dy_f32), ptr(dy_b16), ptr(x), ldx, ptr(gamma), ptr(beta), ptr(mean),
+                                         ptr(rstd), ptr(dres), ptr(dx_f32), ptr(dx_bf16), ptr(dgamma), ptr(dbeta),
+                                         ptr(dx_colsum), rows, d, act, stream()))
+        return
     check(climb_layernorm_bwd(ptr(dy_f32), ptr(dy_b16), ptr(x), ldx, ptr(gamma), ptr(beta), ptr(mean),
                               ptr(rstd), ptr(dres), ptr(dx_f32), ptr(dx_bf16), ptr(dgamma), ptr(dbeta),
                               rows, d, act, stream()))

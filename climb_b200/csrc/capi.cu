@@ -107,6 +107,13 @@ int climb_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x
     return layernorm_bwd(dy_f32, dy_bf16, x, ldx, gamma, beta, mean, rstd, dres, dx_f32, dx_bf16,
                          dgamma, dbeta, rows, d, act, S(stream));
 }
+int climb_layernorm_bwd_colsum(const float* dy_f32, const void* dy_bf16, const float* x, int64_t ldx,
+                               const float* gamma, const float* beta, const float* mean, const float* rstd,
+                               const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                               float* dx_colsum, int rows, int d, int act, void* stream) {
+    return layernorm_bwd(dy_f32, dy_bf16, x, ldx, gamma, beta, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, d,
+                         act, S(stream), dx_colsum);
+}
 
 
 int climb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {

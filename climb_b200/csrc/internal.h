@@ -19,7 +19,7 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
 int layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long long ldx,
                   const float* gamma, const float* beta, const float* mean, const float* rstd,
                   const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                  int rows, int d, int act, cudaStream_t stream);
+                  int rows, int d, int act, cudaStream_t stream, float* dx_colsum = nullptr);
 
 
 // tma_host.cu

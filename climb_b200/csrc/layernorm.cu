@@ -67,14 +67,14 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
     }
 }
 
-template <int NV>
+template <int NV, bool COLSUM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict__ dy_bf16,
               const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
               const float* __restrict__ beta, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const float* __restrict__ dres,
               float* __restrict__ dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int act) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows, int act) {
     constexpr int D = NV * 128;
     __shared__ float s_red[kWarpsPerBlock][128];     // one 128-column slab at a time
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,9 +83,17 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict_
 
     // Only the column accumulators stay in registers across the row: x and dy are read twice (the second
     // read hits L1/L2 -- a row is 4.5 KB) so that two CTAs fit per SM and more loads are in flight.
+    // dx_colsum (COLSUM): column sums of the OUTPUT dx (after the residual-gradient add) = the bias gradient of
+    // the Linear that produced this LayerNorm's input row stream (fc2 / attention-output dense): fused here
+    // instead of another 23 MB pass over dx. Its per-warp accumulators live in shared memory (a third register
+    // set would spill under the 128-register budget of two resident CTAs).
+    __shared__ float4 s_dc[COLSUM ? kWarpsPerBlock : 1][COLSUM ? NV * 32 : 1];
     float4 dg[NV], db[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV; ++i) {
+        dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (COLSUM) s_dc[warp][lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     auto load_dy = [&](int row, int i, const float4& xh, const float4& g) -> float4 {
         float4 dy;
@@ -142,6 +150,11 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict_
                 const float4 r = reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * ldx)[lane + 32 * i];
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
             }
+            if (COLSUM) {
+                float4 acc = s_dc[warp][lane + 32 * i];
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+                s_dc[warp][lane + 32 * i] = acc;
+            }
             if (dx_f32)
                 reinterpret_cast<float4*>(dx_f32 + static_cast<long long>(row) * ldx)[lane + 32 * i] = o;
             if (dx_bf16) {
@@ -153,6 +166,16 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict_
         }
     }
 
+    if (COLSUM) {
+        __syncthreads();
+        const float* flat = reinterpret_cast<const float*>(&s_dc[0][0]);
+        for (int c = threadIdx.x; c < D; c += kWarpsPerBlock * 32) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerBlock; ++w) acc += flat[w * D + c];
+            atomicAdd(dx_colsum + c, acc);
+        }
+    }
     if (dgamma == nullptr && dbeta == nullptr) return;
     // CTA reduction of the per-warp column partials, one 128-column slab at a time
 #pragma unroll
@@ -190,14 +213,24 @@ int launch_fwd(const float* x, long long ldx, const float* gamma, const float* b
 template <int NV>
 int launch_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long long ldx,
                const float* gamma, const float* beta, const float* mean, const float* rstd,
-               const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int rows,
+               const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int rows,
                int act, cudaStream_t stream) {
     int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int cap = 148 * 4;          // two resident CTAs per SM, two rounds; rows are grid-strided beyond that
     if (grid > cap) grid = cap;
-    ln_bwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-        dy_f32, static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres,
-        dx_f32, static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows, act);
+    if (dx_colsum != nullptr) {
+        if constexpr (NV <= 8) {
+            ln_bwd_kernel<NV, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+                dy_f32, static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres,
+                dx_f32, static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows, act);
+        } else {
+            CLIMB_REQUIRE(false, "layernorm_bwd: fused dx_colsum supports d <= 1024");
+        }
+    } else {
+        ln_bwd_kernel<NV, false><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
+            dy_f32, static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres,
+            dx_f32, static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows, act);
+    }
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -230,13 +263,14 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
 int layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long long ldx,
                   const float* gamma, const float* beta, const float* mean, const float* rstd,
                   const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                  int rows, int d, int act, cudaStream_t stream) {
+                  int rows, int d, int act, cudaStream_t stream, float* dx_colsum) {
+    CLIMB_REQUIRE(dx_colsum == nullptr || dx_f32 != nullptr || dx_bf16 != nullptr, "layernorm_bwd: dx_colsum needs a dx output");
     CLIMB_REQUIRE((dy_f32 != nullptr) != (dy_bf16 != nullptr), "layernorm_bwd: exactly one of dy_f32 / dy_bf16");
     CLIMB_REQUIRE(x && gamma && beta && mean && rstd, "layernorm_bwd: null pointer");
     CLIMB_REQUIRE(rows > 0, "layernorm_bwd: no rows");
     CLIMB_REQUIRE(d % 128 == 0 && ldx % 4 == 0, "layernorm_bwd: d=%d / ldx=%lld must be multiples of 128 / 4", d, ldx);
     CLIMB_REQUIRE(act == CLIMB_EPI_NONE || act == CLIMB_EPI_GELU, "layernorm_bwd: act must be NONE or GELU");
-#define ARGS (dy_f32, dy_bf16, x, ldx, gamma, beta, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, act, stream)
+#define ARGS (dy_f32, dy_bf16, x, ldx, gamma, beta, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, dx_colsum, rows, act, stream)
     switch (d / 128) {
         case 1: return launch_bwd<1> ARGS;
         case 2: return launch_bwd<2> ARGS;

@@ -123,6 +123,12 @@ int climb_layernorm_bwd(const float* dy_f32, const void* dy_bf16, const float* x
                         const float* gamma, const float* beta, const float* mean, const float* rstd,
                         const float* dres, float* dx_f32, void* dx_bf16,
                         float* dgamma, float* dbeta, int rows, int d, int act, void* stream);
+/* same, plus dx_colsum[d] += column sums of the output dx (nullable): the bias gradient of the Linear whose
+ * output row stream this LayerNorm normalised (fc2 / attention-output dense), fused into the pass */
+int climb_layernorm_bwd_colsum(const float* dy_f32, const void* dy_bf16, const float* x, int64_t ldx,
+                               const float* gamma, const float* beta, const float* mean, const float* rstd,
+                               const float* dres, float* dx_f32, void* dx_bf16,
+                               float* dgamma, float* dbeta, float* dx_colsum, int rows, int d, int act, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Streaming helpers

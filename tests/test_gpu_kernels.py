@@ -297,6 +297,14 @@ def test_layernorm_fwd_bwd(rows, d, eps, act):
     assert _rel_err(dxb, xr.grad + dres) < 4e-3
     assert _rel_err(dg, gr.grad) < 2e-5, _rel_err(dg, gr.grad)
     assert _rel_err(db, br.grad) < 2e-5
+    if d <= 1024:
+        # fused column sums of the output dx (= bias gradient of the Linear feeding this LayerNorm), accumulating
+        dx3 = torch.empty(rows, d, device="cuda")
+        cs = torch.ones(d, device="cuda")
+        dg3, db3 = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+        L.layernorm_bwd(dy, x, g, b, mean, rstd, dres=dres, dx_f32=dx3, dgamma=dg3, dbeta=db3, act=act, dx_colsum=cs)
+        assert torch.equal(dx3, dx) and _rel_err(dg3, gr.grad) < 2e-5
+        assert _rel_err(cs, 1.0 + (xr.grad + dres).sum(0)) < 2e-5, _rel_err(cs, 1.0 + (xr.grad + dres).sum(0))
     # bf16 dy path
     dx2 = torch.empty(rows, d, device="cuda")
     L.layernorm_bwd(dy.bfloat16(), x, g, b, mean, rstd, dx_f32=dx2, act=act)
