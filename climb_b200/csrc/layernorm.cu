@@ -76,7 +76,6 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict_
               float* __restrict__ dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows, int act) {
     constexpr int D = NV * 128;
-    __shared__ float s_red[kWarpsPerBlock][128];     // one 128-column slab at a time
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
@@ -177,25 +176,27 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict_
         }
     }
     if (dgamma == nullptr && dbeta == nullptr) return;
-    // CTA reduction of the per-warp column partials, one 128-column slab at a time
+    // CTA reduction of the per-warp column partials: shared-memory float atomics into one [2][D] accumulator
+    // (two barriers in total), then one global atomic per column per CTA
+    __shared__ float s_acc[2][D];
+    for (int c = threadIdx.x; c < 2 * D; c += kWarpsPerBlock * 32) (&s_acc[0][0])[c] = 0.0f;
+    __syncthreads();
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-        float* out = which == 0 ? dgamma : dbeta;
-        if (out == nullptr) continue;       // uniform across the CTA
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const float4 v = which == 0 ? dg[i] : db[i];
-            __syncthreads();
-            reinterpret_cast<float4*>(s_red[warp])[lane] = v;
-            __syncthreads();
-            if (threadIdx.x < 128) {
-                float acc = 0.0f;
-#pragma unroll
-                for (int w = 0; w < kWarpsPerBlock; ++w) acc += s_red[w][threadIdx.x];
-                // slab i holds columns (lane + 32 i) * 4 + {0..3} == i*128 + threadIdx.x
-                atomicAdd(out + i * 128 + threadIdx.x, acc);
-            }
+    for (int i = 0; i < NV; ++i) {
+        const int c0 = (lane + 32 * i) * 4;
+        if (dgamma) {
+            atomicAdd(&s_acc[0][c0], dg[i].x); atomicAdd(&s_acc[0][c0 + 1], dg[i].y);
+            atomicAdd(&s_acc[0][c0 + 2], dg[i].z); atomicAdd(&s_acc[0][c0 + 3], dg[i].w);
         }
+        if (dbeta) {
+            atomicAdd(&s_acc[1][c0], db[i].x); atomicAdd(&s_acc[1][c0 + 1], db[i].y);
+            atomicAdd(&s_acc[1][c0 + 2], db[i].z); atomicAdd(&s_acc[1][c0 + 3], db[i].w);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += kWarpsPerBlock * 32) {
+        if (dgamma) atomicAdd(dgamma + c, s_acc[0][c]);
+        if (dbeta) atomicAdd(dbeta + c, s_acc[1][c]);
     }
 }
 
@@ -216,7 +217,7 @@ int launch_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long lo
                const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int rows,
                int act, cudaStream_t stream) {
     int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int cap = 148 * 4;          // two resident CTAs per SM, two rounds; rows are grid-strided beyond that
+    const int cap = 148 * 2;          // persistent: two resident CTAs per SM, rows grid-strided, ONE reduction tail per CTA
     if (grid > cap) grid = cap;
     if (dx_colsum != nullptr) {
         if constexpr (NV <= 8) {
