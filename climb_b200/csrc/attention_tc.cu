@@ -140,6 +140,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    pdl_wait();
 
     float* sXmax = reinterpret_cast<float*>(sm + FwdSmem::kXchg);       // [2][128]
     float* sXsum = sXmax + 256;                                          // [2][128]
@@ -347,6 +348,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
+    pdl_wait();
     const long long ld = 3LL * H * kDh, ldo = static_cast<long long>(H) * kDh;
     const int n_jt = (L + 127) / 128;            // key / query tiles that contain real rows (1 or 2)
 
@@ -599,9 +601,9 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
         attr = true;
     }
     dim3 grid((L + 127) / 128, H, B);
-    attn_tc_fwd_kernel<<<grid, kThreads, FwdSmem::kTotal, stream>>>(mq, mkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, L,
-                                                               H, scale * kLog2e, p_drop > 0.0f ? dropout_threshold(p_drop) : 0u,
-                                                               1.0f / (1.0f - p_drop), seed);
+    CLIMB_CUDA_OK(launch_pdl(attn_tc_fwd_kernel, grid, dim3(kThreads), FwdSmem::kTotal, stream, mq, mkv, key_bias,
+                             static_cast<__nv_bfloat16*>(ctx), lse, L, H, scale * kLog2e,
+                             p_drop > 0.0f ? dropout_threshold(p_drop) : 0u, 1.0f / (1.0f - p_drop), seed));
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -620,9 +622,9 @@ int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, co
         attr = true;
     }
     dim3 grid(H, B);
-    attn_tc_bwd_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(
-        mqkv, mdo, key_bias, static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx), lse,
-        static_cast<__nv_bfloat16*>(dqkv), colsum, L, H, scale * kLog2e, scale);
+    CLIMB_CUDA_OK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(kBwdThreads), BwdSmem::kTotal, stream, mqkv, mdo, key_bias,
+                             static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx), lse,
+                             static_cast<__nv_bfloat16*>(dqkv), colsum, L, H, scale * kLog2e, scale));
     CLIMB_LAUNCH_OK();
     return 0;
 }

@@ -1,6 +1,7 @@
 // extern "C" surface of libclimb_b200.so (see include/climb_b200.h). Thin: argument plumbing and
 // the per-thread error string only; the kernels live in the sibling translation units.
 #include "common.cuh"
+#include <cstdlib>
 #include "internal.h"
 
 #include <cstdarg>
@@ -46,6 +47,13 @@ ProfScope::~ProfScope() {
 using namespace climb;
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+namespace climb {
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("CLIMB_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+}  // namespace climb
 
 extern "C" {
 

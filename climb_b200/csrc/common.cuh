@@ -138,6 +138,32 @@ __device__ __forceinline__ float dswish_f(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched through launch_pdl may be scheduled while the
+// previous kernel of the stream is still draining (its CTAs occupy the SMs that have gone idle in the
+// predecessor's last wave and run their prologue); it must execute pdl_wait() before it reads or
+// writes any global memory the predecessor touches. pdl_wait() is a no-op for ordinary launches.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();      // capi.cu: CLIMB_PDL=0 switches it off
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Counter-based random numbers (Philox4x32-10): dropout masks are a pure function of (seed, element
 // index), so a backward pass -- or a test -- can regenerate them without storing anything.
 // ---------------------------------------------------------------------------------------------

@@ -38,6 +38,7 @@ colsum_kernel(const T* __restrict__ src, long long ld, int rows, int cols, int r
     const int c0 = (blockIdx.x * 32 + lane) * VEC;
     const int r_begin = blockIdx.y * rows_per_cta;
     const int r_end = min(rows, r_begin + rows_per_cta);
+    pdl_wait();
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.0f;
@@ -206,9 +207,11 @@ int colsum(const void* src, int dtype, long long ld, int rows, int cols, float* 
     gy = (rows + rows_per_cta - 1) / rows_per_cta;
     dim3 grid(gx, gy);
     if (dtype == CLIMB_F32)
-        colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(src), ld, rows, cols, rows_per_cta, out);
+        CLIMB_CUDA_OK(launch_pdl(colsum_kernel<float>, grid, dim3(256), 0, stream, static_cast<const float*>(src), ld, rows, cols,
+                                 rows_per_cta, out));
     else
-        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), ld, rows, cols, rows_per_cta, out);
+        CLIMB_CUDA_OK(launch_pdl(colsum_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(src), ld,
+                                 rows, cols, rows_per_cta, out));
     CLIMB_LAUNCH_OK();
     return 0;
 }

@@ -382,6 +382,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // everything above overlapped the previous kernel's tail; operands / epilogue tensors come after
 
     const int tiles_mn = p.m_tiles * p.n_tiles;
     const int total_tiles = tiles_mn * p.split_k;
@@ -791,6 +792,7 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // everything above overlapped the previous kernel's tail; operands / epilogue tensors come after
 
     if (warp == 0) {
         if (lane == 0) producer_loop<BLOCK_N>(tmap_a, tmap_b, p, smem, full_bar, empty_bar, kStages);
@@ -1025,7 +1027,7 @@ int launch_gemm_t(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stre
     const int total = a.m_tiles * a.n_tiles * a.split_k;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
-    gemm_bf16_tcgen05_kernel<BLOCK_N, HAS_INPUT><<<grid, kNumThreads, smem_bytes, stream>>>(ta, tb, a);
+    CLIMB_CUDA_OK(launch_pdl(gemm_bf16_tcgen05_kernel<BLOCK_N, HAS_INPUT>, dim3(grid), dim3(kNumThreads), smem_bytes, stream, ta, tb, a));
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -1056,7 +1058,7 @@ int launch_fast(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
     const int total = a.m_tiles * a.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
-    gemm_fast_kernel<KIND><<<grid, kFastThreads, kFastSmemBytes, stream>>>(ta, tb, a);
+    CLIMB_CUDA_OK(launch_pdl(gemm_fast_kernel<KIND>, dim3(grid), dim3(kFastThreads), kFastSmemBytes, stream, ta, tb, a));
     CLIMB_LAUNCH_OK();
     return 0;
 }

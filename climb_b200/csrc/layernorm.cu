@@ -24,6 +24,7 @@ ln_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restric
     constexpr int D = NV * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kWarpsPerBlock + warp;
+    pdl_wait();
     if (row >= rows) return;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
     float4 v[NV];
@@ -79,6 +80,7 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
+    pdl_wait();
 
     // Only the column accumulators stay in registers across the row: x and dy are read twice (the second
     // read hits L1/L2 -- a row is 4.5 KB) so that two CTAs fit per SM and more loads are in flight.
@@ -205,8 +207,8 @@ int launch_fwd(const float* x, long long ldx, const float* gamma, const float* b
                void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int act,
                cudaStream_t stream) {
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    ln_fwd_kernel<NV><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-        x, ldx, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, act);
+    CLIMB_CUDA_OK(launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream, x, ldx, gamma, beta, eps,
+                             static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, act));
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -221,16 +223,16 @@ int launch_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long lo
     if (grid > cap) grid = cap;
     if (dx_colsum != nullptr) {
         if constexpr (NV <= 8) {
-            ln_bwd_kernel<NV, true><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-                dy_f32, static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres,
-                dx_f32, static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows, act);
+            CLIMB_CUDA_OK(launch_pdl(ln_bwd_kernel<NV, true>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream, dy_f32,
+                                     static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres, dx_f32,
+                                     static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows, act));
         } else {
             CLIMB_REQUIRE(false, "layernorm_bwd: fused dx_colsum supports d <= 1024");
         }
     } else {
-        ln_bwd_kernel<NV, false><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-            dy_f32, static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres,
-            dx_f32, static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows, act);
+        CLIMB_CUDA_OK(launch_pdl(ln_bwd_kernel<NV, false>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream, dy_f32,
+                                 static_cast<const __nv_bfloat16*>(dy_bf16), x, ldx, gamma, beta, mean, rstd, dres, dx_f32,
+                                 static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dx_colsum, rows, act));
     }
     CLIMB_LAUNCH_OK();
     return 0;
