@@ -129,7 +129,7 @@ class ViltBatchC(Structure):
     _fields_ = [("B", c_int), ("T", c_int), ("H", c_int), ("W", c_int),
                 ("input_ids", c_void_p), ("inputs_embeds", c_void_p), ("token_type_ids", c_void_p),
                 ("attention_mask", c_void_p), ("pixel_values", c_void_p), ("image_type_idx", c_void_p),
-                ("image_type_idx_scalar", c_int)]
+                ("image_type_idx_scalar", c_int), ("patch_geom", c_void_p), ("n_patch_slots", c_int)]
 
 
 class AdamWChunkC(Structure):

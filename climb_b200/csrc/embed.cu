@@ -111,6 +111,107 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
     reinterpret_cast<float4*>(x)[i] = make_float4(v.x + m.x, v.y + m.y, v.z + m.z, v.w + m.w);
 }
 
+// ---- variable resolution (ViltEmbeddings.visual_embed with padded images, modeling_vilt.py:121-205) ----------
+// geom[b] = (h_b, w_b): the valid patch rectangle of image b (top-left of the padded hp x wp grid). Image b's
+// valid patches occupy slots s = py * w_b + px < h_b * w_b of its Np slots in raster order; the remaining slots
+// are padding: zero pixels, no position embedding, masked out as attention keys. (The reference fills them with
+// randomly chosen masked patches and permutes the valid ones: every output CLiMB consumes is invariant to both.)
+__global__ void im2col_ragged_kernel(const float* __restrict__ px, const int* __restrict__ geom,
+                                     __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int Np) {
+    const int K = C * P * P;
+    const int k8 = K / 8;
+    const long long total = static_cast<long long>(B) * Np * k8;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long m = i / k8;
+    const int k0 = static_cast<int>(i - m * k8) * 8;
+    const int b = static_cast<int>(m / Np), slot = static_cast<int>(m - static_cast<long long>(b) * Np);
+    const int hb = geom[2 * b], wb = geom[2 * b + 1];
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (slot < hb * wb) {
+        const int py = slot / wb, pxi = slot - py * wb;
+        const int c = k0 / (P * P), rem = k0 - c * P * P, ky = rem / P, kx = rem - ky * P;
+        const float* src = px + ((static_cast<long long>(b) * C + c) * H + (py * P + ky)) * W + pxi * P + kx;
+        const float4 a = *reinterpret_cast<const float4*>(src);
+        const float4 e = *reinterpret_cast<const float4*>(src + 4);
+        o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(e.x, e.y); o.w = pack_bf16(e.z, e.w);
+    }
+    reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+__global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, const float* __restrict__ patch,
+                                             const int* __restrict__ geom, const float* __restrict__ cls,
+                                             const float* __restrict__ pos_emb, const float* __restrict__ mod,
+                                             const int* __restrict__ type_idx, int type_idx_scalar,
+                                             float* __restrict__ x, int B, int T, int Np, int G, int d4) {
+    const int L = T + 1 + Np;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * L * d4) return;
+    const long long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    const int b = static_cast<int>(row / L), l = static_cast<int>(row - static_cast<long long>(b) * L);
+    float4 v, m;
+    if (l < T) {
+        v = reinterpret_cast<const float4*>(text_ln)[(static_cast<long long>(b) * T + l) * d4 + c];
+        m = reinterpret_cast<const float4*>(mod)[c];
+    } else {
+        const int idx = type_idx ? type_idx[b] : type_idx_scalar;
+        m = reinterpret_cast<const float4*>(mod)[static_cast<long long>(idx) * d4 + c];
+        if (l == T) {
+            const float4 a = reinterpret_cast<const float4*>(cls)[c];
+            const float4 p0 = reinterpret_cast<const float4*>(pos_emb)[c];
+            v = make_float4(a.x + p0.x, a.y + p0.y, a.z + p0.z, a.w + p0.w);
+        } else {
+            const int slot = l - T - 1;
+            v = reinterpret_cast<const float4*>(patch)[(static_cast<long long>(b) * Np + slot) * d4 + c];
+            const int hb = geom[2 * b], wb = geom[2 * b + 1];
+            if (slot < hb * wb) {
+                const Taps t = bilinear_taps(slot / wb, slot % wb, hb, wb, G);
+                const float4* g = reinterpret_cast<const float4*>(pos_emb) + d4;      // skip row 0 (the [cls] position)
+                const float4 q00 = g[static_cast<long long>(t.i00) * d4 + c], q01 = g[static_cast<long long>(t.i01) * d4 + c];
+                const float4 q10 = g[static_cast<long long>(t.i10) * d4 + c], q11 = g[static_cast<long long>(t.i11) * d4 + c];
+                v.x += t.w00 * q00.x + t.w01 * q01.x + t.w10 * q10.x + t.w11 * q11.x;
+                v.y += t.w00 * q00.y + t.w01 * q01.y + t.w10 * q10.y + t.w11 * q11.y;
+                v.z += t.w00 * q00.z + t.w01 * q01.z + t.w10 * q10.z + t.w11 * q11.z;
+                v.w += t.w00 * q00.w + t.w01 * q01.w + t.w10 * q10.w + t.w11 * q11.w;
+            }
+        }
+    }
+    reinterpret_cast<float4*>(x)[i] = make_float4(v.x + m.x, v.y + m.y, v.z + m.z, v.w + m.w);
+}
+
+// d_pos[1 + g, :] += sum over images / valid slots of the transposed bilinear taps (per-image grids: no batch pre-sum)
+__global__ void pos_scatter_ragged_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ geom,
+                                              float* __restrict__ d_pos, int B, int T, int Np, int G, int d) {
+    const int L = T + 1 + Np;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * Np * d) return;
+    const long long m = i / d;
+    const int c = static_cast<int>(i - m * d);
+    const int b = static_cast<int>(m / Np), slot = static_cast<int>(m - static_cast<long long>(b) * Np);
+    const int hb = geom[2 * b], wb = geom[2 * b + 1];
+    if (slot >= hb * wb) return;
+    const float g = dx[(static_cast<long long>(b) * L + T + 1 + slot) * d + c];
+    const Taps t = bilinear_taps(slot / wb, slot % wb, hb, wb, G);
+    float* dp = d_pos + d;
+    if (t.w00 != 0.0f) atomicAdd(dp + static_cast<long long>(t.i00) * d + c, t.w00 * g);
+    if (t.w01 != 0.0f) atomicAdd(dp + static_cast<long long>(t.i01) * d + c, t.w01 * g);
+    if (t.w10 != 0.0f) atomicAdd(dp + static_cast<long long>(t.i10) * d + c, t.w10 * g);
+    if (t.w11 != 0.0f) atomicAdd(dp + static_cast<long long>(t.i11) * d + c, t.w11 * g);
+}
+
+// key_bias for padded images: text mask | 0 for [cls] | 0 for valid slots, -10000 for padding slots
+__global__ void key_bias_ragged_kernel(const long long* __restrict__ mask, const int* __restrict__ geom,
+                                       float* __restrict__ out, int B, int T, int L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * L) return;
+    const int b = i / L, j = i - b * L;
+    float v = 0.0f;
+    if (j < T) v = mask ? (1.0f - static_cast<float>(mask[static_cast<long long>(b) * T + j])) * -10000.0f : 0.0f;
+    else if (j > T) v = (j - T - 1) < geom[2 * b] * geom[2 * b + 1] ? 0.0f : -10000.0f;
+    out[i] = v;
+}
+
 // dx [B, L, d] -> dy_text fp32 [B*T, d] (input of the text LayerNorm backward) and
 //                 dpatch bf16 [B*Np, d] (A operand of the patch-projection wgrad)
 __global__ void embed_split_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dy_text,
@@ -158,10 +259,10 @@ __global__ void embed_reduce_bwd_kernel(const float* __restrict__ dx, const int*
 __global__ void embed_finalize_bwd_kernel(const float* __restrict__ S, float* __restrict__ d_cls,
                                           float* __restrict__ d_pos, float* __restrict__ d_mod,
                                           float* __restrict__ d_patch_bias, int n_mod, int T, int hp, int wp,
-                                          int G, int d) {
+                                          int G, int d, int ragged_np) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d) return;
-    const int Np = hp * wp, L = T + 1 + Np;
+    const int Np = ragged_np > 0 ? ragged_np : hp * wp, L = T + 1 + Np;
     const int per = (L + gridDim.y - 1) / gridDim.y;
     const int l0 = blockIdx.y * per, l1 = min(L, l0 + per);
     const float* S0 = S;
@@ -179,7 +280,7 @@ __global__ void embed_finalize_bwd_kernel(const float* __restrict__ S, float* __
             continue;
         }
         pb += g;
-        if (d_pos) {
+        if (d_pos && ragged_np == 0) {       // per-image grids: pos_scatter_ragged_bwd_kernel does the taps
             const int p = l - T - 1;
             const Taps t = bilinear_taps(p / wp, p % wp, hp, wp, G);
             float* dp = d_pos + d;
@@ -265,16 +366,51 @@ int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T,
     return 0;
 }
 
+int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int H, int W, int P, int Np, cudaStream_t stream) {
+    CLIMB_REQUIRE(px && geom && out && B > 0 && Np > 0, "im2col_ragged: bad arguments");
+    CLIMB_REQUIRE(P % 8 == 0 && H % P == 0 && W % P == 0, "im2col_ragged: H, W must be multiples of the patch size (%d x %d, P=%d)", H, W, P);
+    CLIMB_REQUIRE((reinterpret_cast<uintptr_t>(px) & 15) == 0 && W % 4 == 0, "im2col_ragged: pixel rows must be 16-byte aligned");
+    const long long total = static_cast<long long>(B) * Np * (C * P * P / 8);
+    im2col_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, geom, static_cast<__nv_bfloat16*>(out), B, C, H, W, P, Np);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int embed_assemble_ragged(const float* text_ln, const float* patch, const int* geom, const float* cls, const float* pos_emb,
+                          const float* mod, const int* type_idx, int type_idx_scalar, float* x, int B, int T, int Np, int G,
+                          int d, cudaStream_t stream) {
+    CLIMB_REQUIRE(text_ln && patch && geom && cls && pos_emb && mod && x && d % 4 == 0, "embed_assemble_ragged: bad arguments");
+    const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
+    embed_assemble_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, geom, cls, pos_emb, mod, type_idx,
+                                                                            type_idx_scalar, x, B, T, Np, G, d / 4);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
+int key_bias_ragged(const long long* mask, const int* geom, float* out, int B, int T, int L, cudaStream_t stream) {
+    CLIMB_REQUIRE(geom && out && B > 0 && T > 0 && L > T, "key_bias_ragged: bad arguments");
+    key_bias_ragged_kernel<<<(B * L + 255) / 256, 256, 0, stream>>>(mask, geom, out, B, T, L);
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
 int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, float* S, float* d_cls,
                      float* d_pos, float* d_mod, float* d_patch_bias, int n_mod, int B, int T, int hp, int wp,
-                     int G, int d, cudaStream_t stream) {
+                     int G, int d, cudaStream_t stream, const int* geom, int ragged_np) {
     CLIMB_REQUIRE(dx && S && d % 4 == 0, "embed_reduce_bwd: bad arguments");
-    const int L = T + 1 + hp * wp;
+    if (geom == nullptr) ragged_np = 0;
+    const int L = T + 1 + (ragged_np > 0 ? ragged_np : hp * wp);
     embed_reduce_bwd_kernel<<<blocks_for(static_cast<long long>(L) * (d / 4), 128), 128, 0, stream>>>(
         dx, type_idx, type_idx_scalar, S, B, T, L, d / 4);
     CLIMB_LAUNCH_OK();
-    embed_finalize_bwd_kernel<<<dim3(blocks_for(d, 128), 32), 128, 0, stream>>>(S, d_cls, d_pos, d_mod, d_patch_bias, n_mod, T, hp, wp, G, d);
+    embed_finalize_bwd_kernel<<<dim3(blocks_for(d, 128), 32), 128, 0, stream>>>(S, d_cls, d_pos, d_mod, d_patch_bias, n_mod, T, hp, wp, G, d,
+                                                                               ragged_np);
     CLIMB_LAUNCH_OK();
+    if (ragged_np > 0 && d_pos != nullptr) {
+        pos_scatter_ragged_bwd_kernel<<<blocks_for(static_cast<long long>(B) * ragged_np * d, 256), 256, 0, stream>>>(
+            dx, geom, d_pos, B, T, ragged_np, G, d);
+        CLIMB_LAUNCH_OK();
+    }
     return 0;
 }
 

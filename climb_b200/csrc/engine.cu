@@ -57,6 +57,7 @@ struct LayerAct {
 
 struct Plan {
     int B, T, Hh, Ww, hp, wp, Np, L, M, d, ff, heads, layers, Kp, r;
+    const int* geom;    // [B, 2] valid patch rows / cols per image (padded batches) or null
     // embeddings
     float* key_bias;    // [B, L]
     float* text_e;      // [B*T, d] pre-LN sum
@@ -86,6 +87,12 @@ int fill_plan(Plan& P, const climb_vilt_dims* dm, const climb_vilt_params* pr, c
                   bt->H, bt->W, dm->patch);
     P.B = bt->B; P.T = bt->T; P.Hh = bt->H; P.Ww = bt->W;
     P.hp = bt->H / dm->patch; P.wp = bt->W / dm->patch; P.Np = P.hp * P.wp;
+    P.geom = bt->patch_geom;
+    if (P.geom != nullptr) {
+        CLIMB_REQUIRE(bt->n_patch_slots > 0 && bt->n_patch_slots <= P.Np,
+                      "engine: n_patch_slots=%d outside (0, %d] for the padded %d x %d patch grid", bt->n_patch_slots, P.Np, P.hp, P.wp);
+        P.Np = bt->n_patch_slots;
+    }
     P.L = P.T + 1 + P.Np; P.M = P.B * P.L;
     P.d = dm->hidden; P.ff = dm->ffn; P.heads = dm->heads; P.layers = dm->layers;
     P.Kp = dm->channels * dm->patch * dm->patch;
@@ -280,23 +287,31 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
     const int d = P.d, M = P.M, BT = P.B * P.T;
 
     // ---- embeddings (modeling_vilt.py:207-246) ----
-    if (bt->attention_mask) TRY(key_bias(reinterpret_cast<const long long*>(bt->attention_mask), P.key_bias, P.B, P.T, P.L, s));
+    if (P.geom) TRY(key_bias_ragged(reinterpret_cast<const long long*>(bt->attention_mask), P.geom, P.key_bias, P.B, P.T, P.L, s));
+    else if (bt->attention_mask) TRY(key_bias(reinterpret_cast<const long long*>(bt->attention_mask), P.key_bias, P.B, P.T, P.L, s));
     else CLIMB_CUDA_OK(cudaMemsetAsync(P.key_bias, 0, sizeof(float) * P.B * P.L, s));
     TRY(text_gather(reinterpret_cast<const long long*>(bt->input_ids), bt->inputs_embeds,
                     reinterpret_cast<const long long*>(bt->token_type_ids), F(theta, pr->word_emb),
                     F(theta, pr->text_type_emb), F(theta, pr->text_pos_emb), P.text_e, BT, P.T, d, s));
     TRY(layernorm_fwd(P.text_e, d, F(theta, pr->text_ln_w), F(theta, pr->text_ln_b), dm->ln_eps, nullptr, P.text_ln,
                       P.text_mean, P.text_rstd, BT, d, CLIMB_EPI_NONE, s));
-    TRY(im2col(bt->pixel_values, P.im2col, P.B, dm->channels, P.Hh, P.Ww, dm->patch, s));
+    if (P.geom) TRY(im2col_ragged(bt->pixel_values, P.geom, P.im2col, P.B, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s));
+    else TRY(im2col(bt->pixel_values, P.im2col, P.B, dm->channels, P.Hh, P.Ww, dm->patch, s));
     {
         Lin l{P.B * P.Np, d, P.Kp, P.im2col, P.Kp, H(shadow, pr->patch_w)};
         l.bias = F(theta, pr->patch_b); l.C = P.patch_out; l.c_dtype = CLIMB_F32;
         TRY(run_linear(l, s));
     }
-    TRY(pos_interp(F(theta, pr->pos_emb), P.pos_table, P.hp, P.wp, dm->pos_grid, d, s));
-    TRY(embed_assemble(P.text_ln, P.patch_out, P.pos_table, F(theta, pr->cls_token), F(theta, pr->pos_emb),
-                       F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B, P.T,
-                       P.Np, d, s));
+    if (P.geom) {
+        TRY(embed_assemble_ragged(P.text_ln, P.patch_out, P.geom, F(theta, pr->cls_token), F(theta, pr->pos_emb),
+                                  F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B,
+                                  P.T, P.Np, dm->pos_grid, d, s));
+    } else {
+        TRY(pos_interp(F(theta, pr->pos_emb), P.pos_table, P.hp, P.wp, dm->pos_grid, d, s));
+        TRY(embed_assemble(P.text_ln, P.patch_out, P.pos_table, F(theta, pr->cls_token), F(theta, pr->pos_emb),
+                           F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B, P.T,
+                           P.Np, d, s));
+    }
 
     // ---- encoder layers (modeling_vilt.py:503-525) ----
     const float scale = 0.125f;   // 1 / sqrt(64)
@@ -491,7 +506,7 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
         TRY(embed_split_bwd(dx, S.dy_text, S.dpatch, P.B, P.T, P.Np, d, s));
         TRY(embed_reduce_bwd(dx, bt->image_type_idx, bt->image_type_idx_scalar, S.S, G(grad, pr->cls_token),
                              G(grad, pr->pos_emb), G(grad, pr->mod_emb), G(grad, pr->patch_b), dm->n_modality, P.B, P.T,
-                             P.hp, P.wp, dm->pos_grid, d, s));
+                             P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0));
         TRY(layernorm_bwd(S.dy_text, nullptr, P.text_e, d, F(theta, pr->text_ln_w), F(theta, pr->text_ln_b), P.text_mean,
                           P.text_rstd, nullptr, S.de_text, nullptr, G(grad, pr->text_ln_w), G(grad, pr->text_ln_b), BT, d,
                           CLIMB_EPI_NONE, s));

@@ -188,7 +188,7 @@ class B200ViltContinualLearner(ContinualLearner):
         rep = lambda t: t.repeat_interleave(num_images, dim=0)
         type_idx = (torch.arange(num_images, device=px.device, dtype=torch.int32) + 1).repeat(bs)
         pooled = self.vilt_encoder(input_ids=rep(ids), attention_mask=rep(am), token_type_ids=rep(tt),
-                                   pixel_values=px, pixel_mask=encodings.get('pixel_mask') if hasattr(encodings, 'get') else None,
+                                   pixel_values=px, pixel_mask=self._enc(encodings, 'pixel_mask'),
                                    image_token_type_idx=type_idx)
         pooled = pooled.view(bs, num_images * pooled.shape[-1])       # == torch.cat(pooler_outputs, dim=-1)
         return pooled, self.task_layer[task_key](pooled)
@@ -197,10 +197,11 @@ class B200ViltContinualLearner(ContinualLearner):
         """vilt.py:309-350, batched: sequence (b, c) = image b with text choice c."""
         px = encodings['pixel_values']
         bs = px.shape[0]
+        pm = self._enc(encodings, 'pixel_mask')
         pooled = self.vilt_encoder(input_ids=encodings['input_ids'], attention_mask=encodings['attention_mask'],
                                    token_type_ids=encodings['token_type_ids'],
                                    pixel_values=px.repeat_interleave(num_choices, dim=0),
-                                   pixel_mask=None)
+                                   pixel_mask=None if pm is None else pm.repeat_interleave(num_choices, dim=0))
         pooled = pooled.view(bs, num_choices, -1)                     # == stack(dim=0).transpose(0, 1)
         logits = self.task_layer[task_key](pooled).squeeze()
         return pooled, logits

@@ -373,7 +373,10 @@ class B200ViltModel(nn.Module):
         if C != c.num_channels or H % c.patch_size or W % c.patch_size:
             raise NotImplementedError(f"pixel_values {tuple(pixel_values.shape)}: the fixed-resolution path needs "
                                       f"{c.num_channels} channels and H, W multiples of {c.patch_size}")
-        self._check_pixel_mask(pixel_mask)
+        if c.max_image_length is not None and c.max_image_length > 0 and c.max_image_length < (H // c.patch_size) * (W // c.patch_size):
+            raise NotImplementedError("config.max_image_length > 0 makes the reference drop random patches of large images "
+                                      "(modeling_vilt.py:171-187); climb_b200 implements the default max_image_length = -1")
+        geom, n_slots = self._patch_geometry(pixel_mask, B, H, W, dev)
         pos_rows = self.embeddings.text_embeddings.position_embeddings.weight.shape[0]
         if T > pos_rows:
             raise ValueError(f"text length {T} exceeds the {pos_rows} text position embeddings")
@@ -414,6 +417,9 @@ class B200ViltModel(nn.Module):
         b.input_ids, b.inputs_embeds = _lib.ptr(ids), _lib.ptr(emb)
         b.token_type_ids, b.attention_mask = _lib.ptr(tt), _lib.ptr(am)
         b.pixel_values, b.image_type_idx, b.image_type_idx_scalar = _lib.ptr(px), _lib.ptr(idx_t), idx_s
+        if geom is not None:
+            keep.append(geom)
+        b.patch_geom, b.n_patch_slots = _lib.ptr(geom), n_slots
         call.batch = b
         call.trainable = st["trainable"]
         if emb is not None:      # with inputs_embeds the word table is not on the path (grad stays None)
@@ -421,31 +427,32 @@ class B200ViltModel(nn.Module):
         call.workspace, call.ws_bytes = None, 0
         return call
 
-    _MASK_MSG = ("padded images (pixel_mask with zeros) take the variable-resolution visual_embed path "
-                 "(modeling_vilt.py:149-193), which climb_b200 does not implement yet; resize the batch to one "
-                 "resolution")
-
-    def _check_pixel_mask(self, pixel_mask) -> None:
-        """pixel_mask must be all ones on this path. A CUDA mask is validated WITHOUT stalling the
-        stream: the verdict is copied to pinned memory and read once its event has completed (at the
-        latest on the next call), so an offending batch raises one call late instead of silently."""
-        pend = getattr(self, "_mask_check", None)
-        if pend is not None and pend[1].query():
-            self._mask_check = None
-            if int(pend[0].item()) != 0:
-                raise NotImplementedError(self._MASK_MSG)
+    def _patch_geometry(self, pixel_mask, B, H, W, dev):
+        """pixel_mask -> (geom int32 [B, 2] on the device, n_patch_slots) for padded batches, or (None, 0) when
+        every image fills the grid. As visual_embed (modeling_vilt.py:125-129): the mask is sampled at the patch
+        origins (nearest interpolation) and the valid rectangle is read off its first column / row.
+        A mask that lives on the HOST (what ViltProcessor returns before `.to(device)`) gives the reference's
+        exact sequence length (max_b h_b * w_b slots, :163-170) without any device synchronisation; a mask that
+        is already on the GPU is handled without reading it back: all (H/P) * (W/P) slots are kept and the
+        padding ones are masked -- same outputs, a few more masked rows."""
         if pixel_mask is None:
-            return
+            return None, 0
+        P = self.config.patch_size
+        if tuple(pixel_mask.shape) != (B, H, W):
+            raise ValueError(f"pixel_mask shape {tuple(pixel_mask.shape)} does not match pixel_values ({B}, {H}, {W})")
+        xm = pixel_mask[:, ::P, ::P]
+        h = (xm[:, :, 0] != 0).sum(dim=1)
+        w = (xm[:, 0, :] != 0).sum(dim=1)
+        geom = torch.stack([h, w], dim=1).to(torch.int32)
+        full = (H // P) * (W // P)
         if not pixel_mask.is_cuda:
-            if not bool((pixel_mask == 1).all()):
-                raise NotImplementedError(self._MASK_MSG)
-            return
-        if getattr(self, "_mask_check", None) is None:
-            flag = torch.empty(1, dtype=torch.int32, pin_memory=True)
-            flag.copy_((pixel_mask != 1).any().to(torch.int32).reshape(1), non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            self._mask_check = (flag, ev)
+            n = int((h * w).max())
+            if n == full and int((h * w).min()) == full:
+                return None, 0                       # no padding anywhere: the fixed-resolution path
+            if int((h * w).min()) <= 0:
+                raise ValueError("pixel_mask marks an image as entirely padding")
+            return geom.to(dev).contiguous(), n
+        return geom.contiguous(), full
 
     def _static_tables(self):
         """C structs that only change when the arena is rebuilt, the active adapter changes or a
@@ -589,5 +596,5 @@ class B200ViltModel(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k in ("_scratch", "grad_sync", "_static_cache", "_mask_check") else copy.deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_scratch", "grad_sync", "_static_cache") else copy.deepcopy(v, memo)
         return new

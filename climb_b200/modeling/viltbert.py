@@ -90,7 +90,7 @@ class B200ViltBertContinualLearner(B200ViltContinualLearner):
         type_idx = (torch.arange(num_images, device=px.device, dtype=torch.int32) + 1).repeat(bs)
         pooled = self.viltbert_encoder(input_ids=None, inputs_embeds=rep(feats), attention_mask=rep(am),
                                        token_type_ids=rep(tt), pixel_values=px,
-                                       pixel_mask=encodings.get('pixel_mask') if hasattr(encodings, 'get') else None,
+                                       pixel_mask=self._enc(encodings, 'pixel_mask'),
                                        image_token_type_idx=type_idx)
         pooled = pooled.view(bs, num_images * pooled.shape[-1])
         return pooled, self.task_layer[task_key](pooled)

@@ -229,6 +229,13 @@ typedef struct {
     const float* pixel_values;          /* [B, C, H, W] */
     const int32_t* image_type_idx;      /* [B] or NULL -> image_type_idx_scalar for every sequence */
     int image_type_idx_scalar;
+    /* Variable resolution (images padded to a common H x W, ViltEmbeddings.visual_embed modeling_vilt.py:121-205):
+     * patch_geom [B, 2] int32 = valid patch rows / columns (h_b, w_b) of every image = what the reference derives from
+     * pixel_mask (:126-129), n_patch_slots = patch rows per sequence (>= max_b h_b * w_b; the reference uses exactly the
+     * maximum, :163-170). Slots past h_b * w_b are padding: zero pixels, no position embedding, masked as attention keys.
+     * NULL / 0 = fixed resolution: every image fills the whole (H / patch) x (W / patch) grid. */
+    const int32_t* patch_geom;
+    int n_patch_slots;
 } climb_vilt_batch;
 
 /* bytes of the activation workspace a forward needs (save_for_backward = 1 keeps every layer's

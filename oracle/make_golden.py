@@ -33,7 +33,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shim  # noqa: E402
-from oracle.vilt_oracle import (TASK_SPECS, BertDims, ViltDims, bert_param_shapes, synth_batch, synth_bert_state_dict,  # noqa: E402
+from oracle.vilt_oracle import (TASK_SPECS, BertDims, ViltDims, bert_param_shapes, pad_batch_images, synth_batch,  # noqa: E402
+                                synth_bert_state_dict,
                                 synth_state_dict, synth_viltbert_state_dict)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
@@ -73,8 +74,9 @@ def reference_inputs(task, batch):
         px = px.flatten(0, 1)
     if spec["model_type"] == "multi-choice":
         ids, am, tt = ids.flatten(0, 1), am.flatten(0, 1), tt.flatten(0, 1)
-    return {"input_ids": ids, "attention_mask": am, "token_type_ids": tt, "pixel_values": px,
-            "pixel_mask": torch.ones(px.shape[0], px.shape[-2], px.shape[-1], dtype=torch.long)}
+    pm = batch.get("pixel_mask")
+    pm = torch.ones(px.shape[0], px.shape[-2], px.shape[-1], dtype=torch.long) if pm is None else pm.reshape(-1, *pm.shape[-2:])
+    return {"input_ids": ids, "attention_mask": am, "token_type_ids": tt, "pixel_values": px, "pixel_mask": pm}
 
 
 def reference_step(learner, task, batch):
@@ -123,7 +125,7 @@ def store_grad(out, name, g, full):
         out["gsample/" + name] = g.flatten().numpy()[grad_sample_index(g.numel())].copy()
 
 
-def run_task(dims, hw, T, task, B, seed, tag, masked, full_grads):
+def run_task(dims, hw, T, task, B, seed, tag, masked, full_grads, image_sizes=None):
     tasks = ALL_TASKS
     sd = synth_state_dict(dims, tasks, seed=seed)
     learner = build_reference_learner(dims, tasks, sd)
@@ -132,12 +134,16 @@ def run_task(dims, hw, T, task, B, seed, tag, masked, full_grads):
     # ViltConfig dropouts are 0.0): switched off so that the fixture is deterministic
     learner.task_layer["vcr"][0].eval()
     batch = synth_batch(task, B, dims, T=T, image_hw=hw, seed=seed, masked=masked)
+    if image_sizes is not None:       # images of different sizes padded to hw with pixel_mask zeros (visual_embed :149-193)
+        batch = pad_batch_images(batch, image_sizes)
     torch.manual_seed(seed)         # visual_embed's multinomial permutation
     pooled, logits, loss = reference_step(learner, task, batch)
     out = dict(batch_arrays(batch, store_pixels=full_grads), pooled=pooled.detach().numpy(),
                logits=logits.detach().numpy(),
                loss=np.float32(loss.item()), seed=np.int64(seed), task=task, B=np.int64(B), T=np.int64(T),
                hw=np.array(hw), masked=np.int64(masked))
+    if image_sizes is not None:
+        out["image_sizes"] = np.array(image_sizes)
     for n, p in learner.named_parameters():
         g = p.grad
         if g is None:
@@ -335,10 +341,24 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-base", action="store_true")
     ap.add_argument("--only-viltbert", action="store_true", help="regenerate the ViLT-BERT fixtures only")
+    ap.add_argument("--only-ragged", action="store_true", help="regenerate the padded-image (pixel_mask) fixtures only")
     a = ap.parse_args()
     ref_shim.install()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    # padded batches: images of different sizes (pixel_mask zeros), tiny geometry (patch 16, padded to 64 x 80 = 4 x 5
+    # patches) for single-image, image-pair and four-choice tasks, and the ViLT-base geometry (patch 32, 384 x 640)
+    run_task(TINY, (64, 80), TINY_T, "snli-ve", B=4, seed=500, tag="tiny_ragged_snli-ve", masked=True, full_grads=True,
+             image_sizes=[(64, 80), (48, 64), (32, 80), (64, 32)])
+    run_task(TINY, (64, 80), TINY_T, "nlvr2", B=3, seed=501, tag="tiny_ragged_nlvr2", masked=True, full_grads=True,
+             image_sizes=[(64, 80), (48, 48), (32, 64), (64, 48), (16, 80), (48, 80)])
+    run_task(TINY, (64, 80), TINY_T, "vcr", B=3, seed=502, tag="tiny_ragged_vcr", masked=True, full_grads=True,
+             image_sizes=[(48, 80), (64, 64), (32, 48)])
+    if not a.skip_base:
+        run_task(BASE, (384, 640), 40, "vqa", B=3, seed=44, tag="base_ragged_vqa", masked=True, full_grads=False,
+                 image_sizes=[(384, 640), (384, 512), (352, 576)])
+    if a.only_ragged:
+        return
     run_viltbert("vcr", 3, 400, "tiny_viltbert_vcr")
     run_viltbert("nlvr2", 3, 401, "tiny_viltbert_nlvr2")
     run_viltbert("vqa", 3, 402, "tiny_viltbert_vqa")

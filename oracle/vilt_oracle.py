@@ -203,14 +203,50 @@ def visual_embed_fixed(sd, pixel_values: Tensor, dims: ViltDims) -> Tensor:
     return torch.cat([cls, x], dim=1)
 
 
+def patch_geometry(pixel_mask: Tensor, patch_size: int) -> Tuple[Tensor, Tensor]:
+    """Valid patch rows / columns per image, modeling_vilt.py:125-129: the pixel mask is resized to the patch grid
+    by nearest interpolation (= sampled at the patch origins) and read along its first column / row."""
+    xm = pixel_mask[:, ::patch_size, ::patch_size]
+    return (xm[:, :, 0] != 0).sum(dim=1), (xm[:, 0, :] != 0).sum(dim=1)
+
+
+def visual_embed_ragged(sd, pixel_values: Tensor, pixel_mask: Tensor, dims: ViltDims) -> Tuple[Tensor, Tensor]:
+    """ViltEmbeddings.visual_embed for a batch padded to a common H x W (modeling_vilt.py:121-205, default
+    max_image_length = -1): every image keeps ALL its valid patches with the position table interpolated to
+    its own h_b x w_b grid (:132-147); shorter images are padded to max_b h_b * w_b rows whose mask is 0
+    (:163-189). The reference permutes the valid rows (multinomial) and fills the padding with randomly chosen
+    masked patches; the outputs CLiMB consumes are invariant to both, so the oracle keeps raster order and
+    zero padding rows. Returns ([B, 1 + n, d] embeddings, [B, 1 + n] mask)."""
+    e = ENC + "embeddings."
+    x = F.conv2d(pixel_values, sd[e + "patch_embeddings.projection.weight"],
+                 sd[e + "patch_embeddings.projection.bias"], stride=dims.patch_size)
+    B, d = x.shape[:2]
+    hs, ws = patch_geometry(pixel_mask, dims.patch_size)
+    n = int((hs * ws).max())
+    rows, masks = [], []
+    for b in range(B):
+        h, w = int(hs[b]), int(ws[b])
+        v = x[b, :, :h, :w].flatten(1).transpose(0, 1) + interpolated_position_table(sd, dims, h, w)     # [h*w, d]
+        pad = n - h * w
+        rows.append(torch.cat([v, v.new_zeros(pad, d)], dim=0))
+        masks.append(torch.cat([torch.ones(h * w), torch.zeros(pad)]))
+    x = torch.stack(rows, dim=0)
+    cls = sd[e + "cls_token"].expand(B, -1, -1) + sd[e + "position_embeddings"][:, :1, :]
+    return torch.cat([cls, x], dim=1), torch.cat([torch.ones(B, 1), torch.stack(masks, dim=0)], dim=1)
+
+
 def embeddings(sd, dims: ViltDims, input_ids, attention_mask, token_type_ids, pixel_values,
-               image_token_type_idx: int = 1, inputs_embeds=None) -> Tuple[Tensor, Tensor]:
+               image_token_type_idx: int = 1, inputs_embeds=None, pixel_mask=None) -> Tuple[Tensor, Tensor]:
     """ViltEmbeddings.forward, modeling_vilt.py:207-246: text || image with modality-type rows."""
     tt = sd[ENC + "embeddings.token_type_embeddings.weight"]
     text = text_embeddings(sd, input_ids, token_type_ids, dims, inputs_embeds) + tt[0]
-    image = visual_embed_fixed(sd, pixel_values, dims) + tt[image_token_type_idx]
-    masks = torch.cat([attention_mask.to(text.dtype),
-                       torch.ones(image.shape[:2], dtype=text.dtype)], dim=1)
+    if pixel_mask is not None and not bool((pixel_mask != 0).all()):
+        image, image_mask = visual_embed_ragged(sd, pixel_values, pixel_mask, dims)
+    else:
+        image = visual_embed_fixed(sd, pixel_values, dims)
+        image_mask = torch.ones(image.shape[:2], dtype=text.dtype)
+    image = image + tt[image_token_type_idx]
+    masks = torch.cat([attention_mask.to(text.dtype), image_mask.to(text.dtype)], dim=1)
     return torch.cat([text, image], dim=1), masks
 
 
@@ -267,10 +303,10 @@ def vilt_layer(sd, i: int, x: Tensor, ext_mask: Tensor, dims: ViltDims,
 
 def vilt_forward(sd, dims: ViltDims, input_ids, attention_mask, token_type_ids, pixel_values,
                  image_token_type_idx: int = 1, inputs_embeds=None,
-                 adapter: Optional[AdapterSpec] = None, return_hidden: bool = False):
+                 adapter: Optional[AdapterSpec] = None, return_hidden: bool = False, pixel_mask=None):
     """ViltModel.forward -> pooler_output, modeling_vilt.py:777-884, 887-899."""
     x, masks = embeddings(sd, dims, input_ids, attention_mask, token_type_ids, pixel_values,
-                          image_token_type_idx, inputs_embeds)
+                          image_token_type_idx, inputs_embeds, pixel_mask)
     ext = (1.0 - masks)[:, None, None, :] * -10000.0                   # modeling_utils.py:299-311
     for i in range(dims.num_hidden_layers):
         x = vilt_layer(sd, i, x, ext, dims, adapter)
@@ -300,17 +336,37 @@ def learner_forward(sd, dims: ViltDims, task: str, batch: Dict[str, Tensor],
     text choices over the same pixels (:334-349). Returns (pooled, logits)."""
     spec = spec or TASK_SPECS[task]
     ids, am, tt, px = batch["input_ids"], batch["attention_mask"], batch["token_type_ids"], batch["pixel_values"]
+    pm = batch.get("pixel_mask")          # [B, (n_img,) H, W] or absent (= all ones)
     if spec["model_type"] == "multi-choice":
-        outs = [vilt_forward(sd, dims, ids[:, c], am[:, c], tt[:, c], px, 1, adapter=adapter)
+        outs = [vilt_forward(sd, dims, ids[:, c], am[:, c], tt[:, c], px, 1, adapter=adapter, pixel_mask=pm)
                 for c in range(spec["num_choices"])]
         pooled = torch.stack(outs, dim=0).transpose(0, 1)
     elif spec["num_images"] == 1:
-        pooled = vilt_forward(sd, dims, ids, am, tt, px, 1, adapter=adapter)
+        pooled = vilt_forward(sd, dims, ids, am, tt, px, 1, adapter=adapter, pixel_mask=pm)
     else:
-        outs = [vilt_forward(sd, dims, ids, am, tt, px[:, i], i + 1, adapter=adapter)
+        outs = [vilt_forward(sd, dims, ids, am, tt, px[:, i], i + 1, adapter=adapter,
+                             pixel_mask=None if pm is None else pm[:, i])
                 for i in range(spec["num_images"])]
         pooled = torch.cat(outs, dim=-1)
     return pooled, task_head(sd, task, pooled, spec)
+
+
+def pad_batch_images(batch: Dict[str, Tensor], sizes: Sequence[Tuple[int, int]]) -> Dict[str, Tensor]:
+    """Turn a fixed-resolution synthetic batch into what ViltFeatureExtractor returns for images of different
+    sizes (feature_extraction_vilt.py:253-292): image k keeps its top-left sizes[k] = (H_k, W_k) pixels, the
+    rest is zero padding with pixel_mask = 0. sizes runs over the flattened images (B * n_img)."""
+    px = batch["pixel_values"]
+    flat = px.reshape(-1, *px.shape[-3:]).clone()
+    mask = torch.zeros(flat.shape[0], flat.shape[-2], flat.shape[-1], dtype=torch.long)
+    assert len(sizes) == flat.shape[0]
+    for k, (hk, wk) in enumerate(sizes):
+        flat[k, :, hk:, :] = 0
+        flat[k, :, :, wk:] = 0
+        mask[k, :hk, :wk] = 1
+    out = dict(batch)
+    out["pixel_values"] = flat.reshape(px.shape)
+    out["pixel_mask"] = mask.reshape(*px.shape[:-3], *px.shape[-2:])
+    return out
 
 
 def task_loss(task: str, logits: Tensor, target: Tensor) -> Tensor:

@@ -29,8 +29,12 @@ def grad_sample_index(numel):
 
 
 def regen_batch(g, task, dims, T, hw, B, seed, masked):
-    """Regenerate the synthetic batch and check it against what the reference was fed."""
+    """Regenerate the synthetic batch and check it against what the reference was fed. Fixtures with
+    `image_sizes` are padded batches (images of different sizes, pixel_mask zeros)."""
     batch = synth_batch(task, B, dims, T=T, image_hw=hw, seed=seed, masked=masked)
+    if "image_sizes" in g.files:
+        from oracle.vilt_oracle import pad_batch_images
+        batch = pad_batch_images(batch, [tuple(x) for x in g["image_sizes"].tolist()])
     for k in ("input_ids", "attention_mask", "token_type_ids", "target"):
         assert np.array_equal(g["in_" + k], batch[k].numpy()), k
     px = batch["pixel_values"].double()

@@ -59,17 +59,21 @@ def _encodings(task, batch, dev):
         px = px.flatten(0, 1)
     if spec["model_type"] == "multi-choice":
         ids, am, tt = ids.flatten(0, 1), am.flatten(0, 1), tt.flatten(0, 1)
-    enc = {"input_ids": ids, "attention_mask": am, "token_type_ids": tt, "pixel_values": px,
-           "pixel_mask": torch.ones(px.shape[0], px.shape[-2], px.shape[-1], dtype=torch.long)}
+    pm = batch.get("pixel_mask")
+    pm = torch.ones(px.shape[0], px.shape[-2], px.shape[-1], dtype=torch.long) if pm is None else pm.reshape(-1, *pm.shape[-2:])
+    enc = {"input_ids": ids, "attention_mask": am, "token_type_ids": tt, "pixel_values": px, "pixel_mask": pm}
     return {k: v.to(dev) for k, v in enc.items()}
 
 
-def _step(learner, task, batch, fused_loss=False):
+def _step(learner, task, batch, fused_loss=False, host_mask=False):
     dev = torch.device("cuda")
     learner.train()
     if "vcr" in learner.task_layer:
         learner.task_layer["vcr"][0].eval()           # as in the golden run: the head's Dropout(0.1) off
-    pooled, logits = learner.forward_tensors(task, _encodings(task, batch, dev))
+    enc = _encodings(task, batch, dev)
+    if host_mask:                                      # the processor's mask before .to(device): exact sequence length
+        enc["pixel_mask"] = enc["pixel_mask"].cpu()
+    pooled, logits = learner.forward_tensors(task, enc)
     target = batch["target"].to(dev)
     if fused_loss:
         from climb_b200 import ops
@@ -234,3 +238,52 @@ def test_grad_accumulation_and_zero_grad():
     _step(learner, "snli-ve", b2)
     g2 = p.grad.clone()
     assert _rel(g12, g1 + g2) < 1e-3
+
+
+@pytest.mark.parametrize("host_mask", [False, True])
+@pytest.mark.parametrize("tag,task,B,seed", [("tiny_ragged_snli-ve", "snli-ve", 4, 500), ("tiny_ragged_nlvr2", "nlvr2", 3, 501),
+                                              ("tiny_ragged_vcr", "vcr", 3, 502)])
+def test_tiny_padded_images_vs_reference_golden(tag, task, B, seed, host_mask):
+    """Variable-resolution visual_embed (modeling_vilt.py:121-205): images of different sizes padded to one
+    H x W with pixel_mask zeros. host_mask=True: the mask is still on the CPU (as ViltProcessor returns it) and the
+    sequence gets exactly max_b h_b * w_b patch rows like the reference; False: the mask is already on the GPU and
+    all grid slots are kept, the padding ones masked (no device read-back). Same outputs either way."""
+    g = load(tag)
+    batch = regen_batch(g, task, TINY, TINY_T, (64, 80), B, seed, True)
+    learner = _build(TINY, ALL_TASKS, vo.synth_state_dict(TINY, ALL_TASKS, seed=seed))
+    pooled, logits, loss = _step(learner, task, batch, host_mask=host_mask)
+    e_p, e_l = _rel(pooled, g["pooled"]), _rel(logits, g["logits"])
+    print(f"{tag} host_mask={host_mask}: pooled rel {e_p:.3e} logits rel {e_l:.3e} loss {loss.item():.6f} vs {float(g['loss']):.6f}")
+    assert e_p <= TOL_OUT and e_l <= TOL_OUT
+    assert abs(loss.item() - float(g["loss"])) <= TOL_OUT * abs(float(g["loss"]))
+    if task == "vcr":
+        ref_err = _autocast_reference_errors(vo.synth_state_dict(TINY, ALL_TASKS, seed=seed), TINY, task, batch)
+        _check_grads(g, learner, floor=1.0, per_tensor_tol={k: 1.25 * v for k, v in ref_err.items()})
+    else:
+        _check_grads(g, learner)
+
+
+def test_base_padded_images_vs_reference_golden():
+    g = load("base_ragged_vqa")
+    batch = regen_batch(g, "vqa", BASE, 40, (384, 640), 3, 44, True)
+    learner = _build(BASE, ALL_TASKS, vo.synth_state_dict(BASE, ALL_TASKS, seed=44))
+    pooled, logits, loss = _step(learner, "vqa", batch, fused_loss=True, host_mask=True)
+    e_p, e_l = _rel(pooled, g["pooled"]), _rel(logits, g["logits"])
+    print(f"base padded vqa: pooled rel {e_p:.3e} logits rel {e_l:.3e} loss {loss.item():.6f} vs {float(g['loss']):.6f}")
+    assert e_p <= TOL_OUT and e_l <= TOL_OUT
+    assert abs(loss.item() - float(g["loss"])) <= TOL_OUT * abs(float(g["loss"]))
+    _check_grads(g, learner)
+
+
+def test_all_ones_pixel_mask_takes_the_same_path_as_no_mask():
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=3)
+    learner = _build(TINY, ALL_TASKS, sd).eval()
+    batch = vo.synth_batch("snli-ve", 3, TINY, T=TINY_T, image_hw=TINY_HW, seed=8)
+    dev = torch.device("cuda")
+    enc = _encodings("snli-ve", batch, dev)
+    with torch.no_grad():
+        p_gpu_mask, _ = learner.forward_tensors("snli-ve", enc)                       # CUDA mask: ragged kernels, all slots valid
+        p_cpu_mask, _ = learner.forward_tensors("snli-ve", dict(enc, pixel_mask=enc["pixel_mask"].cpu()))   # -> fixed path
+        p_none, _ = learner.forward_tensors("snli-ve", {k: v for k, v in enc.items() if k != "pixel_mask"})
+    assert torch.equal(p_cpu_mask, p_none)
+    assert _rel(p_gpu_mask, p_none) < 1e-5

@@ -172,3 +172,31 @@ def test_optimizer_groups_reproduce_the_reference_quirk():
     assert opt.defaults["betas"] == (0.9, 0.98)
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: vo.linear_warmup_decay(s, 10, 100))
     assert isinstance(opt, torch.optim.Optimizer) and sched is not None
+
+
+def test_patch_geometry_from_pixel_mask():
+    """pixel_mask -> per-image valid patch rows / cols and the sequence's patch-slot count
+    (ViltEmbeddings.visual_embed, modeling_vilt.py:125-129,163-170), host-side, no kernels involved."""
+    import torch
+    from climb_b200.modeling import B200ViltConfig, B200ViltModel
+    from oracle.vilt_oracle import patch_geometry
+    m = B200ViltModel(B200ViltConfig(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256,
+                                     image_size=64, patch_size=32, vocab_size=50, max_position_embeddings=8))
+    B, H, W = 3, 96, 160
+    mask = torch.zeros(B, H, W, dtype=torch.long)
+    sizes = [(96, 160), (64, 96), (32, 160)]
+    for b, (h, w) in enumerate(sizes):
+        mask[b, :h, :w] = 1
+    geom, n = m._patch_geometry(mask, B, H, W, torch.device("cpu"))
+    assert geom.tolist() == [[3, 5], [2, 3], [1, 5]] and n == 15 and geom.dtype == torch.int32
+    hs, ws = patch_geometry(mask, 32)
+    assert hs.tolist() == [3, 2, 1] and ws.tolist() == [5, 3, 5]
+    # no padding anywhere -> fixed-resolution path
+    assert m._patch_geometry(torch.ones(B, H, W, dtype=torch.long), B, H, W, torch.device("cpu")) == (None, 0)
+    assert m._patch_geometry(None, B, H, W, torch.device("cpu")) == (None, 0)
+    # a batch whose largest image is smaller than the padded grid keeps only max(h * w) slots
+    mask2 = torch.zeros(2, H, W, dtype=torch.long)
+    mask2[0, :64, :128] = 1
+    mask2[1, :96, :64] = 1
+    geom2, n2 = m._patch_geometry(mask2, 2, H, W, torch.device("cpu"))
+    assert geom2.tolist() == [[2, 4], [3, 2]] and n2 == 8

@@ -158,3 +158,36 @@ def test_bert_base_matches_reference():
     assert abs(h.norm().item() - float(g["hidden_norm"])) <= 1e-5 * float(g["hidden_norm"])
     assert np.allclose(h[:, 0].numpy(), g["hidden_cls"], atol=2e-5)
     assert np.allclose(h.flatten().numpy()[grad_sample_index(h.numel())], g["hidden_sample"], atol=2e-5)
+
+
+RAGGED = [("tiny_ragged_snli-ve", "snli-ve", 4, 500), ("tiny_ragged_nlvr2", "nlvr2", 3, 501), ("tiny_ragged_vcr", "vcr", 3, 502)]
+
+
+@pytest.mark.parametrize("tag,task,B,seed", RAGGED)
+def test_tiny_padded_images_match_reference(tag, task, B, seed):
+    """Images of different sizes padded to a common H x W with pixel_mask zeros: the variable-resolution
+    visual_embed path (modeling_vilt.py:121-205) -- per-image position grids, masked padding rows."""
+    g = load(tag)
+    batch = regen_batch(g, task, TINY, TINY_T, (64, 80), B, seed, True)
+    assert "pixel_mask" in batch
+    assert np.array_equal(g["in_pixel_values"], batch["pixel_values"].numpy())
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=seed)
+    pooled, logits, loss, grads = _oracle_step(sd, TINY, task, batch)
+    assert np.allclose(pooled.detach().numpy(), g["pooled"], atol=2e-6)
+    assert np.allclose(logits.detach().numpy(), g["logits"], atol=5e-6)
+    assert abs(loss.item() - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    worst = compare_grads(g, grads, rtol_norm=2e-4, tol_elem=5e-4)
+    print("worst grad", worst)
+
+
+def test_base_padded_images_match_reference():
+    """ViLT-base geometry, 384 x 640 padded batch (12 x 20 patch grid) with three image sizes."""
+    g = load("base_ragged_vqa")
+    batch = regen_batch(g, "vqa", BASE, 40, (384, 640), 3, 44, True)
+    sd = vo.synth_state_dict(BASE, ALL_TASKS, seed=44)
+    torch.set_num_threads(8)
+    pooled, logits, loss, grads = _oracle_step(sd, BASE, "vqa", batch)
+    assert np.allclose(pooled.detach().numpy(), g["pooled"], atol=5e-6)
+    assert np.allclose(logits.detach().numpy(), g["logits"], atol=2e-5)
+    assert abs(loss.item() - float(g["loss"])) <= 5e-6 * abs(float(g["loss"]))
+    compare_grads(g, grads, rtol_norm=2e-4, tol_elem=5e-4)
