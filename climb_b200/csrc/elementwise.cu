@@ -43,10 +43,8 @@ colsum_kernel(const T* __restrict__ src, long long ld, int rows, int cols, int r
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.0f;
     if (c0 < cols) {
-        for (int r = r_begin + warp; r < r_end; r += 8) {
-            const T* p = src + static_cast<long long>(r) * ld + c0;
+        auto add = [&](const uint4& u) {
             if constexpr (sizeof(T) == 2) {
-                const uint4 u = *reinterpret_cast<const uint4*>(p);
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -55,10 +53,21 @@ colsum_kernel(const T* __restrict__ src, long long ld, int rows, int cols, int r
                     acc[2 * j + 1] += f.y;
                 }
             } else {
-                const float4 f = *reinterpret_cast<const float4*>(p);
-                acc[0] += f.x; acc[1] += f.y; acc[2] += f.z; acc[3] += f.w;
+                acc[0] += __uint_as_float(u.x); acc[1] += __uint_as_float(u.y);
+                acc[2] += __uint_as_float(u.z); acc[3] += __uint_as_float(u.w);
             }
+        };
+        const T* base = src + c0;
+        int r = r_begin + warp;
+        // four independent 128-bit loads in flight per lane (the kernel is a latency-bound streaming pass)
+        for (; r + 24 < r_end; r += 32) {
+            const uint4 u0 = *reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * ld);
+            const uint4 u1 = *reinterpret_cast<const uint4*>(base + static_cast<long long>(r + 8) * ld);
+            const uint4 u2 = *reinterpret_cast<const uint4*>(base + static_cast<long long>(r + 16) * ld);
+            const uint4 u3 = *reinterpret_cast<const uint4*>(base + static_cast<long long>(r + 24) * ld);
+            add(u0); add(u1); add(u2); add(u3);
         }
+        for (; r < r_end; r += 8) add(*reinterpret_cast<const uint4*>(base + static_cast<long long>(r) * ld));
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) s_part[warp][lane * VEC + j] = acc[j];

@@ -219,7 +219,7 @@ int launch_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long lo
                const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int rows,
                int act, cudaStream_t stream) {
     int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int cap = 148 * 2;          // persistent: two resident CTAs per SM, rows grid-strided, ONE reduction tail per CTA
+    const int cap = 148 * 4;          // two resident CTAs per SM, two rounds (measured: 45.8 us vs 50.1 us with one round of 296)
     if (grid > cap) grid = cap;
     if (dx_colsum != nullptr) {
         if constexpr (NV <= 8) {

@@ -24,6 +24,7 @@ import torch
 from . import _lib
 
 _CHUNK = 1 << 16
+_LOOSE_CHUNK = 1 << 13      # task heads are small tensors launched one by one: smaller chunks = enough CTAs to stream from HBM
 
 
 def _upload_chunks(chunks, device) -> torch.Tensor:
@@ -111,7 +112,7 @@ class ArenaAdamW(torch.optim.Optimizer):
             st = self.state[p]
             if not st or st.get("group") != gi:
                 n = p.numel()
-                chunks = [(o, min(_CHUNK, n - o), gi) for o in range(0, n, _CHUNK)]
+                chunks = [(o, min(_LOOSE_CHUNK, n - o), gi) for o in range(0, n, _LOOSE_CHUNK)]
                 st.setdefault("exp_avg", torch.zeros_like(p, memory_format=torch.contiguous_format))
                 st.setdefault("exp_avg_sq", torch.zeros_like(p, memory_format=torch.contiguous_format))
                 st.setdefault("step", 0)

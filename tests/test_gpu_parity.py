@@ -287,3 +287,41 @@ def test_all_ones_pixel_mask_takes_the_same_path_as_no_mask():
         p_none, _ = learner.forward_tensors("snli-ve", {k: v for k, v in enc.items() if k != "pixel_mask"})
     assert torch.equal(p_cpu_mask, p_none)
     assert _rel(p_gpu_mask, p_none) < 1e-5
+
+
+def test_long_sequence_path_vs_oracle():
+    """L = 8 + 1 + 16 * 16 = 265 > 256 tokens: the general-L attention kernels (attention.cu) inside the engine,
+    forward and backward, against the CPU oracle on fresh inputs (the language-only tasks' reallocate_text_image
+    regime, src/modeling/vilt.py:57-81)."""
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=21)
+    learner = _build(TINY, ALL_TASKS, sd)
+    batch = vo.synth_batch("snli-ve", 2, TINY, T=TINY_T, image_hw=(256, 256), seed=22, masked=True)
+    pooled, logits, loss = _step(learner, "snli-ve", batch)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_p, ref_l = vo.learner_forward(params, TINY, "snli-ve", batch)
+    ref_loss = vo.task_loss("snli-ve", ref_l, batch["target"])
+    ref_loss.backward()
+    assert _rel(pooled, ref_p) <= TOL_OUT and _rel(logits, ref_l) <= TOL_OUT
+    assert abs(loss.item() - ref_loss.item()) <= TOL_OUT * abs(ref_loss.item())
+    named = dict(learner.named_parameters())
+    gscale = max(v.grad.norm().item() for v in params.values() if v.grad is not None)
+    for name in ("vilt_encoder.vilt.encoder.layer.0.attention.attention.query.weight",
+                 "vilt_encoder.vilt.encoder.layer.1.intermediate.dense.weight",
+                 "vilt_encoder.vilt.embeddings.position_embeddings",
+                 "vilt_encoder.vilt.embeddings.patch_embeddings.projection.weight"):
+        ref_g = params[name].grad
+        err = (named[name].grad.float().cpu() - ref_g).norm().item() / max(ref_g.norm().item(), 0.02 * gscale)
+        assert err <= TOL_GRAD, (name, err)
+
+
+def test_single_sequence_batch_and_single_token_text():
+    """Smallest shapes: B = 1, and a text of one token (T = 1)."""
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=31)
+    learner = _build(TINY, ALL_TASKS, sd).eval()
+    dev = torch.device("cuda")
+    for B, T in ((1, TINY_T), (2, 1)):
+        batch = vo.synth_batch("snli-ve", B, TINY, T=T, image_hw=TINY_HW, seed=40 + T)
+        with torch.no_grad():
+            pooled, logits = learner.forward_tensors("snli-ve", _encodings("snli-ve", batch, dev))
+        ref_p, ref_l = vo.learner_forward(sd, TINY, "snli-ve", batch)
+        assert _rel(pooled, ref_p) <= TOL_OUT and _rel(logits.reshape(ref_l.shape), ref_l) <= TOL_OUT, (B, T)
