@@ -579,12 +579,15 @@ class B200ViltModel(nn.Module):
             sync.begin(arena)
             while first >= 0:
                 last = max(0, first - chunk + 1)
-                parts = (_lib.BWD_TAIL if first == n_layers - 1 else 0) | (_lib.BWD_EMBED if last == 0 else 0)
-                run(first, last, parts)
-                lo_elem = 0 if last == 0 else off[f"encoder.layer.{last}.attention.attention.query.weight"]
+                run(first, last, _lib.BWD_TAIL if first == n_layers - 1 else 0)
+                lo_elem = off[f"encoder.layer.{last}.attention.attention.query.weight"]
                 sync.reduce_range(arena, lo_elem, hi_elem)
                 hi_elem = lo_elem
                 first = last - 1
+            # the embeddings go last and alone: their all-reduce (the 94 MB word table dominates) is the only one
+            # with nothing left to hide behind, so the bottom layers' spans are already in flight when it starts
+            run(-1, 0, _lib.BWD_EMBED)
+            sync.reduce_range(arena, 0, hi_elem)
             arena.publish_grads(call.trainable)
             sync.finish(arena)
         call.workspace = None

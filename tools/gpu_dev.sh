@@ -27,6 +27,7 @@ for g in "$@"; do
     bench)    echo "=== bench" | tee -a gpurun_out/summary.txt; timeout 900 python bench.py --steps ${BENCH_STEPS:-10} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "exit=$?" | tee -a gpurun_out/summary.txt; tail -n 5 gpurun_out/bench.err | tee -a gpurun_out/summary.txt; cat gpurun_out/bench.json | tee -a gpurun_out/summary.txt ;;
     benchref) echo "=== benchref" | tee -a gpurun_out/summary.txt; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit=$?" | tee -a gpurun_out/summary.txt; cat gpurun_out/bench_ref.json | tee -a gpurun_out/summary.txt ;;
     launches) echo "=== launches" | tee -a gpurun_out/summary.txt; timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/one_step.py > gpurun_out/launches.log 2>&1; echo "exit=$? rows=$(wc -l < gpurun_out/launches.csv)" | tee -a gpurun_out/summary.txt ;;
+    launches_adapters) echo "=== launches_adapters" | tee -a gpurun_out/summary.txt; MODE=adapters timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_adapters.csv python tools/one_step.py > gpurun_out/launches_adapters.log 2>&1; echo "exit=$? rows=$(wc -l < gpurun_out/launches_adapters.csv)" | tee -a gpurun_out/summary.txt ;;
     ncu_gemm) echo "=== ncu_gemm" | tee -a gpurun_out/summary.txt; WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_bf16_tcgen05 -s 40 -c 4 -f -o gpurun_out/prof_gemm python tools/one_step.py > gpurun_out/ncu_gemm.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt ;;
     ncu_gemm_bwd) echo "=== ncu_gemm_bwd" | tee -a gpurun_out/summary.txt; WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_bf16_tcgen05 -s ${NCU_SKIP:-62} -c ${NCU_COUNT:-8} -f -o gpurun_out/prof_gemm_bwd python tools/one_step.py > gpurun_out/ncu_gemm_bwd.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt ;;
     ncu_fast) echo "=== ncu_fast" | tee -a gpurun_out/summary.txt; WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_fast -s ${NCU_SKIP:-20} -c ${NCU_COUNT:-4} -f -o gpurun_out/prof_fast python tools/one_step.py > gpurun_out/ncu_fast.log 2>&1
