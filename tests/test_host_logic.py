@@ -42,6 +42,11 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.AdamWChunkC) == 16
     assert ctypes.sizeof(_lib.ViltDimsC) == 9 * 4
     assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0
+    assert ctypes.sizeof(_lib.ViltBatchC) == 4 * 4 + 6 * 8 + 8 + 8 + 8      # ..., image_type_idx_scalar(+pad), patch_geom, n_patch_slots(+pad)
+    assert ctypes.sizeof(_lib.BertDimsC) == 5 * 4
+    assert ctypes.sizeof(_lib.BertLayerC) == 12 * 8
+    assert ctypes.sizeof(_lib.BertParamsC) == 5 * 8 + 8
+    assert ctypes.sizeof(_lib.BertBatchC) == 2 * 4 + 3 * 8
 
 
 def test_cpu_tensors_are_rejected_loudly():
@@ -200,3 +205,31 @@ def test_patch_geometry_from_pixel_mask():
     mask2[1, :96, :64] = 1
     geom2, n2 = m._patch_geometry(mask2, 2, H, W, torch.device("cpu"))
     assert geom2.tolist() == [[2, 4], [3, 2]] and n2 == 8
+
+
+def test_viltbert_state_dict_keys_and_registry():
+    """B200ViltBertContinualLearner: same checkpoint keys / shapes as src/modeling/viltbert.py's learner
+    (viltbert_encoder.vilt.*, viltbert_encoder.bert.*, task_layer.*), BERT without a gradient arena, registry entries."""
+    import torch
+    from climb_b200 import modeling as M
+    bd = vo.BertDims(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, vocab_size=200,
+                     max_position_embeddings=16)
+    cfg = M.B200ViltConfig(hidden_size=TINY.hidden_size, num_hidden_layers=TINY.num_hidden_layers,
+                           num_attention_heads=TINY.num_attention_heads, intermediate_size=TINY.intermediate_size,
+                           image_size=TINY.image_size, patch_size=TINY.patch_size, vocab_size=TINY.vocab_size,
+                           max_position_embeddings=TINY.max_position_embeddings)
+    bcfg = M.B200BertConfig(vocab_size=200, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                            max_position_embeddings=16)
+    enc = M.B200ViltBertEncoderWrapper(None, M.B200ViltModel(cfg), M.B200BertModel(bcfg), torch.device("cpu"))
+    learner = M.B200ViltBertContinualLearner(ALL_TASKS, enc, 128, vo.TASK_SPECS)
+    ref = vo.synth_viltbert_state_dict(TINY, bd, ALL_TASKS, seed=1)
+    sd = learner.state_dict()
+    assert set(ref) <= set(sd)
+    extra = set(sd) - set(ref)
+    assert all(k.endswith("position_ids") for k in extra), extra
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    assert learner.get_encoder() is enc and enc.bert._arena.with_grad is False
+    assert hasattr(learner, "create_optimizer") and hasattr(learner, "get_active_adapters")
+    assert set(M.load_encoder_map) == set(M.create_continual_learner_map) == {"vilt-b200", "viltbert-b200"}
+    assert M.model_configs["viltbert-b200"]["encoder_class"] is M.B200ViltBertEncoderWrapper
