@@ -723,11 +723,12 @@ __device__ __forceinline__ void store_unit(uint8_t* stg, const uint32_t (&w)[16]
         *reinterpret_cast<uint4*>(stg + swz128((lane * 4 + g) * 16)) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
     __syncwarp();
     const int rsub = lane >> 2;
+    uint4 val[4];                      // all four shared-memory reads in flight before the first global store
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const uint4 val = *reinterpret_cast<const uint4*>(stg + swz128((it * 32 + lane) * 16));
-        if (it * 8 + rsub < rows_valid) *reinterpret_cast<uint4*>(g_lane + it * step8_bytes) = val;
-    }
+    for (int it = 0; it < 4; ++it) val[it] = *reinterpret_cast<const uint4*>(stg + swz128((it * 32 + lane) * 16));
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+        if (it * 8 + rsub < rows_valid) *reinterpret_cast<uint4*>(g_lane + it * step8_bytes) = val[it];
 }
 // coalesced registers (4 granules per lane, rows lane>>2 + 8 it) -> thread = row registers
 __device__ __forceinline__ void transpose_unit_in(uint8_t* stg, const uint4 (&pf)[4], uint32_t (&w)[16], int lane) {

@@ -8,6 +8,8 @@ from .vilt import (B200ViltContinualLearner, B200ViltEncoderWrapper, convert_bat
                    create_vilt_continual_learner_model, load_vilt_encoder)
 from .vilt_model import AdapterSpec, B200ViltConfig, B200ViltModel
 from .bert_model import B200BertConfig, B200BertModel
+from .downstream import (B200ViltBertForMultipleChoice, B200ViltBertForSequenceClassification, B200ViltForImageClassification,
+                         B200ViltForMultipleChoice, B200ViltForSequenceClassification)
 from .viltbert import (B200ViltBertContinualLearner, B200ViltBertEncoderWrapper, convert_batch_to_viltbert_input_dict,
                        create_viltbert_continual_learner_model, load_viltbert_encoder)
 

@@ -325,3 +325,46 @@ def test_single_sequence_batch_and_single_token_text():
             pooled, logits = learner.forward_tensors("snli-ve", _encodings("snli-ve", batch, dev))
         ref_p, ref_l = vo.learner_forward(sd, TINY, "snli-ve", batch)
         assert _rel(pooled, ref_p) <= TOL_OUT and _rel(logits.reshape(ref_l.shape), ref_l) <= TOL_OUT, (B, T)
+
+
+def test_downstream_classifiers_vs_oracle():
+    """ViltForImageClassification / ViltForSequenceClassification / ViltForMultipleChoice (src/modeling/vilt.py:370-478):
+    encoder + head; the language-only ones broadcast ONE image over the batch, multiple choice is choice-major."""
+    import torch.nn.functional as F
+    from climb_b200.modeling import (B200ViltConfig, B200ViltEncoderWrapper, B200ViltForImageClassification,
+                                     B200ViltForMultipleChoice, B200ViltForSequenceClassification, B200ViltModel)
+    dev = torch.device("cuda")
+    sd = vo.synth_state_dict(TINY, [], seed=13)
+    cfg = B200ViltConfig(hidden_size=TINY.hidden_size, num_hidden_layers=TINY.num_hidden_layers,
+                         num_attention_heads=TINY.num_attention_heads, intermediate_size=TINY.intermediate_size,
+                         image_size=TINY.image_size, patch_size=TINY.patch_size, vocab_size=TINY.vocab_size,
+                         max_position_embeddings=TINY.max_position_embeddings)
+    vilt = B200ViltModel(cfg)
+    vilt.load_state_dict({k[len(vo.ENC):]: v for k, v in sd.items()}, strict=False)
+    enc = B200ViltEncoderWrapper(None, vilt, dev).to(dev)
+    batch = vo.synth_batch("snli-ve", 6, TINY, T=TINY_T, image_hw=TINY_HW, seed=14, masked=True)
+    ids, am, tt, px = (batch[k] for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values"))
+    to = lambda d: {k: v.to(dev) for k, v in d.items()}
+
+    def head_ref(m, pooled):
+        w = {k: v.detach().float().cpu() for k, v in m.clf_layer.state_dict().items()}
+        z = F.linear(pooled, w["0.weight"], w["0.bias"])
+        z = F.gelu(F.layer_norm(z, (z.shape[-1],), w["1.weight"], w["1.bias"], 1e-5))
+        return F.linear(z, w["3.weight"], w["3.bias"])
+
+    with torch.no_grad():
+        m = B200ViltForImageClassification(enc, TINY.hidden_size, 10).to(dev).eval()
+        got = m.forward_tensors(to(dict(input_ids=ids, attention_mask=am, token_type_ids=tt, pixel_values=px)))
+        ref = head_ref(m, vo.vilt_forward(sd, TINY, ids, am, tt, px))
+        assert _rel(got, ref) <= TOL_OUT
+        m = B200ViltForSequenceClassification(enc, TINY.hidden_size, 5).to(dev).eval()
+        got = m.forward_tensors(to(dict(input_ids=ids, attention_mask=am, token_type_ids=tt, pixel_values=px[:1],
+                                        pixel_mask=torch.ones(1, *px.shape[-2:], dtype=torch.long))))
+        ref = head_ref(m, vo.vilt_forward(sd, TINY, ids, am, tt, px[:1].expand(6, -1, -1, -1)))
+        assert _rel(got, ref) <= TOL_OUT
+        m = B200ViltForMultipleChoice(enc, TINY.hidden_size, 3).to(dev).eval()
+        got = m.forward_tensors(to(dict(input_ids=ids, attention_mask=am, token_type_ids=tt, pixel_values=px[:1])))
+        w = {k: v.detach().float().cpu() for k, v in m.clf_layer.state_dict().items()}
+        pooled = vo.vilt_forward(sd, TINY, ids, am, tt, px[:1].expand(6, -1, -1, -1))
+        ref = F.linear(pooled.view(3, -1, TINY.hidden_size).transpose(0, 1), w["1.weight"], w["1.bias"]).squeeze()
+        assert got.shape == (2, 3) and _rel(got, ref) <= TOL_OUT
