@@ -367,4 +367,7 @@ def test_downstream_classifiers_vs_oracle():
         w = {k: v.detach().float().cpu() for k, v in m.clf_layer.state_dict().items()}
         pooled = vo.vilt_forward(sd, TINY, ids, am, tt, px[:1].expand(6, -1, -1, -1))
         ref = F.linear(pooled.view(3, -1, TINY.hidden_size).transpose(0, 1), w["1.weight"], w["1.bias"]).squeeze()
-        assert got.shape == (2, 3) and _rel(got, ref) <= TOL_OUT
+        # a d -> 1 projection of a random-init pooled vector cancels to ~1e-2 of its terms: bound the error by the
+        # magnitude of what is summed, not by the (near-zero) result
+        scale = F.linear(pooled.abs(), w["1.weight"].abs()).max().item()
+        assert got.shape == (2, 3) and (got.float().cpu() - ref).abs().max().item() <= TOL_OUT * scale
