@@ -730,6 +730,23 @@ __device__ __forceinline__ void store_unit(uint8_t* stg, const uint32_t (&w)[16]
     for (int it = 0; it < 4; ++it)
         if (it * 8 + rsub < rows_valid) *reinterpret_cast<uint4*>(g_lane + it * step8_bytes) = val[it];
 }
+// same for 32 B per row (16 bf16 columns): 8 words per thread, two granules per row, 16 rows per iteration.
+// g_lane points at this lane's granule (lane & 1) of row (lane >> 1).
+__device__ __forceinline__ void store_unit_half(uint8_t* stg, const uint32_t (&w)[8], uint8_t* g_lane, long long step16_bytes,
+                                                int rows_valid, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+        *reinterpret_cast<uint4*>(stg + swz128((lane * 2 + g) * 16)) = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+    __syncwarp();
+    const int rsub = lane >> 1;
+    uint4 val[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) val[it] = *reinterpret_cast<const uint4*>(stg + swz128((it * 32 + lane) * 16));
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+        if (it * 16 + rsub < rows_valid) *reinterpret_cast<uint4*>(g_lane + it * step16_bytes) = val[it];
+}
 // coalesced registers (4 granules per lane, rows lane>>2 + 8 it) -> thread = row registers
 __device__ __forceinline__ void transpose_unit_in(uint8_t* stg, const uint4 (&pf)[4], uint32_t (&w)[16], int lane) {
     __syncwarp();
@@ -860,10 +877,29 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int j = 0; j < 16; j += 4) {
                             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + h * 16 + j));
-                            r[j] = __float_as_uint(__uint_as_float(r[j]) + b4.x + __uint_as_float(res[j]));
-                            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y + __uint_as_float(res[j + 1]));
-                            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z + __uint_as_float(res[j + 2]));
-                            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w + __uint_as_float(res[j + 3]));
+                            r[j] = __float_as_uint(__uint_as_float(r[j]) + b4.x);
+                            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
+                            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
+                            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
+                        }
+                        const int hsub = lane >> 1, hg = lane & 1;
+                        if (p.aux != nullptr) {          // bf16 copy of acc + bias (before the residual): adapter input
+                            uint32_t hw[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) hw[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                            uint8_t* a_lane = reinterpret_cast<uint8_t*>(p.aux) + (static_cast<long long>(row0) + hsub) * (p.ldaux * 2) +
+                                              static_cast<long long>(n0 + h * 16) * 2 + hg * 16;
+                            store_unit_half(stg, hw, a_lane, 16 * p.ldaux * 2, rows_valid, lane);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(res[j]));
+                        if (p.c2 != nullptr) {           // bf16 copy of the final value
+                            uint32_t hw[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) hw[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                            uint8_t* c2_lane = reinterpret_cast<uint8_t*>(p.c2) + (static_cast<long long>(row0) + hsub) * (p.ldc2 * 2) +
+                                               static_cast<long long>(n0 + h * 16) * 2 + hg * 16;
+                            store_unit_half(stg, hw, c2_lane, 16 * p.ldc2 * 2, rows_valid, lane);
                         }
                         store_unit(stg, r, c_lane + h * 64, 8 * c_pitch, rows_valid, lane);
                     }
@@ -1071,7 +1107,8 @@ inline bool aligned16(const void* p, long long pitch_bytes) {
 // which specialised kernel (if any) covers this problem; -1 = the generic kernel
 int fast_kind(const climb_gemm_desc* d) {
     if (d->block_n != 0 && d->block_n != kFastBlockN) return -1;
-    if (d->N % kFastBlockN != 0 || d->accumulate || d->split_k > 1 || d->c2 != nullptr || d->colsum != nullptr) return -1;
+    if (d->N % kFastBlockN != 0 || d->accumulate || d->split_k > 1 || d->colsum != nullptr) return -1;
+    if (d->c2 != nullptr && !(d->c_dtype == CLIMB_F32 && aligned16(d->c2, d->ldc2 * 2))) return -1;
     if (d->alpha != 0.0f && d->alpha != 1.0f) return -1;
     const long long tiles = 1LL * ((d->M + kBlockM - 1) / kBlockM) * (d->N / kFastBlockN);
     if (tiles < num_sms()) return -1;                     // small problems: the generic kernel's narrower tiles
@@ -1084,8 +1121,9 @@ int fast_kind(const climb_gemm_desc* d) {
         if (d->epilogue == CLIMB_EPI_MUL_AUX && d->bias == nullptr) return FK_MUL_AUX;
         return -1;
     }
-    if (d->c_dtype == CLIMB_F32 && d->epilogue == CLIMB_EPI_NONE && d->aux == nullptr && d->residual != nullptr &&
-        aligned16(d->C, d->ldc * 4) && aligned16(d->residual, d->ldr * 4))
+    // fp32 C = acc + bias + residual, optionally with bf16 copies of the pre-residual (aux) / final (c2) value
+    if (d->c_dtype == CLIMB_F32 && d->epilogue == CLIMB_EPI_NONE && d->residual != nullptr &&
+        (d->aux == nullptr || aligned16(d->aux, d->ldaux * 2)) && aligned16(d->C, d->ldc * 4) && aligned16(d->residual, d->ldr * 4))
         return FK_RES_F32;
     return -1;
 }

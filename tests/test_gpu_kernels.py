@@ -127,6 +127,16 @@ def test_gemm_fast_kinds(M, K):
     inplace = res.clone()
     L.gemm(a, b, inplace, residual=inplace)
     assert _rel_err(inplace, acc + res) < 1e-5
+    # ... with bf16 copies of the pre-residual (aux) and final (c2) values: the adapter sites
+    aux2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    c2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out2 = torch.empty(M, N, device="cuda")
+    L.gemm(a, b, out2, bias=bias, residual=res, aux=aux2, c2=c2)
+    assert torch.equal(out2, out)
+    assert _rel_err(aux2, acc + bias) < 4e-3 and _rel_err(c2, acc + bias + res) < 4e-3
+    inplace2, c2b = res.clone(), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(a, b, inplace2, residual=inplace2, c2=c2b)           # dgrad-down of an adapter: dx += dz Wd, bf16 copy refreshed
+    assert torch.equal(inplace2, inplace) and _rel_err(c2b, acc + res) < 4e-3
 
 
 def test_gemm_epilogues():
