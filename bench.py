@@ -151,7 +151,7 @@ def run_reference(args):
                                    "is Python under /root/reference, which does not exist on the GPU box"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -369,12 +369,27 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roofline, "attention_roofline": attn_roof, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    # Everything else that might reach stdout (NCCL prints its version banner there when NCCL_DEBUG is set, library
+    # chatter, warnings) is sent to stderr at the file-descriptor level, so stdout carries exactly one JSON line.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
