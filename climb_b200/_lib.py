@@ -51,6 +51,7 @@ class GemmDesc(Structure):
         ("accumulate", c_int),
         ("split_k", c_int),
         ("block_n", c_int),
+        ("independent", c_int),
     ]
 
 

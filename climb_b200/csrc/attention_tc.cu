@@ -349,6 +349,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
     pdl_wait();
+    // 768 CTAs on 148 SMs = 5.19 waves: once the last CTA has started, the next kernel of the stream may be
+    // scheduled onto the SMs the final partial wave leaves idle (it still waits for this grid unless it was
+    // declared independent: the attention-output wgrad is)
+    pdl_launch_dependents();
     const long long ld = 3LL * H * kDh, ldo = static_cast<long long>(H) * kDh;
     const int n_jt = (L + 127) / 128;            // key / query tiles that contain real rows (1 or 2)
 

@@ -53,6 +53,13 @@ bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("CLIMB_PDL"); return !(e && e[0] == '0'); }();
     return on;
 }
+static bool g_pdl_fence = false;
+void pdl_fence_next() { g_pdl_fence = true; }
+bool pdl_take_fence() {
+    const bool f = g_pdl_fence;
+    g_pdl_fence = false;
+    return f;
+}
 }  // namespace climb
 
 extern "C" {

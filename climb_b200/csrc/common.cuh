@@ -145,7 +145,13 @@ __device__ __forceinline__ float dswish_f(float x) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 bool pdl_enabled();      // capi.cu: CLIMB_PDL=0 switches it off
+// the next launch_pdl() on any stream is issued WITHOUT the programmatic attribute = an ordinary stream barrier
+// (needed after a kernel that skipped its pdl_wait: its completion does not imply its predecessor's)
+void pdl_fence_next();
+bool pdl_take_fence();
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -159,7 +165,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && !pdl_take_fence()) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -191,7 +191,7 @@ int run_dgrad(int M, int N, int K, const bf16* dY, const bf16* W, void* dX, int 
 
 // dW[N, K] += dY[M, N]^T * X[M, K]; both operands read in place (MN-major), split over tokens
 int run_wgrad(int M, int N, int K, const bf16* dY, long long lddy, const bf16* X, long long ldx, float* dW,
-              cudaStream_t s) {
+              cudaStream_t s, int independent = 0) {
     climb_gemm_desc g;
     std::memset(&g, 0, sizeof(g));
     g.M = N; g.N = K; g.K = M;
@@ -199,6 +199,7 @@ int run_wgrad(int M, int N, int K, const bf16* dY, long long lddy, const bf16* X
     g.B = X; g.ldb = ldx; g.b_mn_major = 1;
     g.C = dW; g.ldc = K; g.c_dtype = CLIMB_F32;
     g.alpha = 1.0f; g.accumulate = 1; g.split_k = 0;
+    g.independent = independent;
     return gemm_bf16(&g, s);
 }
 
@@ -486,13 +487,15 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             dho = S.dmh;
         }
         TRY(run_dgrad(M, d, d, dho, H(shadow, w.o_w), S.dh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, nullptr, nullptr, s));   // dctx
-        if (base) {
-            TRY(run_wgrad(M, d, d, dho, d, a.ctx, d, G(grad, w.o_w), s));
-            TRY(colsum(dho, CLIMB_BF16, d, M, d, G(grad, w.o_b), s));
-        }
         // the q/k/v bias gradient (column sums of dqkv) comes out of the attention backward's epilogue
         TRY(attention_bwd(a.qkv, P.key_bias, a.ctx, S.dh, a.lse, S.delta, S.dqkv, base ? G(grad, w.qkv_b) : nullptr, P.B,
                           P.L, P.heads, 0.125f, s));
+        if (base) {
+            // dW_o = dho^T ctx depends on nothing the attention backward writes: issued right behind it as an
+            // INDEPENDENT launch, its CTAs fill the SMs that kernel's last partial wave leaves idle
+            TRY(run_wgrad(M, d, d, dho, d, a.ctx, d, G(grad, w.o_w), s, /*independent=*/1));
+            TRY(colsum(dho, CLIMB_BF16, d, M, d, G(grad, w.o_b), s));
+        }
         if (base) TRY(run_wgrad(M, 3 * d, d, S.dqkv, 3 * d, a.h1, d, G(grad, w.qkv_w), s));
         TRY(run_dgrad(M, 3 * d, d, S.dqkv, H(shadow, w.qkv_w), S.dh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, nullptr, nullptr, s));  // dh1
         // dx_in = dx1 + LN1'(dh1)   (written over the old dx buffers)

@@ -50,6 +50,7 @@ struct GemmDeviceArgs {
     int accumulate;
     int split_k;
     int m_tiles, n_tiles, k_blocks_per_split, k_blocks_total;
+    int skip_pdl_wait;            // climb_gemm_desc.independent: do not wait for the previous kernel of the stream
     int num_stages;               // smem ring depth (runtime: deeper when the epilogue needs no input prefetch)
     int scratch_bytes;            // per epilogue warp: 4096 (staging only) or 8192 (+ prefetch half)
 };
@@ -382,7 +383,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();     // everything above overlapped the previous kernel's tail; operands / epilogue tensors come after
+    if (!p.skip_pdl_wait) pdl_wait();     // everything above overlapped the previous kernel's tail; operands / epilogue tensors come after
 
     const int tiles_mn = p.m_tiles * p.n_tiles;
     const int total_tiles = tiles_mn * p.split_k;
@@ -810,7 +811,7 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();     // everything above overlapped the previous kernel's tail; operands / epilogue tensors come after
+    if (!p.skip_pdl_wait) pdl_wait();     // everything above overlapped the previous kernel's tail; operands / epilogue tensors come after
 
     if (warp == 0) {
         if (lane == 0) producer_loop<BLOCK_N>(tmap_a, tmap_b, p, smem, full_bar, empty_bar, kStages);
@@ -1034,11 +1035,15 @@ int launch_gemm_t(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stre
         split = 1;
         const int tiles = a.m_tiles * a.n_tiles;
         if (d->accumulate && d->c_dtype == CLIMB_F32 && a.k_blocks_total >= 16) {
+            // an INDEPENDENT launch runs in the previous kernel's last partial wave: size it for the ~80 % of
+            // the SMs that wave leaves idle, so that none of its CTAs has to queue behind the predecessor's tail
+            const int sms = a.skip_pdl_wait ? (num_sms() * 4) / 5 : num_sms();
             double best = 0.0;
             for (int s = 1; s <= 16 && a.k_blocks_total / s >= 8; ++s) {
                 const long long t = 1LL * tiles * s;
-                const long long waves = (t + num_sms() - 1) / num_sms();
-                const double fill = static_cast<double>(t) / (waves * num_sms());
+                if (a.skip_pdl_wait && t > sms && s > 1) break;          // one wave on the idle SMs only
+                const long long waves = (t + sms - 1) / sms;
+                const double fill = static_cast<double>(t) / (waves * sms);
                 if (fill > best + 0.03) { best = fill; split = s; }
             }
         }
@@ -1065,6 +1070,7 @@ int launch_gemm_t(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stre
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
     CLIMB_CUDA_OK(launch_pdl(gemm_bf16_tcgen05_kernel<BLOCK_N, HAS_INPUT>, dim3(grid), dim3(kNumThreads), smem_bytes, stream, ta, tb, a));
+    if (a.skip_pdl_wait) pdl_fence_next();
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -1096,6 +1102,7 @@ int launch_fast(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
     CLIMB_CUDA_OK(launch_pdl(gemm_fast_kernel<KIND>, dim3(grid), dim3(kFastThreads), kFastSmemBytes, stream, ta, tb, a));
+    if (a.skip_pdl_wait) pdl_fence_next();
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -1176,6 +1183,8 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     a.colsum = d->colsum;
     a.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
     a.accumulate = d->accumulate ? 1 : 0;
+    static const bool indep_ok = [] { const char* e = getenv("CLIMB_NO_INDEPENDENT"); return !(e && e[0] == '1'); }();   // dev A/B switch
+    a.skip_pdl_wait = (d->independent && pdl_enabled() && indep_ok) ? 1 : 0;
 
     if (!g_disable_fast) {
         switch (fast_kind(d)) {

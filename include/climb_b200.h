@@ -81,6 +81,12 @@ typedef struct {
     int accumulate;
     int split_k;
     int block_n;
+    /* Programmatic dependent launch: every kernel of this library waits (griddepcontrol.wait) for the previous kernel
+     * of its stream before touching global memory. independent = 1 declares that this GEMM reads / writes nothing the
+     * PREVIOUS launch on the stream produces or consumes, so its CTAs may start on the SMs that launch's last wave
+     * leaves idle; the launch AFTER it is then issued as a full stream barrier. The engine uses it for the
+     * attention-output wgrad, which follows the attention backward (768 CTAs = 5.19 waves) without depending on it. */
+    int independent;
 } climb_gemm_desc;
 
 int climb_gemm_bf16(const climb_gemm_desc* desc, void* stream);
