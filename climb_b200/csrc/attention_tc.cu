@@ -451,9 +451,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             const uint32_t id_t = umma_instr_desc(128, 64, 1, 1);      // dV / dK: A = P^T / dS^T in place, B MN-major
             const uint32_t id_q = umma_instr_desc(128, 64, 0, 1);      // dQ: A = dS K-major, B = K MN-major
             const uint32_t tile = 128 * kRowB;                          // 16 KB: 128 rows of a [rows x 64] tile
-            for (int n = 0; n < n_blocks; ++n) {
+            // phase A of block n: S = Q_i K_j^T, dP = dO_i V_j^T
+            auto phase_a = [&](int n) {
                 const int j = n / n_jt, i = n - j * n_jt;
-                // phase A
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16(tmem + kTS, umma_smem_desc(sQ + i * tile + kk * 32, 16, 1024),
@@ -463,8 +463,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                     umma_bf16(tmem + kTdP, umma_smem_desc(sDO + i * tile + kk * 32, 16, 1024),
                               umma_smem_desc(sV + j * tile + kk * 32, 16, 1024), id_a, kk > 0 ? 1u : 0u);
                 umma_commit(bar_a);
-                mbar_wait(bar_p, n & 1);
+            };
+            phase_a(0);
+            for (int n = 0; n < n_blocks; ++n) {
+                const int j = n / n_jt, i = n - j * n_jt;
+                mbar_wait(bar_p, n & 1);            // P, dS of block n are in smem; S / dP have been read out of TMEM
                 tc_fence_after();
+                // the NEXT block's S / dP chains go first: the elementwise warps work on them while the three
+                // accumulation chains of this block run (they only need P / dS's smem back before they store)
+                if (n + 1 < n_blocks) phase_a(n + 1);
                 if (i == 0 && j > 0) {                  // previous key tile's dV / dK must have been read out
                     mbar_wait(bar_kv, (j - 1) & 1);
                     tc_fence_after();
@@ -497,9 +504,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             const int j = n / n_jt, i = n - j * n_jt;
             mbar_wait(bar_a, n & 1);
             tc_fence_after();
-            if (n > 0) mbar_wait(bar_b, (n - 1) & 1);           // previous block's chains no longer read P / dS
             const float lse_r = sLse[i * 128 + row], dl_r = sDelta[i * 128 + row];
             const int c = quarter;
+            uint32_t pp[2][8], dd[2][8];
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {                    // two 16-key halves: 32 accumulator registers live
                 uint32_t rs[16], rd[16];
@@ -512,22 +519,27 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                     bias[e] = b4.x - lse_r; bias[e + 1] = b4.y - lse_r; bias[e + 2] = b4.z - lse_r; bias[e + 3] = b4.w - lse_r;
                 }
                 tmem_ld_wait();
-                uint32_t pp[8], dd[8];
 #pragma unroll
                 for (int e = 0; e < 16; e += 2) {
                     const float p0 = ex2_ftz(fmaf(__uint_as_float(rs[e]), scale_log2, bias[e]));
                     const float p1 = ex2_ftz(fmaf(__uint_as_float(rs[e + 1]), scale_log2, bias[e + 1]));
-                    pp[e >> 1] = pack_bf16(p0, p1);
-                    dd[e >> 1] = pack_bf16(p0 * (__uint_as_float(rd[e]) - dl_r), p1 * (__uint_as_float(rd[e + 1]) - dl_r));
+                    pp[hh][e >> 1] = pack_bf16(p0, p1);
+                    dd[hh][e >> 1] = pack_bf16(p0 * (__uint_as_float(rd[e]) - dl_r), p1 * (__uint_as_float(rd[e + 1]) - dl_r));
                 }
+            }
+            // everything above overlapped the previous block's accumulation chains; they must have retired before
+            // P / dS are overwritten
+            if (n > 0) mbar_wait(bar_b, (n - 1) & 1);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
                 // 16 columns = granules (c & 1) * 4 + hh * 2 + {0, 1} of the row in 64-column chunk (c >> 1)
                 uint8_t* pc = sm + BwdSmem::kP + (c >> 1) * (128 * kRowB);
                 uint8_t* dc = sm + BwdSmem::kDS + (c >> 1) * (128 * kRowB);
                 const int g0 = (c & 1) * 4 + hh * 2;
-                *reinterpret_cast<uint4*>(pc + swz(row, g0)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-                *reinterpret_cast<uint4*>(pc + swz(row, g0 + 1)) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
-                *reinterpret_cast<uint4*>(dc + swz(row, g0)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
-                *reinterpret_cast<uint4*>(dc + swz(row, g0 + 1)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
+                *reinterpret_cast<uint4*>(pc + swz(row, g0)) = make_uint4(pp[hh][0], pp[hh][1], pp[hh][2], pp[hh][3]);
+                *reinterpret_cast<uint4*>(pc + swz(row, g0 + 1)) = make_uint4(pp[hh][4], pp[hh][5], pp[hh][6], pp[hh][7]);
+                *reinterpret_cast<uint4*>(dc + swz(row, g0)) = make_uint4(dd[hh][0], dd[hh][1], dd[hh][2], dd[hh][3]);
+                *reinterpret_cast<uint4*>(dc + swz(row, g0 + 1)) = make_uint4(dd[hh][4], dd[hh][5], dd[hh][6], dd[hh][7]);
             }
             fence_proxy_async();
             tc_fence_before();
