@@ -50,28 +50,8 @@ __device__ __forceinline__ void store_row_chunk_bf16(uint8_t* tile, int row, int
     }
 }
 
-// a warp's 32 rows x 64 bf16 (thread = row, 32 packed words) -> global rows, coalesced through a 4 KB
-// swizzled staging block
-__device__ __forceinline__ void store_rows_64(uint8_t* stage, const uint32_t (&pk)[32], __nv_bfloat16* gdst,
-                                              long long ld_elems, int rows_valid, int lane) {
-    __syncwarp();
-#pragma unroll
-    for (int g = 0; g < 8; ++g)
-        *reinterpret_cast<uint4*>(stage + swz(lane, g)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int q = it * 32 + lane;
-        const int rr = q >> 3, g = q & 7;
-        if (rr < rows_valid) {
-            const uint4 val = *reinterpret_cast<const uint4*>(stage + swz(rr, g));
-            *reinterpret_cast<uint4*>(gdst + rr * ld_elems + g * 8) = val;
-        }
-    }
-    __syncwarp();
-}
-
-// same for 32 bf16 columns per row (64 B): two rows share one 128 B staging line
+// a warp's 32 rows x 32 bf16 columns (thread = row, 16 packed words = 64 B) -> global rows, coalesced through a
+// 2 KB swizzled staging block: two rows share one 128 B staging line
 __device__ __forceinline__ void store_rows_32(uint8_t* stage, const uint32_t (&pk)[16], __nv_bfloat16* gdst,
                                               long long ld_elems, int rows_valid, int lane) {
     __syncwarp();
