@@ -341,6 +341,12 @@ def run_ours(args):
                      "bwd": {"achieved": round(ab_b / (ab_ms * 1e-3) / 1e9, 1) if ab_ms else 0.0, "ms_per_step": round(ab_ms / 2, 3)}}
         attn_roof["fwd"]["frac"] = round(attn_roof["fwd"]["achieved"] / peaks["hbm"], 4)
         attn_roof["bwd"]["frac"] = round(attn_roof["bwd"]["achieved"] / peaks["hbm"], 4)
+        ap_ = os.path.join(ROOT, "profiles", "attention_traffic.json")
+        if os.path.exists(ap_):            # ncu dram bytes per launch (one launch = B x heads of one layer)
+            at = json.load(open(ap_))
+            attn_roof["fwd"]["traffic"] = at["fwd"]["dram_bytes_per_launch"]
+            attn_roof["bwd"]["traffic"] = at["bwd"]["dram_bytes_per_launch"]
+            attn_roof["kernel"] = "attn_tc_fwd_kernel / attn_tc_bwd_kernel (tcgen05 + TMEM); achieved = algorithmic bytes / time"
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
