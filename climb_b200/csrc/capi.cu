@@ -53,7 +53,13 @@ bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("CLIMB_PDL"); return !(e && e[0] == '0'); }();
     return on;
 }
-static bool g_pdl_fence = false;
+static bool g_pdl_fence = false, g_pdl_independent = false;
+void pdl_mark_independent() { g_pdl_independent = pdl_enabled(); }
+bool pdl_take_independent() {
+    const bool f = g_pdl_independent;
+    g_pdl_independent = false;
+    return f;
+}
 void pdl_fence_next() { g_pdl_fence = true; }
 bool pdl_take_fence() {
     const bool f = g_pdl_fence;

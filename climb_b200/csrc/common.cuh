@@ -148,8 +148,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();      // capi.cu: CLIMB_PDL=0 switches it off
-// the next launch_pdl() on any stream is issued WITHOUT the programmatic attribute = an ordinary stream barrier
-// (needed after a kernel that skipped its pdl_wait: its completion does not imply its predecessor's)
+// INDEPENDENT launches: a kernel that touches nothing the previous launch of its stream reads or writes may skip its
+// pdl_wait() and run concurrently with that launch (in its last partial wave, or co-resident with its CTAs when the
+// resources allow). The caller marks it with pdl_mark_independent() right before launch_pdl() and passes the kernel a
+// flag that makes it skip the wait. Because such a kernel's completion no longer implies its predecessor's, the first
+// ORDINARY launch after it is issued without the programmatic attribute = a full stream barrier.
+void pdl_mark_independent();
+bool pdl_take_independent();
 void pdl_fence_next();
 bool pdl_take_fence();
 
@@ -165,7 +170,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (pdl_enabled() && !pdl_take_fence()) ? 1 : 0;
+    const bool independent = pdl_take_independent();
+    cfg.numAttrs = (pdl_enabled() && (independent || !pdl_take_fence())) ? 1 : 0;
+    if (independent) pdl_fence_next();
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

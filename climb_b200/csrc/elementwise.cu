@@ -4,6 +4,7 @@
 // pooler (modeling_vilt.py:887-899), and the loss kernels of the trainers (train_vqa.py:95,157;
 // train_nlvr2.py:80,133). All global accesses are 128-bit where alignment allows.
 #include "common.cuh"
+#include <cstdlib>
 #include "climb_b200.h"
 
 namespace climb {

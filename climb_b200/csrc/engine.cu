@@ -454,17 +454,17 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             TRY(run_dgrad(M, r, d, S.dz, H(shadow, w.out_down_w), dx, CLIMB_F32, CLIMB_EPI_NONE, nullptr, 0, dx, dx_h, s));
         }
         // ---- FFN: y = FC2(GELU(FC1(LN2(x1)))) + x1 ----
-        // du = (dx W2) * gelu'(pre). The FC1 bias gradient (column sums of du) is a separate streaming pass:
-        // fused into this K = 768 epilogue it cost 57 us per launch (ncu: a third of the kernel's instructions),
-        // the standalone kernel reads du once more for ~20 us.
-        const bool fuse_db1 = false;
+        // du = (dx W2) * gelu'(pre). The bias gradients are column sums = streaming passes over dx / du. (Fused into
+        // the K = 768 epilogue the FC1 sums cost 57 us per launch, a third of that kernel's instructions; issued as
+        // INDEPENDENT background launches beside the dgrad GEMMs they measured 2 % slower on the whole step than as
+        // ordinary 8-13 us passes: the co-resident CTAs take issue slots and L2 bandwidth from an epilogue-bound GEMM.)
         TRY(run_dgrad(M, d, ff, dx_h, H(shadow, w.fc2_w), S.du, CLIMB_BF16, CLIMB_EPI_MUL_AUX, a.u, ff, nullptr, nullptr, s,
                       nullptr));
         if (base) {
             TRY(run_wgrad(M, d, ff, dx_h, d, a.inter, ff, G(grad, w.fc2_w), s));
             TRY(colsum(dx_h, CLIMB_BF16, d, M, d, G(grad, w.fc2_b), s));
             TRY(run_wgrad(M, ff, d, S.du, ff, a.h2, d, G(grad, w.fc1_w), s));
-            if (!fuse_db1) TRY(colsum(S.du, CLIMB_BF16, ff, M, ff, G(grad, w.fc1_b), s));
+            TRY(colsum(S.du, CLIMB_BF16, ff, M, ff, G(grad, w.fc1_b), s));
         }
         TRY(run_dgrad(M, ff, d, S.du, H(shadow, w.fc1_w), S.dh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, nullptr, nullptr, s));
         // dx1 = dx + LN2'(dh2)

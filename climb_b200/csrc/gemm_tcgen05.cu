@@ -1069,8 +1069,8 @@ int launch_gemm_t(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stre
     const int total = a.m_tiles * a.n_tiles * a.split_k;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
+    if (a.skip_pdl_wait) pdl_mark_independent();
     CLIMB_CUDA_OK(launch_pdl(gemm_bf16_tcgen05_kernel<BLOCK_N, HAS_INPUT>, dim3(grid), dim3(kNumThreads), smem_bytes, stream, ta, tb, a));
-    if (a.skip_pdl_wait) pdl_fence_next();
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -1101,8 +1101,8 @@ int launch_fast(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
     const int total = a.m_tiles * a.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
+    if (a.skip_pdl_wait) pdl_mark_independent();
     CLIMB_CUDA_OK(launch_pdl(gemm_fast_kernel<KIND>, dim3(grid), dim3(kFastThreads), kFastSmemBytes, stream, ta, tb, a));
-    if (a.skip_pdl_wait) pdl_fence_next();
     CLIMB_LAUNCH_OK();
     return 0;
 }
