@@ -270,6 +270,14 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :
+                 : "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, void* smem_dst,
                                             int32_t c0, int32_t c1, int32_t c2) {
     asm volatile(

@@ -10,10 +10,14 @@
 #include "common.cuh"
 #include "climb_b200.h"
 
+#include <cstdlib>
+
 namespace climb {
 namespace {
 
 constexpr int kWarpsPerBlock = 8;
+// dev A/B switch: CLIMB_LN_NO_BULK=1 keeps the register-only backward kernel
+const bool g_ln_no_bulk = [] { const char* e = getenv("CLIMB_LN_NO_BULK"); return e && e[0] == '1'; }();
 
 template <int NV>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -202,6 +206,126 @@ ln_bwd_kernel(const float* __restrict__ dy_f32, const __nv_bfloat16* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward, streaming variant for the encoder's hot calls (dense rows, bf16 dy, residual-gradient add, both
+// outputs): every warp keeps a two-deep ring of whole rows (x, dy, dres = 7.5 KB at d = 768) in shared memory,
+// filled by cp.async.bulk (one lane issues three bulk copies per row against an mbarrier), so 120 KB of loads
+// per SM are in flight independently of the registers; the row is read once from shared memory, the two
+// reductions and the output pass run from registers. (The register-only kernel above re-reads x and dy and has
+// ~3-5 KB in flight per warp: 4.1 TB/s; it remains the path for every other shape / option.)
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+struct LnBulk {
+    static constexpr int D = NV * 128;
+    static constexpr int kWarps = 8;
+    static constexpr int kStages = 2;
+    static constexpr int kRowBytes = D * 4 + D * 2 + D * 4;            // x fp32 | dy bf16 | dres fp32
+    static constexpr int kSmem = kWarps * kStages * kRowBytes + kWarps * kStages * 8;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(LnBulk<NV>::kWarps * 32, 1)
+ln_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
+                   float* __restrict__ dx_f32, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, int rows) {
+    using C = LnBulk<NV>;
+    constexpr int D = C::D;
+    extern __shared__ __align__(128) uint8_t ln_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* ring = ln_smem + warp * (C::kStages * C::kRowBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + C::kWarps * C::kStages * C::kRowBytes) + warp * C::kStages;
+    if (lane == 0) {
+        for (int s = 0; s < C::kStages; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    pdl_wait();
+    const int stride = gridDim.x * C::kWarps;
+    const int row0 = blockIdx.x * C::kWarps + warp;
+    auto issue = [&](int row, int s) {          // lane 0 only
+        uint8_t* dst = ring + s * C::kRowBytes;
+        mbar_arrive_expect_tx(&bars[s], C::kRowBytes);
+        bulk_load_1d(dst, x + static_cast<long long>(row) * D, D * 4, &bars[s]);
+        bulk_load_1d(dst + D * 4, dy + static_cast<long long>(row) * D, D * 2, &bars[s]);
+        bulk_load_1d(dst + D * 6, dres + static_cast<long long>(row) * D, D * 4, &bars[s]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < C::kStages; ++s)
+            if (row0 + s * stride < rows) issue(row0 + s * stride, s);
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    float4 gam[NV], dg[NV], db[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        gam[i] = __ldg(g4 + lane + 32 * i);
+        dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int it = 0;
+    for (int row = row0; row < rows; row += stride, ++it) {
+        const int s = it % C::kStages;
+        const uint32_t parity = (it / C::kStages) & 1;
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        mbar_wait(&bars[s], parity);
+        const uint8_t* buf = ring + s * C::kRowBytes;
+        float4 xh[NV], dyv[NV], rs[NV];
+        float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 xv = reinterpret_cast<const float4*>(buf)[lane + 32 * i];
+            const uint2 p = reinterpret_cast<const uint2*>(buf + D * 4)[lane + 32 * i];
+            rs[i] = reinterpret_cast<const float4*>(buf + D * 6)[lane + 32 * i];
+            const float2 a = unpack_bf16(p.x), b = unpack_bf16(p.y);
+            dyv[i] = make_float4(a.x, a.y, b.x, b.y);
+            xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
+            xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
+            dg[i].x += dyv[i].x * xh[i].x; dg[i].y += dyv[i].y * xh[i].y; dg[i].z += dyv[i].z * xh[i].z; dg[i].w += dyv[i].w * xh[i].w;
+            db[i].x += dyv[i].x; db[i].y += dyv[i].y; db[i].z += dyv[i].z; db[i].w += dyv[i].w;
+            dyv[i].x *= gam[i].x; dyv[i].y *= gam[i].y; dyv[i].z *= gam[i].z; dyv[i].w *= gam[i].w;      // dy * gamma from here on
+            c1 += (dyv[i].x + dyv[i].y) + (dyv[i].z + dyv[i].w);
+            c2 += (dyv[i].x * xh[i].x + dyv[i].y * xh[i].y) + (dyv[i].z * xh[i].z + dyv[i].w * xh[i].w);
+        }
+        // the stage has been read into registers: refill it with the row two steps ahead
+        __syncwarp();
+        if (lane == 0 && row + C::kStages * stride < rows) issue(row + C::kStages * stride, s);
+        c1 = warp_sum(c1) * (1.0f / D);
+        c2 = warp_sum(c2) * (1.0f / D);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float4 o;
+            o.x = rstd * (dyv[i].x - c1 - xh[i].x * c2) + rs[i].x;
+            o.y = rstd * (dyv[i].y - c1 - xh[i].y * c2) + rs[i].y;
+            o.z = rstd * (dyv[i].z - c1 - xh[i].z * c2) + rs[i].z;
+            o.w = rstd * (dyv[i].w - c1 - xh[i].w * c2) + rs[i].w;
+            reinterpret_cast<float4*>(dx_f32 + static_cast<long long>(row) * D)[lane + 32 * i] = o;
+            uint2 pk;
+            pk.x = pack_bf16(o.x, o.y);
+            pk.y = pack_bf16(o.z, o.w);
+            reinterpret_cast<uint2*>(dx_bf16 + static_cast<long long>(row) * D)[lane + 32 * i] = pk;
+        }
+    }
+    if (dgamma == nullptr && dbeta == nullptr) return;
+    // CTA reduction of the column partials through the (now idle) ring of warp 0..: [2][D] floats
+    __syncthreads();
+    float* s_acc = reinterpret_cast<float*>(ln_smem);
+    for (int c = threadIdx.x; c < 2 * D; c += C::kWarps * 32) s_acc[c] = 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c0 = (lane + 32 * i) * 4;
+        atomicAdd(&s_acc[c0], dg[i].x); atomicAdd(&s_acc[c0 + 1], dg[i].y);
+        atomicAdd(&s_acc[c0 + 2], dg[i].z); atomicAdd(&s_acc[c0 + 3], dg[i].w);
+        atomicAdd(&s_acc[D + c0], db[i].x); atomicAdd(&s_acc[D + c0 + 1], db[i].y);
+        atomicAdd(&s_acc[D + c0 + 2], db[i].z); atomicAdd(&s_acc[D + c0 + 3], db[i].w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += C::kWarps * 32) {
+        if (dgamma) atomicAdd(dgamma + c, s_acc[c]);
+        if (dbeta) atomicAdd(dbeta + c, s_acc[D + c]);
+    }
+}
+
 template <int NV>
 int launch_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
                void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int act,
@@ -218,6 +342,26 @@ int launch_bwd(const float* dy_f32, const void* dy_bf16, const float* x, long lo
                const float* gamma, const float* beta, const float* mean, const float* rstd,
                const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dx_colsum, int rows,
                int act, cudaStream_t stream) {
+    // the encoder's hot calls: dense fp32 rows, bf16 dy, residual-gradient add, both outputs, no fused activation
+    if constexpr (NV == 6) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy_bf16) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0;
+        if (dy_bf16 != nullptr && dy_f32 == nullptr && dres != nullptr && dx_f32 != nullptr && dx_bf16 != nullptr && dx_colsum == nullptr &&
+            act == CLIMB_EPI_NONE && ldx == NV * 128 && rows >= 1024 && aligned && !g_ln_no_bulk) {
+            using C = LnBulk<NV>;
+            static bool attr = false;
+            if (!attr) {
+                CLIMB_CUDA_OK(cudaFuncSetAttribute(ln_bwd_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+                attr = true;
+            }
+            int grid = (rows + C::kWarps - 1) / C::kWarps;
+            if (grid > 148) grid = 148;
+            CLIMB_CUDA_OK(launch_pdl(ln_bwd_bulk_kernel<NV>, dim3(grid), dim3(C::kWarps * 32), static_cast<size_t>(C::kSmem), stream,
+                                     static_cast<const __nv_bfloat16*>(dy_bf16), x, gamma, mean, rstd, dres, dx_f32,
+                                     static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows));
+            CLIMB_LAUNCH_OK();
+            return 0;
+        }
+    }
     int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int cap = 148 * 4;          // two resident CTAs per SM, two rounds (measured: 45.8 us vs 50.1 us with one round of 296)
     if (grid > cap) grid = cap;
