@@ -23,6 +23,9 @@
 
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace climb {
 namespace {
 
@@ -83,6 +86,15 @@ __device__ __forceinline__ void staged_colsum_32(const uint8_t* stage, int rows_
     __syncwarp();
 }
 
+// One mbarrier arrival per WARP: the lanes order their own shared-memory writes (fence.proxy.async) and TMEM reads
+// (tcgen05.wait::ld) first, meet at __syncwarp, and one lane arrives. Hundreds of per-thread arrivals on one barrier word
+// serialise in the shared-memory atomic unit -- measured here, they were most of the kernels' time.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -130,7 +142,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tma_prefetch_desc(&map_kv);
             mbar_init(bar_load, 1);
             mbar_init(bar_s, 1);
-            mbar_init(bar_p, kSoftmaxThreads);
+            mbar_init(bar_p, kSoftmaxThreads / 32);
             mbar_init(bar_o, 1);
             fence_barrier_init();
             // loads go out before anything else so that they overlap TMEM allocation and the prologue
@@ -228,8 +240,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         sXsum[half * 128 + row] = sum;
         fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(bar_p);
+        warp_arrive(bar_p, lane);
         softmax_bar_sync();
         sum += sXsum[(half ^ 1) * 128 + row];
         mbar_wait(bar_o, 0);
@@ -257,6 +268,319 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (warp == kCtlWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, persistent (the encoder's hot call: no dropout)
+//
+// One CTA per SM walks over (b, h) items; both 128-row query tiles of an item are in flight at once, each owned by
+// its own softmax group (8 warps: thread = row x column half) and its own MMA-issuing warp, so that one tile's
+// exponentials overlap the other tile's tensor-core chains, accumulator drain and output stores:
+//   producer warp   TMA: Q [256 x 64] + K [256 x 64] (single buffers, refilled as soon as both S chains of the
+//                   item have retired = one item ahead of their use), V [256 x 64] in two stages
+//   MMA warp g      S_g = Q_g K^T (128 x 256 x 64, TMEM columns g*256..), then O_g += P_g[:, chunk] V[chunk, :]
+//                   for the four 64-key chunks as the softmax group hands them over through a two-slot ring
+//                   (O_g aliases S_g's first 64 columns: chunk 0 of S has been consumed by then)
+//   softmax group g row max over the row held in TMEM (two threads per row exchange through smem), exp2, P as
+//                   bf16 into the ring slot in the K-major A-operand layout, 1 / sum folded into the O epilogue
+// Every K / V byte is read once per item (the one-tile-per-CTA kernel above reads them twice).
+// ------------------------------------------------------------------------------------------------
+struct Fwd2Smem {
+    static constexpr int kQ = 0;                    // [256 x 64] bf16: query tile g at g * 16 KB
+    static constexpr int kK = 32 * 1024;            // [256 x 64]
+    static constexpr int kV = 64 * 1024;            // 2 stages x [256 x 64]
+    static constexpr int kP = 128 * 1024;           // 2 groups x 2 slots x [128 x 64] bf16; slot 0 doubles as output staging
+    static constexpr int kBias = 192 * 1024;        // [2 groups][2 stages][256] floats
+    static constexpr int kXchg = 196 * 1024;        // [2 groups][max, sum][2 halves][128] floats
+    static constexpr int kFlag = 200 * 1024;        // [2 groups][2 stages][8] words: this 32-key chunk has a non-zero mask
+    static constexpr int kBar = 200 * 1024 + 128;
+    static constexpr int kTotal = 200 * 1024 + 256 + 1024;
+};
+constexpr int kF2GroupThreads = 256;
+constexpr int kF2ProducerWarp = 16;                 // + TMEM allocation
+constexpr int kF2MmaWarp0 = 17;                     // MMA warp of group g = 17 + g
+constexpr int kF2Threads = 19 * 32;
+
+template <int kId>
+__device__ __forceinline__ void named_bar_sync(int id_offset, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(kId + id_offset), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(kF2Threads, 1)
+attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias,
+                    __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int n_items, int L, int H, float scale_log2,
+                    int stagger, int dbg, long long* tl) {
+#define TL(role, idx) do { if (tl != nullptr && blockIdx.x == 0 && it == 2) tl[(role) * 32 + (idx)] = clock64(); } while (0)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Fwd2Smem::kBar);
+    uint64_t* qk_full = bars;            // [1]  tx
+    uint64_t* qk_free = bars + 1;        // [1]  n_groups commits
+    uint64_t* v_full = bars + 2;         // [2]  tx
+    uint64_t* v_free = bars + 4;         // [2]  n_groups commits
+    uint64_t* s_full = bars + 6;         // [2 groups] commit
+    uint64_t* s_free = bars + 8;         // [2 groups] 8 warp arrivals: O has been read out of TMEM
+    uint64_t* p_full = bars + 10;        // [2 groups][2 slots] 8 warp arrivals
+    uint64_t* p_free = bars + 14;        // [2 groups][2 slots] commit
+    uint64_t* o_full = bars + 18;        // [2 groups] commit
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_groups = L > 128 ? 2 : 1;            // query tiles with real rows
+    const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    pdl_wait();
+    pdl_launch_dependents();     // the next kernel's CTAs may take the SMs whose CTA here has run out of items
+
+    if (warp == kF2ProducerWarp) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_qkv);
+            mbar_init(qk_full, 1);
+            mbar_init(qk_free, n_groups);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&v_full[s], 1);
+                mbar_init(&v_free[s], n_groups);
+                mbar_init(&s_full[s], 1);
+                mbar_init(&s_free[s], kF2GroupThreads / 32);
+                mbar_init(&o_full[s], 1);
+            }
+            for (int s = 0; s < 4; ++s) {
+                mbar_init(&p_full[s], kF2GroupThreads / 32);
+                mbar_init(&p_free[s], 1);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == kF2ProducerWarp) {
+        if (lane == 0) {
+            for (int it = 0; it < n_my; ++it) {
+                const int item = blockIdx.x + it * gridDim.x;
+                const int b = item / H, h = item - b * H;
+                if (it > 0) mbar_wait(qk_free, (it - 1) & 1);
+                const bool skip = (dbg & 2) && it >= 2;
+                if (skip) mbar_arrive(qk_full);
+                else {
+                mbar_arrive_expect_tx(qk_full, 2 * 256 * kRowB);
+                tma_load_3d(&map_qkv, qk_full, sm + Fwd2Smem::kQ, h * kDh, 0, b);
+                tma_load_3d(&map_qkv, qk_full, sm + Fwd2Smem::kK, (H + h) * kDh, 0, b);
+                }
+                const int s = it & 1, k = it >> 1;
+                if (k > 0) mbar_wait(&v_free[s], (k - 1) & 1);
+                if (skip) mbar_arrive(&v_full[s]);
+                else {
+                mbar_arrive_expect_tx(&v_full[s], 256 * kRowB);
+                tma_load_3d(&map_qkv, &v_full[s], sm + Fwd2Smem::kV + s * (256 * kRowB), (2 * H + h) * kDh, 0, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kF2MmaWarp0) {
+        const int g = warp - kF2MmaWarp0;
+        if (lane == 0 && g < n_groups) {
+            const uint32_t sQ = smem_u32(sm + Fwd2Smem::kQ) + g * (128 * kRowB), sK = smem_u32(sm + Fwd2Smem::kK);
+            const uint32_t sP = smem_u32(sm + Fwd2Smem::kP) + g * (2 * 128 * kRowB);
+            const uint32_t t_acc = tmem + g * 256;
+            const uint32_t idesc_s = umma_instr_desc(128, 256, 0, 0);
+            const uint32_t idesc_o = umma_instr_desc(128, 64, 0, 1);
+            // the two groups run half a tile apart (group 1 starts once group 0 has handed over its second chunk), so that
+            // one group's exponentials (the MUFU pipe is the busiest unit) meet the other group's max pass, epilogue and
+            // barrier round trips instead of its exponentials; nothing later couples the groups, so the offset stays
+            if (g == 1 && stagger) mbar_wait(&p_full[1], 0);
+            for (int it = 0; it < n_my; ++it) {
+                TL(g, 0);
+                mbar_wait(qk_full, it & 1);
+                TL(g, 1);
+                if (it > 0) mbar_wait(&s_free[g], (it - 1) & 1);
+                TL(g, 2);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(t_acc, umma_smem_desc(sQ + kk * 32, 16, 1024), umma_smem_desc(sK + kk * 32, 16, 1024), idesc_s,
+                              kk > 0 ? 1u : 0u);
+                umma_commit(&s_full[g]);
+                umma_commit(qk_free);
+                TL(g, 3);
+                const int s = it & 1;
+                const uint32_t sV = smem_u32(sm + Fwd2Smem::kV) + s * (256 * kRowB);
+                mbar_wait(&v_full[s], (it >> 1) & 1);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int slot = c & 1;
+                    mbar_wait(&p_full[g * 2 + slot], (2 * it + (c >> 1)) & 1);
+                    TL(g, 4 + 2 * c);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(t_acc, umma_smem_desc(sP + slot * (128 * kRowB) + kk * 32, 16, 1024),
+                                  umma_smem_desc(sV + (c * 4 + kk) * (16 * kRowB), 256 * kRowB, 1024), idesc_o,
+                                  (c > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&p_free[g * 2 + slot]);
+                    TL(g, 5 + 2 * c);
+                }
+                umma_commit(&o_full[g]);
+                umma_commit(&v_free[s]);
+            }
+        }
+        __syncwarp();
+    } else if ((warp >> 3) < n_groups) {
+        const int g = warp >> 3, wg = warp & 7;              // group, warp inside the group
+        const int lg = wg & 3, half = wg >> 2;               // TMEM lane group, 32-key half of every 64-key chunk
+        const int row = lg * 32 + lane;
+        const int tg = threadIdx.x & (kF2GroupThreads - 1);
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16) + g * 256;
+        float* sBias = reinterpret_cast<float*>(sm + Fwd2Smem::kBias) + g * 512;                 // [2 stages][256]
+        float* sXmax = reinterpret_cast<float*>(sm + Fwd2Smem::kXchg) + g * 512;                 // [2][128]
+        float* sXsum = sXmax + 256;
+        uint8_t* ring = sm + Fwd2Smem::kP + g * (2 * 128 * kRowB);
+        uint32_t* sFlag = reinterpret_cast<uint32_t*>(sm + Fwd2Smem::kFlag) + g * 16;          // [2 stages][8 key chunks]
+        // additive key mask of item `it` for key tg, still in natural-log units (the scaling waits until the value is
+        // stored, so that nothing stalls on the load): -inf past L
+        auto load_bias = [&](int it) -> float {
+            if (tg >= L) return -INFINITY;
+            if (key_bias == nullptr) return 0.0f;
+            const int item = blockIdx.x + it * gridDim.x;
+            return __ldg(key_bias + static_cast<long long>(item / H) * L + tg);
+        };
+        // a 32-key chunk whose mask is all zero (the usual case away from the text padding and the tail past L) takes
+        // the short path: max over the raw scores, one packed FMA per pair of scores
+        auto store_bias = [&](int stage, float v) {
+            sBias[stage * 256 + tg] = v * kLog2e;
+            const uint32_t any = __ballot_sync(0xffffffffu, v != 0.0f);
+            if (lane == 0) sFlag[stage * 8 + wg] = any;
+        };
+        if (n_my > 0) store_bias(0, load_bias(0));
+        const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+        for (int it = 0; it < n_my; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int b = item / H, h = item - b * H;
+            const float bias_next = it + 1 < n_my ? load_bias(it + 1) : 0.0f;
+            // the group meets here once per item: the bias row written during the previous item is visible, and every
+            // warp has finished reading its output staging block (ring slot 0) before chunk 0 is written again
+#define TLS(idx) do { if (wg == 0 && lane == 0) TL(2 + g, idx); } while (0)
+            TLS(0);
+            named_bar_sync<9>(g, kF2GroupThreads);
+            TLS(1);
+            const float* bias = sBias + (it & 1) * 256;
+            const uint32_t* flag = sFlag + (it & 1) * 8;
+            mbar_wait(&s_full[g], it & 1);
+            TLS(2);
+            tc_fence_after();
+            float m = -INFINITY, m_raw = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                if (dbg & 1) { m = 0.0f; break; }
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c * 64 + half * 32, r);
+                const bool masked = flag[c * 2 + half] != 0u;
+                tmem_ld_wait();
+                if (!masked) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        m_raw = fmaxf(m_raw, fmaxf(fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                                   fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 64 + half * 32 + j);
+                        m = fmaxf(m, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), scale_log2, b4.x), fmaf(__uint_as_float(r[j + 1]), scale_log2, b4.y)),
+                                           fmaxf(fmaf(__uint_as_float(r[j + 2]), scale_log2, b4.z), fmaf(__uint_as_float(r[j + 3]), scale_log2, b4.w))));
+                    }
+                }
+            }
+            m = fmaxf(m, m_raw * scale_log2);                  // scale > 0
+            sXmax[half * 128 + row] = m;
+            named_bar_sync<1>(g * 4 + lg, 64);
+            m = fmaxf(m, sXmax[(half ^ 1) * 128 + row]);       // key 0 is always valid: m is finite
+            TLS(3);
+            const uint64_t neg_m2 = pack_f32x2(-m, -m);
+            uint64_t sum2 = 0ull;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c * 64 + half * 32, r);
+                const bool masked = flag[c * 2 + half] != 0u;
+                float p[32];
+                tmem_ld_wait();
+                if (dbg & 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) p[j] = __uint_as_float(r[j]);
+                } else if (!masked) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float x0, x1;
+                        unpack_f32x2(ffma2(pack_u32x2(r[j], r[j + 1]), scale2, neg_m2), x0, x1);
+                        p[j] = ex2_ftz(x0);
+                        p[j + 1] = ex2_ftz(x1);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 64 + half * 32 + j);
+                        p[j] = ex2_ftz(fmaf(__uint_as_float(r[j]), scale_log2, b4.x - m));
+                        p[j + 1] = ex2_ftz(fmaf(__uint_as_float(r[j + 1]), scale_log2, b4.y - m));
+                        p[j + 2] = ex2_ftz(fmaf(__uint_as_float(r[j + 2]), scale_log2, b4.z - m));
+                        p[j + 3] = ex2_ftz(fmaf(__uint_as_float(r[j + 3]), scale_log2, b4.w - m));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    sum2 = fadd2(sum2, fadd2(pack_f32x2(p[j], p[j + 1]), pack_f32x2(p[j + 2], p[j + 3])));
+                const int slot = c & 1, use = 2 * it + (c >> 1);
+                TLS(4 + 4 * c);
+                if (use > 0) mbar_wait(&p_free[g * 2 + slot], (use - 1) & 1);     // the chains that read this slot have retired
+                TLS(5 + 4 * c);
+                store_row_chunk_bf16(ring + slot * (128 * kRowB), row, half, p);
+                fence_proxy_async();
+                TLS(6 + 4 * c);
+                warp_arrive(&p_full[g * 2 + slot], lane);
+                TLS(7 + 4 * c);
+            }
+            float sum, sum_hi;
+            unpack_f32x2(sum2, sum, sum_hi);
+            sum += sum_hi;
+            sXsum[half * 128 + row] = sum;
+            store_bias((it + 1) & 1, bias_next);
+            named_bar_sync<1>(g * 4 + lg, 64);
+            sum += sXsum[(half ^ 1) * 128 + row];
+            TLS(20);
+            mbar_wait(&o_full[g], it & 1);
+            TLS(21);
+            tc_fence_after();
+            uint32_t pk[16];
+            {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + half * 32, r);
+                tmem_ld_wait();
+                warp_arrive(&s_free[g], lane);         // the next item's S chain may overwrite the accumulator
+                const float inv = 1.0f / sum;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    pk[j] = pack_bf16(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+            }
+            const int qrow0 = g * 128 + lg * 32;
+            const int rows_valid = min(32, max(0, L - qrow0));
+            if (!(dbg & 4))
+            store_rows_32(ring + wg * 2048, pk, ctx + (static_cast<long long>(b) * L + qrow0) * (H * kDh) + h * kDh + half * 32,
+                          static_cast<long long>(H) * kDh, rows_valid, lane);
+            if (half == 0 && g * 128 + row < L) lse[(static_cast<long long>(b) * H + h) * L + g * 128 + row] = (m + log2f(sum)) * kLn2;
+            TLS(22);
+        }
+    }
+#undef TLS
+#undef TL
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kF2ProducerWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
     }
 }
 
@@ -321,7 +645,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     float* sColV = reinterpret_cast<float*>(sm + BwdSmem::kColV);
     uint64_t* bar_load = reinterpret_cast<uint64_t*>(sm + BwdSmem::kBar);
     uint64_t* bar_a = bar_load + 1;      // S, dP of a block are in TMEM
-    uint64_t* bar_p = bar_load + 2;      // P, dS of a block are in smem (kBwdEwThreads arrivals)
+    uint64_t* bar_p = bar_load + 2;      // P, dS of a block are in smem (one arrival per elementwise warp)
     uint64_t* bar_b = bar_load + 3;      // dV / dK / dQ chains of a block have retired
     uint64_t* bar_kv = bar_load + 4;     // dV_j, dK_j have been read out of TMEM (kBwdOutThreads arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 5);
@@ -345,9 +669,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             tma_prefetch_desc(&map_do);
             mbar_init(bar_load, 1);
             mbar_init(bar_a, 1);
-            mbar_init(bar_p, kBwdEwThreads);
+            mbar_init(bar_p, kBwdEwThreads / 32);
             mbar_init(bar_b, 1);
-            mbar_init(bar_kv, kBwdOutThreads);
+            mbar_init(bar_kv, kBwdOutThreads / 32);
             fence_barrier_init();
             // loads go out first: they overlap TMEM allocation and the delta prologue of the other warps
             mbar_arrive_expect_tx(bar_load, 4 * 256 * kRowB);
@@ -522,8 +846,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                 *reinterpret_cast<uint4*>(dc + swz(row, g0 + 1)) = make_uint4(dd[hh][4], dd[hh][5], dd[hh][6], dd[hh][7]);
             }
             fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(bar_p);
+            warp_arrive(bar_p, lane);
             if (i == n_jt - 1 && out_warp) {
                 // dV_j, dK_j are complete once this block's chains retire; each warp converts 32 of the 64 columns
                 mbar_wait(bar_b, n & 1);
@@ -543,8 +866,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                         pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
                     store_rows_32(stage, pk, dst + (which == 0 ? H * kDh : 2 * H * kDh), ld, rows_valid, lane);
                 }
-                tc_fence_before();
-                mbar_arrive(bar_kv);
+                warp_arrive(bar_kv, lane);
             }
         }
         // dQ tiles: complete after the last block
@@ -573,11 +895,540 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, persistent (128 < L <= 256: two key tiles x two query tiles per (b, h) item)
+//
+// One CTA per SM walks over (b, h) items. The block loop of an item is the one of the kernel above; what changes is
+// that nothing of an item's set-up or drain is exposed any more:
+//   producer warp   the eight 16 KB operand tiles (K0 V0 | Q0 dO0 | Q1 dO1 | K1 V1) are refilled with the NEXT item's
+//                   data as soon as the last chain that reads them has retired (K0 / V0 after block 1 of 4, ...), so the
+//                   128 KB of an item stream in behind the previous item's blocks without a second set of buffers
+//   16 elementwise  P / dS of the block; on the side, one sixteenth of the NEXT item's per-row scalars per block
+//   warps           (delta = rowsum(dO * O) from coalesced global loads, lse, key mask, column sums of dO)
+//   4 drain warps   dK_j / dV_j / dQ_i: TMEM -> bf16 -> staged, coalesced global stores (+ column sums of dQ); the
+//                   elementwise warps never leave the block loop
+//   MMA warp        issues the next block's S / dP chains (of the next item, at the item boundary) before the current
+//                   block's three accumulation chains whenever their operands have landed
+// ------------------------------------------------------------------------------------------------
+struct Bwd2Smem {
+    static constexpr int kQ = 0;                 // [2 tiles][128 x 64] bf16
+    static constexpr int kDO = 32 * 1024;
+    static constexpr int kK = 64 * 1024;
+    static constexpr int kV = 96 * 1024;
+    static constexpr int kP = 128 * 1024;        // [128 x 128] bf16 = two 16 KB chunks of 64 columns
+    static constexpr int kDS = 160 * 1024;
+    static constexpr int kLse = 192 * 1024;      // [2 stages][256] floats each
+    static constexpr int kDelta = 194 * 1024;
+    static constexpr int kBias = 196 * 1024;
+    static constexpr int kColV = 198 * 1024;     // [2 stages][64] floats: column sums of dO
+    static constexpr int kFlag = 198 * 1024 + 512;   // [2 stages][8] words: the 32-key chunk has a non-zero mask
+    static constexpr int kBar = 198 * 1024 + 640;
+    static constexpr int kStage = 199 * 1024;    // 4 drain warps x 2 KB
+    static constexpr int kNext = 207 * 1024;     // [O, dO][512 threads] x 16 B: the next item's rows on their way to delta (cp.async)
+    static constexpr int kTotal = 223 * 1024 + 1024;
+};
+// Block n of an item works on key tile j = n / 2 and query tile i = 0 1 1 0 (even items) or 1 0 0 1 (odd items): the query
+// tile an item ends with is the one the next item needs last, so every operand tile has at least one block of the
+// previous item left to arrive in
+__device__ __forceinline__ int bwd2_qtile(int it, int n) { return (((n + 1) >> 1) ^ it) & 1; }
+constexpr int kB2EwThreads = 512;
+constexpr int kB2MmaWarp = 16, kB2DrainWarp0 = 17;     // drain warp 0 is also the TMA producer (and owns the TMEM allocation)
+constexpr int kB2ProducerWarp = kB2DrainWarp0;
+constexpr int kB2DrainThreads = 128;
+constexpr int kB2Threads = 21 * 32;
+
+__global__ void __launch_bounds__(kB2Threads, 1)
+attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                    const float* __restrict__ key_bias, const __nv_bfloat16* __restrict__ ctx,
+                    const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
+                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int n_items, int L, int H,
+                    float scale_log2, float scale, long long* tl) {
+#define TLB(role, idx) do { if (tl != nullptr && blockIdx.x == 0 && it == 2) tl[(role) * 64 + (idx)] = clock64(); } while (0)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* sLse = reinterpret_cast<float*>(sm + Bwd2Smem::kLse);
+    float* sDelta = reinterpret_cast<float*>(sm + Bwd2Smem::kDelta);
+    float* sBias = reinterpret_cast<float*>(sm + Bwd2Smem::kBias);
+    float* sColV = reinterpret_cast<float*>(sm + Bwd2Smem::kColV);
+    uint32_t* sFlag = reinterpret_cast<uint32_t*>(sm + Bwd2Smem::kFlag);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Bwd2Smem::kBar);
+    uint64_t* full = bars;               // [4] tx: K0 V0 | Q0 dO0 | Q1 dO1 | K1 V1 of an item have landed
+    uint64_t* freeb = bars + 4;          // [4] commit: the last chain of the item that reads the tiles has retired
+    uint64_t* bar_a = bars + 8;          // S, dP of a block are in TMEM
+    uint64_t* bar_p = bars + 9;          // P, dS of a block are in smem (16 warp arrivals); S / dP have been read
+    uint64_t* bar_b = bars + 10;         // the accumulation chains of a block have retired
+    uint64_t* kv_full = bars + 11;       // dK_j, dV_j complete
+    uint64_t* kv_free = bars + 12;       // ... and read out of TMEM (4 warp arrivals)
+    uint64_t* dq_full = bars + 13;       // dQ_0, dQ_1 complete
+    uint64_t* dq_free = bars + 14;       // ... and read out of TMEM (4 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const long long ld = 3LL * H * kDh, ldo = static_cast<long long>(H) * kDh;
+    constexpr uint32_t tile = 128 * kRowB;                          // 16 KB: 128 rows of a [rows x 64] tile
+    pdl_wait();
+    pdl_launch_dependents();
+
+    // operand tile group t of item `it` -> smem (producer warp, one lane)
+    auto issue_tiles = [&](int t, int it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / H, h = item - b * H;
+        mbar_arrive_expect_tx(&full[t], 2 * tile);
+        if (t == 0 || t == 3) {
+            const int r0 = t == 0 ? 0 : 128;
+            tma_load_3d(&map_qkv, &full[t], sm + Bwd2Smem::kK + (t == 0 ? 0 : tile), (H + h) * kDh, r0, b);
+            tma_load_3d(&map_qkv, &full[t], sm + Bwd2Smem::kV + (t == 0 ? 0 : tile), (2 * H + h) * kDh, r0, b);
+        } else {
+            const int r0 = t == 1 ? 0 : 128;
+            tma_load_3d(&map_qkv, &full[t], sm + Bwd2Smem::kQ + (t == 1 ? 0 : tile), h * kDh, r0, b);
+            tma_load_3d(&map_do, &full[t], sm + Bwd2Smem::kDO + (t == 1 ? 0 : tile), h * kDh, r0, b);
+        }
+    };
+
+    float cv_keep[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cv_keep[e] = 0.0f;
+    if (warp == kB2ProducerWarp) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_qkv);
+            tma_prefetch_desc(&map_do);
+            for (int t = 0; t < 4; ++t) {
+                mbar_init(&full[t], 1);
+                mbar_init(&freeb[t], 1);
+            }
+            mbar_init(bar_a, 1);
+            mbar_init(bar_p, kB2EwThreads / 32);
+            mbar_init(bar_b, 1);
+            mbar_init(kv_full, 1);
+            mbar_init(kv_free, kB2DrainThreads / 32);
+            mbar_init(dq_full, 1);
+            mbar_init(dq_free, kB2DrainThreads / 32);
+            fence_barrier_init();
+            for (int t = 0; t < 4; ++t) issue_tiles(t, 0);           // the first item's operands overlap the prologue
+        }
+        reinterpret_cast<float4*>(sColV)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    } else if (warp < 16) {
+        // per-row scalars of the FIRST item (stage 0); later items get theirs from the block loop of the item before
+        const int item = blockIdx.x;
+        const int b = item / H, h = item - b * H;
+        const long long stat = (static_cast<long long>(b) * H + h) * L;
+        if (threadIdx.x < 256) {
+            const int r = threadIdx.x;
+            sLse[r] = r < L ? lse[stat + r] * kLog2e : INFINITY;
+            const float kb = r < L ? (key_bias ? key_bias[static_cast<long long>(b) * L + r] : 0.0f) : -INFINITY;
+            sBias[r] = kb * kLog2e;
+            const uint32_t any = __ballot_sync(0xffffffffu, kb != 0.0f);
+            if (lane == 0) sFlag[warp] = any;
+        }
+        const int sub = lane & 7, rsel = lane >> 3;
+        float cv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cv[e] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = warp * 16 + q * 4 + rsel;
+            float dl = 0.0f;
+            if (r < L) {
+                const long long off = (static_cast<long long>(b) * L + r) * ldo + h * kDh + sub * 8;
+                const uint4 a = *reinterpret_cast<const uint4*>(ctx + off);
+                const uint4 d = *reinterpret_cast<const uint4*>(dctx + off);
+                const uint32_t av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 x = unpack_bf16(av[e]), y = unpack_bf16(dv[e]);
+                    dl = fmaf(x.x, y.x, dl);
+                    dl = fmaf(x.y, y.y, dl);
+                    cv[2 * e] += y.x;
+                    cv[2 * e + 1] += y.y;
+                }
+            }
+            dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+            if (sub == 0) sDelta[r] = dl;
+        }
+        if (colsum != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 8);
+                cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 16);
+                cv_keep[e] = cv[e];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == kB2MmaWarp) {
+        if (lane == 0) {
+            const uint32_t sQ = smem_u32(sm + Bwd2Smem::kQ), sDO = smem_u32(sm + Bwd2Smem::kDO);
+            const uint32_t sK = smem_u32(sm + Bwd2Smem::kK), sV = smem_u32(sm + Bwd2Smem::kV);
+            const uint32_t sP = smem_u32(sm + Bwd2Smem::kP), sDS = smem_u32(sm + Bwd2Smem::kDS);
+            const uint32_t id_a = umma_instr_desc(128, 128, 0, 0);     // S / dP: both operands K-major
+            const uint32_t id_t = umma_instr_desc(128, 64, 1, 1);      // dV / dK: A = P^T / dS^T in place, B MN-major
+            const uint32_t id_q = umma_instr_desc(128, 64, 0, 1);      // dQ: A = dS K-major, B = K MN-major
+            // phase A of block n: S = Q_i K_j^T, dP = dO_i V_j^T
+            auto phase_a = [&](int it, int n) {
+                const int j = n >> 1, i = bwd2_qtile(it, n);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + kTS, umma_smem_desc(sQ + i * tile + kk * 32, 16, 1024),
+                              umma_smem_desc(sK + j * tile + kk * 32, 16, 1024), id_a, kk > 0 ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + kTdP, umma_smem_desc(sDO + i * tile + kk * 32, 16, 1024),
+                              umma_smem_desc(sV + j * tile + kk * 32, 16, 1024), id_a, kk > 0 ? 1u : 0u);
+                umma_commit(bar_a);
+            };
+            auto tiles_ready = [&](int it, int n) {
+                return mbar_try_wait(&full[(n >> 1) ? 3 : 0], it & 1) && mbar_try_wait(&full[bwd2_qtile(it, n) ? 2 : 1], it & 1);
+            };
+            auto wait_tiles = [&](int it, int n) {
+                mbar_wait(&full[(n >> 1) ? 3 : 0], it & 1);
+                mbar_wait(&full[bwd2_qtile(it, n) ? 2 : 1], it & 1);
+            };
+            wait_tiles(0, 0);
+            tc_fence_after();
+            phase_a(0, 0);
+            int gb = 0;
+            for (int it = 0; it < n_my; ++it) {
+#pragma unroll 1
+                for (int n = 0; n < 4; ++n, ++gb) {
+                    const int j = n >> 1, i = bwd2_qtile(it, n), pos = n & 1;
+                    TLB(0, n * 8 + 0);
+                    mbar_wait(bar_p, gb & 1);      // P, dS of the block are in smem; S / dP have been read out of TMEM
+                    TLB(0, n * 8 + 1);
+                    tc_fence_after();
+                    // the NEXT block's S / dP chains go first when their operands are there: the elementwise warps work
+                    // on them while the three accumulation chains of this block run
+                    const bool has_next = n < 3 || it + 1 < n_my;
+                    const int nit = n < 3 ? it : it + 1, nn = n < 3 ? n + 1 : 0;
+                    bool a_done = false;
+                    if (has_next && tiles_ready(nit, nn)) {
+                        tc_fence_after();
+                        phase_a(nit, nn);
+                        a_done = true;
+                    }
+                    TLB(0, n * 8 + 2);
+                    if (pos == 0) {                         // the previous key tile's dV / dK must have been read out
+                        const int kvc = it * 2 + j;
+                        if (kvc > 0) mbar_wait(kv_free, (kvc - 1) & 1);
+                    }
+                    if (n == 0 && it > 0) mbar_wait(dq_free, (it - 1) & 1);
+                    tc_fence_after();
+                    TLB(0, n * 8 + 3);
+                    // phase B: k runs over the 128 query rows (dV, dK) or the 128 keys (dQ), 16 per UMMA
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16(tmem + kTdV, umma_smem_desc(sP + k * (16 * kRowB), tile, 1024),
+                                  umma_smem_desc(sDO + i * tile + k * (16 * kRowB), tile, 1024), id_t, (pos > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16(tmem + kTdK, umma_smem_desc(sDS + k * (16 * kRowB), tile, 1024),
+                                  umma_smem_desc(sQ + i * tile + k * (16 * kRowB), tile, 1024), id_t, (pos > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16(tmem + kTdQ + i * 64, umma_smem_desc(sDS + (k >> 2) * tile + (k & 3) * 32, 16, 1024),
+                                  umma_smem_desc(sK + j * tile + k * (16 * kRowB), tile, 1024), id_q, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(bar_b);
+                    if (pos == 1) umma_commit(kv_full);          // n == 1 also frees K0 / V0, n == 3 K1 / V1
+                    if (n == 2) umma_commit(&freeb[i ? 2 : 1]);  // the query tile of blocks 1 and 2
+                    if (n == 3) {
+                        umma_commit(dq_full);
+                        umma_commit(&freeb[i ? 2 : 1]);          // the query tile of blocks 0 and 3
+                    }
+                    TLB(0, n * 8 + 4);
+                    if (a_done) TLB(0, n * 8 + 5);
+                    if (has_next && !a_done) {
+                        wait_tiles(nit, nn);
+                        tc_fence_after();
+                        phase_a(nit, nn);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kB2DrainWarp0) {
+        const int lg = warp & 3;                                 // the TMEM lane group this warp may read
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16);
+        uint8_t* stage = sm + Bwd2Smem::kStage + (warp - kB2DrainWarp0) * 2048;
+        const bool producer = warp == kB2ProducerWarp && lane == 0;
+        for (int it = 0; it < n_my; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int b = item / H, h = item - b * H;
+            for (int j = 0; j < 2; ++j) {
+                if (warp == kB2DrainWarp0 && lane == 0) TLB(2, j * 8 + 0);
+                mbar_wait(kv_full, (it * 2 + j) & 1);
+                if (warp == kB2DrainWarp0 && lane == 0) TLB(2, j * 8 + 1);
+                tc_fence_after();
+                // producer duty, in the order the tiles come free: K0 V0 after block 1 (= dK_0 / dV_0 complete), Q0 dO0 after
+                // block 2, the rest after block 3 (= dK_1 / dV_1 complete)
+                const int q_mid = bwd2_qtile(it, 1) ? 2 : 1, q_end = bwd2_qtile(it, 3) ? 2 : 1;     // tile groups of the two query tiles
+                if (producer && it + 1 < n_my) {
+                    if (j == 0) {
+                        issue_tiles(0, it + 1);
+                    } else {
+                        mbar_wait(&freeb[q_end], it & 1);
+                        issue_tiles(q_end, it + 1);
+                        issue_tiles(3, it + 1);
+                    }
+                }
+                __syncwarp();
+                const int key0 = j * 128 + lg * 32;
+                const int rows_valid = min(32, max(0, L - key0));
+                __nv_bfloat16* dst = dqkv + (static_cast<long long>(b) * L + key0) * ld + h * kDh;
+                uint32_t pk[2][16];
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {          // 0: dK (scaled), 1: dV
+                    const uint32_t col = which == 0 ? kTdK : kTdV;
+                    const float sc = which == 0 ? scale : 1.0f;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_row + col + half * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            pk[half][e] = pack_bf16(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
+                    }
+                    if (which == 1) warp_arrive(kv_free, lane);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+                        store_rows_32(stage, pk[half], dst + (which == 0 ? H * kDh : 2 * H * kDh) + half * 32, ld, rows_valid, lane);
+                }
+                if (producer && j == 0 && it + 1 < n_my) {
+                    mbar_wait(&freeb[q_mid], it & 1);            // block 2 has retired
+                    issue_tiles(q_mid, it + 1);
+                }
+                __syncwarp();
+            }
+            if (warp == kB2DrainWarp0 && lane == 0) TLB(2, 16);
+            mbar_wait(dq_full, it & 1);
+            if (warp == kB2DrainWarp0 && lane == 0) TLB(2, 17);
+            tc_fence_after();
+            for (int i = 0; i < 2; ++i) {
+                const int q0 = i * 128 + lg * 32;
+                const int rows_valid = min(32, max(0, L - q0));
+                uint32_t pk[2][16];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + kTdQ + i * 64 + half * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        pk[half][e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
+                }
+                if (i == 1) warp_arrive(dq_free, lane);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    store_rows_32(stage, pk[half], dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32, ld, rows_valid, lane);
+                    if (colsum) staged_colsum_32(stage, rows_valid, lane, colsum + h * kDh + half * 32);
+                }
+            }
+            if (warp == kB2DrainWarp0 && lane == 0) TLB(2, 18);
+        }
+    } else if (warp < 16) {
+        if (colsum != nullptr) {
+            // v-bias gradient of the first item: warp partials (lanes 0..7 hold 8 columns each) -> CTA sums in smem
+            if (lane < 8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(sColV + lane * 8 + e, cv_keep[e]);
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kB2EwThreads) : "memory");
+        const int lg = warp & 3, quarter = warp >> 2;       // TMEM lane group, 32-key chunk of the block
+        const int row = lg * 32 + lane;
+        const int sub = lane & 7, rsel = lane >> 3;
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16);
+        const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+        const uint32_t s_next = smem_u32(sm + Bwd2Smem::kNext) + threadIdx.x * 16;
+        int gb = 0;
+        for (int it = 0; it < n_my; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int h = item % H;
+            const int st = it & 1;
+            const bool has_next = it + 1 < n_my;
+            const int item2 = item + gridDim.x;
+            const int b2 = item2 / H, h2 = item2 - b2 * H;
+            const float* sLseC = sLse + st * 256;
+            const float* sDeltaC = sDelta + st * 256;
+            const float* sBiasC = sBias + st * 256;
+#pragma unroll 1
+            for (int n = 0; n < 4; ++n, ++gb) {
+                const int j = n >> 1, i = bwd2_qtile(it, n);
+                // ---- global loads for the NEXT item's per-row scalars: issued first, consumed after the block's math ----
+                float n_lse = 0.0f, n_kb = 0.0f;
+                if (n == 0 && has_next && threadIdx.x < 256) {
+                    const int r = threadIdx.x;
+                    n_lse = r < L ? __ldg(lse + (static_cast<long long>(b2) * H + h2) * L + r) : INFINITY;
+                    n_kb = r < L ? (key_bias ? __ldg(key_bias + static_cast<long long>(b2) * L + r) : 0.0f) : -INFINITY;
+                }
+                const int dr = warp * 16 + n * 4 + rsel;             // the next item's row whose delta this lane octet computes
+                const bool dvalid = has_next && dr < L;
+                if (has_next) {
+                    // through shared memory (cp.async), not registers: nothing of the block's math waits on these loads
+                    const long long off = dvalid ? (static_cast<long long>(b2) * L + dr) * ldo + h2 * kDh + sub * 8 : 0;
+                    cp_async_16(s_next, ctx + off, dvalid);
+                    cp_async_16(s_next + 512 * 16, dctx + off, dvalid);
+                    cp_async_commit();
+                }
+#define TLE(idx) do { if (threadIdx.x == 0) TLB(1, n * 8 + (idx)); } while (0)
+                TLE(0);
+                mbar_wait(bar_a, gb & 1);
+                TLE(1);
+                tc_fence_after();
+                if (n == 0 && colsum != nullptr && threadIdx.x < 64) {
+                    // column sums of this item's dO (= its share of the v-bias gradient) were gathered during the previous item
+                    const float v = sColV[st * 64 + threadIdx.x];
+                    sColV[st * 64 + threadIdx.x] = 0.0f;
+                    atomicAdd(colsum + 2 * H * kDh + h * kDh + threadIdx.x, v);
+                }
+                const float lse_r = sLseC[i * 128 + row], dl_r = sDeltaC[i * 128 + row];
+                const int c = quarter;
+                const bool masked = sFlag[st * 8 + j * 4 + c] != 0u;
+                uint32_t pp[2][8], dd[2][8];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {                    // two 16-key halves: 32 accumulator registers live
+                    uint32_t rs[16], rd[16];
+                    tmem_ld_32x16_a(t_row + kTS + c * 32 + hh * 16, rs);
+                    tmem_ld_32x16_a(t_row + kTdP + c * 32 + hh * 16, rd);
+                    if (!masked) {
+                        const uint64_t neg_lse2 = pack_f32x2(-lse_r, -lse_r), neg_dl2 = pack_f32x2(-dl_r, -dl_r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; e += 2) {
+                            float x0, x1, d0, d1;
+                            unpack_f32x2(ffma2(pack_u32x2(rs[e], rs[e + 1]), scale2, neg_lse2), x0, x1);
+                            const float p0 = ex2_ftz(x0), p1 = ex2_ftz(x1);
+                            unpack_f32x2(fmul2(pack_f32x2(p0, p1), fadd2(pack_u32x2(rd[e], rd[e + 1]), neg_dl2)), d0, d1);
+                            pp[hh][e >> 1] = pack_bf16(p0, p1);
+                            dd[hh][e >> 1] = pack_bf16(d0, d1);
+                        }
+                    } else {
+                        float bias[16];
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(sBiasC + j * 128 + c * 32 + hh * 16 + e);
+                            bias[e] = b4.x - lse_r; bias[e + 1] = b4.y - lse_r; bias[e + 2] = b4.z - lse_r; bias[e + 3] = b4.w - lse_r;
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; e += 2) {
+                            const float p0 = ex2_ftz(fmaf(__uint_as_float(rs[e]), scale_log2, bias[e]));
+                            const float p1 = ex2_ftz(fmaf(__uint_as_float(rs[e + 1]), scale_log2, bias[e + 1]));
+                            pp[hh][e >> 1] = pack_bf16(p0, p1);
+                            dd[hh][e >> 1] = pack_bf16(p0 * (__uint_as_float(rd[e]) - dl_r), p1 * (__uint_as_float(rd[e + 1]) - dl_r));
+                        }
+                    }
+                }
+                // everything above overlapped the previous block's accumulation chains; they must have retired before
+                // P / dS are overwritten
+                TLE(2);
+                if (gb > 0) mbar_wait(bar_b, (gb - 1) & 1);
+                TLE(3);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    // 16 columns = granules (c & 1) * 4 + hh * 2 + {0, 1} of the row in 64-column chunk (c >> 1)
+                    uint8_t* pc = sm + Bwd2Smem::kP + (c >> 1) * (128 * kRowB);
+                    uint8_t* dc = sm + Bwd2Smem::kDS + (c >> 1) * (128 * kRowB);
+                    const int g0 = (c & 1) * 4 + hh * 2;
+                    *reinterpret_cast<uint4*>(pc + swz(row, g0)) = make_uint4(pp[hh][0], pp[hh][1], pp[hh][2], pp[hh][3]);
+                    *reinterpret_cast<uint4*>(pc + swz(row, g0 + 1)) = make_uint4(pp[hh][4], pp[hh][5], pp[hh][6], pp[hh][7]);
+                    *reinterpret_cast<uint4*>(dc + swz(row, g0)) = make_uint4(dd[hh][0], dd[hh][1], dd[hh][2], dd[hh][3]);
+                    *reinterpret_cast<uint4*>(dc + swz(row, g0 + 1)) = make_uint4(dd[hh][4], dd[hh][5], dd[hh][6], dd[hh][7]);
+                }
+                fence_proxy_async();
+                TLE(4);
+                // ---- the next item's scalars: stage st ^ 1 (nobody reads it before the next item's first block) ----
+                if (has_next) {
+                    cp_async_wait<0>();
+                    uint4 n_o, n_do;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_o.x), "=r"(n_o.y), "=r"(n_o.z), "=r"(n_o.w) : "r"(s_next));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_do.x), "=r"(n_do.y), "=r"(n_do.z), "=r"(n_do.w) : "r"(s_next + 512 * 16));
+                    const uint32_t av[4] = {n_o.x, n_o.y, n_o.z, n_o.w}, dv[4] = {n_do.x, n_do.y, n_do.z, n_do.w};
+                    float dl = 0.0f, cv[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 x = unpack_bf16(av[e]), y = unpack_bf16(dv[e]);
+                        dl = fmaf(x.x, y.x, dl);
+                        dl = fmaf(x.y, y.y, dl);
+                        cv[2 * e] = y.x;
+                        cv[2 * e + 1] = y.y;
+                    }
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+                    if (sub == 0) sDelta[(st ^ 1) * 256 + dr] = dl;
+                    if (colsum != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 8);
+                            cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 16);
+                        }
+                        if (lane < 8) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) atomicAdd(sColV + (st ^ 1) * 64 + lane * 8 + e, cv[e]);
+                        }
+                    }
+                    if (n == 0 && threadIdx.x < 256) {
+                        sLse[(st ^ 1) * 256 + threadIdx.x] = n_lse * kLog2e;
+                        sBias[(st ^ 1) * 256 + threadIdx.x] = n_kb * kLog2e;
+                        const uint32_t any = __ballot_sync(0xffffffffu, n_kb != 0.0f);
+                        if (lane == 0) sFlag[(st ^ 1) * 8 + warp] = any;
+                    }
+                }
+                TLE(5);
+                warp_arrive(bar_p, lane);
+                TLE(6);
+            }
+        }
+    }
+#undef TLE
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kB2ProducerWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+#undef TLB
 int make_map3(CUtensorMap* map, const void* ptr, int B, int L, long long row_elems, int box_rows) {
     const long long dims[3] = {row_elems, L, B};
     const long long strides[2] = {row_elems, static_cast<long long>(L) * row_elems};
     const int box[3] = {64, box_rows, 1};
     return encode_tmap_bf16(map, ptr, 3, dims, strides, box);
+}
+
+// CLIMB_ATTN_V1=1 keeps the one-tile-per-CTA kernels (A/B measurements only)
+bool attn_v1() {
+    static int v1 = -1;
+    if (v1 < 0) {
+        const char* e = std::getenv("CLIMB_ATTN_V1");
+        v1 = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v1 == 1;
+}
+
+int env_flag(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e != nullptr && e[0] != 0 ? std::atoi(e) : dflt;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 }  // namespace
@@ -586,6 +1437,39 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
                      cudaStream_t stream, float p_drop, unsigned long long seed) {
     CLIMB_REQUIRE(L <= 256, "attention_tc_fwd: L=%d > 256", L);
     CLIMB_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "attention_tc_fwd: dropout p=%f outside [0, 1)", p_drop);
+    if (p_drop == 0.0f && !attn_v1()) {
+        CUtensorMap mqkv;
+        int rc2 = make_map3(&mqkv, qkv, B, L, 3LL * H * kDh, 256);
+        if (rc2) return rc2;
+        static bool attr2 = false;
+        if (!attr2) {
+            CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem::kTotal));
+            attr2 = true;
+        }
+        const int n_items = B * H;
+        static long long* tl = nullptr;
+        static int tl_calls = 0;
+        if (env_flag("CLIMB_ATTN_TL", 0) && tl == nullptr) {
+            cudaMalloc(&tl, 4 * 32 * sizeof(long long));
+            cudaMemset(tl, 0, 4 * 32 * sizeof(long long));
+        }
+        CLIMB_CUDA_OK(launch_pdl(attn_tc_fwd2_kernel, dim3(std::min(n_items, sm_count())), dim3(kF2Threads), Fwd2Smem::kTotal, stream,
+                                 mqkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, n_items, L, H, scale * kLog2e, env_flag("CLIMB_ATTN_STAGGER", 1), env_flag("CLIMB_ATTN_DBG", 0), tl));
+        CLIMB_LAUNCH_OK();
+        if (tl != nullptr && ++tl_calls == 20) {
+            long long h[128];
+            cudaDeviceSynchronize();
+            cudaMemcpy(h, tl, sizeof(h), cudaMemcpyDeviceToHost);
+            long long t0 = h[0];
+            for (int r = 0; r < 4; ++r) {
+                printf("TL role %d:", r);
+                for (int i = 0; i < 24; ++i) printf(" %lld", h[r * 32 + i] ? h[r * 32 + i] - t0 : -1);
+                printf("\n");
+            }
+            fflush(stdout);
+        }
+        return 0;
+    }
     CUtensorMap mq, mkv;
     int rc = make_map3(&mq, qkv, B, L, 3LL * H * kDh, 128);
     if (rc) return rc;
@@ -607,6 +1491,42 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
 int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
                      void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream) {
     CLIMB_REQUIRE(L <= 256, "attention_tc_bwd: L=%d > 256", L);
+    if (L > 128 && !attn_v1()) {
+        CUtensorMap mqkv2, mdo2;
+        int rc2 = make_map3(&mqkv2, qkv, B, L, 3LL * H * kDh, 128);
+        if (rc2) return rc2;
+        rc2 = make_map3(&mdo2, dctx, B, L, static_cast<long long>(H) * kDh, 128);
+        if (rc2) return rc2;
+        static bool attr2 = false;
+        if (!attr2) {
+            CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Smem::kTotal));
+            attr2 = true;
+        }
+        const int n_items = B * H;
+        static long long* tlb = nullptr;
+        static int tl_calls = 0;
+        if (env_flag("CLIMB_ATTN_TL", 0) && tlb == nullptr) {
+            cudaMalloc(&tlb, 192 * sizeof(long long));
+            cudaMemset(tlb, 0, 192 * sizeof(long long));
+        }
+        CLIMB_CUDA_OK(launch_pdl(attn_tc_bwd2_kernel, dim3(std::min(n_items, sm_count())), dim3(kB2Threads), Bwd2Smem::kTotal, stream,
+                                 mqkv2, mdo2, key_bias, static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx),
+                                 lse, static_cast<__nv_bfloat16*>(dqkv), colsum, n_items, L, H, scale * kLog2e, scale, tlb));
+        CLIMB_LAUNCH_OK();
+        if (tlb != nullptr && ++tl_calls == 20) {
+            long long h[192];
+            cudaDeviceSynchronize();
+            cudaMemcpy(h, tlb, sizeof(h), cudaMemcpyDeviceToHost);
+            long long t0 = h[0];
+            for (int r = 0; r < 3; ++r) {
+                printf("TLB role %d:", r);
+                for (int i = 0; i < 32; ++i) printf("%s%lld", (i % 8) ? " " : " | ", h[r * 64 + i] ? h[r * 64 + i] - t0 : -1);
+                printf("\n");
+            }
+            fflush(stdout);
+        }
+        return 0;
+    }
     CUtensorMap mqkv, mdo;
     int rc = make_map3(&mqkv, qkv, B, L, 3LL * H * kDh, 256);
     if (rc) return rc;

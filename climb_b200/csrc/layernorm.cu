@@ -326,10 +326,107 @@ ln_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
     }
 }
 
+// Forward, streaming variant for the encoder's hot calls (dense rows, bf16 output + statistics): same per-warp
+// cp.async.bulk row ring as the backward (three stages of one 3 KB row, two CTAs per SM).
+template <int NV>
+struct LnFwdBulk {
+    static constexpr int D = NV * 128;
+    static constexpr int kWarps = 8;
+    static constexpr int kStages = 3;
+    static constexpr int kRowBytes = D * 4;
+    static constexpr int kSmem = kWarps * kStages * kRowBytes + kWarps * kStages * 8;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(LnFwdBulk<NV>::kWarps * 32, 2)
+ln_fwd_bulk_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows) {
+    using C = LnFwdBulk<NV>;
+    constexpr int D = C::D;
+    extern __shared__ __align__(128) uint8_t ln_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* ring = ln_smem + warp * (C::kStages * C::kRowBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + C::kWarps * C::kStages * C::kRowBytes) + warp * C::kStages;
+    if (lane == 0) {
+        for (int s = 0; s < C::kStages; ++s) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    pdl_wait();
+    const int stride = gridDim.x * C::kWarps;
+    const int row0 = blockIdx.x * C::kWarps + warp;
+    auto issue = [&](int row, int s) {
+        mbar_arrive_expect_tx(&bars[s], C::kRowBytes);
+        bulk_load_1d(ring + s * C::kRowBytes, x + static_cast<long long>(row) * D, C::kRowBytes, &bars[s]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < C::kStages; ++s)
+            if (row0 + s * stride < rows) issue(row0 + s * stride, s);
+    }
+    float4 gam[NV], bet[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+        bet[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    }
+    int it = 0;
+    for (int row = row0; row < rows; row += stride, ++it) {
+        const int s = it % C::kStages;
+        mbar_wait(&bars[s], (it / C::kStages) & 1);
+        const float4* buf = reinterpret_cast<const float4*>(ring + s * C::kRowBytes);
+        float4 v[NV];
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i] = buf[lane + 32 * i];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        __syncwarp();
+        if (lane == 0 && row + C::kStages * stride < rows) issue(row + C::kStages * stride, s);
+        const float mean = warp_sum(sum) * (1.0f / D);
+        float sq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = mean;
+            if (rstd_out) rstd_out[row] = rstd;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            uint2 p;
+            p.x = pack_bf16(v[i].x * rstd * gam[i].x + bet[i].x, v[i].y * rstd * gam[i].y + bet[i].y);
+            p.y = pack_bf16(v[i].z * rstd * gam[i].z + bet[i].z, v[i].w * rstd * gam[i].w + bet[i].w);
+            reinterpret_cast<uint2*>(y + static_cast<long long>(row) * D)[lane + 32 * i] = p;
+        }
+    }
+}
+
 template <int NV>
 int launch_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
                void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int act,
                cudaStream_t stream) {
+    if constexpr (NV == 6) {
+        if (y_bf16 != nullptr && y_f32 == nullptr && act == CLIMB_EPI_NONE && ldx == NV * 128 && rows >= 1024 &&
+            (reinterpret_cast<uintptr_t>(x) & 15) == 0 && !g_ln_no_bulk) {
+            using C = LnFwdBulk<NV>;
+            static bool attr = false;
+            if (!attr) {
+                CLIMB_CUDA_OK(cudaFuncSetAttribute(ln_fwd_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+                attr = true;
+            }
+            int g2 = (rows + C::kWarps - 1) / C::kWarps;
+            if (g2 > 148 * 2) g2 = 148 * 2;
+            CLIMB_CUDA_OK(launch_pdl(ln_fwd_bulk_kernel<NV>, dim3(g2), dim3(C::kWarps * 32), static_cast<size_t>(C::kSmem), stream, x, gamma,
+                                     beta, eps, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, rows));
+            CLIMB_LAUNCH_OK();
+            return 0;
+        }
+    }
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     CLIMB_CUDA_OK(launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(kWarpsPerBlock * 32), 0, stream, x, ldx, gamma, beta, eps,
                              static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, act));

@@ -241,7 +241,9 @@ def _attn_ref(qkv, key_bias, B, L_, H, scale):
 
 @pytest.mark.parametrize("B,L_,H,masked", [(2, 237, 12, False), (3, 237, 12, True), (2, 13, 2, True),
                                            (1, 64, 1, False), (2, 200, 3, True), (1, 281, 2, True),
-                                           (2, 256, 2, True), (2, 128, 1, False), (3, 129, 2, True), (5, 1, 1, False)])
+                                           (2, 256, 2, True), (2, 128, 1, False), (3, 129, 2, True), (5, 1, 1, False),
+                                           # more (b, h) items than SMs: the persistent kernels walk 2-5 items per CTA
+                                           (40, 237, 12, True), (64, 237, 12, False), (30, 100, 12, True), (26, 129, 7, True)])
 def test_attention_fwd_bwd(B, L_, H, masked):
     L = _lib()
     torch.manual_seed(B * 100 + L_)
@@ -336,7 +338,12 @@ def test_layernorm_bwd_streaming_kernel(rows):
     x = torch.randn(rows, d, device="cuda") * 3 + 1
     g = torch.randn(d, device="cuda")
     b = torch.randn(d, device="cuda")
-    _, _, mean, rstd = L.layernorm_fwd(x, g, b, 1e-12, out_bf16=True, out_f32=False)
+    # (the forward with bf16 output only and >= 1024 dense rows is the streaming forward kernel)
+    yb, _, mean, rstd = L.layernorm_fwd(x, g, b, 1e-12, out_bf16=True, out_f32=False)
+    y_ref = torch.nn.functional.layer_norm(x, (d,), g, b, 1e-12)
+    assert _rel_err(yb, y_ref) < 4e-3, _rel_err(yb, y_ref)
+    assert (yb.float() - y_ref.bfloat16().float()).abs().max().item() <= 2 ** -6 * y_ref.abs().max().item()
+    assert _max_err(mean, x.mean(1)) < 1e-5 and _rel_err(rstd, x.var(1, unbiased=False).add(1e-12).rsqrt()) < 1e-5
     dy = torch.randn(rows, d, device="cuda").bfloat16()
     dres = torch.randn(rows, d, device="cuda")
     xr, gr, br = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
