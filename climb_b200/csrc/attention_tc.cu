@@ -26,6 +26,13 @@
 #include <algorithm>
 #include <cstdlib>
 
+// CLIMB_ATTN_TIMELINE=1 (compile time, dev only) makes CTA 0 of the persistent kernels record clock64() at the hand-over
+// points of its third item; CLIMB_ATTN_TL=1 (environment) then prints the cycle stamps after the 20th launch. That timeline is
+// what located the kernels' limits (attention section); the default build carries none of it.
+#ifndef CLIMB_ATTN_TIMELINE
+#define CLIMB_ATTN_TIMELINE 0
+#endif
+
 namespace climb {
 namespace {
 
@@ -75,14 +82,46 @@ __device__ __forceinline__ void store_rows_32(uint8_t* stage, const uint32_t (&p
     __syncwarp();
 }
 
-// column sums of the 32 x 32 block that store_rows_32 just staged: lane l owns column l
-__device__ __forceinline__ void staged_colsum_32(const uint8_t* stage, int rows_valid, int lane, float* dst) {
-    float cs = 0.0f;
-    for (int rr = 0; rr < rows_valid; ++rr) {
-        const uint16_t h16 = *reinterpret_cast<const uint16_t*>(stage + swz(rr >> 1, (rr & 1) * 4 + (lane >> 3)) + (lane & 7) * 2);
-        cs += __uint_as_float(static_cast<uint32_t>(h16) << 16);
+// the same block straight from registers: lane = row writes its 64 B (two full 32 B sectors) with four 16 B stores. The
+// warp touches 32 rows per instruction instead of 8, but nothing is staged, re-read or synchronised: the drain warps of the
+// persistent backward are a serial resource, and this is a third of the staged version's time
+__device__ __forceinline__ void store_rows_32_direct(const uint32_t (&pk)[16], __nv_bfloat16* gdst, long long ld_elems, int rows_valid,
+                                                     int lane) {
+    if (lane < rows_valid) {
+        uint4* dst = reinterpret_cast<uint4*>(gdst + lane * ld_elems);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
     }
-    atomicAdd(dst + lane, cs);
+}
+
+// column sums of the 32 x 32 bf16 block that store_rows_32 just staged (rows past the valid ones hold exact zeros here):
+// lane = (row group of 4, 8-column granule): four independent 16 B loads, then a butterfly over the eight row groups
+__device__ __forceinline__ void staged_colsum_32(const uint8_t* stage, int lane, float* dst) {
+    const int g = lane & 3, rg = lane >> 2;
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int rr = rg * 4 + q;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + swz(rr >> 1, (rr & 1) * 4 + g));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16(w[e]);
+            cs[2 * e] += f.x;
+            cs[2 * e + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
+    }
+    if (lane < 4) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(dst + lane * 8 + e, cs[e]);
+    }
     __syncwarp();
 }
 
@@ -310,8 +349,12 @@ __device__ __forceinline__ void named_bar_sync(int id_offset, int threads) {
 __global__ void __launch_bounds__(kF2Threads, 1)
 attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias,
                     __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int n_items, int L, int H, float scale_log2,
-                    int stagger, int dbg, long long* tl) {
+                    int stagger, long long* tl) {
+#if CLIMB_ATTN_TIMELINE
 #define TL(role, idx) do { if (tl != nullptr && blockIdx.x == 0 && it == 2) tl[(role) * 32 + (idx)] = clock64(); } while (0)
+#else
+#define TL(role, idx) do { } while (0)
+#endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Fwd2Smem::kBar);
@@ -365,20 +408,13 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
                 const int item = blockIdx.x + it * gridDim.x;
                 const int b = item / H, h = item - b * H;
                 if (it > 0) mbar_wait(qk_free, (it - 1) & 1);
-                const bool skip = (dbg & 2) && it >= 2;
-                if (skip) mbar_arrive(qk_full);
-                else {
                 mbar_arrive_expect_tx(qk_full, 2 * 256 * kRowB);
                 tma_load_3d(&map_qkv, qk_full, sm + Fwd2Smem::kQ, h * kDh, 0, b);
                 tma_load_3d(&map_qkv, qk_full, sm + Fwd2Smem::kK, (H + h) * kDh, 0, b);
-                }
                 const int s = it & 1, k = it >> 1;
                 if (k > 0) mbar_wait(&v_free[s], (k - 1) & 1);
-                if (skip) mbar_arrive(&v_full[s]);
-                else {
                 mbar_arrive_expect_tx(&v_full[s], 256 * kRowB);
                 tma_load_3d(&map_qkv, &v_full[s], sm + Fwd2Smem::kV + s * (256 * kRowB), (2 * H + h) * kDh, 0, b);
-                }
             }
         }
         __syncwarp();
@@ -476,7 +512,6 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
             float m = -INFINITY, m_raw = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
-                if (dbg & 1) { m = 0.0f; break; }
                 uint32_t r[32];
                 tmem_ld_32x32(t_row + c * 64 + half * 32, r);
                 const bool masked = flag[c * 2 + half] != 0u;
@@ -509,10 +544,7 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
                 const bool masked = flag[c * 2 + half] != 0u;
                 float p[32];
                 tmem_ld_wait();
-                if (dbg & 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) p[j] = __uint_as_float(r[j]);
-                } else if (!masked) {
+                if (!masked) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         float x0, x1;
@@ -567,7 +599,6 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
             }
             const int qrow0 = g * 128 + lg * 32;
             const int rows_valid = min(32, max(0, L - qrow0));
-            if (!(dbg & 4))
             store_rows_32(ring + wg * 2048, pk, ctx + (static_cast<long long>(b) * L + qrow0) * (H * kDh) + h * kDh + half * 32,
                           static_cast<long long>(H) * kDh, rows_valid, lane);
             if (half == 0 && g * 128 + row < L) lse[(static_cast<long long>(b) * H + h) * L + g * 128 + row] = (m + log2f(sum)) * kLn2;
@@ -883,7 +914,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                 for (int e = 0; e < 16; ++e)
                     pk[e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
                 store_rows_32(stage, pk, dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32, ld, rows_valid, lane);
-                if (colsum) staged_colsum_32(stage, rows_valid, lane, colsum + h * kDh + half * 32);
+                if (colsum) staged_colsum_32(stage, lane, colsum + h * kDh + half * 32);
             }
         }
     }
@@ -920,7 +951,7 @@ struct Bwd2Smem {
     static constexpr int kLse = 192 * 1024;      // [2 stages][256] floats each
     static constexpr int kDelta = 194 * 1024;
     static constexpr int kBias = 196 * 1024;
-    static constexpr int kColV = 198 * 1024;     // [2 stages][64] floats: column sums of dO
+    static constexpr int kColV = 198 * 1024;     // [64] column sums of dO, [64] column sums of dQ, over all of the CTA's items
     static constexpr int kFlag = 198 * 1024 + 512;   // [2 stages][8] words: the 32-key chunk has a non-zero mask
     static constexpr int kBar = 198 * 1024 + 640;
     static constexpr int kStage = 199 * 1024;    // 4 drain warps x 2 KB
@@ -932,18 +963,44 @@ struct Bwd2Smem {
 // previous item left to arrive in
 __device__ __forceinline__ int bwd2_qtile(int it, int n) { return (((n + 1) >> 1) ^ it) & 1; }
 constexpr int kB2EwThreads = 512;
-constexpr int kB2MmaWarp = 16, kB2DrainWarp0 = 17;     // drain warp 0 is also the TMA producer (and owns the TMEM allocation)
+constexpr int kB2MmaWarpA = 16, kB2MmaWarpB = 17, kB2DrainWarp0 = 18;     // drain warp 0 is also the TMA producer (and owns the TMEM allocation)
 constexpr int kB2ProducerWarp = kB2DrainWarp0;
 constexpr int kB2DrainThreads = 128;
-constexpr int kB2Threads = 21 * 32;
+constexpr int kB2Threads = 22 * 32;
+
+// A shared-memory descriptor split into its words: the start-address field (bits 0..13 of the low word, in 16-byte units)
+// is the only thing that changes between the instructions of a chain, so an operand costs one 32-bit add
+struct DescBase {
+    uint32_t lo, hi;
+    __device__ explicit DescBase(uint64_t d) : lo(static_cast<uint32_t>(d)), hi(static_cast<uint32_t>(d >> 32)) {}
+};
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 __global__ void __launch_bounds__(kB2Threads, 1)
 attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                     const float* __restrict__ key_bias, const __nv_bfloat16* __restrict__ ctx,
                     const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
-                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int n_items, int L, int H,
+                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int n_batch, int L, int H,
                     float scale_log2, float scale, long long* tl) {
+#if CLIMB_ATTN_TIMELINE
 #define TLB(role, idx) do { if (tl != nullptr && blockIdx.x == 0 && it == 2) tl[(role) * 64 + (idx)] = clock64(); } while (0)
+#else
+#define TLB(role, idx) do { } while (0)
+#endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* sLse = reinterpret_cast<float*>(sm + Bwd2Smem::kLse);
@@ -955,16 +1012,22 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     uint64_t* full = bars;               // [4] tx: K0 V0 | Q0 dO0 | Q1 dO1 | K1 V1 of an item have landed
     uint64_t* freeb = bars + 4;          // [4] commit: the last chain of the item that reads the tiles has retired
     uint64_t* bar_a = bars + 8;          // S, dP of a block are in TMEM
-    uint64_t* bar_p = bars + 9;          // P, dS of a block are in smem (16 warp arrivals); S / dP have been read
+    uint64_t* bar_p = bars + 9;          // P, dS of a block are in smem (16 warp arrivals)
     uint64_t* bar_b = bars + 10;         // the accumulation chains of a block have retired
     uint64_t* kv_full = bars + 11;       // dK_j, dV_j complete
     uint64_t* kv_free = bars + 12;       // ... and read out of TMEM (4 warp arrivals)
-    uint64_t* dq_full = bars + 13;       // dQ_0, dQ_1 complete
-    uint64_t* dq_free = bars + 14;       // ... and read out of TMEM (4 warp arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* dq_full = bars + 13;       // [2] dQ_i complete: the query tile of blocks 1 and 2 after block 2, the other after block 3
+    uint64_t* dq_free = bars + 15;       // [2] ... and read out of TMEM (4 warp arrivals)
+    uint64_t* bar_s = bars + 17;         // S, dP of a block have been read out of TMEM (16 warp arrivals): the next block's chains may start
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    // a CTA stays with ONE head (h = CTA index mod H) and walks over the batch: the q / v bias gradients of the head add up in
+    // shared memory and leave as 128 global atomics per CTA instead of 128 per item. The host guarantees gridDim.x >= H.
+    const int h = static_cast<int>(blockIdx.x) % H;
+    const int b_first = static_cast<int>(blockIdx.x) / H;
+    const int b_step = (static_cast<int>(gridDim.x) - h + H - 1) / H;          // CTAs that share this head
+    const int n_my = b_first < n_batch ? (n_batch - b_first + b_step - 1) / b_step : 0;
     const long long ld = 3LL * H * kDh, ldo = static_cast<long long>(H) * kDh;
     constexpr uint32_t tile = 128 * kRowB;                          // 16 KB: 128 rows of a [rows x 64] tile
     pdl_wait();
@@ -972,8 +1035,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
 
     // operand tile group t of item `it` -> smem (producer warp, one lane)
     auto issue_tiles = [&](int t, int it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int b = item / H, h = item - b * H;
+        const int b = b_first + it * b_step;
         mbar_arrive_expect_tx(&full[t], 2 * tile);
         if (t == 0 || t == 3) {
             const int r0 = t == 0 ? 0 : 128;
@@ -999,11 +1061,14 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             }
             mbar_init(bar_a, 1);
             mbar_init(bar_p, kB2EwThreads / 32);
+            mbar_init(bar_s, kB2EwThreads / 32);
             mbar_init(bar_b, 1);
             mbar_init(kv_full, 1);
             mbar_init(kv_free, kB2DrainThreads / 32);
-            mbar_init(dq_full, 1);
-            mbar_init(dq_free, kB2DrainThreads / 32);
+            for (int t = 0; t < 2; ++t) {
+                mbar_init(&dq_full[t], 1);
+                mbar_init(&dq_free[t], kB2DrainThreads / 32);
+            }
             fence_barrier_init();
             for (int t = 0; t < 4; ++t) issue_tiles(t, 0);           // the first item's operands overlap the prologue
         }
@@ -1013,8 +1078,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         tmem_relinquish();
     } else if (warp < 16) {
         // per-row scalars of the FIRST item (stage 0); later items get theirs from the block loop of the item before
-        const int item = blockIdx.x;
-        const int b = item / H, h = item - b * H;
+        const int b = b_first;
         const long long stat = (static_cast<long long>(b) * H + h) * L;
         if (threadIdx.x < 256) {
             const int r = threadIdx.x;
@@ -1051,105 +1115,94 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             dl += __shfl_xor_sync(0xffffffffu, dl, 4);
             if (sub == 0) sDelta[r] = dl;
         }
-        if (colsum != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 8);
-                cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 16);
-                cv_keep[e] = cv[e];
-            }
-        }
+        for (int e = 0; e < 8; ++e) cv_keep[e] = cv[e];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == kB2MmaWarp) {
+    if (warp == kB2MmaWarpA) {
+        // S = Q_i K_j^T, dP = dO_i V_j^T of the NEXT block: issued the moment the elementwise warps have read the current
+        // block's S / dP out of TMEM. The two issuing warps split the block's 32 instructions (an issue costs a thread
+        // ~40 cycles of descriptor arithmetic around the tcgen05.mma; the 128 x 64 x 16 / 128 x 128 x 16 shapes here keep the
+        // tensor pipe busy for 32 / 64, so a single issuer would be the kernel's speed limit).
         if (lane == 0) {
-            const uint32_t sQ = smem_u32(sm + Bwd2Smem::kQ), sDO = smem_u32(sm + Bwd2Smem::kDO);
-            const uint32_t sK = smem_u32(sm + Bwd2Smem::kK), sV = smem_u32(sm + Bwd2Smem::kV);
-            const uint32_t sP = smem_u32(sm + Bwd2Smem::kP), sDS = smem_u32(sm + Bwd2Smem::kDS);
-            const uint32_t id_a = umma_instr_desc(128, 128, 0, 0);     // S / dP: both operands K-major
-            const uint32_t id_t = umma_instr_desc(128, 64, 1, 1);      // dV / dK: A = P^T / dS^T in place, B MN-major
-            const uint32_t id_q = umma_instr_desc(128, 64, 0, 1);      // dQ: A = dS K-major, B = K MN-major
-            // phase A of block n: S = Q_i K_j^T, dP = dO_i V_j^T
+            const uint32_t id_a = umma_instr_desc(128, 128, 0, 0);     // both operands K-major
+            const DescBase dQ_k(umma_smem_desc(smem_u32(sm + Bwd2Smem::kQ), 16, 1024)), dK_k(umma_smem_desc(smem_u32(sm + Bwd2Smem::kK), 16, 1024));
+            const DescBase dDO_k(umma_smem_desc(smem_u32(sm + Bwd2Smem::kDO), 16, 1024)), dV_k(umma_smem_desc(smem_u32(sm + Bwd2Smem::kV), 16, 1024));
             auto phase_a = [&](int it, int n) {
-                const int j = n >> 1, i = bwd2_qtile(it, n);
+                const uint32_t j = n >> 1, i = bwd2_qtile(it, n);
+                mbar_wait(&full[j ? 3 : 0], it & 1);
+                mbar_wait(&full[i ? 2 : 1], it & 1);
+                tc_fence_after();
+                const uint32_t oi = i * (tile >> 4), oj = j * (tile >> 4);
+                // the two chains alternate: consecutive instructions never accumulate into the same TMEM columns
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tmem + kTS, umma_smem_desc(sQ + i * tile + kk * 32, 16, 1024),
-                              umma_smem_desc(sK + j * tile + kk * 32, 16, 1024), id_a, kk > 0 ? 1u : 0u);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tmem + kTdP, umma_smem_desc(sDO + i * tile + kk * 32, 16, 1024),
-                              umma_smem_desc(sV + j * tile + kk * 32, 16, 1024), id_a, kk > 0 ? 1u : 0u);
+                for (uint32_t kk = 0; kk < 4; ++kk) {
+                    umma_bf16_lohi(tmem + kTS, dQ_k.lo + oi + kk * 2, dQ_k.hi, dK_k.lo + oj + kk * 2, dK_k.hi, id_a, kk > 0 ? 1u : 0u);
+                    umma_bf16_lohi(tmem + kTdP, dDO_k.lo + oi + kk * 2, dDO_k.hi, dV_k.lo + oj + kk * 2, dV_k.hi, id_a, kk > 0 ? 1u : 0u);
+                }
                 umma_commit(bar_a);
             };
-            auto tiles_ready = [&](int it, int n) {
-                return mbar_try_wait(&full[(n >> 1) ? 3 : 0], it & 1) && mbar_try_wait(&full[bwd2_qtile(it, n) ? 2 : 1], it & 1);
-            };
-            auto wait_tiles = [&](int it, int n) {
-                mbar_wait(&full[(n >> 1) ? 3 : 0], it & 1);
-                mbar_wait(&full[bwd2_qtile(it, n) ? 2 : 1], it & 1);
-            };
-            wait_tiles(0, 0);
-            tc_fence_after();
             phase_a(0, 0);
             int gb = 0;
             for (int it = 0; it < n_my; ++it) {
 #pragma unroll 1
                 for (int n = 0; n < 4; ++n, ++gb) {
-                    const int j = n >> 1, i = bwd2_qtile(it, n), pos = n & 1;
+                    if (n == 3 && it + 1 >= n_my) break;
                     TLB(0, n * 8 + 0);
-                    mbar_wait(bar_p, gb & 1);      // P, dS of the block are in smem; S / dP have been read out of TMEM
+                    mbar_wait(bar_s, gb & 1);      // S / dP of the block have been read out of TMEM (its P / dS are still being made)
                     TLB(0, n * 8 + 1);
-                    tc_fence_after();
-                    // the NEXT block's S / dP chains go first when their operands are there: the elementwise warps work
-                    // on them while the three accumulation chains of this block run
-                    const bool has_next = n < 3 || it + 1 < n_my;
-                    const int nit = n < 3 ? it : it + 1, nn = n < 3 ? n + 1 : 0;
-                    bool a_done = false;
-                    if (has_next && tiles_ready(nit, nn)) {
-                        tc_fence_after();
-                        phase_a(nit, nn);
-                        a_done = true;
-                    }
+                    phase_a(n < 3 ? it : it + 1, n < 3 ? n + 1 : 0);
                     TLB(0, n * 8 + 2);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kB2MmaWarpB) {
+        // dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j of the current block
+        if (lane == 0) {
+            const uint32_t id_t = umma_instr_desc(128, 64, 1, 1);      // dV / dK: A = P^T / dS^T in place, B MN-major
+            const uint32_t id_q = umma_instr_desc(128, 64, 0, 1);      // dQ: A = dS K-major, B = K MN-major
+            const DescBase dP_m(umma_smem_desc(smem_u32(sm + Bwd2Smem::kP), tile, 1024)), dDS_m(umma_smem_desc(smem_u32(sm + Bwd2Smem::kDS), tile, 1024));
+            const DescBase dDS_k(umma_smem_desc(smem_u32(sm + Bwd2Smem::kDS), 16, 1024));
+            const DescBase dDO_m(umma_smem_desc(smem_u32(sm + Bwd2Smem::kDO), tile, 1024)), dQ_m(umma_smem_desc(smem_u32(sm + Bwd2Smem::kQ), tile, 1024));
+            const DescBase dK_m(umma_smem_desc(smem_u32(sm + Bwd2Smem::kK), tile, 1024));
+            constexpr uint32_t kstep = (16 * kRowB) >> 4;                 // 16 rows of a [rows x 64] tile, in descriptor units
+            int gb = 0;
+            for (int it = 0; it < n_my; ++it) {
+#pragma unroll 1
+                for (int n = 0; n < 4; ++n, ++gb) {
+                    const uint32_t j = n >> 1, i = bwd2_qtile(it, n), pos = n & 1;
+                    TLB(3, n * 8 + 0);
+                    mbar_wait(bar_p, gb & 1);      // P, dS of the block are in smem
+                    TLB(3, n * 8 + 1);
                     if (pos == 0) {                         // the previous key tile's dV / dK must have been read out
                         const int kvc = it * 2 + j;
                         if (kvc > 0) mbar_wait(kv_free, (kvc - 1) & 1);
                     }
-                    if (n == 0 && it > 0) mbar_wait(dq_free, (it - 1) & 1);
+                    if (n < 2 && it > 0) mbar_wait(&dq_free[i], (it - 1) & 1);    // first chain of the item into dQ_i
                     tc_fence_after();
-                    TLB(0, n * 8 + 3);
-                    // phase B: k runs over the 128 query rows (dV, dK) or the 128 keys (dQ), 16 per UMMA
+                    TLB(3, n * 8 + 2);
+                    const uint32_t oi = i * (tile >> 4), oj = j * (tile >> 4);
+                    // k runs over the 128 query rows (dV, dK) or the 128 keys (dQ), 16 per UMMA
+                    // (the three chains alternate: consecutive instructions never accumulate into the same TMEM columns)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_bf16(tmem + kTdV, umma_smem_desc(sP + k * (16 * kRowB), tile, 1024),
-                                  umma_smem_desc(sDO + i * tile + k * (16 * kRowB), tile, 1024), id_t, (pos > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_bf16(tmem + kTdK, umma_smem_desc(sDS + k * (16 * kRowB), tile, 1024),
-                                  umma_smem_desc(sQ + i * tile + k * (16 * kRowB), tile, 1024), id_t, (pos > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_bf16(tmem + kTdQ + i * 64, umma_smem_desc(sDS + (k >> 2) * tile + (k & 3) * 32, 16, 1024),
-                                  umma_smem_desc(sK + j * tile + k * (16 * kRowB), tile, 1024), id_q, (j > 0 || k > 0) ? 1u : 0u);
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        umma_bf16_lohi(tmem + kTdV, dP_m.lo + k * kstep, dP_m.hi, dDO_m.lo + oi + k * kstep, dDO_m.hi, id_t, (pos > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16_lohi(tmem + kTdK, dDS_m.lo + k * kstep, dDS_m.hi, dQ_m.lo + oi + k * kstep, dQ_m.hi, id_t, (pos > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16_lohi(tmem + kTdQ + i * 64, dDS_k.lo + (k >> 2) * (tile >> 4) + (k & 3) * 2, dDS_k.hi, dK_m.lo + oj + k * kstep, dK_m.hi,
+                                       id_q, (j > 0 || k > 0) ? 1u : 0u);
+                    }
                     umma_commit(bar_b);
                     if (pos == 1) umma_commit(kv_full);          // n == 1 also frees K0 / V0, n == 3 K1 / V1
-                    if (n == 2) umma_commit(&freeb[i ? 2 : 1]);  // the query tile of blocks 1 and 2
-                    if (n == 3) {
-                        umma_commit(dq_full);
-                        umma_commit(&freeb[i ? 2 : 1]);          // the query tile of blocks 0 and 3
+                    if (n >= 2) {                                // the last block of query tile i: blocks 1 + 2 or 0 + 3
+                        umma_commit(&dq_full[i]);
+                        umma_commit(&freeb[i ? 2 : 1]);
                     }
-                    TLB(0, n * 8 + 4);
-                    if (a_done) TLB(0, n * 8 + 5);
-                    if (has_next && !a_done) {
-                        wait_tiles(nit, nn);
-                        tc_fence_after();
-                        phase_a(nit, nn);
-                    }
+                    TLB(3, n * 8 + 3);
                 }
             }
         }
@@ -1159,16 +1212,16 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16);
         uint8_t* stage = sm + Bwd2Smem::kStage + (warp - kB2DrainWarp0) * 2048;
         const bool producer = warp == kB2ProducerWarp && lane == 0;
+#define TLD(idx) do { if (warp == kB2DrainWarp0 + 1 && lane == 0) TLB(2, j * 16 + (idx)); } while (0)
         for (int it = 0; it < n_my; ++it) {
-            const int item = blockIdx.x + it * gridDim.x;
-            const int b = item / H, h = item - b * H;
+            const int b = b_first + it * b_step;
             for (int j = 0; j < 2; ++j) {
-                if (warp == kB2DrainWarp0 && lane == 0) TLB(2, j * 8 + 0);
+                TLD(0);
                 mbar_wait(kv_full, (it * 2 + j) & 1);
-                if (warp == kB2DrainWarp0 && lane == 0) TLB(2, j * 8 + 1);
+                TLD(1);
                 tc_fence_after();
-                // producer duty, in the order the tiles come free: K0 V0 after block 1 (= dK_0 / dV_0 complete), Q0 dO0 after
-                // block 2, the rest after block 3 (= dK_1 / dV_1 complete)
+                // producer duty, in the order the tiles come free: K0 V0 after block 1 (= dK_0 / dV_0 complete), the query tile of
+                // blocks 1 and 2 after block 2 (below), the rest after block 3 (= dK_1 / dV_1 complete)
                 const int q_mid = bwd2_qtile(it, 1) ? 2 : 1, q_end = bwd2_qtile(it, 3) ? 2 : 1;     // tile groups of the two query tiles
                 if (producer && it + 1 < n_my) {
                     if (j == 0) {
@@ -1198,24 +1251,23 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                             pk[half][e] = pack_bf16(__uint_as_float(r[2 * e]) * sc, __uint_as_float(r[2 * e + 1]) * sc);
                     }
                     if (which == 1) warp_arrive(kv_free, lane);
+                    TLD(2 + 2 * which);
 #pragma unroll
                     for (int half = 0; half < 2; ++half)
-                        store_rows_32(stage, pk[half], dst + (which == 0 ? H * kDh : 2 * H * kDh) + half * 32, ld, rows_valid, lane);
+                        store_rows_32_direct(pk[half], dst + (which == 0 ? H * kDh : 2 * H * kDh) + half * 32, ld, rows_valid, lane);
+                    TLD(3 + 2 * which);
                 }
-                if (producer && j == 0 && it + 1 < n_my) {
-                    mbar_wait(&freeb[q_mid], it & 1);            // block 2 has retired
-                    issue_tiles(q_mid, it + 1);
-                }
+                // then one dQ tile per pass: the query tile of blocks 1 and 2 is complete after block 2 (drained here while block 3
+                // runs), the other one after block 3. The next item starts with the tile that was drained first.
+                const int i = bwd2_qtile(it, j == 0 ? 1 : 3);
+                mbar_wait(&dq_full[i], it & 1);
+                TLD(6);
+                tc_fence_after();
+                if (producer && j == 0 && it + 1 < n_my) issue_tiles(q_mid, it + 1);      // block 2 has retired
                 __syncwarp();
-            }
-            if (warp == kB2DrainWarp0 && lane == 0) TLB(2, 16);
-            mbar_wait(dq_full, it & 1);
-            if (warp == kB2DrainWarp0 && lane == 0) TLB(2, 17);
-            tc_fence_after();
-            for (int i = 0; i < 2; ++i) {
                 const int q0 = i * 128 + lg * 32;
-                const int rows_valid = min(32, max(0, L - q0));
-                uint32_t pk[2][16];
+                const int q_valid = min(32, max(0, L - q0));
+                uint32_t qk[2][16];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t r[32];
@@ -1223,73 +1275,100 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        pk[half][e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
+                        qk[half][e] = pack_bf16(__uint_as_float(r[2 * e]) * scale, __uint_as_float(r[2 * e + 1]) * scale);
                 }
-                if (i == 1) warp_arrive(dq_free, lane);
+                warp_arrive(&dq_free[i], lane);
+                TLD(7);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    store_rows_32(stage, pk[half], dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32, ld, rows_valid, lane);
-                    if (colsum) staged_colsum_32(stage, rows_valid, lane, colsum + h * kDh + half * 32);
+                    __nv_bfloat16* qdst = dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32;
+                    if (colsum) {       // the q-bias gradient needs the block transposed: through the staging buffer
+                        store_rows_32(stage, qk[half], qdst, ld, q_valid, lane);
+                        staged_colsum_32(stage, lane, sColV + 64 + half * 32);
+                    } else {
+                        store_rows_32_direct(qk[half], qdst, ld, q_valid, lane);
+                    }
+                    TLD(8 + half);
                 }
             }
-            if (warp == kB2DrainWarp0 && lane == 0) TLB(2, 18);
         }
+    // (end of the drain role)
+#undef TLD
     } else if (warp < 16) {
-        if (colsum != nullptr) {
-            // v-bias gradient of the first item: warp partials (lanes 0..7 hold 8 columns each) -> CTA sums in smem
-            if (lane < 8) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) atomicAdd(sColV + lane * 8 + e, cv_keep[e]);
-            }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kB2EwThreads) : "memory");
         const int lg = warp & 3, quarter = warp >> 2;       // TMEM lane group, 32-key chunk of the block
         const int row = lg * 32 + lane;
         const int sub = lane & 7, rsel = lane >> 3;
         const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16);
         const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
         const uint32_t s_next = smem_u32(sm + Bwd2Smem::kNext) + threadIdx.x * 16;
+        // rows (set q = 0..3) of item `target`'s O and dO on their way to delta: through shared memory (cp.async), issued one
+        // block before they are consumed, so that nothing ever waits on them
+        auto prefetch_rows = [&](int target, int q) {
+            const int b2 = b_first + target * b_step, h2 = h;
+            const int dr = warp * 16 + q * 4 + rsel;
+            const bool dvalid = dr < L;
+            const long long off = dvalid ? (static_cast<long long>(b2) * L + dr) * ldo + h2 * kDh + sub * 8 : 0;
+            cp_async_16(s_next, ctx + off, dvalid);
+            cp_async_16(s_next + 512 * 16, dctx + off, dvalid);
+            cp_async_commit();
+        };
+        if (n_my > 1) prefetch_rows(1, 0);
         int gb = 0;
+        float n_lse = 0.0f, n_kb = 0.0f;
         for (int it = 0; it < n_my; ++it) {
-            const int item = blockIdx.x + it * gridDim.x;
-            const int h = item % H;
             const int st = it & 1;
             const bool has_next = it + 1 < n_my;
-            const int item2 = item + gridDim.x;
-            const int b2 = item2 / H, h2 = item2 - b2 * H;
+            const int b2 = b_first + (it + 1) * b_step, h2 = h;
             const float* sLseC = sLse + st * 256;
             const float* sDeltaC = sDelta + st * 256;
             const float* sBiasC = sBias + st * 256;
 #pragma unroll 1
             for (int n = 0; n < 4; ++n, ++gb) {
                 const int j = n >> 1, i = bwd2_qtile(it, n);
-                // ---- global loads for the NEXT item's per-row scalars: issued first, consumed after the block's math ----
-                float n_lse = 0.0f, n_kb = 0.0f;
-                if (n == 0 && has_next && threadIdx.x < 256) {
-                    const int r = threadIdx.x;
-                    n_lse = r < L ? __ldg(lse + (static_cast<long long>(b2) * H + h2) * L + r) : INFINITY;
-                    n_kb = r < L ? (key_bias ? __ldg(key_bias + static_cast<long long>(b2) * L + r) : 0.0f) : -INFINITY;
-                }
-                const int dr = warp * 16 + n * 4 + rsel;             // the next item's row whose delta this lane octet computes
-                const bool dvalid = has_next && dr < L;
+                // ---- the NEXT item's per-row scalars (stage st ^ 1: nobody reads it before the next item's first block), one
+                //      sixteenth per warp and block, in the time this warp would otherwise spend waiting for S / dP ----
                 if (has_next) {
-                    // through shared memory (cp.async), not registers: nothing of the block's math waits on these loads
-                    const long long off = dvalid ? (static_cast<long long>(b2) * L + dr) * ldo + h2 * kDh + sub * 8 : 0;
-                    cp_async_16(s_next, ctx + off, dvalid);
-                    cp_async_16(s_next + 512 * 16, dctx + off, dvalid);
-                    cp_async_commit();
+                    const int dr = warp * 16 + n * 4 + rsel;
+                    cp_async_wait<0>();
+                    uint4 n_o, n_do;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_o.x), "=r"(n_o.y), "=r"(n_o.z), "=r"(n_o.w) : "r"(s_next));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_do.x), "=r"(n_do.y), "=r"(n_do.z), "=r"(n_do.w) : "r"(s_next + 512 * 16));
+                    const uint32_t av[4] = {n_o.x, n_o.y, n_o.z, n_o.w}, dv[4] = {n_do.x, n_do.y, n_do.z, n_do.w};
+                    float dl = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 x = unpack_bf16(av[e]), y = unpack_bf16(dv[e]);
+                        dl = fmaf(x.x, y.x, dl);
+                        dl = fmaf(x.y, y.y, dl);
+                        cv_keep[2 * e] += y.x;          // column sums of dO (the v-bias gradient): per lane over ALL of the CTA's
+                        cv_keep[2 * e + 1] += y.y;      // items, reduced once at the end (zero-filled rows add nothing)
+                    }
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+                    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+                    if (sub == 0) sDelta[(st ^ 1) * 256 + dr] = dl;
+                    if (threadIdx.x < 256) {
+                        if (n == 0) {
+                            const int r = threadIdx.x;
+                            n_lse = r < L ? __ldg(lse + (static_cast<long long>(b2) * H + h2) * L + r) : INFINITY;
+                            n_kb = r < L ? (key_bias ? __ldg(key_bias + static_cast<long long>(b2) * L + r) : 0.0f) : -INFINITY;
+                        } else if (n == 1) {
+                            sLse[(st ^ 1) * 256 + threadIdx.x] = n_lse * kLog2e;
+                            sBias[(st ^ 1) * 256 + threadIdx.x] = n_kb * kLog2e;
+                            const uint32_t any = __ballot_sync(0xffffffffu, n_kb != 0.0f);
+                            if (lane == 0) sFlag[(st ^ 1) * 8 + warp] = any;
+                        }
+                    }
+                }
+                {   // rows for the NEXT block's share of the scalars: a whole block of lead time
+                    const int nit = n < 3 ? it : it + 1, nn = n < 3 ? n + 1 : 0;
+                    if (nit + 1 < n_my) prefetch_rows(nit + 1, nn);
                 }
 #define TLE(idx) do { if (threadIdx.x == 0) TLB(1, n * 8 + (idx)); } while (0)
                 TLE(0);
                 mbar_wait(bar_a, gb & 1);
                 TLE(1);
                 tc_fence_after();
-                if (n == 0 && colsum != nullptr && threadIdx.x < 64) {
-                    // column sums of this item's dO (= its share of the v-bias gradient) were gathered during the previous item
-                    const float v = sColV[st * 64 + threadIdx.x];
-                    sColV[st * 64 + threadIdx.x] = 0.0f;
-                    atomicAdd(colsum + 2 * H * kDh + h * kDh + threadIdx.x, v);
-                }
                 const float lse_r = sLseC[i * 128 + row], dl_r = sDeltaC[i * 128 + row];
                 const int c = quarter;
                 const bool masked = sFlag[st * 8 + j * 4 + c] != 0u;
@@ -1302,6 +1381,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     if (!masked) {
                         const uint64_t neg_lse2 = pack_f32x2(-lse_r, -lse_r), neg_dl2 = pack_f32x2(-dl_r, -dl_r);
                         tmem_ld_wait();
+                        if (hh == 1) warp_arrive(bar_s, lane);      // this warp's share of S / dP is in registers
 #pragma unroll
                         for (int e = 0; e < 16; e += 2) {
                             float x0, x1, d0, d1;
@@ -1319,6 +1399,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                             bias[e] = b4.x - lse_r; bias[e + 1] = b4.y - lse_r; bias[e + 2] = b4.z - lse_r; bias[e + 3] = b4.w - lse_r;
                         }
                         tmem_ld_wait();
+                        if (hh == 1) warp_arrive(bar_s, lane);
 #pragma unroll
                         for (int e = 0; e < 16; e += 2) {
                             const float p0 = ex2_ftz(fmaf(__uint_as_float(rs[e]), scale_log2, bias[e]));
@@ -1346,53 +1427,31 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                 }
                 fence_proxy_async();
                 TLE(4);
-                // ---- the next item's scalars: stage st ^ 1 (nobody reads it before the next item's first block) ----
-                if (has_next) {
-                    cp_async_wait<0>();
-                    uint4 n_o, n_do;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_o.x), "=r"(n_o.y), "=r"(n_o.z), "=r"(n_o.w) : "r"(s_next));
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(n_do.x), "=r"(n_do.y), "=r"(n_do.z), "=r"(n_do.w) : "r"(s_next + 512 * 16));
-                    const uint32_t av[4] = {n_o.x, n_o.y, n_o.z, n_o.w}, dv[4] = {n_do.x, n_do.y, n_do.z, n_do.w};
-                    float dl = 0.0f, cv[8];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 x = unpack_bf16(av[e]), y = unpack_bf16(dv[e]);
-                        dl = fmaf(x.x, y.x, dl);
-                        dl = fmaf(x.y, y.y, dl);
-                        cv[2 * e] = y.x;
-                        cv[2 * e + 1] = y.y;
-                    }
-                    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
-                    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
-                    dl += __shfl_xor_sync(0xffffffffu, dl, 4);
-                    if (sub == 0) sDelta[(st ^ 1) * 256 + dr] = dl;
-                    if (colsum != nullptr) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 8);
-                            cv[e] += __shfl_xor_sync(0xffffffffu, cv[e], 16);
-                        }
-                        if (lane < 8) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) atomicAdd(sColV + (st ^ 1) * 64 + lane * 8 + e, cv[e]);
-                        }
-                    }
-                    if (n == 0 && threadIdx.x < 256) {
-                        sLse[(st ^ 1) * 256 + threadIdx.x] = n_lse * kLog2e;
-                        sBias[(st ^ 1) * 256 + threadIdx.x] = n_kb * kLog2e;
-                        const uint32_t any = __ballot_sync(0xffffffffu, n_kb != 0.0f);
-                        if (lane == 0) sFlag[(st ^ 1) * 8 + warp] = any;
-                    }
-                }
                 TLE(5);
                 warp_arrive(bar_p, lane);
                 TLE(6);
+            }
+        }
+        if (colsum != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                cv_keep[e] += __shfl_xor_sync(0xffffffffu, cv_keep[e], 8);
+                cv_keep[e] += __shfl_xor_sync(0xffffffffu, cv_keep[e], 16);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(sColV + lane * 8 + e, cv_keep[e]);
             }
         }
     }
 #undef TLE
     tc_fence_before();
     __syncthreads();
+    if (colsum != nullptr && n_my > 0 && threadIdx.x < 128) {
+        // [0, 64): column sums of dO = the head's v-bias gradient; [64, 128): column sums of dQ = its q-bias gradient
+        const int t = threadIdx.x & 63;
+        atomicAdd(colsum + (threadIdx.x < 64 ? 2 * H * kDh : 0) + h * kDh + t, sColV[threadIdx.x]);
+    }
     if (warp == kB2ProducerWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
@@ -1447,15 +1506,20 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
             attr2 = true;
         }
         const int n_items = B * H;
-        static long long* tl = nullptr;
+        long long* tl = nullptr;
+#if CLIMB_ATTN_TIMELINE
+        static long long* tl_buf = nullptr;
         static int tl_calls = 0;
-        if (env_flag("CLIMB_ATTN_TL", 0) && tl == nullptr) {
-            cudaMalloc(&tl, 4 * 32 * sizeof(long long));
-            cudaMemset(tl, 0, 4 * 32 * sizeof(long long));
+        if (env_flag("CLIMB_ATTN_TL", 0) && tl_buf == nullptr) {
+            cudaMalloc(&tl_buf, 4 * 32 * sizeof(long long));
+            cudaMemset(tl_buf, 0, 4 * 32 * sizeof(long long));
         }
+        tl = tl_buf;
+#endif
         CLIMB_CUDA_OK(launch_pdl(attn_tc_fwd2_kernel, dim3(std::min(n_items, sm_count())), dim3(kF2Threads), Fwd2Smem::kTotal, stream,
-                                 mqkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, n_items, L, H, scale * kLog2e, env_flag("CLIMB_ATTN_STAGGER", 1), env_flag("CLIMB_ATTN_DBG", 0), tl));
+                                 mqkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, n_items, L, H, scale * kLog2e, env_flag("CLIMB_ATTN_STAGGER", 1), tl));
         CLIMB_LAUNCH_OK();
+#if CLIMB_ATTN_TIMELINE
         if (tl != nullptr && ++tl_calls == 20) {
             long long h[128];
             cudaDeviceSynchronize();
@@ -1468,6 +1532,7 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
             }
             fflush(stdout);
         }
+#endif
         return 0;
     }
     CUtensorMap mq, mkv;
@@ -1491,7 +1556,7 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
 int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
                      void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream) {
     CLIMB_REQUIRE(L <= 256, "attention_tc_bwd: L=%d > 256", L);
-    if (L > 128 && !attn_v1()) {
+    if (L > 128 && H <= sm_count() && !attn_v1()) {
         CUtensorMap mqkv2, mdo2;
         int rc2 = make_map3(&mqkv2, qkv, B, L, 3LL * H * kDh, 128);
         if (rc2) return rc2;
@@ -1502,29 +1567,34 @@ int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, co
             CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Smem::kTotal));
             attr2 = true;
         }
-        const int n_items = B * H;
-        static long long* tlb = nullptr;
+        long long* tlb = nullptr;
+#if CLIMB_ATTN_TIMELINE
+        static long long* tlb_buf = nullptr;
         static int tl_calls = 0;
-        if (env_flag("CLIMB_ATTN_TL", 0) && tlb == nullptr) {
-            cudaMalloc(&tlb, 192 * sizeof(long long));
-            cudaMemset(tlb, 0, 192 * sizeof(long long));
+        if (env_flag("CLIMB_ATTN_TL", 0) && tlb_buf == nullptr) {
+            cudaMalloc(&tlb_buf, 256 * sizeof(long long));
+            cudaMemset(tlb_buf, 0, 256 * sizeof(long long));
         }
-        CLIMB_CUDA_OK(launch_pdl(attn_tc_bwd2_kernel, dim3(std::min(n_items, sm_count())), dim3(kB2Threads), Bwd2Smem::kTotal, stream,
+        tlb = tlb_buf;
+#endif
+        CLIMB_CUDA_OK(launch_pdl(attn_tc_bwd2_kernel, dim3(std::min(B * H, sm_count())), dim3(kB2Threads), Bwd2Smem::kTotal, stream,
                                  mqkv2, mdo2, key_bias, static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx),
-                                 lse, static_cast<__nv_bfloat16*>(dqkv), colsum, n_items, L, H, scale * kLog2e, scale, tlb));
+                                 lse, static_cast<__nv_bfloat16*>(dqkv), colsum, B, L, H, scale * kLog2e, scale, tlb));
         CLIMB_LAUNCH_OK();
+#if CLIMB_ATTN_TIMELINE
         if (tlb != nullptr && ++tl_calls == 20) {
-            long long h[192];
+            long long h[256];
             cudaDeviceSynchronize();
             cudaMemcpy(h, tlb, sizeof(h), cudaMemcpyDeviceToHost);
             long long t0 = h[0];
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < 4; ++r) {
                 printf("TLB role %d:", r);
                 for (int i = 0; i < 32; ++i) printf("%s%lld", (i % 8) ? " " : " | ", h[r * 64 + i] ? h[r * 64 + i] - t0 : -1);
                 printf("\n");
             }
             fflush(stdout);
         }
+#endif
         return 0;
     }
     CUtensorMap mqkv, mdo;

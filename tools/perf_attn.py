@@ -34,9 +34,11 @@ def main():
 
     ms_f = timeit(lambda i: L.attention_fwd(qkvs[i], kb, B, Lq, H, 0.125))
     ms_b = timeit(lambda i: L.attention_bwd(qkvs[i], kb, outs[i][0], dctxs[i], outs[i][1], B, Lq, H, 0.125))
+    cs = torch.zeros(3 * d, device=dev)
+    ms_bc = timeit(lambda i: L.attention_bwd(qkvs[i], kb, outs[i][0], dctxs[i], outs[i][1], B, Lq, H, 0.125, colsum=cs))
     by_f = B * (4 * Lq * d * 2 + Lq * H * 4)
     print(f"attn B={B} L={Lq} v1={os.environ.get('CLIMB_ATTN_V1', '0')}: fwd {ms_f * 1e3:.1f} us ({by_f / ms_f / 1e6:.0f} GB/s) "
-          f"bwd {ms_b * 1e3:.1f} us ({2 * by_f / ms_b / 1e6:.0f} GB/s)", flush=True)
+          f"bwd {ms_b * 1e3:.1f} us ({2 * by_f / ms_b / 1e6:.0f} GB/s) bwd+bias-grads {ms_bc * 1e3:.1f} us", flush=True)
 
 
 if __name__ == "__main__":
