@@ -82,18 +82,6 @@ __device__ __forceinline__ void store_rows_32(uint8_t* stage, const uint32_t (&p
     __syncwarp();
 }
 
-// the same block straight from registers: lane = row writes its 64 B (two full 32 B sectors) with four 16 B stores. The
-// warp touches 32 rows per instruction instead of 8, but nothing is staged, re-read or synchronised: the drain warps of the
-// persistent backward are a serial resource, and this is a third of the staged version's time
-__device__ __forceinline__ void store_rows_32_direct(const uint32_t (&pk)[16], __nv_bfloat16* gdst, long long ld_elems, int rows_valid,
-                                                     int lane) {
-    if (lane < rows_valid) {
-        uint4* dst = reinterpret_cast<uint4*>(gdst + lane * ld_elems);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-    }
-}
-
 // column sums of the 32 x 32 bf16 block that store_rows_32 just staged (rows past the valid ones hold exact zeros here):
 // lane = (row group of 4, 8-column granule): four independent 16 B loads, then a butterfly over the eight row groups
 __device__ __forceinline__ void staged_colsum_32(const uint8_t* stage, int lane, float* dst) {
@@ -1254,7 +1242,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     TLD(2 + 2 * which);
 #pragma unroll
                     for (int half = 0; half < 2; ++half)
-                        store_rows_32_direct(pk[half], dst + (which == 0 ? H * kDh : 2 * H * kDh) + half * 32, ld, rows_valid, lane);
+                        store_rows_32(stage, pk[half], dst + (which == 0 ? H * kDh : 2 * H * kDh) + half * 32, ld, rows_valid, lane);
                     TLD(3 + 2 * which);
                 }
                 // then one dQ tile per pass: the query tile of blocks 1 and 2 is complete after block 2 (drained here while block 3
@@ -1282,12 +1270,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     __nv_bfloat16* qdst = dqkv + (static_cast<long long>(b) * L + q0) * ld + h * kDh + half * 32;
-                    if (colsum) {       // the q-bias gradient needs the block transposed: through the staging buffer
-                        store_rows_32(stage, qk[half], qdst, ld, q_valid, lane);
-                        staged_colsum_32(stage, lane, sColV + 64 + half * 32);
-                    } else {
-                        store_rows_32_direct(qk[half], qdst, ld, q_valid, lane);
-                    }
+                    // (staged, coalesced stores: writing the rows straight from registers -- 32 rows per instruction -- was measured
+                    //  25 % slower for the whole kernel)
+                    store_rows_32(stage, qk[half], qdst, ld, q_valid, lane);
+                    if (colsum) staged_colsum_32(stage, lane, sColV + 64 + half * 32);
                     TLD(8 + half);
                 }
             }
