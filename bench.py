@@ -346,7 +346,8 @@ def run_ours(args):
             at = json.load(open(ap_))
             attn_roof["fwd"]["traffic"] = at["fwd"]["dram_bytes_per_launch"]
             attn_roof["bwd"]["traffic"] = at["bwd"]["dram_bytes_per_launch"]
-            attn_roof["kernel"] = "attn_tc_fwd_kernel / attn_tc_bwd_kernel (tcgen05 + TMEM); achieved = algorithmic bytes / time"
+            attn_roof["kernel"] = ("attn_tc_fwd2_kernel / attn_tc_bwd2_kernel (persistent, tcgen05 + TMEM); achieved = algorithmic bytes / time; "
+                                   "the tensor pipe (operand fetch from shared memory + MMA) and the MUFU pipe bound these kernels before HBM does: DESIGN.md")
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

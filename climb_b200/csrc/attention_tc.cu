@@ -122,6 +122,59 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
+__device__ __forceinline__ void tmem_ld_32x16_a(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// A shared-memory descriptor split into its words: the start-address field (bits 0..13 of the low word, in 16-byte units)
+// is the only thing that changes between the instructions of a chain, so an operand costs one 32-bit add
+struct DescBase {
+    uint32_t lo, hi;
+    __device__ explicit DescBase(uint64_t d) : lo(static_cast<uint32_t>(d)), hi(static_cast<uint32_t>(d >> 32)) {}
+};
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// 2^x for x <= 0 on the FMA pipe (two values per instruction): the MUFU pipe runs 16 ex2 per clock and SM (measured,
+// tools/probe/mufu_probe.cu) and is the softmax's busiest unit; the packed-FMA evaluation runs beside it.
+// x = n + f, n = round(x) through the 1.5 * 2^23 trick, |f| <= 1/2; 2^f by a degree-4 minimax polynomial (relative error
+// 2.7e-6, far inside the bf16 rounding of P); n goes straight into the exponent field. x is clamped at -126.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& y0, float& y1) {
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+    const uint64_t x = pack_f32x2(x0, x1);
+    const uint64_t t = fadd2(x, pack_f32x2(12582912.0f, 12582912.0f));
+    const uint64_t f = fadd2(x, fadd2(pack_f32x2(12582912.0f, 12582912.0f), t ^ 0x8000000080000000ull));     // x - (t - magic)
+    uint64_t pl = ffma2(pack_f32x2(0.009570099413394928f, 0.009570099413394928f), f, pack_f32x2(0.05591785907745361f, 0.05591785907745361f));
+    pl = ffma2(pl, f, pack_f32x2(0.240247443318367f, 0.240247443318367f));
+    pl = ffma2(pl, f, pack_f32x2(0.6931217908859253f, 0.6931217908859253f));
+    pl = ffma2(pl, f, pack_f32x2(0.9999992847442627f, 0.9999992847442627f));
+    float p0, p1, t0, t1;
+    unpack_f32x2(pl, p0, p1);
+    unpack_f32x2(t, t0, t1);
+    y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -409,8 +462,10 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
     } else if (warp >= kF2MmaWarp0) {
         const int g = warp - kF2MmaWarp0;
         if (lane == 0 && g < n_groups) {
-            const uint32_t sQ = smem_u32(sm + Fwd2Smem::kQ) + g * (128 * kRowB), sK = smem_u32(sm + Fwd2Smem::kK);
-            const uint32_t sP = smem_u32(sm + Fwd2Smem::kP) + g * (2 * 128 * kRowB);
+            const DescBase dQ(umma_smem_desc(smem_u32(sm + Fwd2Smem::kQ) + g * (128 * kRowB), 16, 1024));
+            const DescBase dK(umma_smem_desc(smem_u32(sm + Fwd2Smem::kK), 16, 1024));
+            const DescBase dP(umma_smem_desc(smem_u32(sm + Fwd2Smem::kP) + g * (2 * 128 * kRowB), 16, 1024));
+            const DescBase dV(umma_smem_desc(smem_u32(sm + Fwd2Smem::kV), 256 * kRowB, 1024));       // V read in place as an MN-major B operand
             const uint32_t t_acc = tmem + g * 256;
             const uint32_t idesc_s = umma_instr_desc(128, 256, 0, 0);
             const uint32_t idesc_o = umma_instr_desc(128, 64, 0, 1);
@@ -426,14 +481,13 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
                 TL(g, 2);
                 tc_fence_after();
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(t_acc, umma_smem_desc(sQ + kk * 32, 16, 1024), umma_smem_desc(sK + kk * 32, 16, 1024), idesc_s,
-                              kk > 0 ? 1u : 0u);
+                for (uint32_t kk = 0; kk < 4; ++kk)
+                    umma_bf16_lohi(t_acc, dQ.lo + kk * 2, dQ.hi, dK.lo + kk * 2, dK.hi, idesc_s, kk > 0 ? 1u : 0u);
                 umma_commit(&s_full[g]);
                 umma_commit(qk_free);
                 TL(g, 3);
                 const int s = it & 1;
-                const uint32_t sV = smem_u32(sm + Fwd2Smem::kV) + s * (256 * kRowB);
+                const uint32_t v_lo = dV.lo + s * ((256 * kRowB) >> 4);
                 mbar_wait(&v_full[s], (it >> 1) & 1);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
@@ -442,10 +496,9 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
                     TL(g, 4 + 2 * c);
                     tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(t_acc, umma_smem_desc(sP + slot * (128 * kRowB) + kk * 32, 16, 1024),
-                                  umma_smem_desc(sV + (c * 4 + kk) * (16 * kRowB), 256 * kRowB, 1024), idesc_o,
-                                  (c > 0 || kk > 0) ? 1u : 0u);
+                    for (uint32_t kk = 0; kk < 4; ++kk)
+                        umma_bf16_lohi(t_acc, dP.lo + slot * ((128 * kRowB) >> 4) + kk * 2, dP.hi, v_lo + (c * 4 + kk) * ((16 * kRowB) >> 4), dV.hi,
+                                       idesc_o, (c > 0 || kk > 0) ? 1u : 0u);
                     umma_commit(&p_free[g * 2 + slot]);
                     TL(g, 5 + 2 * c);
                 }
@@ -497,14 +550,11 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
             mbar_wait(&s_full[g], it & 1);
             TLS(2);
             tc_fence_after();
+            // ---- pass 1: row max. The four 32-column loads alternate between two register sets, each issued before the
+            //      previous one is reduced, so only the first load's latency is exposed ----
             float m = -INFINITY, m_raw = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + c * 64 + half * 32, r);
-                const bool masked = flag[c * 2 + half] != 0u;
-                tmem_ld_wait();
-                if (!masked) {
+            auto row_max = [&](const uint32_t (&r)[32], int c) {
+                if (flag[c * 2 + half] == 0u) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         m_raw = fmaxf(m_raw, fmaxf(fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
@@ -517,39 +567,68 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
                                            fmaxf(fmaf(__uint_as_float(r[j + 2]), scale_log2, b4.z), fmaf(__uint_as_float(r[j + 3]), scale_log2, b4.w))));
                     }
                 }
+            };
+            uint32_t ra[16], rb[16];
+            {
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(t_row + half * 32, r0);
+                tmem_ld_wait();
+                tmem_ld_32x32(t_row + 64 + half * 32, r1);
+                row_max(r0, 0);
+                tmem_ld_wait();
+                tmem_ld_32x32(t_row + 128 + half * 32, r0);
+                row_max(r1, 1);
+                tmem_ld_wait();
+                tmem_ld_32x32(t_row + 192 + half * 32, r1);
+                row_max(r0, 2);
+                tmem_ld_wait();
+                tmem_ld_32x16_a(t_row + half * 32, ra);          // pass 2's first 16 columns travel during the exchange below
+                row_max(r1, 3);
             }
             m = fmaxf(m, m_raw * scale_log2);                  // scale > 0
             sXmax[half * 128 + row] = m;
             named_bar_sync<1>(g * 4 + lg, 64);
             m = fmaxf(m, sXmax[(half ^ 1) * 128 + row]);       // key 0 is always valid: m is finite
             TLS(3);
+            // ---- pass 2: P = exp2(S * scale + mask - m) in 16-column steps; the next step's load is always in flight, and the
+            //      next chunk's first step is issued before this chunk's store / fence / hand-over ----
             const uint64_t neg_m2 = pack_f32x2(-m, -m);
             uint64_t sum2 = 0ull;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + c * 64 + half * 32, r);
-                const bool masked = flag[c * 2 + half] != 0u;
-                float p[32];
-                tmem_ld_wait();
+            // 16 scores -> 16 probabilities: mask-free chunks use one packed FMA per pair and evaluate every other pair on the
+            // FMA pipe instead of MUFU
+            auto probs16 = [&](const uint32_t (&r)[16], float* p, bool masked, const float* bias16) {
                 if (!masked) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float x0, x1;
+                    for (int j = 0; j < 16; j += 4) {
+                        float x0, x1, x2, x3;
                         unpack_f32x2(ffma2(pack_u32x2(r[j], r[j + 1]), scale2, neg_m2), x0, x1);
+                        unpack_f32x2(ffma2(pack_u32x2(r[j + 2], r[j + 3]), scale2, neg_m2), x2, x3);
                         p[j] = ex2_ftz(x0);
                         p[j + 1] = ex2_ftz(x1);
+                        exp2_poly2(x2, x3, p[j + 2], p[j + 3]);
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 64 + half * 32 + j);
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias16 + j);
                         p[j] = ex2_ftz(fmaf(__uint_as_float(r[j]), scale_log2, b4.x - m));
                         p[j + 1] = ex2_ftz(fmaf(__uint_as_float(r[j + 1]), scale_log2, b4.y - m));
                         p[j + 2] = ex2_ftz(fmaf(__uint_as_float(r[j + 2]), scale_log2, b4.z - m));
                         p[j + 3] = ex2_ftz(fmaf(__uint_as_float(r[j + 3]), scale_log2, b4.w - m));
                     }
                 }
+            };
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const bool masked = flag[c * 2 + half] != 0u;
+                const float* bias32 = bias + c * 64 + half * 32;
+                float p[32];
+                tmem_ld_wait();
+                tmem_ld_32x16_a(t_row + c * 64 + half * 32 + 16, rb);
+                probs16(ra, p, masked, bias32);
+                tmem_ld_wait();
+                if (c < 3) tmem_ld_32x16_a(t_row + (c + 1) * 64 + half * 32, ra);
+                probs16(rb, p + 16, masked, bias32 + 16);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     sum2 = fadd2(sum2, fadd2(pack_f32x2(p[j], p[j + 1]), pack_f32x2(p[j + 2], p[j + 3])));
@@ -634,15 +713,6 @@ constexpr int kBwdOutThreads = 256;
 constexpr int kBwdCtlWarp = kBwdEwWarps;
 constexpr int kBwdThreads = kBwdEwThreads + 32;
 
-__device__ __forceinline__ void tmem_ld_32x16_a(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
 
 // Bias gradients of the q / k / v projections = column sums of dQ / dK / dV over all tokens:
 //   dV:  sum_keys dV = sum_q dO (sum_keys P) = sum_q dO     (softmax rows sum to one) -> reduced from the dO rows
@@ -956,27 +1026,6 @@ constexpr int kB2ProducerWarp = kB2DrainWarp0;
 constexpr int kB2DrainThreads = 128;
 constexpr int kB2Threads = 22 * 32;
 
-// A shared-memory descriptor split into its words: the start-address field (bits 0..13 of the low word, in 16-byte units)
-// is the only thing that changes between the instructions of a chain, so an operand costs one 32-bit add
-struct DescBase {
-    uint32_t lo, hi;
-    __device__ explicit DescBase(uint64_t d) : lo(static_cast<uint32_t>(d)), hi(static_cast<uint32_t>(d >> 32)) {}
-};
-__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-        "}\n"
-        :
-        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 
 __global__ void __launch_bounds__(kB2Threads, 1)
 attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,

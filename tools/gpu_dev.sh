@@ -33,8 +33,8 @@ for g in "$@"; do
     ncu_fast) echo "=== ncu_fast" | tee -a gpurun_out/summary.txt; WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_fast -s ${NCU_SKIP:-20} -c ${NCU_COUNT:-4} -f -o gpurun_out/prof_fast python tools/one_step.py > gpurun_out/ncu_fast.log 2>&1
               WARM=2 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_fast -s ${NCU_SKIP2:-62} -c ${NCU_COUNT2:-5} -f -o gpurun_out/prof_fast_bwd python tools/one_step.py >> gpurun_out/ncu_fast.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt ;;
     ncu_attn) echo "=== ncu_attn" | tee -a gpurun_out/summary.txt
-              WARM=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_tc_fwd -s 4 -c 2 -f -o gpurun_out/prof_attn_fwd python tools/one_step.py > gpurun_out/ncu_attn.log 2>&1
-              WARM=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_tc_bwd -s 4 -c 2 -f -o gpurun_out/prof_attn_bwd python tools/one_step.py >> gpurun_out/ncu_attn.log 2>&1
+              WARM=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_tc_fwd -s 4 -c 1 -f -o gpurun_out/prof_attn_fwd python tools/one_step.py > gpurun_out/ncu_attn.log 2>&1
+              WARM=2 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_tc_bwd -s 4 -c 1 -f -o gpurun_out/prof_attn_bwd python tools/one_step.py >> gpurun_out/ncu_attn.log 2>&1
               echo "exit=$?" | tee -a gpurun_out/summary.txt ;;
     *)        run "$(echo $g | tr '/:. ' '____')" 900 $g ;;
   esac
