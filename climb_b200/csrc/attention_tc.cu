@@ -1046,8 +1046,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     float* sColV = reinterpret_cast<float*>(sm + Bwd2Smem::kColV);
     uint32_t* sFlag = reinterpret_cast<uint32_t*>(sm + Bwd2Smem::kFlag);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Bwd2Smem::kBar);
-    uint64_t* full = bars;               // [4] tx: K0 V0 | Q0 dO0 | Q1 dO1 | K1 V1 of an item have landed
-    uint64_t* freeb = bars + 4;          // [4] commit: the last chain of the item that reads the tiles has retired
+    uint64_t* full = bars;               // [4] tx: K0 V0 | Q0 dO0 | Q1 dO1 | K1 V1 of an item have landed (refilled when kv_full / dq_full say their last reader retired)
     uint64_t* bar_a = bars + 8;          // S, dP of a block are in TMEM
     uint64_t* bar_p = bars + 9;          // P, dS of a block are in smem (16 warp arrivals)
     uint64_t* bar_b = bars + 10;         // the accumulation chains of a block have retired
@@ -1094,7 +1093,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             tma_prefetch_desc(&map_do);
             for (int t = 0; t < 4; ++t) {
                 mbar_init(&full[t], 1);
-                mbar_init(&freeb[t], 1);
             }
             mbar_init(bar_a, 1);
             mbar_init(bar_p, kB2EwThreads / 32);
@@ -1188,10 +1186,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             for (int it = 0; it < n_my; ++it) {
 #pragma unroll 1
                 for (int n = 0; n < 4; ++n, ++gb) {
-                    if (n == 3 && it + 1 >= n_my) break;
                     TLB(0, n * 8 + 0);
                     mbar_wait(bar_s, gb & 1);      // S / dP of the block have been read out of TMEM (its P / dS are still being made)
                     TLB(0, n * 8 + 1);
+                    if (n == 3 && it + 1 >= n_my) break;
                     phase_a(n < 3 ? it : it + 1, n < 3 ? n + 1 : 0);
                     TLB(0, n * 8 + 2);
                 }
@@ -1235,10 +1233,8 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     }
                     umma_commit(bar_b);
                     if (pos == 1) umma_commit(kv_full);          // n == 1 also frees K0 / V0, n == 3 K1 / V1
-                    if (n >= 2) {                                // the last block of query tile i: blocks 1 + 2 or 0 + 3
-                        umma_commit(&dq_full[i]);
-                        umma_commit(&freeb[i ? 2 : 1]);
-                    }
+                    if (n >= 2) umma_commit(&dq_full[i]);        // the last block of query tile i (blocks 1 + 2 or 0 + 3): dQ_i is complete,
+                                                                 // and Q_i / dO_i may be refilled
                     TLB(3, n * 8 + 3);
                 }
             }
@@ -1264,8 +1260,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     if (j == 0) {
                         issue_tiles(0, it + 1);
                     } else {
-                        mbar_wait(&freeb[q_end], it & 1);
-                        issue_tiles(q_end, it + 1);
+                        issue_tiles(q_end, it + 1);       // block 3 has retired (kv_full of key tile 1): its query tile and K1 / V1 are free
                         issue_tiles(3, it + 1);
                     }
                 }
@@ -1357,6 +1352,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             const float* sLseC = sLse + st * 256;
             const float* sDeltaC = sDelta + st * 256;
             const float* sBiasC = sBias + st * 256;
+            // the elementwise warps meet once per item: the scalar stage about to be rewritten (st ^ 1) was the previous item's, and
+            // its last reader must be done; this also makes the stage hand-over independent of the mbarrier chain through the MMA warps
+            if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(kB2EwThreads) : "memory");
 #pragma unroll 1
             for (int n = 0; n < 4; ++n, ++gb) {
                 const int j = n >> 1, i = bwd2_qtile(it, n);
@@ -1467,6 +1465,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                 TLE(6);
             }
         }
+        if (gb > 0) mbar_wait(bar_b, (gb - 1) & 1);      // (every barrier phase is observed before the CTA retires)
         if (colsum != nullptr) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
