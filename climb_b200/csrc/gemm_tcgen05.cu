@@ -53,6 +53,7 @@ struct GemmDeviceArgs {
     int skip_pdl_wait;            // climb_gemm_desc.independent: do not wait for the previous kernel of the stream
     int num_stages;               // smem ring depth (runtime: deeper when the epilogue needs no input prefetch)
     int scratch_bytes;            // per epilogue warp: 4096 (staging only) or 8192 (+ prefetch half)
+    int full_tiles, total_vtiles; // fast kernels: tiles [0, full_tiles) are 256 columns wide, the rest come as two 128-column halves
 };
 
 template <int BLOCK_N>
@@ -769,6 +770,97 @@ __device__ __forceinline__ void load_unit(uint4 (&pf)[4], const uint8_t* g_lane,
     }
 }
 
+// Tail tiles at half width. A persistent grid of W CTAs over T = m_tiles x n_tiles tiles runs ceil(T / W) rounds; when
+// the last round has R <= W / 2 tiles (N = 768 at M = 15168: 357 tiles = 2 rounds + 61), those R tiles are issued as 2 R
+// tiles of 128 columns: the last round costs ~0.55 of a full tile on twice as many SMs instead of 1.0 on R of them.
+// Virtual tile v < full_tiles is tile v; v >= full_tiles is half ((v - full_tiles) & 1) of tile full_tiles + (v - full_tiles) / 2.
+struct FastTile {
+    int m_blk, n0, width;
+};
+__device__ __forceinline__ FastTile fast_tile(const GemmDeviceArgs& p, int v) {
+    int t = v, half = 0, width = kFastBlockN;
+    if (v >= p.full_tiles) {
+        t = p.full_tiles + ((v - p.full_tiles) >> 1);
+        half = (v - p.full_tiles) & 1;
+        width = kFastBlockN / 2;
+    }
+    FastTile r;
+    r.m_blk = t / p.n_tiles;
+    r.n0 = (t - r.m_blk * p.n_tiles) * kFastBlockN + half * (kFastBlockN / 2);
+    r.width = width;
+    return r;
+}
+
+__device__ __forceinline__ void fast_producer_loop(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmDeviceArgs& p,
+                                                   uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar) {
+    using L = SmemLayout<kFastBlockN>;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int v = blockIdx.x; v < p.total_vtiles; v += gridDim.x) {
+        const FastTile tr = fast_tile(p, v);
+        // a K-major B tile is one TMA box of 256 rows: a half tile still loads the whole box (rows past N are zero fill) and
+        // the MMA reads its first 128 rows; an MN-major B tile is four boxes of 64 columns: a half tile loads two
+        const uint32_t bytes = L::kABytes + ((p.b_mn_major && tr.width != kFastBlockN) ? L::kBBytes / 2 : L::kBBytes);
+        for (int kb = 0; kb < p.k_blocks_total; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            if (!p.a_mn_major) {
+                tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * kBlockK, tr.m_blk * kBlockM);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kBlockM / 64; ++j)
+                    tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (kBlockK * 128), tr.m_blk * kBlockM + j * 64, kb * kBlockK);
+            }
+            if (!p.b_mn_major) {
+                tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * kBlockK, tr.n0);
+            } else {
+                for (int j = 0; j < tr.width / 64; ++j)
+                    tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (kBlockK * 128), tr.n0 + j * 64, kb * kBlockK);
+            }
+            if (++stage == kFastStages) { stage = 0; phase ^= 1u; }
+        }
+    }
+}
+
+__device__ __forceinline__ void fast_mma_loop(const GemmDeviceArgs& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                              uint64_t* acc_full, uint64_t* acc_empty, uint32_t tmem_base) {
+    using L = SmemLayout<kFastBlockN>;
+    const uint32_t idesc_full = make_instr_desc(kBlockM, kFastBlockN, p.a_mn_major, p.b_mn_major);
+    const uint32_t idesc_half = make_instr_desc(kBlockM, kFastBlockN / 2, p.a_mn_major, p.b_mn_major);
+    const uint32_t a_lbo = p.a_mn_major ? kBlockK * 128 : 16;
+    const uint32_t b_lbo = p.b_mn_major ? kBlockK * 128 : 16;
+    const uint32_t a_kstep = p.a_mn_major ? 16 * 128 : 32;   // bytes per UMMA_K = 16
+    const uint32_t b_kstep = p.b_mn_major ? 16 * 128 : 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int v = blockIdx.x; v < p.total_vtiles; v += gridDim.x) {
+        const uint32_t idesc = v < p.full_tiles ? idesc_full : idesc_half;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kFastBlockN);
+        for (int kb = 0; kb < p.k_blocks_total; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                const uint64_t da = make_smem_desc(sa + kk * a_kstep, a_lbo, 1024);
+                const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, 1024);
+                umma_bf16(d_tmem, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);       // frees the smem slot when MMAs retire
+            if (++stage == kFastStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&acc_full[acc]);              // accumulator complete -> epilogue
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kFastThreads, 1)
 gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -814,9 +906,9 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (!p.skip_pdl_wait) pdl_wait();     // everything above overlapped the previous kernel's tail; operands / epilogue tensors come after
 
     if (warp == 0) {
-        if (lane == 0) producer_loop<BLOCK_N>(tmap_a, tmap_b, p, smem, full_bar, empty_bar, kStages);
+        if (lane == 0) fast_producer_loop(tmap_a, tmap_b, p, smem, full_bar, empty_bar);
     } else if (warp == 1) {
-        if (lane == 0) mma_loop<BLOCK_N>(p, smem, full_bar, empty_bar, acc_full, acc_empty, tmem_base, kStages);
+        if (lane == 0) fast_mma_loop(p, smem, full_bar, empty_bar, acc_full, acc_empty, tmem_base);
     } else {
         constexpr bool kF32 = KIND == FK_RES_F32;
         constexpr bool kHasIn = KIND == FK_MUL_AUX || KIND == FK_RES_F32;
@@ -826,7 +918,7 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int lane_grp = warp & 3;                    // TMEM lanes [32 * lane_grp, +32) are this warp's
         const int cg = ew >> 2;                           // chunks cg, cg + 4 of every tile
         uint8_t* stg = smem + kStages * L::kStageBytes + L::kBarrierBytes + ew * kFastUnitBytes;
-        const int total_tiles = p.m_tiles * p.n_tiles;
+        const int total_tiles = p.total_vtiles;
         const int rsub = lane >> 2, gj = lane & 3;
         // byte pitches: output rows / input rows, and 8 rows at a time for the coalesced mapping
         const long long c_pitch = p.ldc * (kF32 ? 4 : 2);
@@ -836,11 +928,11 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint4 pf[kHasIn ? kUnits : 1][4];
         // fetch the input of chunk cc of tile t (coalesced mapping) into pf
         auto prefetch = [&](int t, int cc, int h) {
-            const int mb = t / p.n_tiles, nb = t - mb * p.n_tiles;
-            const int r0 = mb * kBlockM + lane_grp * 32;
+            const FastTile tp = fast_tile(p, t);
+            const int r0 = tp.m_blk * kBlockM + lane_grp * 32;
             const int rv = min(32, max(0, p.M - r0));
             const uint8_t* g = in_base + (static_cast<long long>(r0) + rsub) * in_pitch +
-                               static_cast<long long>(nb * BLOCK_N + cc * 32) * (kF32 ? 4 : 2) + gj * 16;
+                               static_cast<long long>(tp.n0 + cc * 32) * (kF32 ? 4 : 2) + gj * 16;
             load_unit(pf[h], g + h * 64, 8 * in_pitch, rv, lane);
         };
         if (kHasIn && static_cast<int>(blockIdx.x) < total_tiles) {
@@ -851,18 +943,18 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_blk = tile / p.n_tiles;
-            const int n_blk = tile - m_blk * p.n_tiles;
-            const int row0 = m_blk * kBlockM + lane_grp * 32;
+            const FastTile tr = fast_tile(p, tile);
+            const int n_chunks = tr.width / 32;
+            const int row0 = tr.m_blk * kBlockM + lane_grp * 32;
             const int rows_valid = min(32, max(0, p.M - row0));
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 #pragma unroll 1
-            for (int c = cg; c < BLOCK_N / 32; c += kColGroups) {
-                const int n0 = n_blk * BLOCK_N + c * 32;
+            for (int c = cg; c < n_chunks; c += kColGroups) {
+                const int n0 = tr.n0 + c * 32;
                 int nt = tile, nc = c + kColGroups;           // this warp's next chunk
-                if (nc >= BLOCK_N / 32) { nt = tile + gridDim.x; nc = cg; }
+                if (nc >= n_chunks) { nt = tile + gridDim.x; nc = cg; }
                 uint8_t* c_lane = reinterpret_cast<uint8_t*>(p.C) + (static_cast<long long>(row0) + rsub) * c_pitch +
                                   static_cast<long long>(n0) * (kF32 ? 4 : 2) + gj * 16;
                 if constexpr (KIND == FK_RES_F32) {
@@ -1100,6 +1192,11 @@ int launch_fast(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
     }
     const int total = a.m_tiles * a.n_tiles;
     const int grid = total < num_sms() ? total : num_sms();
+    // the last round's tiles at half width when they occupy at most half of the grid (see fast_tile)
+    const int rest = total % grid;
+    static const bool tail_split = [] { const char* e = std::getenv("CLIMB_GEMM_TAIL_SPLIT"); return e == nullptr || e[0] != '0'; }();
+    a.full_tiles = (tail_split && total > grid && rest > 0 && 2 * rest <= grid) ? total - rest : total;
+    a.total_vtiles = total + (total - a.full_tiles);
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
     if (a.skip_pdl_wait) pdl_mark_independent();
     CLIMB_CUDA_OK(launch_pdl(gemm_fast_kernel<KIND>, dim3(grid), dim3(kFastThreads), kFastSmemBytes, stream, ta, tb, a));

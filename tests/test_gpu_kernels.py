@@ -84,13 +84,14 @@ def test_gemm_wgrad_splitk_accumulate(split_k):
     assert _rel_err(dw, ref) < 1e-5, _rel_err(dw, ref)
 
 
-@pytest.mark.parametrize("M,K", [(2500, 768), (15168, 768), (2400, 200), (2433, 3072)])
-def test_gemm_fast_kinds(M, K):
+@pytest.mark.parametrize("M,K,N", [(2500, 768, 2304), (15168, 768, 2304), (2400, 200, 2304), (2433, 3072, 2304),
+                                   # N = 768 at the bench's M: 357 tiles = 2 rounds + 61 -> the last 61 run as 122 half-width tiles
+                                   (15168, 768, 768), (15168, 3072, 768), (15104, 768, 1024), (9600, 256, 512)])
+def test_gemm_fast_kinds(M, K, N):
     """The specialised 16-epilogue-warp kernels (N % 256 == 0, >= 148 tiles): bf16 + bias, GELU with saved
-    derivative, multiply-by-aux, fp32 + bias + residual; ragged last row tile, ragged K."""
+    derivative, multiply-by-aux, fp32 + bias + residual; ragged last row tile, ragged K; tail tiles at half width."""
     L = _lib()
     torch.manual_seed(M + K)
-    N = 2304
     a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
     b = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
     bias = torch.randn(N, device="cuda")
