@@ -1032,7 +1032,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     const float* __restrict__ key_bias, const __nv_bfloat16* __restrict__ ctx,
                     const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
                     __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int n_batch, int L, int H,
-                    float scale_log2, float scale, long long* tl) {
+                    float scale_log2, float scale, int colsum_q, long long* tl) {
 #if CLIMB_ATTN_TIMELINE
 #define TLB(role, idx) do { if (tl != nullptr && blockIdx.x == 0 && it == 2) tl[(role) * 64 + (idx)] = clock64(); } while (0)
 #else
@@ -1317,7 +1317,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     // (staged, coalesced stores: writing the rows straight from registers -- 32 rows per instruction -- was measured
                     //  25 % slower for the whole kernel)
                     store_rows_32(stage, qk[half], qdst, ld, q_valid, lane);
-                    if (colsum) staged_colsum_32(stage, lane, sColV + 64 + half * 32);
+                    if (colsum_q) staged_colsum_32(stage, lane, sColV + 64 + half * 32);
                     TLD(8 + half);
                 }
             }
@@ -1481,7 +1481,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
 #undef TLE
     tc_fence_before();
     __syncthreads();
-    if (colsum != nullptr && n_my > 0 && threadIdx.x < 128) {
+    if (colsum != nullptr && n_my > 0 && threadIdx.x < (colsum_q ? 128 : 64)) {
         // [0, 64): column sums of dO = the head's v-bias gradient; [64, 128): column sums of dQ = its q-bias gradient
         const int t = threadIdx.x & 63;
         atomicAdd(colsum + (threadIdx.x < 64 ? 2 * H * kDh : 0) + h * kDh + t, sColV[threadIdx.x]);
@@ -1601,6 +1601,9 @@ int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, co
             CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Smem::kTotal));
             attr2 = true;
         }
+        // The drain warps are the backward's serial resource; transposing the dQ blocks for their column sums inside them
+        // costs 13 us per launch. CLIMB_ATTN_COLSUM_Q=1 keeps the sums in the kernel.
+        const int colsum_q = (colsum != nullptr && env_flag("CLIMB_ATTN_COLSUM_Q", 0)) ? 1 : 0;
         long long* tlb = nullptr;
 #if CLIMB_ATTN_TIMELINE
         static long long* tlb_buf = nullptr;
@@ -1613,8 +1616,13 @@ int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, co
 #endif
         CLIMB_CUDA_OK(launch_pdl(attn_tc_bwd2_kernel, dim3(std::min(B * H, sm_count())), dim3(kB2Threads), Bwd2Smem::kTotal, stream,
                                  mqkv2, mdo2, key_bias, static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx),
-                                 lse, static_cast<__nv_bfloat16*>(dqkv), colsum, B, L, H, scale * kLog2e, scale, tlb));
+                                 lse, static_cast<__nv_bfloat16*>(dqkv), colsum, B, L, H, scale * kLog2e, scale, colsum_q, tlb));
         CLIMB_LAUNCH_OK();
+        // the q-bias gradient: a streaming pass over the dq columns just written (23 MB at the bench shape, still in L2)
+        if (colsum != nullptr && !colsum_q) {
+            const int rc3 = climb::colsum(dqkv, CLIMB_BF16, 3LL * H * kDh, B * L, H * kDh, colsum, stream);
+            if (rc3) return rc3;
+        }
 #if CLIMB_ATTN_TIMELINE
         if (tlb != nullptr && ++tl_calls == 20) {
             long long h[256];
