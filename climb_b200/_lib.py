@@ -176,6 +176,16 @@ class BertBatchC(Structure):
                 ("attention_mask", c_void_p)]
 
 
+class ImageDescC(Structure):
+    """climb_image_desc (include/climb_b200.h)."""
+    _fields_ = [("src_off", c_int64), ("tmp_off", c_int64), ("in_h", ctypes.c_int32), ("in_w", ctypes.c_int32),
+                ("out_h", ctypes.c_int32), ("out_w", ctypes.c_int32), ("ksize_h", ctypes.c_int32), ("ksize_v", ctypes.c_int32),
+                ("bounds_h_off", c_int64), ("coef_h_off", c_int64), ("bounds_v_off", c_int64), ("coef_v_off", c_int64)]
+
+
+climb_image_preprocess = _sig("climb_image_preprocess", [_P, _P, _P, _P, c_int, c_int64, _P, _P, c_int, c_int,
+                                                         POINTER(c_float), POINTER(c_float), _P])
+
 climb_bert_forward_workspace_bytes = _sig("climb_bert_forward_workspace_bytes", [POINTER(BertDimsC), POINTER(BertBatchC)],
                                           c_int64)
 climb_bert_forward = _sig("climb_bert_forward", [POINTER(BertDimsC), POINTER(BertParamsC), POINTER(BertBatchC), _P, _P, _P,

@@ -205,4 +205,11 @@ int climb_dropout_add(const float* x, const float* res, float* y, int64_t n, flo
     return dropout_add(x, res, y, n, p, seed, S(stream));
 }
 
+int climb_image_preprocess(const uint8_t* src, uint8_t* tmp, const climb_image_desc* descs, const int32_t* tables, int B,
+                           int64_t max_tmp_pixels, float* pixel_values, int64_t* pixel_mask, int Hp, int Wp, const float* mean,
+                           const float* std, void* stream) {
+    return image_preprocess(src, tmp, descs, tables, B, max_tmp_pixels, pixel_values, reinterpret_cast<long long*>(pixel_mask), Hp, Wp,
+                            mean, std, S(stream));
+}
+
 }  // extern "C"

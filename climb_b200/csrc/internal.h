@@ -82,6 +82,11 @@ int bert_forward(const climb_bert_dims* dm, const climb_bert_params* pr, const c
                  unsigned long long seed, float* out, cudaStream_t s);
 int dropout_add(const float* x, const float* res, float* y, long long n, float p, unsigned long long seed, cudaStream_t s);
 
+// image_pre.cu
+int image_preprocess(const uint8_t* src, uint8_t* tmp, const climb_image_desc* descs_dev, const int* tables_dev, int B,
+                     long long max_tmp_pixels, float* pixel_values, long long* pixel_mask, int Hp, int Wp, const float* mean,
+                     const float* stdv, cudaStream_t stream);
+
 // engine.cu
 long long vilt_forward_workspace_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
                                        const climb_vilt_batch* batch, int save);

@@ -39,6 +39,8 @@ class B200ViltEncoderWrapper(EncoderWrapper):
         self.device = device
         self.max_text_length = self.vilt.config.max_position_embeddings
         self.encoder_dim = self.vilt.config.hidden_size
+        self.gpu_image_pipeline = True      # process_inputs: image half of the ViltProcessor on the GPU (False = the reference's PIL path)
+        self._image_fe, self._image_fe_key = None, None
 
     def reset_processor(self, max_text_length: int, img_size: tuple):
         self.max_text_length = max_text_length
@@ -59,6 +61,23 @@ class B200ViltEncoderWrapper(EncoderWrapper):
         if self.processor is None:
             raise RuntimeError("this encoder was built without a ViltProcessor: call forward_tensors() / pass "
                                "encodings, or construct it with processor=ViltProcessor.from_pretrained(...)")
+        fe = getattr(self.processor, "feature_extractor", None)
+        tok = getattr(self.processor, "tokenizer", None)
+        if (self.gpu_image_pipeline and fe is not None and tok is not None and torch.device(self.device).type == "cuda"
+                and getattr(fe, "do_resize", True) and getattr(fe, "do_normalize", True) and int(getattr(fe, "resample", 3)) == 3):
+            # ViltProcessor.__call__ = tokenizer(text) + feature_extractor(images) (processing_vilt.py:63-107): the text half stays
+            # on the host tokenizer, the image half (PIL bicubic resize, normalise, pad, pixel mask: the reference's CPU
+            # bottleneck) runs on the GPU with the extractor's own parameters, bit-exact (climb_b200/image_processing.py)
+            from ..image_processing import B200ViltFeatureExtractor
+            key = (fe.size, getattr(fe, "size_divisor", 32), tuple(fe.image_mean), tuple(fe.image_std))
+            if self._image_fe is None or self._image_fe_key != key:
+                self._image_fe = B200ViltFeatureExtractor(size=key[0], size_divisor=key[1], image_mean=key[2], image_std=key[3],
+                                                          device=self.device)
+                self._image_fe_key = key
+            enc = tok(text=texts, max_length=self.max_text_length, padding=True, truncation=True, return_tensors='pt')
+            out = {k: v.to(self.device, non_blocking=True) for k, v in enc.items()}
+            out.update(self._image_fe(images))
+            return out
         encodings = self.processor(images=images, text=texts, max_length=self.max_text_length,
                                    padding=True, truncation=True, return_tensors='pt').to(self.device)
         return encodings

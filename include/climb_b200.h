@@ -316,6 +316,26 @@ int climb_bert_forward(const climb_bert_dims* dims, const climb_bert_params* par
  * Element i of stream `seed` is kept iff philox(seed, i) >= p: the mask is a pure function of (seed, i). */
 int climb_dropout_add(const float* x, const float* res, float* y, int64_t n, float p, uint64_t seed, void* stream);
 
+/* ---- image side of the input pipeline ------------------------------------------------------
+ * Replaces ViltFeatureExtractor.__call__ (adapter-transformers/src/transformers/models/vilt/feature_extraction_vilt.py:
+ * 253-292, called from ViltEncoderWrapper.process_inputs, src/modeling/vilt.py:83-96): Pillow BICUBIC resize of uint8 RGB
+ * images, float32 (x / 255 - mean) / std, zero padding to the batch maximum and the pixel mask, bit-exact with the CPU path.
+ * All pointers are DEVICE pointers except mean / std (host, 3 floats each). `tables` holds, per image and axis, the bounds
+ * [out, 2] (first input index, tap count) and int32 coefficients [out, ksize] (2^-22 units) of Pillow's precompute_coeffs /
+ * normalize_coeffs_8bpc; the offsets in the descriptors index it in ints. tmp receives the horizontally resampled images. */
+typedef struct {
+    int64_t src_off;                    /* bytes into src: image [in_h, in_w, 3] uint8 */
+    int64_t tmp_off;                    /* bytes into tmp: [in_h, out_w, 3] uint8 */
+    int32_t in_h, in_w, out_h, out_w;
+    int32_t ksize_h, ksize_v;
+    int64_t bounds_h_off, coef_h_off, bounds_v_off, coef_v_off;
+} climb_image_desc;
+
+int climb_image_preprocess(const uint8_t* src, uint8_t* tmp, const climb_image_desc* descs, const int32_t* tables, int B,
+                           int64_t max_tmp_pixels /* max over images of in_h * out_w */,
+                           float* pixel_values /* [B, 3, Hp, Wp] */, int64_t* pixel_mask /* [B, Hp, Wp] */, int Hp, int Wp,
+                           const float* mean, const float* std, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ for g in "$@"; do
     ln)       run ln 600 tests/test_gpu_kernels.py -k "layernorm" ;;
     parity)   run parity 900 tests/test_gpu_parity.py -s ;;
     cl)       run cl 900 tests/test_gpu_cl.py -s ;;
+    image)    run image 600 tests/test_image_pre.py ;;
     viltbert) run viltbert 900 tests/test_gpu_viltbert.py -s ;;
     perf)     echo "=== perf" | tee -a gpurun_out/summary.txt; timeout 600 python tools/perf_kernels.py > gpurun_out/perf.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; cat gpurun_out/perf.log | tee -a gpurun_out/summary.txt ;;
     perfgen)  echo "=== perf (generic GEMM kernel only)" | tee -a gpurun_out/summary.txt; CLIMB_GEMM_GENERIC=1 timeout 600 python tools/perf_kernels.py > gpurun_out/perf_generic.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; head -n 12 gpurun_out/perf_generic.log | tee -a gpurun_out/summary.txt ;;
