@@ -1,81 +1,100 @@
-"""Experience replay with the reference's hook surface (src/cl_algorithms/experience_replay.py):
-host-side index buffers and one extra train_step with a FRESH optimizer per replay step (SURVEY.md
-appendix C8). The encoder step it triggers is the CUDA path; `sample_concat_batch` additionally
-offers the north-star variant in which replay rows are concatenated to the current batch on the
-device (documented deviation: it changes the optimisation semantics, so it is opt-in)."""
+"""Experience replay behind the hook surface CLiMB's driver and trainers call
+(src/cl_algorithms/experience_replay.py; call sites train_upstream_continual_learning.py:205-214 and
+train_vqa.py:186-188, 223-226):
+
+    memory = ExperienceReplayMemory()
+    memory.add_task_memory_buffer(args, task_key, task_config, task_trainer, memory_percentage, sampling_strategy)
+    if memory.do_replay(): task = memory.sample_replay_task(); memory.run_replay_step(task_key=task, model=model)
+
+The bookkeeping is host-side index arithmetic; the encoder step a replay triggers is the CUDA path. Two things
+are kept exactly, because the reference's results depend on them:
+
+  * the python `random` stream is consumed in the reference's order -- one random.sample over the training
+    indices when a buffer is created (:104-106), one random.choice per replay task (:50), one random.sample
+    over the memory per replay batch (:120) -- so a seeded run replays the SAME samples as the reference
+    (pinned by tests/golden/trainer_vqa_er.npz, recorded from the unmodified classes);
+  * a replay step is a separate optimizer step with a FRESH AdamW from model.create_optimizer(hparams): no
+    moments, base learning rate, no schedule (:61-63).
+
+`concat_encodings` is the north-star variant (BASELINE.json): replay rows concatenated to the current batch on
+the device and pushed through ONE encoder pass. It changes the optimisation semantics (one step instead of
+two), so nothing here uses it implicitly; tools/bench_configs.py times it for BASELINE config 4.
+"""
 from __future__ import annotations
 
 import logging
 import random
-from typing import Dict
+from typing import Dict, List
 
 import torch
 
 logger = logging.getLogger(__name__)
 
-
-class ExperienceReplayMemory:
-    def __init__(self):
-        self.memory_buffers = {}
-
-    def add_task_memory_buffer(self, args, task_key: str, task_config: Dict, task_trainer, memory_percentage: float,
-                               sampling_strategy: str):
-        self.memory_buffers[task_key] = TaskMemoryBuffer(args, task_key, task_config, task_trainer, memory_percentage,
-                                                         sampling_strategy)
-
-    def do_replay(self) -> bool:
-        return True if len(self.memory_buffers) > 0 else False
-
-    def sample_replay_task(self) -> str:
-        return random.choice(list(self.memory_buffers.keys()))
-
-    def run_replay_step(self, task_key: str, model) -> torch.Tensor:
-        """experience_replay.py:53-67: new AdamW (no moments, base lr, no schedule) + one train_step."""
-        task_buffer = self.memory_buffers[task_key]
-        task_trainer = task_buffer.task_trainer
-        optimizer = model.create_optimizer(task_trainer.hparams)
-        replay_batch = task_buffer.sample_replay_batch()
-        replay_loss, output, _, _ = task_trainer.train_step(model, replay_batch, optimizer)
-        logger.info("%s replay step: loss = %.5f", task_buffer.task_name, float(replay_loss))
-        return replay_loss
+# sequences per sample: a replay batch holds batch_size / this many samples, so that every replay step
+# pushes the same number of sequences through the encoder (experience_replay.py:93-98)
+_SEQUENCES_PER_SAMPLE = {"nlvr2": 2, "vcr": 4}
+_SAMPLING_STRATEGIES = ("random",)
 
 
 class TaskMemoryBuffer:
+    """Indices of the training samples of one finished task that may be replayed later."""
+
     def __init__(self, args, task_key: str, task_config: Dict, task_trainer, memory_percentage: float,
                  sampling_strategy: str):
-        self.task_key = task_key
-        self.task_name = task_config.get('task_name', task_key)
-        self.task_config = task_config
-        self.task_trainer = task_trainer
-        self.dataset = task_trainer.get_train_dataloader().dataset
-        self.batch_collate_fn = task_trainer.get_collate_fn()
-        if task_key == 'nlvr2':
-            self.batch_size = int(args.batch_size / 2)
-        elif task_key == 'vcr':
-            self.batch_size = int(args.batch_size / 4)
-        else:
-            self.batch_size = args.batch_size
-        self.memory_percentage = memory_percentage
-        assert self.memory_percentage < 1.0
-        self.memory_size = int(memory_percentage * len(self.dataset))
-        self.sampling_strategy = sampling_strategy
-        assert sampling_strategy in ['random']
-        self.memory_idxs = random.sample(list(range(len(self.dataset))), self.memory_size)
-        logger.info("Created %s replay memory buffer, with %d samples in the memory", self.task_name, len(self.memory_idxs))
+        loader = task_trainer.get_train_dataloader()
+        self.task_key, self.task_config, self.task_trainer = task_key, task_config, task_trainer
+        self.task_name = task_config.get("task_name", task_key)
+        self.dataset, self.batch_collate_fn = loader.dataset, task_trainer.get_collate_fn()
+        self.batch_size = int(args.batch_size / _SEQUENCES_PER_SAMPLE.get(task_key, 1))
+        assert memory_percentage < 1.0, "memory_percentage is a fraction of the training set"
+        assert sampling_strategy in _SAMPLING_STRATEGIES, f"sampling strategy {sampling_strategy!r} is not implemented"
+        self.memory_percentage, self.sampling_strategy = memory_percentage, sampling_strategy
+        n_train = len(self.dataset)
+        self.memory_size = int(memory_percentage * n_train)
+        self.memory_idxs: List[int] = random.sample(list(range(n_train)), self.memory_size)
+        logger.info("%s: replay memory of %d / %d training samples", self.task_name, self.memory_size, n_train)
 
-    def __len__(self):
+    def __len__(self) -> int:
         return len(self.memory_idxs)
 
     def sample_replay_batch(self) -> Dict:
-        sampled_instances = random.sample(self.memory_idxs, self.batch_size)
-        return self.batch_collate_fn([self.dataset[i] for i in sampled_instances])
+        chosen = random.sample(self.memory_idxs, self.batch_size)
+        return self.batch_collate_fn([self.dataset[i] for i in chosen])
+
+
+class ExperienceReplayMemory:
+    """task_key -> TaskMemoryBuffer, in the order the tasks were learned."""
+
+    def __init__(self):
+        self.memory_buffers: Dict[str, TaskMemoryBuffer] = {}
+
+    def add_task_memory_buffer(self, args, task_key: str, task_config: Dict, task_trainer, memory_percentage: float,
+                               sampling_strategy: str) -> None:
+        self.memory_buffers[task_key] = TaskMemoryBuffer(args, task_key, task_config, task_trainer,
+                                                         memory_percentage, sampling_strategy)
+
+    def do_replay(self) -> bool:
+        return len(self.memory_buffers) > 0
+
+    def sample_replay_task(self) -> str:
+        return random.choice(list(self.memory_buffers))
+
+    def run_replay_step(self, task_key: str, model) -> torch.Tensor:
+        buffer = self.memory_buffers[task_key]
+        trainer = buffer.task_trainer
+        fresh_optimizer = model.create_optimizer(trainer.hparams)
+        loss = trainer.train_step(model, buffer.sample_replay_batch(), fresh_optimizer)[0]
+        logger.info("%s replay step: loss = %.5f", buffer.task_name, loss.item())
+        return loss
 
 
 def concat_encodings(current: Dict[str, torch.Tensor], replay: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """North-star ER variant: current || replay rows concatenated ON THE DEVICE before one encoder pass.
-    Both must be single-image encodings of the same text length and resolution."""
-    out = {}
-    for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "pixel_mask"):
-        if k in current and k in replay:
-            out[k] = torch.cat([current[k], replay[k]], dim=0)
-    return out
+    """Current-task rows || replay rows on the device, for one encoder pass over both (north-star ER variant).
+    Both must be single-image encodings with the same text length and image size."""
+    keys = [k for k in ("input_ids", "attention_mask", "token_type_ids", "pixel_values", "pixel_mask")
+            if k in current and k in replay]
+    for k in keys:
+        if current[k].shape[1:] != replay[k].shape[1:]:
+            raise ValueError(f"{k}: current rows {tuple(current[k].shape[1:])} and replay rows "
+                             f"{tuple(replay[k].shape[1:])} differ; pad both to a common text length / image size first")
+    return {k: torch.cat([current[k], replay[k]], dim=0) for k in keys}

@@ -1,0 +1,161 @@
+"""Generate tests/golden/trainer_*.npz by running the UNMODIFIED reference trainers -- VQATrainer.train /
+.train_step / .eval (src/train/visionlanguage_tasks/train_vqa.py), NLVR2Trainer (train_nlvr2.py),
+ExperienceReplayMemory / TaskMemoryBuffer (src/cl_algorithms/experience_replay.py) and
+ViltContinualLearner.create_optimizer + get_polynomial_decay_schedule_with_warmup -- over the synthetic
+datasets of oracle/trainer_oracle.py on CPU.
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden_trainer
+
+TEST INFRASTRUCTURE (build container only: needs /root/reference). The trainer objects are allocated without
+running their __init__ (which opens the COCO / VQA / NLVR2 files) and given the attributes __init__ would
+have set; every method that then runs -- train, train_step, forward_pass, eval, compute_score_with_logits,
+run_replay_step, sample_replay_batch -- is the reference's own code. The model is the reference's
+ViltContinualLearner with process_inputs replaced by the pool lookup (no tokenizer vocabulary offline).
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from oracle import trainer_oracle as to  # noqa: E402
+from oracle.make_golden import ALL_TASKS, GOLDEN_DIR, TINY, TINY_HW, TINY_T, build_reference_learner, grad_sample_index  # noqa: E402
+from oracle.vilt_oracle import synth_state_dict  # noqa: E402
+
+PARAM_FULL_MAX = 4096
+
+
+def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algorithm, replay_frequency, record):
+    from modeling.vilt import convert_batch_to_vilt_input_dict
+    if task == "vqa":
+        from train.visionlanguage_tasks.train_vqa import VQATrainer as cls
+        loaders = dict(vqa_train_dataloader=train_dl, vqa_val_dataloader=val_dl)
+        crit = torch.nn.BCEWithLogitsLoss(reduction="mean")
+    else:
+        from train.visionlanguage_tasks.train_nlvr2 import NLVR2Trainer as cls
+        loaders = dict(nlvr_train_dataloader=train_dl, nlvr_val_dataloader=val_dl)
+        crit = torch.nn.CrossEntropyLoss()
+    t = cls.__new__(cls)
+    torch.nn.Module.__init__(t)                      # TaskTrainer is an nn.Module (task_trainer.py:5-9)
+    t.args = types.SimpleNamespace(cl_algorithm=cl_algorithm, replay_frequency=replay_frequency)
+    t.device = torch.device("cpu")
+    t.batch2inputs_converter = convert_batch_to_vilt_input_dict
+    for k, v in loaders.items():
+        setattr(t, k, v)
+    t.num_epochs, t.hparams, t.loss_criterion = num_epochs, hparams, crit
+    t.max_steps, t.warmup_ratio = len(train_dl) * num_epochs, 0.1
+    # recorders around the unmodified methods (instance attributes shadow the class's functions)
+    ref_train_step, ref_eval, ref_forward = cls.train_step, cls.eval, cls.forward_pass
+
+    def train_step(model, batch, optimizer=None, scheduler=None, ewc=None):
+        if scheduler is not None:
+            record["lr"].append(optimizer.param_groups[0]["lr"])
+        out = ref_train_step(t, model, batch, optimizer, scheduler, ewc)
+        if scheduler is not None:
+            record["loss"].append(float(out[0]))
+        return out
+
+    def forward_pass(model, batch, do_eval=False):
+        out = ref_forward(t, model, batch, do_eval)
+        if do_eval:
+            record["_eval_tmp"].append(out[1].detach().clone())
+        return out
+
+    def eval_(model):
+        record["_eval_tmp"] = []
+        score = ref_eval(t, model)
+        record["eval_score"].append(score)
+        record["eval_logits"].append(torch.cat(record.pop("_eval_tmp")))
+        return score
+
+    t.train_step, t.eval, t.forward_pass = train_step, eval_, forward_pass
+    return t
+
+
+def run(tag):
+    from cl_algorithms.experience_replay import ExperienceReplayMemory
+    import cl_algorithms.experience_replay as er_mod
+    import train.visionlanguage_tasks.train_vqa as tv
+    import train.visionlanguage_tasks.train_nlvr2 as tn
+    tv.tqdm = tn.tqdm = lambda it, **k: it
+    sc = to.SCENARIOS[tag]
+    dims = TINY
+    sd = synth_state_dict(dims, ALL_TASKS, seed=sc["seed"])
+    learner = build_reference_learner(dims, ALL_TASKS, sd)
+    pools, train_dl, val_dl, replay_dl = to.build_data(sc, dims, TINY_T, TINY_HW)
+    proc = to.PoolProcessor(pools, torch.device("cpu"))
+    learner.vilt_encoder.process_inputs = proc
+    record = {"loss": [], "lr": [], "replay": [], "eval_score": [], "eval_logits": []}
+    cl = "experience_replay" if sc["replay"] else "sequential_ft"
+    replay_memory = None
+    random.seed(sc["seed"])
+    torch.manual_seed(sc["seed"])                    # visual_embed's multinomial permutation
+    if sc["replay"]:
+        r = sc["replay"]
+        prev_rec = {"loss": [], "lr": [], "eval_score": [], "eval_logits": []}
+        prev = make_reference_trainer(r["task"], replay_dl, replay_dl, r["hparams"], 1, cl, 0, prev_rec)
+        replay_memory = ExperienceReplayMemory()
+        replay_memory.add_task_memory_buffer(args=types.SimpleNamespace(batch_size=sc["batch_size"]), task_key=r["task"],
+                                             task_config={"task_name": r["task"]}, task_trainer=prev,
+                                             memory_percentage=r["memory_percentage"], sampling_strategy="random")
+        memory_idxs = list(replay_memory.memory_buffers[r["task"]].memory_idxs)
+        ref_replay = ExperienceReplayMemory.run_replay_step
+        sampled = []
+        ref_sample = er_mod.TaskMemoryBuffer.sample_replay_batch
+
+        def sample_replay_batch(self):
+            b = ref_sample(self)
+            sampled.append([h[1] for h in b["raw_texts"]])
+            return b
+
+        er_mod.TaskMemoryBuffer.sample_replay_batch = sample_replay_batch
+
+        def run_replay_step(task_key, model):
+            loss = ref_replay(replay_memory, task_key=task_key, model=model)
+            record["replay"].append((task_key, float(loss)))
+            return loss
+
+        replay_memory.run_replay_step = run_replay_step
+    trainer = make_reference_trainer(sc["task"], train_dl, val_dl, sc["hparams"], sc["num_epochs"], cl,
+                                     sc["replay"]["replay_frequency"] if sc["replay"] else 100, record)
+    best_score, best_model = trainer.train(learner, replay_memory=replay_memory)
+    out = {"loss": np.array(record["loss"], np.float64), "lr": np.array(record["lr"], np.float64),
+           "eval_score": np.array(record["eval_score"], np.float64), "best_score": np.float64(best_score),
+           "best_epoch": np.int64(best_model["epoch"]), "seed": np.int64(sc["seed"]),
+           "process_inputs_calls": np.int64(proc.calls)}
+    for e, lg in enumerate(record["eval_logits"]):
+        out[f"eval_logits/{e}"] = lg.numpy()
+    if sc["replay"]:
+        out["replay_loss"] = np.array([l for _, l in record["replay"]], np.float64)
+        out["replay_task"] = np.array([t for t, _ in record["replay"]])
+        out["memory_idxs"] = np.array(memory_idxs, np.int64)
+        out["replay_samples"] = np.array(sampled, np.int64)
+    for which, m in (("final", learner), ("best", best_model["model"])):
+        for n, p in m.named_parameters():
+            v = p.detach()
+            out[f"{which}_norm/{n}"] = np.float64(v.double().norm().item())
+            if which == "final":
+                flat = v.flatten().numpy()
+                out[f"final_sample/{n}"] = flat.copy() if flat.size <= PARAM_FULL_MAX else flat[grad_sample_index(flat.size)].copy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"{tag}.npz"), **out)
+    print(f"{tag}: loss {record['loss'][0]:.4f} -> {record['loss'][-1]:.4f}  eval {record['eval_score']}  best epoch "
+          f"{best_model['epoch']}  replay {record['replay']}")
+
+
+def main():
+    ref_shim.install()
+    torch.set_num_threads(os.cpu_count() or 1)
+    for tag in to.SCENARIOS:
+        run(tag)
+
+
+if __name__ == "__main__":
+    main()

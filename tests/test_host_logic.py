@@ -233,3 +233,45 @@ def test_viltbert_state_dict_keys_and_registry():
     assert hasattr(learner, "create_optimizer") and hasattr(learner, "get_active_adapters")
     assert set(M.load_encoder_map) == set(M.create_continual_learner_map) == {"vilt-b200", "viltbert-b200"}
     assert M.model_configs["viltbert-b200"]["encoder_class"] is M.B200ViltBertEncoderWrapper
+
+
+def test_adapter_handler_surface_matches_the_driver_calls():
+    """AdapterHandler as train_upstream_continual_learning.py:167-170, 195-197 uses it (src/cl_algorithms/adapters.py)."""
+    import types
+    from climb_b200.cl_algorithms import AdapterHandler
+    from climb_b200.cl_algorithms.adapters import ADAPTER_MAP, SUPPORTED_ADAPTER_METHODS
+    from climb_b200.modeling import AdapterSpec
+    assert SUPPORTED_ADAPTER_METHODS == ['vanilla'] and {'houlsby', 'pfeiffer'} <= set(ADAPTER_MAP)
+    args = types.SimpleNamespace(adapter_config="houlsby", adapter_reduction_factor=4, ordered_cl_tasks=["vqa", "nlvr2"])
+    handler = AdapterHandler("vanilla", args)
+    assert handler.adapter_config.reduction_factor == 4 and handler.adapter_config.non_linearity == "swish"
+    assert AdapterSpec.from_config("houlsby").reduction_factor == 16, "the override must not leak into the preset"
+    learner = _learner()
+    handler.add_adapters_to_model(learner)
+    r = TINY.hidden_size // 4
+    for task in args.ordered_cl_tasks:
+        w = dict(learner.named_parameters())[f"vilt_encoder.vilt.encoder.layer.0.output.adapters.{task}.adapter_down.0.weight"]
+        assert tuple(w.shape) == (r, TINY.hidden_size)
+    handler.activate_adapter_for_training("vqa", learner)
+    assert learner.get_active_adapters() == "vqa"
+    trainable = {n for n, p in learner.named_parameters() if p.requires_grad}
+    assert all(".adapters.vqa." in n or n.startswith("task_layer.") for n in trainable) and any(".adapters.vqa." in n for n in trainable)
+    handler.activate_adapter_for_eval("nlvr2", learner)
+    assert learner.get_active_adapters() == "nlvr2"
+    keep = types.SimpleNamespace(adapter_config="pfeiffer", adapter_reduction_factor=0, ordered_cl_tasks=[])
+    assert AdapterHandler("vanilla", keep).adapter_config.reduction_factor == 16      # <= 0 keeps the config's own value
+    with pytest.raises(ValueError):
+        AdapterHandler("fusion", args)
+    with pytest.raises(ValueError):
+        AdapterHandler("vanilla", types.SimpleNamespace(adapter_config="compacter", adapter_reduction_factor=0, ordered_cl_tasks=[]))
+
+
+def test_concat_encodings_checks_shapes():
+    from climb_b200.cl_algorithms.experience_replay import concat_encodings
+    cur = {"input_ids": torch.zeros(3, 8, dtype=torch.long), "pixel_values": torch.zeros(3, 3, 32, 32), "extra": 1}
+    rep = {"input_ids": torch.ones(2, 8, dtype=torch.long), "pixel_values": torch.ones(2, 3, 32, 32)}
+    out = concat_encodings(cur, rep)
+    assert set(out) == {"input_ids", "pixel_values"} and out["input_ids"].shape == (5, 8) and out["pixel_values"][3:].min() == 1
+    rep["pixel_values"] = torch.ones(2, 3, 32, 64)
+    with pytest.raises(ValueError):
+        concat_encodings(cur, rep)
