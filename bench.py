@@ -130,6 +130,15 @@ def cpu_reference_steps(steps: int, warmup: int, batch: int = 4):
     return batch / sec, cores, sec
 
 
+def workload_config(batch_per_gpu: int, world: int) -> dict:
+    """The `config` object of the JSON line: the same for both arms (the reference arm adds its bounded sample)."""
+    return {"workload": "ViLT-base sequential-FT VQAv2-shaped synthetic step (fwd+BCEx3129+bwd+AdamW), "
+                        "BASELINE.json configs[1]", "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * world,
+            "text_tokens": T_TEXT, "image": f"{IMG}x{IMG} -> 14x14 patches + cls", "seq_len": 237,
+            "layers": 12, "hidden": 768, "parallelism": f"dp{world}",
+            "l2": "activation working set ~5 GB per step >> 126 MB L2; 4 rotating input batches"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -143,8 +152,8 @@ def run_reference(args):
         "impl": "reference", "metric": "ViLT upstream-CL training throughput", "value": sps, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ViLT-base sequential-FT VQAv2-shaped synthetic step (fwd+loss+bwd+AdamW), "
-                               "40 text tokens + 14x14 patches + cls = 237 tokens", "sample_batch": 4},
+        "config": dict(workload_config(args.batch, args.gpus),
+                       sample="each step = one B=4 batch of the workload (BASELINE config 1), fp32 on the host cores"),
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of B=4 (BASELINE config 1) through oracle/vilt_oracle.py, "
                                    "the CPU restatement pinned to the reference by tests/golden; the reference itself "
@@ -361,11 +370,7 @@ def run_ours(args):
             "metric": "ViLT upstream-CL training throughput", "value": round(value, 1), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ViLT-base sequential-FT VQAv2-shaped synthetic step (fwd+BCEx3129+bwd+AdamW), "
-                                   "BASELINE.json configs[1]", "batch_per_gpu": B, "global_batch": B * world,
-                       "text_tokens": T_TEXT, "image": f"{IMG}x{IMG} -> 14x14 patches + cls", "seq_len": 237,
-                       "layers": 12, "hidden": 768, "parallelism": f"dp{world}",
-                       "l2": "activation working set ~5 GB per step >> 126 MB L2; 4 rotating input batches"},
+            "config": workload_config(B, world),
             "samples_per_s_per_gpu": round(value / world, 1),
             "model_tflops_per_gpu": round(value / world * FLOPS_PER_SAMPLE_STEP / 1e12, 1),
             "step_frac_of_tensor_roofline": round(value / world * FLOPS_PER_SAMPLE_STEP / 1e12 / peaks["tf_sustained"], 4),
