@@ -73,6 +73,7 @@ extern "C" {
 const char* climb_last_error(void) { return g_last_error; }
 int climb_version(void) { return 100; }
 uint64_t climb_launch_count(void) { return g_launch_count; }
+int climb_gemm_pair_mode(int mode) { return climb::gemm_pair_mode(mode); }
 
 int climb_profile_begin(void) {
     for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -861,6 +861,150 @@ __device__ __forceinline__ void fast_mma_loop(const GemmDeviceArgs& p, uint8_t* 
     }
 }
 
+// The epilogue warps of the specialised kernels (warps 2 .. 17): accumulator tile (this CTA's 128 TMEM lanes x tile width)
+// -> registers -> epilogue arithmetic -> coalesced global stores. Shared by the one-CTA kernel (tile_rows = 128,
+// row_off = 0, tiles blockIdx.x, + gridDim.x, ...) and the CTA-pair kernel (tile_rows = 256, row_off = 128 * cluster rank,
+// tiles pair, + pairs, ...; the accumulator is handed back on the LEADER's acc_empty barrier).
+template <int KIND, bool PAIR>
+__device__ __forceinline__ void fast_epilogue(const GemmDeviceArgs& p, uint8_t* stg_base, uint64_t* acc_full, uint64_t* acc_empty,
+                                              uint32_t acc_empty_leader, uint32_t tmem_base, int warp, int lane, int tile0,
+                                              int tstride, int tile_rows, int row_off) {
+    constexpr int BLOCK_N = kFastBlockN;
+    constexpr bool kF32 = KIND == FK_RES_F32;
+    constexpr bool kHasIn = KIND == FK_MUL_AUX || KIND == FK_RES_F32;
+    constexpr int kUnits = kF32 ? 2 : 1;              // 64 B units per 32-column chunk
+    constexpr int kColGroups = kFastEpiWarps / 4;
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;                    // TMEM lanes [32 * lane_grp, +32) are this warp's
+    const int cg = ew >> 2;                           // chunks cg, cg + 4 of every tile
+    uint8_t* stg = stg_base + ew * kFastUnitBytes;
+    const int total_tiles = p.total_vtiles;
+    const int rsub = lane >> 2, gj = lane & 3;
+    // byte pitches: output rows / input rows, and 8 rows at a time for the coalesced mapping
+    const long long c_pitch = p.ldc * (kF32 ? 4 : 2);
+    const long long in_pitch = kF32 ? p.ldr * 4 : p.ldaux * 2;
+    const uint8_t* in_base = kF32 ? reinterpret_cast<const uint8_t*>(p.residual) : reinterpret_cast<const uint8_t*>(p.aux);
+
+    uint4 pf[kHasIn ? kUnits : 1][4];
+    // fetch the input of chunk cc of tile t (coalesced mapping) into pf
+    auto prefetch = [&](int t, int cc, int h) {
+        const FastTile tp = fast_tile(p, t);
+        const int r0 = tp.m_blk * tile_rows + row_off + lane_grp * 32;
+        const int rv = min(32, max(0, p.M - r0));
+        const uint8_t* g = in_base + (static_cast<long long>(r0) + rsub) * in_pitch +
+                           static_cast<long long>(tp.n0 + cc * 32) * (kF32 ? 4 : 2) + gj * 16;
+        load_unit(pf[h], g + h * 64, 8 * in_pitch, rv, lane);
+    };
+    if (kHasIn && tile0 < total_tiles) {
+#pragma unroll
+        for (int h = 0; h < kUnits; ++h) prefetch(tile0, cg, h);
+    }
+
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tstride) {
+        const FastTile tr = fast_tile(p, tile);
+        const int n_chunks = tr.width / 32;
+        const int row0 = tr.m_blk * tile_rows + row_off + lane_grp * 32;
+        const int rows_valid = min(32, max(0, p.M - row0));
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+        for (int c = cg; c < n_chunks; c += kColGroups) {
+            const int n0 = tr.n0 + c * 32;
+            int nt = tile, nc = c + kColGroups;           // this warp's next chunk
+            if (nc >= n_chunks) { nt = tile + tstride; nc = cg; }
+            uint8_t* c_lane = reinterpret_cast<uint8_t*>(p.C) + (static_cast<long long>(row0) + rsub) * c_pitch +
+                              static_cast<long long>(n0) * (kF32 ? 4 : 2) + gj * 16;
+            if constexpr (KIND == FK_RES_F32) {
+                // two 16-column halves, each with its own in-flight residual unit
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[16], res[16];
+                    tmem_ld_32x16(t_row + static_cast<uint32_t>(c * 32 + h * 16), r);
+                    transpose_unit_in(stg, pf[h], res, lane);
+                    if (nt < total_tiles) prefetch(nt, nc, h);
+                    tmem_ld_wait_regs16(r);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + h * 16 + j));
+                        r[j] = __float_as_uint(__uint_as_float(r[j]) + b4.x);
+                        r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
+                        r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
+                        r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
+                    }
+                    const int hsub = lane >> 1, hg = lane & 1;
+                    if (p.aux != nullptr) {          // bf16 copy of acc + bias (before the residual): adapter input
+                        uint32_t hw[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hw[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        uint8_t* a_lane = reinterpret_cast<uint8_t*>(p.aux) + (static_cast<long long>(row0) + hsub) * (p.ldaux * 2) +
+                                          static_cast<long long>(n0 + h * 16) * 2 + hg * 16;
+                        store_unit_half(stg, hw, a_lane, 16 * p.ldaux * 2, rows_valid, lane);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(res[j]));
+                    if (p.c2 != nullptr) {           // bf16 copy of the final value
+                        uint32_t hw[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hw[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        uint8_t* c2_lane = reinterpret_cast<uint8_t*>(p.c2) + (static_cast<long long>(row0) + hsub) * (p.ldc2 * 2) +
+                                           static_cast<long long>(n0 + h * 16) * 2 + hg * 16;
+                        store_unit_half(stg, hw, c2_lane, 16 * p.ldc2 * 2, rows_valid, lane);
+                    }
+                    store_unit(stg, r, c_lane + h * 64, 8 * c_pitch, rows_valid, lane);
+                }
+            } else {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), r);
+                uint32_t ain[16];
+                if constexpr (KIND == FK_MUL_AUX) {
+                    transpose_unit_in(stg, pf[0], ain, lane);
+                    if (nt < total_tiles) prefetch(nt, nc, 0);
+                }
+                tmem_ld_wait_regs(r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (KIND != FK_MUL_AUX && p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                    }
+                }
+                uint32_t pk[16];
+                if constexpr (KIND == FK_MUL_AUX) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 a = unpack_bf16(ain[j]);
+                        pk[j] = pack_bf16(v[2 * j] * a.x, v[2 * j + 1] * a.y);
+                    }
+                } else if constexpr (KIND == FK_GELU_SAVE) {
+                    uint32_t gpk[16];
+                    gelu_and_grad_chunk(v, gpk);
+                    uint8_t* a_lane = reinterpret_cast<uint8_t*>(p.aux) + (static_cast<long long>(row0) + rsub) * (p.ldaux * 2) +
+                                      static_cast<long long>(n0) * 2 + gj * 16;
+                    store_unit(stg, gpk, a_lane, 8 * p.ldaux * 2, rows_valid, lane);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                }
+                store_unit(stg, pk, c_lane, 8 * c_pitch, rows_valid, lane);
+            }
+        }
+        tc_fence_before();
+        if constexpr (PAIR) mbar_arrive_cluster(acc_empty_leader + static_cast<uint32_t>(acc) * 8u);
+        else mbar_arrive(&acc_empty[acc]);
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kFastThreads, 1)
 gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -910,137 +1054,8 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) fast_mma_loop(p, smem, full_bar, empty_bar, acc_full, acc_empty, tmem_base);
     } else {
-        constexpr bool kF32 = KIND == FK_RES_F32;
-        constexpr bool kHasIn = KIND == FK_MUL_AUX || KIND == FK_RES_F32;
-        constexpr int kUnits = kF32 ? 2 : 1;              // 64 B units per 32-column chunk
-        constexpr int kColGroups = kFastEpiWarps / 4;
-        const int ew = warp - 2;
-        const int lane_grp = warp & 3;                    // TMEM lanes [32 * lane_grp, +32) are this warp's
-        const int cg = ew >> 2;                           // chunks cg, cg + 4 of every tile
-        uint8_t* stg = smem + kStages * L::kStageBytes + L::kBarrierBytes + ew * kFastUnitBytes;
-        const int total_tiles = p.total_vtiles;
-        const int rsub = lane >> 2, gj = lane & 3;
-        // byte pitches: output rows / input rows, and 8 rows at a time for the coalesced mapping
-        const long long c_pitch = p.ldc * (kF32 ? 4 : 2);
-        const long long in_pitch = kF32 ? p.ldr * 4 : p.ldaux * 2;
-        const uint8_t* in_base = kF32 ? reinterpret_cast<const uint8_t*>(p.residual) : reinterpret_cast<const uint8_t*>(p.aux);
-
-        uint4 pf[kHasIn ? kUnits : 1][4];
-        // fetch the input of chunk cc of tile t (coalesced mapping) into pf
-        auto prefetch = [&](int t, int cc, int h) {
-            const FastTile tp = fast_tile(p, t);
-            const int r0 = tp.m_blk * kBlockM + lane_grp * 32;
-            const int rv = min(32, max(0, p.M - r0));
-            const uint8_t* g = in_base + (static_cast<long long>(r0) + rsub) * in_pitch +
-                               static_cast<long long>(tp.n0 + cc * 32) * (kF32 ? 4 : 2) + gj * 16;
-            load_unit(pf[h], g + h * 64, 8 * in_pitch, rv, lane);
-        };
-        if (kHasIn && static_cast<int>(blockIdx.x) < total_tiles) {
-#pragma unroll
-            for (int h = 0; h < kUnits; ++h) prefetch(blockIdx.x, cg, h);
-        }
-
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const FastTile tr = fast_tile(p, tile);
-            const int n_chunks = tr.width / 32;
-            const int row0 = tr.m_blk * kBlockM + lane_grp * 32;
-            const int rows_valid = min(32, max(0, p.M - row0));
-            mbar_wait(&acc_full[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-#pragma unroll 1
-            for (int c = cg; c < n_chunks; c += kColGroups) {
-                const int n0 = tr.n0 + c * 32;
-                int nt = tile, nc = c + kColGroups;           // this warp's next chunk
-                if (nc >= n_chunks) { nt = tile + gridDim.x; nc = cg; }
-                uint8_t* c_lane = reinterpret_cast<uint8_t*>(p.C) + (static_cast<long long>(row0) + rsub) * c_pitch +
-                                  static_cast<long long>(n0) * (kF32 ? 4 : 2) + gj * 16;
-                if constexpr (KIND == FK_RES_F32) {
-                    // two 16-column halves, each with its own in-flight residual unit
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t r[16], res[16];
-                        tmem_ld_32x16(t_row + static_cast<uint32_t>(c * 32 + h * 16), r);
-                        transpose_unit_in(stg, pf[h], res, lane);
-                        if (nt < total_tiles) prefetch(nt, nc, h);
-                        tmem_ld_wait_regs16(r);
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + h * 16 + j));
-                            r[j] = __float_as_uint(__uint_as_float(r[j]) + b4.x);
-                            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
-                            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
-                            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
-                        }
-                        const int hsub = lane >> 1, hg = lane & 1;
-                        if (p.aux != nullptr) {          // bf16 copy of acc + bias (before the residual): adapter input
-                            uint32_t hw[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) hw[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                            uint8_t* a_lane = reinterpret_cast<uint8_t*>(p.aux) + (static_cast<long long>(row0) + hsub) * (p.ldaux * 2) +
-                                              static_cast<long long>(n0 + h * 16) * 2 + hg * 16;
-                            store_unit_half(stg, hw, a_lane, 16 * p.ldaux * 2, rows_valid, lane);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(res[j]));
-                        if (p.c2 != nullptr) {           // bf16 copy of the final value
-                            uint32_t hw[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) hw[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                            uint8_t* c2_lane = reinterpret_cast<uint8_t*>(p.c2) + (static_cast<long long>(row0) + hsub) * (p.ldc2 * 2) +
-                                               static_cast<long long>(n0 + h * 16) * 2 + hg * 16;
-                            store_unit_half(stg, hw, c2_lane, 16 * p.ldc2 * 2, rows_valid, lane);
-                        }
-                        store_unit(stg, r, c_lane + h * 64, 8 * c_pitch, rows_valid, lane);
-                    }
-                } else {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), r);
-                    uint32_t ain[16];
-                    if constexpr (KIND == FK_MUL_AUX) {
-                        transpose_unit_in(stg, pf[0], ain, lane);
-                        if (nt < total_tiles) prefetch(nt, nc, 0);
-                    }
-                    tmem_ld_wait_regs(r);
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (KIND != FK_MUL_AUX && p.bias != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
-                    }
-                    uint32_t pk[16];
-                    if constexpr (KIND == FK_MUL_AUX) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float2 a = unpack_bf16(ain[j]);
-                            pk[j] = pack_bf16(v[2 * j] * a.x, v[2 * j + 1] * a.y);
-                        }
-                    } else if constexpr (KIND == FK_GELU_SAVE) {
-                        uint32_t gpk[16];
-                        gelu_and_grad_chunk(v, gpk);
-                        uint8_t* a_lane = reinterpret_cast<uint8_t*>(p.aux) + (static_cast<long long>(row0) + rsub) * (p.ldaux * 2) +
-                                          static_cast<long long>(n0) * 2 + gj * 16;
-                        store_unit(stg, gpk, a_lane, 8 * p.ldaux * 2, rows_valid, lane);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-                    }
-                    store_unit(stg, pk, c_lane, 8 * c_pitch, rows_valid, lane);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);
-            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
-        }
+        fast_epilogue<KIND, false>(p, smem + kStages * L::kStageBytes + L::kBarrierBytes, acc_full, acc_empty, 0u, tmem_base, warp,
+                                   lane, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), kBlockM, 0);
     }
 
     tc_fence_before();
@@ -1048,6 +1063,307 @@ gemm_fast_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant of the specialised kernels (tcgen05 cta_group::2). A 2-CTA cluster owns a 256 x 256 tile: CTA r stages
+// rows [128 r, 128 r + 128) of the A tile and columns [128 r, +128) of the B tile (32 KB per k-block instead of 48 KB: six
+// ring stages), the leader issues 256 x 256 x 16 MMAs that read both CTAs' shared memory, and each CTA's TMEM receives
+// the accumulator rows of its own A half -- so the epilogue is the one-CTA epilogue on rows offset by 128 r. Per FLOP every
+// SM fetches 2/3 of the operand bytes of the 128 x 256 kernel from L2 and from shared memory (the
+// K = 768 launches are bound by that traffic). Half-width tail tiles work as before (MMA N = 128, 64 B columns per CTA).
+// Used for K-major A operands (forward Linears and dgrads) of the kinds pair_kind_enabled() selects.
+// ------------------------------------------------------------------------------------------
+constexpr int kPairStages = 6;
+constexpr int kPairTileM = 2 * kBlockM;
+constexpr int kPairABytes = kBlockM * kBlockK * 2;                 // this CTA's 128 rows of A
+constexpr int kPairBBytes = (kFastBlockN / 2) * kBlockK * 2;       // this CTA's 128 columns of B
+constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
+constexpr int kPairBarrierBytes = 1024;
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kPairBarrierBytes + kFastEpiWarps * kFastUnitBytes + 1024;
+static_assert(kPairSmemBytes <= 227 * 1024, "pair GEMM shared memory budget");
+
+__device__ __forceinline__ void pair_producer_loop(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmDeviceArgs& p,
+                                                   uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar, uint32_t rank,
+                                                   int pair, int n_pairs) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int v = pair; v < p.total_vtiles; v += n_pairs) {
+        const FastTile tr = fast_tile(p, v);
+        const int half_w = tr.width / 2;                            // B columns staged by each CTA
+        // a K-major B half is one TMA box of 128 rows (a half-width tile still loads the box and the MMA reads its first 64
+        // rows); an MN-major B half is half_w / 64 boxes of 64 columns
+        const uint32_t b_bytes = p.b_mn_major ? static_cast<uint32_t>(half_w / 64) * (kBlockK * 128) : kPairBBytes;
+        for (int kb = 0; kb < p.k_blocks_total; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * kPairStageBytes;
+            uint8_t* sb = sa + kPairABytes;
+            const uint32_t full_leader = cluster_map_shared(&full_bar[stage], 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (kPairABytes + b_bytes));   // both CTAs' bytes
+            tma_load_2d_pair(&tmap_a, full_leader, sa, kb * kBlockK, tr.m_blk * kPairTileM + static_cast<int>(rank) * kBlockM);
+            if (!p.b_mn_major) {
+                tma_load_2d_pair(&tmap_b, full_leader, sb, kb * kBlockK, tr.n0 + static_cast<int>(rank) * half_w);
+            } else {
+                for (int j = 0; j < half_w / 64; ++j)
+                    tma_load_2d_pair(&tmap_b, full_leader, sb + j * (kBlockK * 128), tr.n0 + static_cast<int>(rank) * half_w + j * 64,
+                                     kb * kBlockK);
+            }
+            if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+    }
+}
+
+// leader CTA only
+__device__ __forceinline__ void pair_mma_loop(const GemmDeviceArgs& p, uint8_t* smem, uint64_t* full_bar, uint64_t* empty_bar,
+                                              uint64_t* acc_full, uint64_t* acc_empty, uint32_t tmem_base, int pair, int n_pairs) {
+    const uint32_t idesc_full = make_instr_desc(kPairTileM, kFastBlockN, 0, p.b_mn_major);
+    const uint32_t idesc_half = make_instr_desc(kPairTileM, kFastBlockN / 2, 0, p.b_mn_major);
+    const uint32_t b_lbo = p.b_mn_major ? kBlockK * 128 : 16;
+    const uint32_t b_kstep = p.b_mn_major ? 16 * 128 : 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int v = pair; v < p.total_vtiles; v += n_pairs) {
+        const uint32_t idesc = v < p.full_tiles ? idesc_full : idesc_half;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kFastBlockN);
+        for (int kb = 0; kb < p.k_blocks_total; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+            const uint32_t sb = sa + kPairABytes;
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                const uint64_t da = make_smem_desc(sa + kk * 32, 16, 1024);
+                const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, 1024);
+                umma_bf16_pair(d_tmem, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[stage]);      // frees the slot in BOTH CTAs when the MMAs retire
+            if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&acc_full[acc]);             // accumulator complete -> both CTAs' epilogues
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kFastThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmDeviceArgs p) {
+    constexpr uint32_t kTmemCols = kAccStages * kFastBlockN;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* bar_base = smem + kPairStages * kPairStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* acc_full = empty_bar + 8;
+    uint64_t* acc_empty = acc_full + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = static_cast<int>(blockIdx.x >> 1);
+    const int n_pairs = static_cast<int>(gridDim.x >> 1);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < kPairStages; ++s) {
+            mbar_init(&full_bar[s], 1);        // the leader's expect_tx arrival (+ the bytes of both CTAs)
+            mbar_init(&empty_bar[s], 1);       // one multicast tcgen05.commit
+        }
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 2 * kFastEpiWarps * 32);     // the epilogue threads of both CTAs (leader's barrier is the one used)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_slot, kTmemCols);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();                        // barriers of BOTH CTAs are initialised before any remote arrival
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (!p.skip_pdl_wait) pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) pair_producer_loop(tmap_a, tmap_b, p, smem, full_bar, empty_bar, rank, pair, n_pairs);
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) pair_mma_loop(p, smem, full_bar, empty_bar, acc_full, acc_empty, tmem_base, pair, n_pairs);
+    } else {
+        fast_epilogue<KIND, true>(p, smem + kPairStages * kPairStageBytes + kPairBarrierBytes, acc_full, acc_empty,
+                                  cluster_map_shared(&acc_empty[0], 0), tmem_base, warp, lane, pair, n_pairs, kPairTileM,
+                                  static_cast<int>(rank) * kBlockM);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                        // both CTAs are done with the pair's tensor memory and barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair weight-gradient kernel: dW[M, N] (fp32) += A^T B with BOTH operands MN-major (A = dY [tokens, M],
+// B = X [tokens, N], read in place), split over the token dimension, fp32 vector atomics into dW. The wgrads are all
+// main loop (119+ k-blocks per tile, a 64 KB epilogue), which is where halving the B fetch per SM pays in full.
+// 256 x 256 tile per pair: CTA r stages dY columns [128 r, +128) and X columns [128 r, +128) of the tile as two
+// 64-wide boxes each. Needs M % 256 == 0 and N % 256 == 0 (every Linear of ViLT / BERT-base).
+// ------------------------------------------------------------------------------------------
+constexpr int kWgradSmemBytes = kPairStages * kPairStageBytes + kPairBarrierBytes + kNumEpiWarps * kEpiHalfBytes + 1024;
+static_assert(kWgradSmemBytes <= 227 * 1024, "pair wgrad shared memory budget");
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const GemmDeviceArgs p) {
+    constexpr uint32_t kTmemCols = kAccStages * kFastBlockN;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* bar_base = smem + kPairStages * kPairStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* acc_full = empty_bar + 8;
+    uint64_t* acc_empty = acc_full + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = static_cast<int>(blockIdx.x >> 1);
+    const int n_pairs = static_cast<int>(gridDim.x >> 1);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < kPairStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 2 * kNumEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_slot, kTmemCols);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (!p.skip_pdl_wait) pdl_wait();
+
+    const int tiles_mn = p.m_tiles * p.n_tiles;
+    const int total_tiles = tiles_mn * p.split_k;
+    constexpr int kBox = kBlockK * 128;            // one 64 (mn) x 64 (k) box
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                const int split = tile / tiles_mn;
+                const int mn = tile - split * tiles_mn;
+                const int m_blk = mn / p.n_tiles;
+                const int n_blk = mn - m_blk * p.n_tiles;
+                const int kb0 = split * p.k_blocks_per_split;
+                const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+                const int m0 = m_blk * kPairTileM + static_cast<int>(rank) * kBlockM;
+                const int n0 = n_blk * kFastBlockN + static_cast<int>(rank) * (kFastBlockN / 2);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* sa = smem + stage * kPairStageBytes;
+                    uint8_t* sb = sa + kPairABytes;
+                    const uint32_t full_leader = cluster_map_shared(&full_bar[stage], 0);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * kPairStageBytes);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tma_load_2d_pair(&tmap_a, full_leader, sa + j * kBox, m0 + j * 64, kb * kBlockK);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) tma_load_2d_pair(&tmap_b, full_leader, sb + j * kBox, n0 + j * 64, kb * kBlockK);
+                    if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_instr_desc(kPairTileM, kFastBlockN, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                const int split = tile / tiles_mn;
+                const int kb0 = split * p.k_blocks_per_split;
+                const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kFastBlockN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+                    const uint32_t sb = sa + kPairABytes;
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                        const uint64_t da = make_smem_desc(sa + kk * (16 * 128), kBox, 1024);
+                        const uint64_t db = make_smem_desc(sb + kk * (16 * 128), kBox, 1024);
+                        umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit_pair(&empty_bar[stage]);
+                    if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_pair(&acc_full[acc]);
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        const int ew = warp - 2;                  // 0..7
+        const int lane_grp = warp & 3;
+        const int col_half = ew >> 2;
+        uint8_t* scratch = smem + kPairStages * kPairStageBytes + kPairBarrierBytes + ew * kEpiHalfBytes;
+        const uint32_t acc_empty_leader = cluster_map_shared(&acc_empty[0], 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+            const int split = tile / tiles_mn;
+            const int mn = tile - split * tiles_mn;
+            const int m_blk = mn / p.n_tiles;
+            const int n_blk = mn - m_blk * p.n_tiles;
+            const int row0 = m_blk * kPairTileM + static_cast<int>(rank) * kBlockM + lane_grp * 32;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(acc * kFastBlockN);
+#pragma unroll 1
+            for (int c = col_half; c < kFastBlockN / 32; c += 2) {
+                const int n0 = n_blk * kFastBlockN + c * 32;
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), r);
+                tmem_ld_wait();
+                store_rows<8>(scratch, r, reinterpret_cast<uint8_t*>(p.C) + (static_cast<long long>(row0) * p.ldc + n0) * 4,
+                              p.ldc * 4, 32, lane, true);
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(acc_empty_leader + static_cast<uint32_t>(acc) * 8u);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
     }
 }
 
@@ -1204,8 +1520,88 @@ int launch_fast(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
     return 0;
 }
 
+template <int KIND>
+int launch_pair(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream) {
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d(&ta, d->A, d->K, d->M, d->lda, kBlockK, kBlockM);
+    if (rc) return rc;
+    if (!d->b_mn_major) rc = make_tmap_2d(&tb, d->B, d->K, d->N, d->ldb, kBlockK, kFastBlockN / 2);
+    else                rc = make_tmap_2d(&tb, d->B, d->N, d->K, d->ldb, 64, kBlockK);
+    if (rc) return rc;
+    a.m_tiles = (d->M + kPairTileM - 1) / kPairTileM;
+    a.n_tiles = d->N / kFastBlockN;
+    a.k_blocks_total = (d->K + kBlockK - 1) / kBlockK;
+    a.k_blocks_per_split = a.k_blocks_total;
+    a.split_k = 1;
+    a.num_stages = kPairStages;
+    a.scratch_bytes = kFastUnitBytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CLIMB_CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+        attr_set = true;
+    }
+    const int total = a.m_tiles * a.n_tiles;
+    const int max_pairs = num_sms() / 2;
+    const int pairs = total < max_pairs ? total : max_pairs;
+    const int rest = total % pairs;
+    static const bool tail_split = [] { const char* e = std::getenv("CLIMB_GEMM_TAIL_SPLIT"); return e == nullptr || e[0] != '0'; }();
+    a.full_tiles = (tail_split && total > pairs && rest > 0 && 2 * rest <= pairs) ? total - rest : total;
+    a.total_vtiles = total + (total - a.full_tiles);
+    ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
+    if (a.skip_pdl_wait) pdl_mark_independent();
+    CLIMB_CUDA_OK(launch_pdl_cluster(gemm_pair_kernel<KIND>, dim3(2 * pairs), dim3(kFastThreads), kPairSmemBytes, stream, 2u, ta, tb, a));
+    CLIMB_LAUNCH_OK();
+    return 0;
+}
+
 inline bool aligned16(const void* p, long long pitch_bytes) {
     return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && pitch_bytes % 16 == 0;
+}
+
+// is this the weight-gradient form the pair wgrad kernel covers?
+bool pair_wgrad_ok(const climb_gemm_desc* d) {
+    return d->accumulate && d->c_dtype == CLIMB_F32 && d->a_mn_major && d->b_mn_major && !d->independent &&
+           d->M % kPairTileM == 0 && d->N % kFastBlockN == 0 && d->K >= 16 * kBlockK && d->split_k <= 0 &&
+           (d->block_n == 0 || d->block_n == kFastBlockN) && d->bias == nullptr && d->residual == nullptr && d->aux == nullptr &&
+           d->c2 == nullptr && d->colsum == nullptr && d->epilogue == CLIMB_EPI_NONE && (d->alpha == 0.0f || d->alpha == 1.0f) &&
+           aligned16(d->C, d->ldc * 4) && aligned16(d->A, d->lda * 2) && aligned16(d->B, d->ldb * 2);
+}
+
+int launch_pair_wgrad(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream) {
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d(&ta, d->A, d->M, d->K, d->lda, 64, kBlockK);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tb, d->B, d->N, d->K, d->ldb, 64, kBlockK);
+    if (rc) return rc;
+    a.m_tiles = d->M / kPairTileM;
+    a.n_tiles = d->N / kFastBlockN;
+    a.k_blocks_total = (d->K + kBlockK - 1) / kBlockK;
+    const int pairs_max = num_sms() / 2;
+    const int tiles = a.m_tiles * a.n_tiles;
+    // split over the tokens so that tiles x splits fills whole rounds of the pair grid
+    int split = 1;
+    double best = 0.0;
+    for (int sp = 1; sp <= 16 && a.k_blocks_total / sp >= 8; ++sp) {
+        const long long t = 1LL * tiles * sp;
+        const long long rounds = (t + pairs_max - 1) / pairs_max;
+        const double fill = static_cast<double>(t) / (rounds * pairs_max);
+        if (fill > best + 0.03) { best = fill; split = sp; }
+    }
+    a.k_blocks_per_split = (a.k_blocks_total + split - 1) / split;
+    a.split_k = (a.k_blocks_total + a.k_blocks_per_split - 1) / a.k_blocks_per_split;
+    a.num_stages = kPairStages;
+    a.scratch_bytes = kEpiHalfBytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CLIMB_CUDA_OK(cudaFuncSetAttribute(gemm_pair_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBytes));
+        attr_set = true;
+    }
+    const int total = tiles * a.split_k;
+    const int pairs = total < pairs_max ? total : pairs_max;
+    ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
+    CLIMB_CUDA_OK(launch_pdl_cluster(gemm_pair_wgrad_kernel, dim3(2 * pairs), dim3(kNumThreads), kWgradSmemBytes, stream, 2u, ta, tb, a));
+    CLIMB_LAUNCH_OK();
+    return 0;
 }
 
 // which specialised kernel (if any) covers this problem; -1 = the generic kernel
@@ -1244,6 +1640,22 @@ int launch_gemm(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream
 
 // dev switch (CLIMB_GEMM_GENERIC=1): route everything through the generic kernel, for A/B timing
 static const bool g_disable_fast = [] { const char* e = getenv("CLIMB_GEMM_GENERIC"); return e && e[0] == '1'; }();
+// dev switch (CLIMB_GEMM_PAIR=1): the CTA-pair (cta_group::2) variants of the specialised kernels
+// CTA-pair (cta_group::2) kernels. Default: the weight-gradient kernel, and the pair variants of the two specialised kinds
+// that measured faster in pairs (FK_BF16 +4..6 %, FK_MUL_AUX +4 %; the epilogue-bound FK_GELU_SAVE / FK_RES_F32 did not gain).
+// A/B switches: CLIMB_GEMM_PAIR=0 none of them, =1 all four kinds; CLIMB_GEMM_PAIR_WGRAD=0 the generic split-K wgrad kernel.
+static int g_pair_mode = [] { const char* e = getenv("CLIMB_GEMM_PAIR"); return e == nullptr ? 2 : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2)); }();
+static bool g_pair_wgrad = [] { const char* e = getenv("CLIMB_GEMM_PAIR_WGRAD"); return g_pair_mode != 0 && !(e && e[0] == '0'); }();
+// climb_gemm_pair_mode (C ABI): 0 = one-CTA kernels only, 1 = every pair kernel, 2 = the default selection; returns the old mode
+int gemm_pair_mode(int mode) {
+    const int old = g_pair_mode;
+    if (mode >= 0 && mode <= 2) { g_pair_mode = mode; g_pair_wgrad = mode != 0; }
+    return old;
+}
+inline bool pair_kind_enabled(int kind) {
+    if (g_pair_mode == 1) return true;
+    return g_pair_mode == 2 && (kind == FK_BF16 || kind == FK_MUL_AUX);
+}
 
 int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     CLIMB_REQUIRE(d != nullptr, "null gemm descriptor");
@@ -1283,8 +1695,21 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     static const bool indep_ok = [] { const char* e = getenv("CLIMB_NO_INDEPENDENT"); return !(e && e[0] == '1'); }();   // dev A/B switch
     a.skip_pdl_wait = (d->independent && pdl_enabled() && indep_ok) ? 1 : 0;
 
+    if (!g_disable_fast && g_pair_wgrad && pair_wgrad_ok(d)) return launch_pair_wgrad(d, a, stream);
     if (!g_disable_fast) {
-        switch (fast_kind(d)) {
+        const int kind = fast_kind(d);
+        // CTA-pair kernels (cta_group::2): K-major A, at least one 256-row tile per pair of SMs
+        if (kind >= 0 && pair_kind_enabled(kind) && !d->a_mn_major &&
+            1LL * ((d->M + kPairTileM - 1) / kPairTileM) * (d->N / kFastBlockN) >= num_sms() / 2) {
+            switch (kind) {
+                case FK_BF16: return launch_pair<FK_BF16>(d, a, stream);
+                case FK_GELU_SAVE: return launch_pair<FK_GELU_SAVE>(d, a, stream);
+                case FK_MUL_AUX: return launch_pair<FK_MUL_AUX>(d, a, stream);
+                case FK_RES_F32: return launch_pair<FK_RES_F32>(d, a, stream);
+                default: break;
+            }
+        }
+        switch (kind) {
             case FK_BF16: return launch_fast<FK_BF16>(d, a, stream);
             case FK_GELU_SAVE: return launch_fast<FK_GELU_SAVE>(d, a, stream);
             case FK_MUL_AUX: return launch_fast<FK_MUL_AUX>(d, a, stream);

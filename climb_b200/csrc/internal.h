@@ -6,6 +6,7 @@
 namespace climb {
 
 int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream);
+int gemm_pair_mode(int mode);
 
 int attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H,
                   float scale, cudaStream_t stream);

@@ -44,6 +44,12 @@ int climb_version(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t climb_launch_count(void);
 
+/* Which tcgen05 GEMM kernels climb_gemm_bf16 may choose (measurement / test switch; the default is the product path):
+ * 0 = one-CTA kernels only, 1 = every CTA-pair (cta_group::2) kernel, 2 = default selection (pair weight-gradient kernel +
+ * the pair variants of the plain and multiply-by-aux epilogues). Any other value only queries. Returns the previous mode.
+ * The environment variable CLIMB_GEMM_PAIR (0 / 1) sets the initial mode. */
+int climb_gemm_pair_mode(int mode);
+
 /* Device-time profiler used by bench.py's roofline: between begin and end every GEMM / attention
  * launcher is bracketed by two CUDA events ON ITS LAUNCH STREAM. climb_profile_end synchronises and
  * returns per category (0 = tcgen05 GEMM, 1 = attention fwd, 2 = attention bwd [3 kernels], 3 = unused)

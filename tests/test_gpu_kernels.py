@@ -84,10 +84,37 @@ def test_gemm_wgrad_splitk_accumulate(split_k):
     assert _rel_err(dw, ref) < 1e-5, _rel_err(dw, ref)
 
 
+@pytest.fixture(params=[0, 1], ids=["one_cta", "cta_pair"])
+def pair_mode(request):
+    """Run a GEMM test on the one-CTA kernels (mode 0) and on every CTA-pair (tcgen05 cta_group::2) kernel (mode 1);
+    the library default (mode 2) picks per epilogue kind."""
+    from climb_b200 import _lib as lib
+    old = lib.climb_gemm_pair_mode(request.param)
+    yield request.param
+    lib.climb_gemm_pair_mode(old)
+
+
+@pytest.mark.parametrize("tokens,n_out,k_in", [(15168, 3072, 768), (15168, 768, 3072), (15168, 2304, 768), (3001, 768, 768),
+                                               (12544, 768, 3072), (1100, 256, 512)])
+def test_gemm_wgrad_layer_shapes(tokens, n_out, k_in, pair_mode):
+    """The weight gradients of the ViLT-base Linears at the bench's token count (and a token count that is not a multiple
+    of the 64-row k-block): generic split-K kernel by default, the CTA-pair (cta_group::2) wgrad kernel when enabled."""
+    L = _lib()
+    torch.manual_seed(tokens + n_out)
+    dy = (torch.randn(tokens, n_out, device="cuda") * 0.5).bfloat16()
+    x = torch.randn(tokens, k_in, device="cuda").bfloat16()
+    dw = torch.full((n_out, k_in), 0.5, device="cuda", dtype=torch.float32)
+    L.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, accumulate=True)
+    ref = 0.5 + dy.float().t() @ x.float()
+    assert _rel_err(dw, ref) < 1e-5, _rel_err(dw, ref)
+    L.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, accumulate=True)          # accumulates on top
+    assert _rel_err(dw, 2 * ref - 0.5) < 1e-5
+
+
 @pytest.mark.parametrize("M,K,N", [(2500, 768, 2304), (15168, 768, 2304), (2400, 200, 2304), (2433, 3072, 2304),
                                    # N = 768 at the bench's M: 357 tiles = 2 rounds + 61 -> the last 61 run as 122 half-width tiles
                                    (15168, 768, 768), (15168, 3072, 768), (15104, 768, 1024), (9600, 256, 512)])
-def test_gemm_fast_kinds(M, K, N):
+def test_gemm_fast_kinds(M, K, N, pair_mode):
     """The specialised 16-epilogue-warp kernels (N % 256 == 0, >= 148 tiles): bf16 + bias, GELU with saved
     derivative, multiply-by-aux, fp32 + bias + residual; ragged last row tile, ragged K; tail tiles at half width."""
     L = _lib()

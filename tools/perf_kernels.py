@@ -59,6 +59,8 @@ def main():
             ms = timeit(lambda: fn(bn))
             out[f"{name}/bn{bn}"] = {"ms": round(ms, 4), "tflops": round(flops / ms / 1e9, 1)}
             print(name, bn, out[f"{name}/bn{bn}"], flush=True)
+    if os.environ.get("ONLY_GEMM") == "1":          # A/B runs of the GEMM kernels only (e.g. CLIMB_GEMM_PAIR=0/1)
+        return
     # cuBLAS reference points (library, for context only)
     ms = timeit(lambda: torch.matmul(x, w1.t()))
     out["cublas_fc1"] = {"ms": round(ms, 4), "tflops": round(2 * M * ff * d / ms / 1e9, 1)}
