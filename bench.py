@@ -335,7 +335,7 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": "gemm_fast_kernel<KIND> + gemm_bf16_tcgen05_kernel (all tcgen05 GEMM launches of the step)",
+        roofline = {"bound": "tensor", "kernel": "gemm_pair_kernel<KIND> / gemm_pair_wgrad_kernel (cta_group::2) + gemm_fast_kernel<KIND> + gemm_bf16_tcgen05_kernel (all tcgen05 GEMM launches of the step)",
                     "achieved": round(achieved, 1),
                     "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4),
                     "traffic": traffic, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
