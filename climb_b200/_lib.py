@@ -67,6 +67,10 @@ climb_last_error = _sig("climb_last_error", [], c_char_p)
 climb_version = _sig("climb_version", [])
 climb_launch_count = _sig("climb_launch_count", [], ctypes.c_uint64)
 climb_gemm_pair_mode = _sig("climb_gemm_pair_mode", [ctypes.c_int])
+climb_wordpiece_create = _sig("climb_wordpiece_create", [c_char_p, ctypes.c_int64, c_int, c_int], c_void_p)
+climb_wordpiece_destroy = _sig("climb_wordpiece_destroy", [c_void_p], None)
+climb_wordpiece_encode = _sig("climb_wordpiece_encode", [c_void_p, c_char_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                                         ctypes.POINTER(c_int), c_int])
 climb_profile_begin = _sig("climb_profile_begin", [])
 climb_profile_end = _sig("climb_profile_end", [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int])
 climb_gemm_bf16 = _sig("climb_gemm_bf16", [POINTER(GemmDesc), _P])

@@ -40,7 +40,9 @@ class B200ViltEncoderWrapper(EncoderWrapper):
         self.max_text_length = self.vilt.config.max_position_embeddings
         self.encoder_dim = self.vilt.config.hidden_size
         self.gpu_image_pipeline = True      # process_inputs: image half of the ViltProcessor on the GPU (False = the reference's PIL path)
+        self.native_tokenizer = True        # process_inputs: BERT WordPiece in native host code (False = the processor's own tokenizer)
         self._image_fe, self._image_fe_key = None, None
+        self._native_tok, self._native_tok_key = None, None
 
     def reset_processor(self, max_text_length: int, img_size: tuple):
         self.max_text_length = max_text_length
@@ -56,6 +58,21 @@ class B200ViltEncoderWrapper(EncoderWrapper):
         te = self.vilt.embeddings.text_embeddings
         te.position_embeddings = nn.Embedding(max_len, cfg.hidden_size).from_pretrained(extended, freeze=False)
         te.register_buffer("position_ids", torch.arange(max_len).expand((1, -1)))
+
+    def tokenize(self, tok, texts: List[str]) -> Dict:
+        """The tokenizer call of ViltProcessor.__call__ (processing_vilt.py:72-89) as process_inputs makes it
+        (vilt.py:93-95: padding=True, truncation=True, max_length). A transformers BertTokenizer(Fast) is replaced by the
+        native WordPiece pipeline over its own vocabulary / casing (climb_b200/text_processing.py: identical ids, rows
+        written into pinned staging memory); anything else is called as is."""
+        # (tokens ADDED on top of the vocabulary are matched in the raw text by the library; only BERT's own specials are here)
+        if (self.native_tokenizer and type(tok).__name__ in ("BertTokenizerFast", "BertTokenizer") and hasattr(tok, "get_vocab")
+                and set(getattr(tok, "get_added_vocab", dict)()) <= {"[UNK]", "[SEP]", "[PAD]", "[CLS]", "[MASK]"}):
+            if self._native_tok is None or self._native_tok_key != id(tok):
+                from ..text_processing import B200BertTokenizer
+                self._native_tok, self._native_tok_key = B200BertTokenizer.from_hf(tok), id(tok)
+            return self._native_tok(texts, max_length=self.max_text_length, padding=True, truncation=True,
+                                    pin_memory=torch.cuda.is_available())
+        return tok(text=texts, max_length=self.max_text_length, padding=True, truncation=True, return_tensors='pt')
 
     def process_inputs(self, images: List, texts: List[str]) -> Dict:
         if self.processor is None:
@@ -74,7 +91,7 @@ class B200ViltEncoderWrapper(EncoderWrapper):
                 self._image_fe = B200ViltFeatureExtractor(size=key[0], size_divisor=key[1], image_mean=key[2], image_std=key[3],
                                                           device=self.device)
                 self._image_fe_key = key
-            enc = tok(text=texts, max_length=self.max_text_length, padding=True, truncation=True, return_tensors='pt')
+            enc = self.tokenize(tok, texts)
             out = {k: v.to(self.device, non_blocking=True) for k, v in enc.items()}
             out.update(self._image_fe(images))
             return out

@@ -342,6 +342,22 @@ int climb_image_preprocess(const uint8_t* src, uint8_t* tmp, const climb_image_d
                            float* pixel_values /* [B, 3, Hp, Wp] */, int64_t* pixel_mask /* [B, Hp, Wp] */, int Hp, int Wp,
                            const float* mean, const float* std, void* stream);
 
+/* ---- text side of the input pipeline -------------------------------------------------------
+ * Replaces the tokenizer call of ViltProcessor.__call__ (processing_vilt.py:72-89, from ViltEncoderWrapper.process_inputs,
+ * src/modeling/vilt.py:83-96): BertTokenizerFast(text, padding=True, truncation=True, max_length=...) = special-token split,
+ * BertNormalizer, BertPreTokenizer, WordPiece, [CLS] ... [SEP], truncation, padding. HOST code (no device work): rows are
+ * written into caller memory, typically the pinned staging buffer of the batch's host-to-device copy.
+ * vocab: the bytes of a BERT vocab.txt (one token per line, id = line number). lowercase = do_lower_case (also strips accents,
+ * as BERT does when strip_accents is unset). Returns NULL (see climb_last_error) if [UNK] [CLS] [SEP] [PAD] are missing. */
+typedef struct climb_wordpiece climb_wordpiece;
+climb_wordpiece* climb_wordpiece_create(const char* vocab, int64_t vocab_bytes, int lowercase, int handle_chinese_chars);
+void climb_wordpiece_destroy(climb_wordpiece* tokenizer);
+/* texts: n UTF-8 strings back to back, text i = bytes [offsets[i], offsets[i + 1]). Outputs are [n, max_length] int64, every
+ * element written: ids padded with [PAD], mask 1 on real tokens, token types 0. *longest = the longest row incl. [CLS] / [SEP]
+ * (padding=True keeps columns [0, longest)). Texts are split over up to n_threads host threads. */
+int climb_wordpiece_encode(const climb_wordpiece* tokenizer, const char* texts, const int64_t* offsets, int n, int max_length,
+                           int64_t* input_ids, int64_t* attention_mask, int64_t* token_type_ids, int* longest, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif
