@@ -59,7 +59,7 @@ def test_bucketed_mean_allreduce_world2_gloo():
 # ---------------------------------------------------------------------------------------------------------
 # the overlapped (chunked) backward + GradSync.begin / reduce_range / finish, as bench.py --gpus N runs it
 # ---------------------------------------------------------------------------------------------------------
-def _chunked_worker(rank, world, port, out, frozen_bottom):
+def _chunked_worker(rank, world, port, out, mode):
     """The REAL B200ViltModel._run_backward and GradSync on CPU tensors over gloo. Stubbed for the test: the C entry
     point (records its (first, last, parts) arguments and writes rank-dependent 'gradients' into the spans that call
     completes), _lib.ptr / stream (no device here) and ReduceOp.AVG (gloo has no AVG: SUM then divide)."""
@@ -72,8 +72,11 @@ def _chunked_worker(rank, world, port, out, frozen_bottom):
     try:
         torch.manual_seed(0)
         learner = _learner()
-        if frozen_bottom:
+        if mode == "frozen_bottom":
             learner.get_encoder().freeze_bottom_k_layers(1)
+        elif mode == "adapters":                 # base frozen, one Houlsby adapter trains: two small spans per layer
+            learner.add_adapter("vqa", "houlsby")
+            learner.train_adapter("vqa")
         vilt = learner.get_encoder().vilt
         arena = vilt._arena
         arena.sync(allow_cpu=True)
@@ -145,12 +148,12 @@ def _chunked_worker(rank, world, port, out, frozen_bottom):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("frozen_bottom", [False, True])
-def test_chunked_backward_overlapped_allreduce_world2_gloo(frozen_bottom):
+@pytest.mark.parametrize("mode", ["full", "frozen_bottom", "adapters"])
+def test_chunked_backward_overlapped_allreduce_world2_gloo(mode):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_chunked_worker, args=(2, port, out, frozen_bottom), nprocs=2, join=True)
+    mp.spawn(_chunked_worker, args=(2, port, out, mode), nprocs=2, join=True)
     assert out[0] and out[1]
