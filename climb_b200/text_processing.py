@@ -44,10 +44,24 @@ class B200BertTokenizer:
             data = "\n".join(toks).encode("utf-8")
         self.do_lower_case, self.tokenize_chinese_chars = bool(do_lower_case), bool(tokenize_chinese_chars)
         self.n_threads = n_threads if n_threads is not None else min(8, os.cpu_count() or 1)
-        self._handle = _lib.climb_wordpiece_create(data, len(data), int(self.do_lower_case), int(self.tokenize_chinese_chars))
+        self._vocab_bytes = data
+        self._create()
+
+    def _create(self):
+        self._handle = _lib.climb_wordpiece_create(self._vocab_bytes, len(self._vocab_bytes), int(self.do_lower_case),
+                                                   int(self.tokenize_chinese_chars))
         if not self._handle:
             msg = _lib.climb_last_error()
             raise _lib.ClimbError(msg.decode() if msg else "climb_wordpiece_create failed")
+
+    def __getstate__(self):                 # the native handle does not survive pickling (torch.save(model)): rebuilt on load
+        state = dict(self.__dict__)
+        state["_handle"] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._create()
 
     @classmethod
     def from_hf(cls, tokenizer, **kw) -> "B200BertTokenizer":

@@ -149,6 +149,10 @@ def test_threads_edge_cases_and_errors():
     assert torch.equal(c["input_ids"], a["input_ids"][:50, :T]) and bool((a["input_ids"][:50, T:] == v["[PAD]"]).all())
     lst = B200BertTokenizer(list(v))(texts[:50], max_length=40)
     assert torch.equal(lst["input_ids"], c["input_ids"])
+    import copy
+    import pickle
+    again = pickle.loads(pickle.dumps(tok))                      # torch.save(model) pickles the wrapper: the native handle is rebuilt
+    assert torch.equal(again(texts[:50], max_length=40)["input_ids"], c["input_ids"]) and copy.deepcopy(tok) is tok
     with pytest.raises(_lib.ClimbError):
         B200BertTokenizer(["a", "b", "[UNK]"])                   # no [CLS] / [SEP] / [PAD]
     with pytest.raises(NotImplementedError):
