@@ -24,6 +24,11 @@ for g in "$@"; do
     perf)     echo "=== perf" | tee -a gpurun_out/summary.txt; timeout 600 python tools/perf_kernels.py > gpurun_out/perf.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; cat gpurun_out/perf.log | tee -a gpurun_out/summary.txt ;;
     perfgen)  echo "=== perf (generic GEMM kernel only)" | tee -a gpurun_out/summary.txt; CLIMB_GEMM_GENERIC=1 timeout 600 python tools/perf_kernels.py > gpurun_out/perf_generic.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt; head -n 12 gpurun_out/perf_generic.log | tee -a gpurun_out/summary.txt ;;
     gemm_fast) run gemm_fast 600 tests/test_gpu_kernels.py -k "gemm_fast" ;;
+    pair)     run pair 600 tests/test_gpu_kernels.py -k "gemm_fast or wgrad" ;;      # both pair modes (pair_mode fixture)
+    pair_ab)  echo "=== pair_ab (per-GEMM timings, one-CTA vs CTA-pair kernels)" | tee -a gpurun_out/summary.txt
+              for p in 0 1; do echo "-- CLIMB_GEMM_PAIR=$p" | tee -a gpurun_out/summary.txt; ONLY_GEMM=1 CLIMB_GEMM_PAIR=$p timeout 120 python tools/perf_kernels.py 2>&1 | tee -a gpurun_out/summary.txt; done ;;
+    ncu_pair) echo "=== ncu_pair" | tee -a gpurun_out/summary.txt; timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_pair -s 2 -c 2 -f -o gpurun_out/prof_pair python tools/ncu_pair.py > gpurun_out/ncu_pair.log 2>&1; echo "exit=$?" | tee -a gpurun_out/summary.txt ;;
+    trainer)  run trainer 600 tests/test_gpu_zz_trainer.py -s ;;
     smoke)    echo "=== smoke" | tee -a gpurun_out/summary.txt; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "exit=$? $(tail -n 2 gpurun_out/smoke.log | tr '\n' ' ')" | tee -a gpurun_out/summary.txt ;;
     bench)    echo "=== bench" | tee -a gpurun_out/summary.txt; timeout 900 python bench.py --steps ${BENCH_STEPS:-10} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "exit=$?" | tee -a gpurun_out/summary.txt; tail -n 5 gpurun_out/bench.err | tee -a gpurun_out/summary.txt; cat gpurun_out/bench.json | tee -a gpurun_out/summary.txt ;;
     benchref) echo "=== benchref" | tee -a gpurun_out/summary.txt; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit=$?" | tee -a gpurun_out/summary.txt; cat gpurun_out/bench_ref.json | tee -a gpurun_out/summary.txt ;;
