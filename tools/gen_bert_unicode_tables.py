@@ -14,6 +14,14 @@ Per code point c, uncased mode, normalize_str(c) is one of
                                           syllables decompose algorithmically and are not listed
 cased mode (do_lower_case = False: clean_text + handle_chinese_chars only) has its own REMOVED / SPACE / CJK ranges.
 PUNCT = code points BertPreTokenizer isolates ("a" + c + "a" splits into three pieces).
+
+NFD also puts runs of combining marks into canonical order. Nonspacing marks are dropped afterwards, so the order only shows
+between the few marks that SURVIVE (the library's category table is older than its normalisation table: 83 code points are
+non-starters to NFD but not nonspacing to the filter). Probed as well:
+    NONSTARTER_KEEP = survivors c for which "x" + U+302E + c + U+1D165 comes back with U+1D165 before U+302E (c did not break
+                      the run), with their combining class (pairwise probing of all survivors agrees with these classes);
+    TRANSPARENT     = code points that are dropped AND do not break a run (controls removed before NFD, nonspacing marks with
+                      a non-zero class); every other dropped code point (nonspacing marks of class 0) ends the run.
 """
 import os
 import sys
@@ -72,6 +80,32 @@ def classify(norm):
     return removed, space, cjk, mapping
 
 
+def probe_reordering(norm):
+    import itertools
+    import unicodedata
+    hi, lo = chr(0x302E), chr(0x1D165)
+    assert norm.normalize_str("x" + hi + lo) == "x" + lo + hi, "the probe marks are not reordered by this library version"
+    keep, transparent = [], []
+    for cp in range(0x110000):
+        if 0xD800 <= cp <= 0xDFFF:
+            continue
+        c = chr(cp)
+        iso = norm.normalize_str("x" + c)
+        out = norm.normalize_str("x" + hi + c + lo)
+        if iso == "x":
+            if out == "x" + lo + hi:
+                transparent.append(cp)
+        elif hi in out and lo in out and out.index(lo) < out.index(hi):
+            assert iso == "x" + c, hex(cp)           # no surviving non-starter is also mapped
+            keep.append(cp)
+    cls = {cp: unicodedata.combining(chr(cp)) for cp in keep}
+    assert all(v > 0 for v in cls.values())
+    for a, b in itertools.permutations(keep, 2):    # the classes explain every pairwise swap the library makes
+        swapped = norm.normalize_str("x" + chr(a) + chr(b)) == "x" + chr(b) + chr(a)
+        assert swapped == (cls[a] > cls[b]), (hex(a), hex(b))
+    return [(cp, cls[cp]) for cp in keep], transparent
+
+
 def emit_ranges(f, name, rs):
     f.write(f"static const uint32_t {name}[][2] = {{\n")
     for i in range(0, len(rs), 6):
@@ -89,6 +123,7 @@ def main():
     assert not c_map, c_map[:3]
     pre = BertPreTokenizer()
     punct = [cp for cp in range(0x110000) if not (0xD800 <= cp <= 0xDFFF) and len(pre.pre_tokenize_str("a" + chr(cp) + "a")) == 3]
+    keep, transparent = probe_reordering(uncased)
     with open(OUT, "w") as f:
         f.write("// GENERATED by tools/gen_bert_unicode_tables.py (probing tokenizers %s: BertNormalizer / BertPreTokenizer over every\n"
                 "// Unicode scalar value). Do not edit. Inclusive code-point ranges, sorted; MAP entries sorted by code point.\n\n" % tokenizers.__version__)
@@ -99,6 +134,13 @@ def main():
         emit_ranges(f, "kCasedSpace", ranges(c_space))
         emit_ranges(f, "kCasedCjk", ranges(c_cjk))
         emit_ranges(f, "kPunct", ranges(punct))
+        emit_ranges(f, "kUncasedTransparent", ranges(transparent))
+        f.write("struct BertNonStarter { uint32_t cp; uint32_t cls; };\n")
+        f.write("static const BertNonStarter kUncasedNonStarterKeep[] = {\n")
+        for i in range(0, len(keep), 6):
+            f.write("    " + " ".join(f"{{0x{a:X}, {c}}}," for a, c in keep[i:i + 6]) + "\n")
+        f.write("};\n")
+        f.write(f"static const int kUncasedNonStarterKeep_count = {len(keep)};\n\n")
         # MAP: key table (cp, offset, length) + flat output array
         flat, keys = [], []
         for cp, cps in u_map:
@@ -115,7 +157,8 @@ def main():
             f.write("    " + " ".join(f"0x{a:X}," for a in flat[i:i + 12]) + "\n")
         f.write("};\n")
     print(f"{OUT}: uncased removed {len(u_removed)} space {len(u_space)} cjk {len(u_cjk)} map {len(u_map)} ({len(flat)} cps); "
-          f"cased removed {len(c_removed)} space {len(c_space)} cjk {len(c_cjk)}; punct {len(punct)}", file=sys.stderr)
+          f"cased removed {len(c_removed)} space {len(c_space)} cjk {len(c_cjk)}; punct {len(punct)}; surviving non-starters "
+          f"{len(keep)}, transparent {len(transparent)}", file=sys.stderr)
 
 
 if __name__ == "__main__":
