@@ -275,3 +275,60 @@ def test_concat_encodings_checks_shapes():
     rep["pixel_values"] = torch.ones(2, 3, 32, 64)
     with pytest.raises(ValueError):
         concat_encodings(cur, rep)
+
+
+def _keys_fixture():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")) as f:
+        return json.load(f)
+
+
+def _describe(model):
+    sd, enc = model.state_dict(), model.get_encoder().state_dict()
+    fmt = lambda d: [[k, list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in d.items()]
+    return {"state_dict": fmt(sd), "encoder_state_dict": fmt(enc),
+            "named_parameters": [[n, bool(p.requires_grad)] for n, p in model.named_parameters()]}
+
+
+def _same_surface(ours, ref, check_order=True):
+    for part in ("state_dict", "encoder_state_dict"):
+        a = {k: (tuple(s), d) for k, s, d in ours[part]}
+        b = {k: (tuple(s), d) for k, s, d in ref[part]}
+        assert set(a) == set(b), (part, sorted(set(a) ^ set(b))[:8])
+        assert a == b, (part, [k for k in a if a[k] != b[k]][:8])
+    if check_order:
+        assert ours["named_parameters"] == ref["named_parameters"]
+    else:
+        assert dict(map(tuple, ours["named_parameters"])) == dict(map(tuple, ref["named_parameters"]))
+
+
+def test_checkpoint_surface_equals_the_reference_learners():
+    """Every state_dict key / shape / dtype (buffers included), the encoder-only state dict the driver also saves
+    (train_upstream_continual_learning.py:264-266) and the named_parameters() order + requires_grad flags of the UNMODIFIED
+    reference learners (tests/golden/state_dict_keys.json, oracle/make_golden_keys.py): plain, with Houlsby adapters for two
+    tasks after train_adapter('nlvr2'), with a Pfeiffer adapter, and ViLT-BERT."""
+    import torch
+    from climb_b200 import modeling as M
+    g = _keys_fixture()
+    learner = _learner()
+    _same_surface(_describe(learner), g["vilt"])
+    for task in ("vqa", "nlvr2"):
+        learner.add_adapter(task, {"reduction_factor": 4, "non_linearity": "swish", "mh_adapter": True, "output_adapter": True})
+    learner.train_adapter("nlvr2")
+    learner.set_active_adapters("nlvr2")
+    # (order included: EWC and the optimizers iterate named_parameters())
+    _same_surface(_describe(learner), g["vilt_adapters"], check_order=True)
+    learner2 = _learner()
+    learner2.add_adapter("snli-ve", {"reduction_factor": 2, "non_linearity": "relu", "mh_adapter": False, "output_adapter": True})
+    _same_surface(_describe(learner2), g["vilt_pfeiffer"], check_order=True)
+    bd = dict(vocab_size=200, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, max_position_embeddings=16)
+    cfg = M.B200ViltConfig(hidden_size=TINY.hidden_size, num_hidden_layers=TINY.num_hidden_layers,
+                           num_attention_heads=TINY.num_attention_heads, intermediate_size=TINY.intermediate_size,
+                           image_size=TINY.image_size, patch_size=TINY.patch_size, vocab_size=TINY.vocab_size,
+                           max_position_embeddings=TINY.max_position_embeddings)
+    enc = M.B200ViltBertEncoderWrapper(None, M.B200ViltModel(cfg), M.B200BertModel(M.B200BertConfig(**bd)), torch.device("cpu"))
+    vb = M.B200ViltBertContinualLearner(ALL_TASKS, enc, 128, vo.TASK_SPECS)
+    _same_surface(_describe(vb), g["viltbert"])
+    # and a reference-format checkpoint loads strictly
+    ref_sd = {k: torch.zeros(s, dtype=getattr(torch, d)) for k, s, d in g["vilt"]["state_dict"]}
+    assert _learner().load_state_dict(ref_sd, strict=True) is not None
