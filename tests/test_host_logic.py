@@ -332,3 +332,40 @@ def test_checkpoint_surface_equals_the_reference_learners():
     # and a reference-format checkpoint loads strictly
     ref_sd = {k: torch.zeros(s, dtype=getattr(torch, d)) for k, s, d in g["vilt"]["state_dict"]}
     assert _learner().load_state_dict(ref_sd, strict=True) is not None
+
+
+def test_ewc_realigns_saved_state_when_the_arena_layout_changes():
+    """EWC keeps theta* and F as flat tensors in the arena's layout (cl_algorithms/ewc.py); if parameters are added afterwards
+    (an adapter), every saved slice must follow its NAME to the new offset, and the new names must carry no penalty
+    (theta* = theta, F = 0) -- the reference keys both dicts by name (src/cl_algorithms/ewc.py:41-43, 82-86)."""
+    import types
+    from climb_b200.cl_algorithms import EWC
+    learner = _learner()
+    arena = learner.get_encoder().vilt._arena
+    arena.sync(allow_cpu=True)
+    ewc = EWC(types.SimpleNamespace(ewc_fisher_sample_percentage=1.0, ewc_loss_weight=100.0))
+    assert ewc.do_ewc() is False
+    g = torch.Generator().manual_seed(0)
+    theta_star = torch.randn(arena.size, generator=g)
+    fisher = torch.rand(arena.size, generator=g)
+    old_off, old_num = dict(arena.offsets), dict(arena.numels)
+    ewc.param_dict["vqa"], ewc.fisher_dict["vqa"], ewc._offsets["vqa"] = theta_star.clone(), fisher.clone(), dict(old_off)
+    ewc.fisher_names["vqa"] = list(old_off)
+    ewc.task_keys.append("vqa")
+    assert ewc.do_ewc() is True
+    same_t, same_f = ewc._aligned("vqa", arena)                     # unchanged layout: the saved tensors themselves
+    assert same_t is ewc.param_dict["vqa"] and same_f is ewc.fisher_dict["vqa"]
+    learner.add_adapter("nlvr2", "houlsby")                          # new parameters in the middle of every layer
+    assert arena.sync(allow_cpu=True) is True and arena.offsets != old_off
+    new_t, new_f = ewc._aligned("vqa", arena)
+    assert new_t.numel() == arena.size and ewc._offsets["vqa"] == arena.offsets
+    for n, o in arena.offsets.items():
+        k = arena.numels[n]
+        if n in old_off:
+            assert torch.equal(new_t[o:o + k], theta_star[old_off[n]:old_off[n] + old_num[n]]), n
+            assert torch.equal(new_f[o:o + k], fisher[old_off[n]:old_off[n] + old_num[n]]), n
+        else:
+            assert ".adapters.nlvr2." in n
+            assert torch.equal(new_t[o:o + k], arena.theta[o:o + k]) and bool((new_f[o:o + k] == 0).all()), n
+    with pytest.raises(TypeError):
+        ewc.compute_ewc_loss(types.SimpleNamespace(get_encoder=lambda: types.SimpleNamespace()))
