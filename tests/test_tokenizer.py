@@ -197,3 +197,15 @@ def test_threads_edge_cases_and_errors():
         tok([["a", "b"]])
     with pytest.raises(_lib.ClimbError):
         tok(["a"], max_length=1)
+
+
+@pytest.mark.parametrize("case_idx", [0, 1, 3])
+def test_python_restatement_matches_reference_golden(case_idx):
+    """oracle/wordpiece_oracle.py (the slow tokenizer restated with file:line citations) against the same golden vectors."""
+    from oracle import wordpiece_oracle as wo
+    g = _golden()
+    case, texts, vocab = g["cases"][case_idx], g["texts"], _vocab_dict()
+    for bi, b in enumerate(range(0, len(texts), case["batch"])):
+        ids, mask, types = wo.encode_batch(texts[b:b + case["batch"]], vocab, case["max_length"], case["do_lower_case"])
+        assert ids == case["input_ids"][bi], (bi, texts[b:b + case["batch"]])
+        assert mask == case["attention_mask"][bi] and types == case["token_type_ids"][bi]
