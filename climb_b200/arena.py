@@ -142,12 +142,19 @@ class ParamArena:
         slices whose p.grad is None (fresh step) or foreign are zeroed; slices that are already
         p.grad keep their contents (gradient accumulation, EWC's un-zeroed Fisher loop ewc.py:55-64)."""
         trainable = list(trainable)
+        if not trainable:
+            return          # nothing of this arena is written: gradients other nodes already published stay as they are
         fresh = [(n, p) for n, p in trainable if not self._is_arena_grad(n, p)]
-        if len(fresh) == len(trainable):
-            self.grad.zero_()
+        if len(fresh) == len(trainable) and not self._any_published():
+            self.grad.zero_()           # fresh step, nothing accumulated anywhere in the arena: one memset
         else:
             for n, _ in fresh:
                 self._grad_views[n].zero_()
+
+    def _any_published(self) -> bool:
+        """Does any parameter of the arena currently hold an arena-backed .grad (accumulated by an earlier backward of
+        this step, possibly for parameters outside the caller's `trainable` list)?"""
+        return any(self._is_arena_grad(n, p) for n, p in self._named_params() if n in self._grad_views)
 
     def publish_grads(self, trainable: Iterable[Tuple[str, nn.Parameter]]) -> None:
         """After the backward: hand the arena slices to autograd's .grad fields."""

@@ -108,8 +108,21 @@ class EWC:
         arena.sync()
         theta_star, fisher = self._aligned(ewc_task_key, arena)
         named = dict(arena.named_items())
-        trainable = [(n, named[n]) for n in self.fisher_names[ewc_task_key] if n in named and named[n].requires_grad]
-        return ewc_task_key, ops.ewc_penalty(arena, theta_star, fisher, self.ewc_loss_weight, trainable)
+        tracked = [n for n in self.fisher_names[ewc_task_key] if n in named]
+        trainable = [(n, named[n]) for n in tracked if named[n].requires_grad]
+        fisher_bwd = None
+        if len(trainable) != len(tracked):
+            # some Fisher-tracked parameters are frozen now (freeze_bottom_k_layers, train_adapter): they still count in
+            # the loss, but the backward pass must not write into their gradient slots
+            key = (ewc_task_key, fisher.data_ptr(), tuple(n for n, _ in trainable))
+            if getattr(self, "_bwd_cache", (None, None))[0] != key:
+                fb = torch.zeros_like(fisher)
+                for n, _ in trainable:
+                    o, k = arena.offsets[n], arena.numels[n]
+                    fb[o:o + k] = fisher[o:o + k]
+                self._bwd_cache = (key, fb)
+            fisher_bwd = self._bwd_cache[1]
+        return ewc_task_key, ops.ewc_penalty(arena, theta_star, fisher, self.ewc_loss_weight, trainable, fisher_bwd)
 
     def do_ewc(self):
         return True if len(self.task_keys) > 0 else False

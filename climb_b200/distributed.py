@@ -89,7 +89,14 @@ class GradSync:
 
     def _sync_loose(self, p: torch.Tensor) -> None:
         if p.grad is not None:
-            dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
+            w = shard_weight()
+            if w != 1.0:
+                p.grad.mul_(w)
+            if p.grad.is_cuda:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
+            else:       # gloo (CPU tests) has no AVG
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
+                p.grad.div_(dist.get_world_size(self.group))
 
     # ---- overlapped path -------------------------------------------------------------------------
     def _spans(self, arena):
@@ -113,7 +120,10 @@ class GradSync:
         for s, e in self._spans(arena):
             s2, e2 = max(s, lo), min(e, hi)
             if e2 > s2:
+                w = shard_weight()
                 for bs, be in bucketize([(s2, e2)], self.bucket_elems):
+                    if w != 1.0:
+                        arena.grad[bs:be].mul_(w)
                     self._works.append(dist.all_reduce(arena.grad[bs:be], op=dist.ReduceOp.AVG, group=self.group,
                                                        async_op=True))
 
@@ -131,6 +141,10 @@ class GradSync:
             trainable = {n for n, p in items if p.requires_grad}
             spans = trainable_spans(arena.offsets, arena.numels, names, trainable)
             self._cache = (key, bucketize(spans, self.bucket_elems), spans)
+        w = shard_weight()
+        if w != 1.0:
+            for s, e in self._cache[1]:
+                arena.grad[s:e].mul_(w)
         allreduce_mean_(arena.grad, self._cache[1], self.group)
 
     def detach(self):
@@ -146,6 +160,97 @@ def attach(learner, bucket_mb: float = 64.0, group=None, layers_per_chunk: int =
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
     return GradSync(learner, bucket_mb, group, layers_per_chunk)
+
+
+def attach_if_distributed(learner, **kw):
+    """What create_*_continual_learner_model calls: under a multi-rank torch.distributed launch (torchrun + the
+    unchanged CLiMB driver) attach the gradient synchronisation and make rank 0 the only writer of
+    checkpoints; a single process gets the learner back untouched."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    sync = GradSync(learner, **kw)
+    rank_zero_only_io()
+    return sync
+
+
+# ---- the unchanged harness under torchrun ---------------------------------------------------------------------------
+# The trainers build plain (unsharded) loaders (vqa_dataset.py:262-268), so every rank draws the SAME batch (same seed,
+# train_upstream_continual_learning.py:103). The registry's batch2inputs_converter is the one hook between the loader and
+# the model: forward_pass calls it on the batch dict and afterwards reads the labels from the SAME dict
+# (train_vqa.py:127,156) -- so slicing the dict IN PLACE to this rank's rows shards inputs and labels consistently.
+# Evaluation stays replicated (the trainers divide by the full dataset length, train_vqa.py:263): the slice is applied in
+# training mode only, which the learner announces through set_training_mode() from its train() / eval().
+_training_mode = True
+_last_shard = None          # (rows on this rank, rows of the whole batch) of the most recent sharded batch
+_SHARD_MARK = "_b200_rank_slice"
+
+
+def set_training_mode(mode: bool) -> None:
+    global _training_mode
+    _training_mode = bool(mode)
+
+
+def shard_batch_inplace(batch: dict, size_key_candidates=("raw_texts", "texts", "images", "labels", "target_scores")) -> dict:
+    """Cut every per-sample entry of a collated batch (lists and tensors whose length is the batch size) down to
+    this rank's contiguous rows, in place. NLVR2 image pairs / VCR four-choice tuples are single entries of those lists,
+    so they stay together. No-op outside a multi-rank run, in evaluation mode, and on a dict that was cut already."""
+    global _last_shard
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or not _training_mode:
+        return batch
+    if batch.get(_SHARD_MARK):
+        return batch
+    n = next((len(batch[k]) for k in size_key_candidates if k in batch and hasattr(batch[k], "__len__")), None)
+    if n is None:
+        raise KeyError(f"cannot tell the batch size: none of {size_key_candidates} in the batch")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    per = (n + world - 1) // world
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    if hi <= lo:
+        raise RuntimeError(f"batch of {n} samples leaves rank {rank} of {world} without rows: use a batch size >= the "
+                           "number of ranks (and drop_last / a multiple of it for exact gradient means)")
+    for k, v in list(batch.items()):
+        if isinstance(v, str) or not hasattr(v, "__len__") or len(v) != n:
+            continue
+        batch[k] = v[lo:hi]
+    batch[_SHARD_MARK] = True
+    _last_shard = (hi - lo, n)
+    return batch
+
+
+def shard_weight() -> float:
+    """Factor that turns the mean over ranks of per-rank MEAN-loss gradients into the whole-batch mean when the rows
+    do not divide evenly: rows_here * world / rows_total (1.0 for even splits)."""
+    if _last_shard is None or not dist.is_initialized():
+        return 1.0
+    return _last_shard[0] * dist.get_world_size() / _last_shard[1]
+
+
+def sharding(converter):
+    """Wrap a batch2inputs_converter (model_configs[...]['batch2inputs_converter']) so that it first cuts the batch
+    dict to this rank's rows."""
+    def convert(batch, *a, **k):
+        if isinstance(batch, dict):
+            shard_batch_inplace(batch)
+        return converter(batch, *a, **k)
+    convert.__name__ = getattr(converter, "__name__", "convert")
+    convert.__wrapped__ = converter
+    return convert
+
+
+_io_patched = False
+
+
+def rank_zero_only_io() -> None:
+    """The driver saves checkpoints from every process (train_upstream_continual_learning.py:235,265-266); with replicated
+    parameters the files are identical, so ranks > 0 skip the write instead of racing on the same path. wandb is
+    switched off on them as well. json results stay as they are (same content from every rank, a few hundred bytes)."""
+    global _io_patched
+    if _io_patched or not dist.is_initialized() or dist.get_rank() == 0:
+        return
+    import os
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    torch.save = lambda *a, **k: None
+    _io_patched = True
 
 
 def shard_batch(batch: dict, rank: int, world: int, group_size: int = 1) -> dict:

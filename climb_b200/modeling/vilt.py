@@ -65,7 +65,16 @@ class B200ViltEncoderWrapper(EncoderWrapper):
         native WordPiece pipeline over its own vocabulary / casing (climb_b200/text_processing.py: identical ids, rows
         written into pinned staging memory); anything else is called as is."""
         # (tokens ADDED on top of the vocabulary are matched in the raw text by the library; only BERT's own specials are here)
-        if (self.native_tokenizer and type(tok).__name__ in ("BertTokenizerFast", "BertTokenizer") and hasattr(tok, "get_vocab")
+        # The native path covers what process_inputs sends on the hot path: one string per sample through a BERT tokenizer
+        # with default normalisation. Text PAIRS (convert_mc_batch_to_vilt_input_dict, vilt.py:561-567: [[a, b], ...] ->
+        # token_type_ids 1 on the second segment, pair truncation) and tokenizers built with non-default strip_accents /
+        # never_split keep the processor's own tokenizer.
+        init = getattr(tok, "init_kwargs", {}) or {}
+        plain = all(isinstance(t, str) for t in texts)
+        default_norm = init.get("strip_accents", None) is None and not init.get("never_split", None) \
+            and getattr(tok, "strip_accents", None) is None
+        if (self.native_tokenizer and plain and default_norm
+                and type(tok).__name__ in ("BertTokenizerFast", "BertTokenizer") and hasattr(tok, "get_vocab")
                 and set(getattr(tok, "get_added_vocab", dict)()) <= {"[UNK]", "[SEP]", "[PAD]", "[CLS]", "[MASK]"}):
             if self._native_tok is None or self._native_tok_key != id(tok):
                 from ..text_processing import B200BertTokenizer
@@ -184,6 +193,13 @@ class B200ViltContinualLearner(ContinualLearner):
         return ArenaAdamW(groups, lr=hparams['lr'], eps=hparams['adam_epsilon'], betas=(0.9, 0.98),
                           arenas=[self.vilt_encoder.vilt._arena])
 
+    def train(self, mode: bool = True):
+        """nn.Module.train / eval, plus: tell the rank-slicing batch converter (climb_b200.distributed.sharding) whether
+        the harness is training (batches are cut to this rank's rows) or evaluating (replicated, train_vqa.py:246-282)."""
+        from ..distributed import set_training_mode
+        set_training_mode(mode)
+        return super().train(mode)
+
     # ---- forward ------------------------------------------------------------------------------
     def forward(self, task_key: str, images: List, texts: List[str]):
         task_config = self.task_configs[task_key]
@@ -259,42 +275,106 @@ class B200ViltContinualLearner(ContinualLearner):
         return self.vilt_encoder.vilt.active_adapters
 
 
-def load_vilt_encoder(pretrained_vilt_name, device, processor=None, config=None, state_dict=None) -> B200ViltEncoderWrapper:
-    """load_vilt_encoder of vilt.py:481-514. `pretrained_vilt_name` may be
-      * a B200ViltConfig / transformers ViltConfig / dict (random init, as ViltModel(config)),
-      * a path to a torch checkpoint holding a ViltModel or CLiMB encoder state dict,
-      * a hub name -- resolved through transformers.ViltModel.from_pretrained when that is importable
-        and the weights are cached (no network is assumed)."""
-    import os
-    if config is None and not isinstance(pretrained_vilt_name, str):
-        config = pretrained_vilt_name
-    if isinstance(pretrained_vilt_name, str) and os.path.isfile(pretrained_vilt_name):
-        state_dict = torch.load(pretrained_vilt_name, map_location="cpu")
-    elif isinstance(pretrained_vilt_name, str) and state_dict is None:
-        from transformers import ViltModel, ViltProcessor      # stock or vendored transformers
-        hf = ViltModel.from_pretrained(pretrained_vilt_name)
-        config, state_dict = hf.config, hf.state_dict()
+def _resolve_pretrained(pretrained_vilt_name, processor, config):
+    """Processor and config as load_vilt_encoder resolves them (vilt.py:498, 505): ViltProcessor.from_pretrained /
+    ViltConfig.from_pretrained of `pretrained_vilt_name` (a hub name or a local directory; stock or vendored
+    transformers), unless the caller handed them in."""
+    if isinstance(pretrained_vilt_name, str):
         if processor is None:
+            from transformers import ViltProcessor
             processor = ViltProcessor.from_pretrained(pretrained_vilt_name)
-    vilt = B200ViltModel(config)
+        if config is None:
+            from transformers import ViltConfig
+            config = ViltConfig.from_pretrained(pretrained_vilt_name)
+    elif config is None and pretrained_vilt_name is not None:
+        config = pretrained_vilt_name             # a config object / dict stands in for the hub name (offline use)
+    return processor, config
+
+
+def _read_checkpoint(checkpoint_name, state_dict):
+    import os
     if state_dict is not None:
-        sd = {k[len("vilt."):] if k.startswith("vilt.") else k: v for k, v in state_dict.items()}
-        missing, unexpected = vilt.load_state_dict(sd, strict=False)
-        if unexpected:
-            raise RuntimeError(f"unexpected keys in ViLT checkpoint: {unexpected[:5]} ...")
-        logger.info("loaded ViLT weights (%d missing keys)", len(missing))
-    enc = B200ViltEncoderWrapper(processor, vilt, device)
+        return dict(state_dict)
+    if isinstance(checkpoint_name, str) and os.path.isfile(checkpoint_name):
+        return torch.load(checkpoint_name, map_location="cpu")
+    return None
+
+
+def _load_vilt_weights(enc: "B200ViltEncoderWrapper", checkpoint_name, sd: Dict) -> Dict:
+    """The pre-finetuned branch of load_vilt_encoder (vilt.py:504-512): a checkpoint written by
+    `encoder.state_dict()` (keys `vilt.*`; a bare ViltModel state dict is accepted too). The modality table grows
+    to three rows when the checkpoint was trained with NLVR2 -- the reference tests the file NAME, the
+    tensor's own shape is checked as well. Returns the entries that do not belong to ViltModel (`bert.*`)."""
+    type_key = "embeddings.token_type_embeddings.weight"
+    vilt_sd, rest = {}, {}
+    for k, v in sd.items():
+        if k.startswith("vilt."):
+            vilt_sd[k[len("vilt."):]] = v
+        elif k.startswith("bert."):
+            rest[k] = v
+        else:
+            vilt_sd[k] = v
+    rows = vilt_sd[type_key].shape[0] if type_key in vilt_sd else 0
+    have = enc.vilt.embeddings.token_type_embeddings.weight.shape[0]
+    if have < 3 and (rows == 3 or (isinstance(checkpoint_name, str) and 'nlvr2' in checkpoint_name and rows in (0, 3))):
+        enc.expand_modality_type_embeddings()
+    missing, unexpected = enc.vilt.load_state_dict(vilt_sd, strict=False)
+    if unexpected:
+        raise RuntimeError(f"unexpected keys in ViLT checkpoint: {unexpected[:5]} ...")
+    hard_missing = [m for m in missing if "position_ids" not in m and ".adapters." not in m]
+    if hard_missing:
+        raise RuntimeError(f"ViLT checkpoint misses {len(hard_missing)} tensors: {hard_missing[:5]} ...")
+    return rest
+
+
+def load_vilt_encoder(checkpoint_name, device, pretrained_vilt_name=None, *, processor=None, config=None,
+                      state_dict=None) -> B200ViltEncoderWrapper:
+    """load_vilt_encoder of vilt.py:481-514, same positional signature `(checkpoint_name, device,
+    pretrained_vilt_name)` -- the callers pass all three positionally (train_language.py:279, train_vision.py:311).
+
+      checkpoint_name == pretrained_vilt_name (a hub name / local directory): ViltModel.from_pretrained weights;
+      otherwise `checkpoint_name` is a file written by `torch.save(encoder.state_dict())`: the model is built from
+      the config of `pretrained_vilt_name`, the modality table is expanded for NLVR2 checkpoints, the weights are loaded.
+
+    Offline extensions (keyword-only, plus: a config object / dict in place of either name means random init with
+    that config and no processor lookup): `processor`, `config`, `state_dict`."""
+    if pretrained_vilt_name is None:
+        pretrained_vilt_name = checkpoint_name          # what create_vilt_continual_learner_model passes (vilt.py:536-538)
+    logger.info("Loading ViLT encoder model: %s", checkpoint_name)
+    sd = _read_checkpoint(checkpoint_name, state_dict)
+    if sd is None and isinstance(checkpoint_name, str):
+        if checkpoint_name != pretrained_vilt_name:
+            raise FileNotFoundError(f"ViLT encoder checkpoint not found: {checkpoint_name}")
+        from transformers import ViltModel               # the pretrained branch (vilt.py:500-502)
+        hf = ViltModel.from_pretrained(pretrained_vilt_name)
+        config = config if config is not None else hf.config
+        sd = hf.state_dict()
+    if not isinstance(checkpoint_name, str) and config is None:
+        config = checkpoint_name
+    processor, config = _resolve_pretrained(pretrained_vilt_name, processor, config)
+    enc = B200ViltEncoderWrapper(processor, B200ViltModel(config), device)
+    if sd is not None:
+        rest = _load_vilt_weights(enc, checkpoint_name, sd)
+        if rest:
+            raise RuntimeError(f"unexpected keys in ViLT checkpoint: {sorted(rest)[:5]} ... (a ViLT-BERT checkpoint? "
+                               "use load_viltbert_encoder)")
     enc.to(device)
+    logger.info("Successfully loaded pretrained ViLT encoder")
     return enc
 
 
-def create_vilt_continual_learner_model(model_name_or_path, ordered_cl_tasks, model_config, task_configs, device,
+def create_vilt_continual_learner_model(model_name_or_path, ordered_cl_tasks, model_config, task_configs, device, *,
                                         processor=None):
-    """create_vilt_continual_learner_model of vilt.py:516-546 (same positional signature)."""
-    encoder = load_vilt_encoder(model_name_or_path, device, processor=processor)
+    """create_vilt_continual_learner_model of vilt.py:516-546 (same positional signature). When torch.distributed is
+    initialised with more than one rank the learner's gradients are averaged over the ranks after every backward
+    (climb_b200.distributed.attach): with the rank-slicing batch converter of the registry this is all a torchrun
+    launch of the unchanged harness needs."""
+    encoder = load_vilt_encoder(model_name_or_path, device, model_name_or_path, processor=processor)
     model = B200ViltContinualLearner(ordered_cl_tasks=ordered_cl_tasks, encoder=encoder,
                                      encoder_dim=model_config['encoder_dim'], task_configs=task_configs)
     model.to(device)
+    from ..distributed import attach_if_distributed
+    attach_if_distributed(model)
     return model
 
 

@@ -99,36 +99,62 @@ class B200ViltBertContinualLearner(B200ViltContinualLearner):
         return self.viltbert_encoder
 
 
-def load_viltbert_encoder(pretrained_vilt_name, device, processor=None, config=None, state_dict=None, bert=None,
-                          bert_config=None) -> B200ViltBertEncoderWrapper:
-    """load_viltbert_encoder of viltbert.py:456-489. `bert` may be a B200BertModel, a BERT state dict, or None
-    (-> transformers BertModel.from_pretrained('bert-base-uncased') when that is importable and cached; there
-    is no network on the build / GPU boxes, so tests and bench pass a config for random init)."""
-    from .vilt import load_vilt_encoder
-    base = load_vilt_encoder(pretrained_vilt_name, device, processor=processor, config=config, state_dict=state_dict)
+def load_viltbert_encoder(checkpoint_name, device, pretrained_vilt_name=None, *, processor=None, config=None,
+                          state_dict=None, bert=None, bert_config=None) -> B200ViltBertEncoderWrapper:
+    """load_viltbert_encoder of viltbert.py:456-489, same positional signature `(checkpoint_name, device,
+    pretrained_vilt_name)`. A checkpoint file holds `vilt.*` and `bert.*` keys (the wrapper's own state dict).
+    Keyword-only offline extensions: `bert` may be a B200BertModel or a BERT state dict, `bert_config` asks for a
+    random-init BERT; otherwise BertModel.from_pretrained('bert-base-uncased') as in the reference (:474)."""
+    from .vilt import _load_vilt_weights, _read_checkpoint, _resolve_pretrained
+    if pretrained_vilt_name is None:
+        pretrained_vilt_name = checkpoint_name
+    logger.info("Loading ViLT encoder model: %s", checkpoint_name)
+    sd = _read_checkpoint(checkpoint_name, state_dict)
+    if sd is None and isinstance(checkpoint_name, str):
+        if checkpoint_name != pretrained_vilt_name:
+            raise FileNotFoundError(f"ViLT-BERT encoder checkpoint not found: {checkpoint_name}")
+        from transformers import ViltModel
+        hf = ViltModel.from_pretrained(pretrained_vilt_name)
+        config = config if config is not None else hf.config
+        sd = hf.state_dict()
+    if not isinstance(checkpoint_name, str) and config is None:
+        config = checkpoint_name
+    processor, config = _resolve_pretrained(pretrained_vilt_name, processor, config)
+    ckpt_bert = {k[len("bert."):]: v for k, v in (sd or {}).items() if k.startswith("bert.")}
     if not isinstance(bert, B200BertModel):
-        bert_sd = bert
-        if bert_sd is None and bert_config is None:
-            from transformers import BertModel
-            hf = BertModel.from_pretrained("bert-base-uncased")
-            bert_config, bert_sd = hf.config, hf.state_dict()
+        bert_sd = bert if bert is not None else (ckpt_bert or None)
+        if bert_config is None:
+            if bert_sd is None:
+                from transformers import BertModel
+                hf = BertModel.from_pretrained("bert-base-uncased")
+                bert_config, bert_sd = hf.config, hf.state_dict()
+            else:
+                bert_config = B200BertConfig()           # bert-base-uncased geometry
         bert = B200BertModel(bert_config)
         if bert_sd is not None:
             missing, unexpected = bert.load_state_dict(bert_sd, strict=False)
             if unexpected:
                 raise RuntimeError(f"unexpected keys in BERT checkpoint: {unexpected[:5]} ...")
-    enc = B200ViltBertEncoderWrapper(base.processor, base.vilt, bert, device)
+    elif ckpt_bert:
+        bert.load_state_dict(ckpt_bert, strict=False)
+    enc = B200ViltBertEncoderWrapper(processor, B200ViltModel(config), bert, device)
+    if sd is not None:
+        _load_vilt_weights(enc, checkpoint_name, sd)
     enc.to(device)
+    logger.info("Successfully loaded pretrained ViLT-BERT encoder")
     return enc
 
 
-def create_viltbert_continual_learner_model(model_name_or_path, ordered_cl_tasks, model_config, task_configs, device,
+def create_viltbert_continual_learner_model(model_name_or_path, ordered_cl_tasks, model_config, task_configs, device, *,
                                             processor=None, bert=None, bert_config=None):
     """create_viltbert_continual_learner_model of viltbert.py:491-520 (same positional signature)."""
-    encoder = load_viltbert_encoder(model_name_or_path, device, processor=processor, bert=bert, bert_config=bert_config)
+    encoder = load_viltbert_encoder(model_name_or_path, device, model_name_or_path, processor=processor, bert=bert,
+                                    bert_config=bert_config)
     model = B200ViltBertContinualLearner(ordered_cl_tasks=ordered_cl_tasks, encoder=encoder,
                                          encoder_dim=model_config['encoder_dim'], task_configs=task_configs)
     model.to(device)
+    from ..distributed import attach_if_distributed
+    attach_if_distributed(model)
     return model
 
 

@@ -163,18 +163,21 @@ class _EWCPenaltyFn(torch.autograd.Function):
     straight into the gradient arena in one streaming pass (ewc.py:75-87)."""
 
     @staticmethod
-    def forward(ctx, anchor, arena, theta_star, fisher, lam, trainable):
+    def forward(ctx, anchor, arena, theta_star, fisher, lam, trainable, fisher_bwd=None):
         n = arena.size
         partials = torch.empty(2048, dtype=torch.float32, device=arena.theta.device)
         loss = torch.empty((), dtype=torch.float32, device=arena.theta.device)
         _lib.check(_lib.climb_ewc_penalty(_lib.ptr(arena.theta), _lib.ptr(theta_star), _lib.ptr(fisher), n, float(lam),
                                           _lib.ptr(partials), 2048, _lib.ptr(loss), None, 0.0, None, _lib.stream()))
-        ctx.arena, ctx.theta_star, ctx.fisher, ctx.lam, ctx.trainable, ctx.partials = arena, theta_star, fisher, lam, trainable, partials
+        ctx.arena, ctx.theta_star, ctx.lam, ctx.trainable, ctx.partials = arena, theta_star, lam, trainable, partials
+        ctx.fisher = fisher if fisher_bwd is None else fisher_bwd       # gradient weights: F restricted to the trainable slices
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
         arena = ctx.arena
+        if not ctx.trainable:           # no Fisher-tracked parameter trains (frozen base + adapters): nothing to add
+            return None, None, None, None, None, None, None
         arena.prepare_grads(ctx.trainable)
         scratch = torch.empty((), dtype=torch.float32, device=arena.theta.device)
         # the upstream gradient (1 in the trainers' (loss + ewc_loss).backward()) is read on the device
@@ -183,9 +186,11 @@ class _EWCPenaltyFn(torch.autograd.Function):
                                           float(ctx.lam), _lib.ptr(ctx.partials), 2048, _lib.ptr(scratch),
                                           _lib.ptr(arena.grad), 1.0, _lib.ptr(g), _lib.stream()))
         arena.publish_grads(ctx.trainable)
-        return None, None, None, None, None, None
+        return None, None, None, None, None, None, None
 
 
-def ewc_penalty(arena, theta_star: torch.Tensor, fisher: torch.Tensor, lam: float, trainable):
+def ewc_penalty(arena, theta_star: torch.Tensor, fisher: torch.Tensor, lam: float, trainable, fisher_bwd=None):
+    """fisher_bwd: F with the slices of frozen parameters zeroed -- the loss counts every Fisher-tracked parameter (as the
+    reference's sum does), the gradient only reaches the trainable ones (autograd gives frozen leaves no .grad)."""
     anchor = torch.zeros((), device=arena.theta.device, requires_grad=True)
-    return _EWCPenaltyFn.apply(anchor, arena, theta_star, fisher, lam, trainable)
+    return _EWCPenaltyFn.apply(anchor, arena, theta_star, fisher, lam, trainable, fisher_bwd)

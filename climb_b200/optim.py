@@ -93,8 +93,20 @@ class ArenaAdamW(torch.optim.Optimizer):
         for aid, (a, table, n_chunks) in self._table_cache[1].items():
             st = self._arena_state.get(aid)
             if st is None or st["theta_ptr"] != a.theta.data_ptr():
-                st = dict(exp_avg=torch.zeros_like(a.theta), exp_avg_sq=torch.zeros_like(a.theta),
-                          theta_ptr=a.theta.data_ptr(), step=0)
+                new = dict(exp_avg=torch.zeros_like(a.theta), exp_avg_sq=torch.zeros_like(a.theta),
+                           theta_ptr=a.theta.data_ptr(), step=0, layout={n: (a.offsets[n], a.numels[n]) for n in a.offsets})
+                if st is not None:
+                    # the arena was rebuilt under a live optimizer (add_adapter, reallocate_text_image,
+                    # expand_modality_type_embeddings, .to(device)): carry the moments and the step over BY NAME, as
+                    # torch.optim keeps its per-parameter state across such edits; tensors that are new or changed shape
+                    # start from zero moments
+                    for n, (o_new, k_new) in new["layout"].items():
+                        old = st["layout"].get(n)
+                        if old is not None and old[1] == k_new:
+                            new["exp_avg"][o_new:o_new + k_new].copy_(st["exp_avg"][old[0]:old[0] + k_new])
+                            new["exp_avg_sq"][o_new:o_new + k_new].copy_(st["exp_avg_sq"][old[0]:old[0] + k_new])
+                    new["step"] = st["step"]
+                st = new
                 self._arena_state[aid] = st
             st["step"] += 1
             # the kernel also refreshes the bf16 shadow of everything it updates; parameters it skipped

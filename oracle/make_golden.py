@@ -125,9 +125,19 @@ def store_grad(out, name, g, full):
         out["gsample/" + name] = g.flatten().numpy()[grad_sample_index(g.numel())].copy()
 
 
+# VCR fixtures use scaled encoder-layer / head matrices: at the plain 0.02 init the four choices of a sample pool to the same
+# vector and the fixture pins nothing about the multi-choice backward (see synth_state_dict)
+VCR_SCALES = dict(layer_scale=6.0, head_scale=20.0)
+
+
+def scales_for(task):
+    return VCR_SCALES if task == "vcr" else dict(layer_scale=1.0, head_scale=1.0)
+
+
 def run_task(dims, hw, T, task, B, seed, tag, masked, full_grads, image_sizes=None):
     tasks = ALL_TASKS
-    sd = synth_state_dict(dims, tasks, seed=seed)
+    sc = scales_for(task)
+    sd = synth_state_dict(dims, tasks, seed=seed, **sc)
     learner = build_reference_learner(dims, tasks, sd)
     learner.train()
     # the only active dropout on the path is the VCR head's Dropout(0.1) (src/modeling/vilt.py:199-202;
@@ -141,7 +151,8 @@ def run_task(dims, hw, T, task, B, seed, tag, masked, full_grads, image_sizes=No
     out = dict(batch_arrays(batch, store_pixels=full_grads), pooled=pooled.detach().numpy(),
                logits=logits.detach().numpy(),
                loss=np.float32(loss.item()), seed=np.int64(seed), task=task, B=np.int64(B), T=np.int64(T),
-               hw=np.array(hw), masked=np.int64(masked))
+               hw=np.array(hw), masked=np.int64(masked), layer_scale=np.float32(sc["layer_scale"]),
+               head_scale=np.float32(sc["head_scale"]))
     if image_sizes is not None:
         out["image_sizes"] = np.array(image_sizes)
     for n, p in learner.named_parameters():
@@ -278,7 +289,8 @@ def run_viltbert(task, B, seed, tag, masked=True):
     """ViLT-BERT (BASELINE.json config 5's encoder) on the tiny geometry: forward_single_image /
     forward_multi_images / forward_multi_choice of viltbert.py:231-345, loss, backward."""
     dims, bdims = TINY, TINY_BERT
-    sd = synth_viltbert_state_dict(dims, bdims, ALL_TASKS, seed=seed)
+    sc = scales_for(task)
+    sd = synth_viltbert_state_dict(dims, bdims, ALL_TASKS, seed=seed, **sc)
     learner = build_reference_viltbert(dims, bdims, ALL_TASKS, sd)
     learner.train()
     learner.task_layer["vcr"][0].eval()
@@ -303,7 +315,8 @@ def run_viltbert(task, B, seed, tag, masked=True):
         feats = learner.viltbert_encoder.get_bert_outputs(input_ids=ids, attention_mask=am, token_type_ids=tt)
     out = dict(batch_arrays(batch), pooled=pooled.detach().numpy(), logits=logits.detach().numpy(), bert_hidden=feats.numpy(),
                loss=np.float32(loss.item()), seed=np.int64(seed), task=task, B=np.int64(B), T=np.int64(TINY_T),
-               hw=np.array(TINY_HW), masked=np.int64(masked))
+               hw=np.array(TINY_HW), masked=np.int64(masked), layer_scale=np.float32(sc["layer_scale"]),
+               head_scale=np.float32(sc["head_scale"]))
     no_grad = []
     for n_, p in learner.named_parameters():
         if p.grad is None:
@@ -342,10 +355,17 @@ def main():
     ap.add_argument("--skip-base", action="store_true")
     ap.add_argument("--only-viltbert", action="store_true", help="regenerate the ViLT-BERT fixtures only")
     ap.add_argument("--only-ragged", action="store_true", help="regenerate the padded-image (pixel_mask) fixtures only")
+    ap.add_argument("--only-vcr", action="store_true", help="regenerate the three VCR (multi-choice) fixtures only")
     a = ap.parse_args()
     ref_shim.install()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if a.only_vcr:
+        run_task(TINY, (64, 80), TINY_T, "vcr", B=3, seed=502, tag="tiny_ragged_vcr", masked=True, full_grads=True,
+                 image_sizes=[(48, 80), (64, 64), (32, 48)])
+        run_viltbert("vcr", 3, 400, "tiny_viltbert_vcr")
+        run_task(TINY, TINY_HW, TINY_T, "vcr", B=3, seed=103, tag="tiny_vcr", masked=True, full_grads=True)
+        return
     # padded batches: images of different sizes (pixel_mask zeros), tiny geometry (patch 16, padded to 64 x 80 = 4 x 5
     # patches) for single-image, image-pair and four-choice tasks, and the ViLT-base geometry (patch 32, 384 x 640)
     run_task(TINY, (64, 80), TINY_T, "snli-ve", B=4, seed=500, tag="tiny_ragged_snli-ve", masked=True, full_grads=True,

@@ -160,6 +160,8 @@ class TrainerOracle:
         self.loss_criterion = (torch.nn.BCEWithLogitsLoss(reduction="mean") if task == "vqa"
                                else torch.nn.CrossEntropyLoss())                          # train_vqa.py:95, train_nlvr2.py:80
         self.record = {"loss": [], "lr": [], "replay": [], "eval_score": [], "eval_logits": []}
+        # model_config['batch2inputs_converter'] (train_vqa.py:62): convert_batch_to_vilt_input_dict, vilt.py:548-553
+        self.batch2inputs_converter = lambda batch: {"images": batch["images"], "texts": batch["raw_texts"]}
 
     # what TaskMemoryBuffer reads (experience_replay.py:86-88)
     def get_train_dataloader(self):
@@ -170,7 +172,7 @@ class TrainerOracle:
 
     def forward_pass(self, model, batch, do_eval=False):
         """train_vqa.py:120-132."""
-        inputs = {"images": batch["images"], "texts": batch["raw_texts"]}
+        inputs = self.batch2inputs_converter(batch)
         if do_eval:
             with torch.no_grad():
                 return model(task_key=self.task, **inputs)

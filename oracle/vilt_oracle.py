@@ -135,11 +135,18 @@ def param_shapes(dims: ViltDims, tasks: Sequence[str] = (), adapters: Optional[D
 
 def synth_state_dict(dims: ViltDims, tasks: Sequence[str] = (), seed: int = 42,
                      adapters: Optional[Dict[str, int]] = None,
-                     adapter_sites: Sequence[str] = ("mh", "output")) -> "OrderedDict[str, Tensor]":
+                     adapter_sites: Sequence[str] = ("mh", "output"),
+                     layer_scale: float = 1.0, head_scale: float = 1.0) -> "OrderedDict[str, Tensor]":
     """Seeded synthetic weights. Same family as the reference's _init_weights (normal(0, 0.02),
     modeling_vilt.py:597-611) but with non-trivial LayerNorm gains and biases so that every term of
     the arithmetic is exercised. One torch.Generator per tensor: values do not depend on which other
-    tensors exist."""
+    tensors exist.
+
+    layer_scale / head_scale multiply the weight MATRICES of the encoder layers / the multi-choice head. At the
+    0.02 init a tiny encoder passes almost nothing from the other tokens into row 0 ([CLS]), so the four VCR
+    choices of a sample (same image, same [CLS] token) pool to nearly the same vector, the loss sits at ln 4 and
+    every gradient is a residual of cancelling terms: a fixture that pins nothing. The VCR fixtures therefore
+    use layer_scale = 6, head_scale = 20 (information flows, loss != ln 4, gradients well conditioned)."""
     sd: "OrderedDict[str, Tensor]" = OrderedDict()
     for idx, (name, shape) in enumerate(param_shapes(dims, tasks, adapters, adapter_sites).items()):
         g = torch.Generator().manual_seed(seed * 1_000_003 + _stable_hash(name))
@@ -150,6 +157,10 @@ def synth_state_dict(dims: ViltDims, tasks: Sequence[str] = (), seed: int = 42,
             t = 0.02 * torch.randn(shape, generator=g)
         else:
             t = 0.02 * torch.randn(shape, generator=g)
+            if layer_scale != 1.0 and len(shape) >= 2 and "encoder.layer." in name and ".adapters." not in name:
+                t = t * layer_scale
+            if head_scale != 1.0 and name.startswith("task_layer.") and len(shape) == 2 and shape[0] == 1:
+                t = t * head_scale
         sd[name] = t.float()
     return sd
 
@@ -525,11 +536,12 @@ def synth_bert_state_dict(b: BertDims, seed: int = 42, prefix: str = VB_BERT) ->
     return sd
 
 
-def synth_viltbert_state_dict(dims: ViltDims, b: BertDims, tasks: Sequence[str] = (), seed: int = 42):
+def synth_viltbert_state_dict(dims: ViltDims, b: BertDims, tasks: Sequence[str] = (), seed: int = 42,
+                              layer_scale: float = 1.0, head_scale: float = 1.0):
     """ViltBertContinualLearner state dict: the ViLT learner's tensors under `viltbert_encoder.vilt.` (same
     values as synth_state_dict: the generator is keyed by the ViLT-learner name) + BERT + task heads."""
     sd: "OrderedDict[str, Tensor]" = OrderedDict()
-    for k, v in synth_state_dict(dims, tasks, seed).items():
+    for k, v in synth_state_dict(dims, tasks, seed, layer_scale=layer_scale, head_scale=head_scale).items():
         sd[VB_ENC + k[len(ENC):] if k.startswith(ENC) else k] = v
     sd.update(synth_bert_state_dict(b, seed))
     return sd

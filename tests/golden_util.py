@@ -22,6 +22,13 @@ def load(tag):
     return np.load(os.path.join(GOLDEN_DIR, tag + ".npz"), allow_pickle=False)
 
 
+def fixture_scales(g):
+    """layer_scale / head_scale the fixture's weights were generated with (the VCR fixtures: see
+    oracle.vilt_oracle.synth_state_dict); 1.0 for fixtures written before the knobs existed."""
+    return dict(layer_scale=float(g["layer_scale"]) if "layer_scale" in g.files else 1.0,
+                head_scale=float(g["head_scale"]) if "head_scale" in g.files else 1.0)
+
+
 def grad_sample_index(numel):
     if numel <= GRAD_SAMPLES:
         return np.arange(numel)

@@ -157,3 +157,85 @@ def test_chunked_backward_overlapped_allreduce_world2_gloo(mode):
     out = mgr.dict()
     mp.spawn(_chunked_worker, args=(2, port, out, mode), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the UNCHANGED harness under torchrun: the registry's batch2inputs_converter cuts the batch dict to this rank's rows
+# ---------------------------------------------------------------------------------------------------------
+def _harness_worker(rank, world, port, out):
+    """The restated VQATrainer.train_step (oracle/trainer_oracle.py, train_vqa.py:134-174) over the CPU oracle learner,
+    with the REGISTRY's converter (model_configs['vilt-b200']['batch2inputs_converter']). Every rank is handed the SAME
+    5-sample batch dict (plain loaders, same seed); after the rank-weighted gradient mean each rank must hold the
+    gradient of the WHOLE batch."""
+    from climb_b200 import distributed as cdist
+    from climb_b200.modeling import model_configs
+    from oracle import trainer_oracle as to
+    from oracle import vilt_oracle as vo
+    from tests.golden_util import ALL_TASKS, TINY, TINY_HW, TINY_T
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        pool = to.TaskPool("vqa", 5, TINY, TINY_T, TINY_HW, seed=900)
+        items = pool.items(0, 5)
+        sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=900)
+        proc = to.PoolProcessor({"vqa": pool}, torch.device("cpu"))
+
+        def grads_of(sharded: bool):
+            model = to.OracleLearner(TINY, ALL_TASKS, sd, proc)
+            trainer = to.TrainerOracle("vqa", to.Batches(items, 5), to.Batches(items, 5), {"lr": 1e-3}, 1, torch.device("cpu"))
+            if sharded:
+                trainer.batch2inputs_converter = model_configs["vilt-b200"]["batch2inputs_converter"]
+            batch = to.collate(items)
+            loss, output, _, _ = trainer.train_step(model, batch)
+            return model, batch, output, {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+
+        cdist.set_training_mode(False)                    # evaluation: replicated, the dict is left alone
+        _, batch_eval, out_eval, g_full = grads_of(sharded=True)
+        ok = len(batch_eval["raw_texts"]) == 5 and out_eval[1].shape[0] == 5 and cdist._SHARD_MARK not in batch_eval
+        cdist.set_training_mode(True)
+        _, batch, output, g_rank = grads_of(sharded=True)
+        rows = 3 if rank == 0 else 2                      # ceil(5 / 2) rows on rank 0, the rest on rank 1
+        ok = ok and len(batch["raw_texts"]) == rows and len(batch["images"]) == rows and batch["target_scores"].shape[0] == rows
+        ok = ok and output[1].shape[0] == rows
+        ok = ok and torch.equal(batch["target_scores"], to.collate(items)["target_scores"][0 if rank == 0 else 3: 3 if rank == 0 else 5])
+        ok = ok and abs(cdist.shard_weight() - rows * world / 5.0) < 1e-12
+        worst = 0.0
+        gscale = max(g.norm().item() for g in g_full.values())     # (the key-bias gradients are analytically zero: fp32 noise)
+        for n, g in g_rank.items():
+            flat = g.clone().flatten() * cdist.shard_weight()
+            cdist.allreduce_mean_(flat, [(0, flat.numel())])
+            ref = g_full[n].flatten()
+            worst = max(worst, (flat - ref).norm().item() / max(ref.norm().item(), 1e-3 * gscale))
+        ok = ok and worst < 2e-5
+        # a second conversion of the same dict (EWC's Fisher loop, replay) must not cut it again
+        model_configs["vilt-b200"]["batch2inputs_converter"](batch)
+        ok = ok and len(batch["raw_texts"]) == rows
+        out[rank] = (bool(ok), worst)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_registry_converter_shards_the_unchanged_harness_world2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_harness_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0][0] and out[1][0], dict(out)
+
+
+def test_learner_train_eval_drive_the_sharding_mode_and_single_process_is_untouched():
+    from climb_b200 import distributed as cdist
+    from climb_b200.modeling import model_configs
+    from tests.test_host_logic import _learner
+    learner = _learner()
+    learner.eval()
+    assert cdist._training_mode is False
+    learner.train()
+    assert cdist._training_mode is True
+    batch = {"images": [1, 2, 3], "raw_texts": ["a", "b", "c"], "labels": torch.arange(3)}
+    inputs = model_configs["vilt-b200"]["batch2inputs_converter"](batch)       # no process group: nothing is cut
+    assert inputs == {"images": [1, 2, 3], "texts": ["a", "b", "c"]} and len(batch["labels"]) == 3
+    assert cdist.attach_if_distributed(learner) is None

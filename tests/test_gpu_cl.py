@@ -164,3 +164,102 @@ def test_ewc_fisher_and_penalty_vs_reference_golden():
         if ref_g.norm() < 1e-12:
             continue
         assert _rel(p.grad, ref_g) < 1e-4, name
+
+
+def test_ewc_backward_leaves_frozen_parameters_and_published_gradients_alone():
+    """(a) with a frozen base + adapters no Fisher-tracked parameter trains -- the EWC node's backward must not wipe
+    the gradients the encoder already published; (b) with the bottom layers frozen the penalty still COUNTS their terms but
+    its gradient reaches the trainable parameters only."""
+    from climb_b200.cl_algorithms import EWC
+    dev = torch.device("cuda")
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=12)
+    learner = _build(TINY, ALL_TASKS, sd)
+    arena = learner.vilt_encoder.vilt._arena
+    arena.sync(dev)
+    ewc = EWC(types.SimpleNamespace(ewc_fisher_sample_percentage=1.0, ewc_loss_weight=10.0))
+    names = [n for n, _ in arena.named_items()]
+    ewc.task_keys = ["vqa"]
+    ewc.param_dict["vqa"] = (arena.theta + 0.01).detach().clone()
+    ewc.fisher_dict["vqa"] = torch.full_like(arena.theta, 0.5)
+    ewc.fisher_names["vqa"] = names
+    ewc._offsets["vqa"] = dict(arena.offsets)
+    # (b) bottom layer frozen
+    learner.get_encoder().freeze_bottom_k_layers(1)
+    learner.zero_grad(set_to_none=True)
+    _, loss = ewc.compute_ewc_loss(learner)
+    n_real = sum(arena.numels.values())
+    assert abs(loss.item() - 10.0 * 0.5 * 1e-4 * n_real) <= 2e-3 * loss.item()         # every tracked parameter counts
+    loss.backward()
+    frozen = "encoder.layer.0.intermediate.dense.weight"
+    live = "encoder.layer.1.intermediate.dense.weight"
+    named = dict(arena.named_items())
+    assert named[frozen].grad is None and float(arena.grad_view(frozen).abs().max()) == 0.0
+    assert torch.allclose(named[live].grad, torch.full_like(named[live], 2 * 10.0 * 0.5 * -0.01), rtol=1e-3)
+    # (a) adapters: the encoder publishes adapter gradients, then the EWC node runs with an empty trainable list
+    learner2 = _build(TINY, ALL_TASKS, sd, adapters={"vqa": ("houlsby", 4)})
+    learner2.train_adapter("vqa")
+    arena2 = learner2.vilt_encoder.vilt._arena
+    arena2.sync(dev)
+    batch = vo.synth_batch("vqa", 2, TINY, T=TINY_T, image_hw=TINY_HW, seed=3)
+    ewc2 = EWC(types.SimpleNamespace(ewc_fisher_sample_percentage=1.0, ewc_loss_weight=10.0))
+    base_names = [n for n, _ in arena2.named_items() if ".adapters." not in n]
+    ewc2.task_keys = ["vqa"]
+    ewc2.param_dict["vqa"] = (arena2.theta + 0.01).detach().clone()
+    ewc2.fisher_dict["vqa"] = torch.full_like(arena2.theta, 0.5)
+    ewc2.fisher_names["vqa"] = base_names
+    ewc2._offsets["vqa"] = dict(arena2.offsets)
+    learner2.train()
+    _, logits = learner2.forward_tensors("vqa", _encodings("vqa", batch, dev))
+    task_loss = torch.nn.BCEWithLogitsLoss()(logits, batch["target"].to(dev)) * logits.shape[1]
+    task_loss.backward(retain_graph=False)
+    ad = next(n for n, _ in arena2.named_items() if ".adapters.vqa.adapter_up.weight" in n)
+    g_before = dict(arena2.named_items())[ad].grad.clone()
+    assert g_before.abs().max() > 0
+    _, pen = ewc2.compute_ewc_loss(learner2)
+    pen.backward()
+    assert torch.equal(dict(arena2.named_items())[ad].grad, g_before)
+    assert all(p.grad is None for n, p in arena2.named_items() if ".adapters." not in n)
+
+
+def test_arena_adamw_keeps_its_moments_when_the_arena_is_rebuilt():
+    """add_adapter / expand_modality_type_embeddings / reallocate_text_image rebuild the flat arena under a live
+    optimizer: exp_avg / exp_avg_sq / step are carried over by parameter name."""
+    dev = torch.device("cuda")
+    sd = vo.synth_state_dict(TINY, ["vqa"], seed=14)
+    learner = _build(TINY, ["vqa"], sd)
+    opt = learner.create_optimizer({"lr": 1e-3, "weight_decay": 0.0, "adam_epsilon": 1e-8})
+    batch = vo.synth_batch("vqa", 2, TINY, T=TINY_T, image_hw=TINY_HW, seed=4)
+
+    seen = {}
+
+    def step():
+        _, logits = learner.forward_tensors("vqa", _encodings("vqa", batch, dev))
+        (torch.nn.BCEWithLogitsLoss()(logits, batch["target"].to(dev)) * logits.shape[1]).backward()
+        seen["g"] = dict(learner.get_encoder().vilt.named_parameters())["encoder.layer.1.output.dense.weight"].grad.flatten().clone()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    learner.train()
+    step()
+    arena = learner.vilt_encoder.vilt._arena
+    st = opt._arena_state[id(arena)]
+    name = "encoder.layer.1.output.dense.weight"
+    o, k = arena.offsets[name], arena.numels[name]
+    m_before = st["exp_avg"][o:o + k].clone()
+    assert m_before.abs().max() > 0 and st["step"] == 1
+    learner.get_encoder().expand_modality_type_embeddings()          # replaces an nn.Embedding: the arena is rebuilt
+    old_theta = arena.theta
+    arena.sync(dev)
+    assert arena.theta is not old_theta
+    # the replaced embedding is a new Parameter: the optimizer must be told, as with torch.optim (the trainers build a
+    # fresh optimizer per task; here we only check the carried state of the tensors it still owns)
+    opt.param_groups[0]["params"] = [p for p in opt.param_groups[0]["params"]
+                                     if p.shape != (2, TINY.hidden_size)] + [learner.get_encoder().vilt.embeddings.token_type_embeddings.weight]
+    step()
+    st2 = opt._arena_state[id(arena)]
+    assert st2["step"] == 2 and st2["theta_ptr"] == arena.theta.data_ptr()
+    o2 = arena.offsets[name]
+    m_after = st2["exp_avg"][o2:o2 + k]
+    # exp_avg after the second step = 0.9 * m1 + 0.1 * g2 (a reset would give 0.1 * g2 and step == 1)
+    expect = 0.9 * m_before + 0.1 * seen["g"]
+    assert ((m_after - expect).norm() / expect.norm()).item() < 1e-5

@@ -9,8 +9,8 @@ import pytest
 import torch
 
 from oracle import vilt_oracle as vo
-from tests.golden_util import ALL_TASKS, TINY, TINY_HW, TINY_T, grad_sample_index, load, regen_batch
-from tests.test_gpu_parity import TOL_OUT, _autocast_reference_errors, _check_grads, _encodings, _rel
+from tests.golden_util import ALL_TASKS, TINY, TINY_HW, TINY_T, fixture_scales, grad_sample_index, load, regen_batch
+from tests.test_gpu_parity import TOL_OUT, _check_grads, _encodings, _rel, check_outputs, gate
 
 pytestmark = pytest.mark.gpu
 
@@ -46,7 +46,7 @@ def _build(dims, bdims, tasks, sd, p=0.0):
 def test_tiny_viltbert_vs_reference_golden(task, seed):
     g = load(f"tiny_viltbert_{task}")
     batch = regen_batch(g, task, TINY, TINY_T, TINY_HW, 3, seed, True)
-    sd = vo.synth_viltbert_state_dict(TINY, TINY_BERT, ALL_TASKS, seed=seed)
+    sd = vo.synth_viltbert_state_dict(TINY, TINY_BERT, ALL_TASKS, seed=seed, **fixture_scales(g))
     learner = _build(TINY, TINY_BERT, ALL_TASKS, sd)
     assert set(learner.state_dict().keys()) >= set(sd.keys())          # checkpoint keys of the reference learner
     dev = torch.device("cuda")
@@ -63,22 +63,13 @@ def test_tiny_viltbert_vs_reference_golden(task, seed):
     target = batch["target"].to(dev)
     loss = (torch.nn.BCEWithLogitsLoss()(logits, target) * target.shape[1]) if task == "vqa" else torch.nn.CrossEntropyLoss()(logits, target)
     loss.backward()
-    e_p, e_l = _rel(pooled, g["pooled"]), _rel(logits, g["logits"])
-    print(f"viltbert {task}: bert rel {e_f:.3e} pooled rel {e_p:.3e} logits rel {e_l:.3e} loss {loss.item():.6f} vs {float(g['loss']):.6f}")
-    assert e_f <= TOL_OUT and e_p <= TOL_OUT and e_l <= TOL_OUT
-    assert abs(loss.item() - float(g["loss"])) <= TOL_OUT * abs(float(g["loss"]))
+    gate(f"tiny_viltbert_{task}/bert", e_f, TOL_OUT)
+    check_outputs(f"tiny_viltbert_{task}", pooled, logits, loss.item(), g["pooled"], g["logits"], g["loss"])
     # parameters the reference leaves without a gradient stay without one: all of BERT, ViLT's word table, other heads
     grads = {n: p.grad for n, p in learner.named_parameters()}
     for n in g["no_grad"].tolist():
         assert grads[n] is None, n
-    if task == "vcr":      # see tests/test_gpu_parity.py: cancelling dlogits, bound relative to the reference's own bf16 loss
-        vsd = {(vo.ENC + k[len(vo.VB_ENC):] if k.startswith(vo.VB_ENC) else k): v for k, v in sd.items()
-               if not k.startswith(vo.VB_BERT)}
-        ref_err = _autocast_reference_errors(vsd, TINY, task, batch)
-        ref_err = {(vo.VB_ENC + k[len(vo.ENC):] if k.startswith(vo.ENC) else k): v for k, v in ref_err.items()}
-        _check_grads(g, learner, floor=1.0, per_tensor_tol={k: 1.25 * v for k, v in ref_err.items()})
-    else:
-        _check_grads(g, learner)
+    _check_grads(g, learner, f"tiny_viltbert_{task}")
 
 
 def test_bert_base_vs_reference_golden():
@@ -99,7 +90,8 @@ def test_bert_base_vs_reference_golden():
     e_cls = _rel(hc[:, 0], g["hidden_cls"])
     e_s = _rel(hc.flatten()[torch.from_numpy(grad_sample_index(hc.numel()))], g["hidden_sample"])
     print(f"bert-base: cls rel {e_cls:.3e} sample rel {e_s:.3e} norm {hc.norm().item():.3f} vs {float(g['hidden_norm']):.3f}")
-    assert e_cls <= TOL_OUT and e_s <= TOL_OUT
+    gate("base_bert/cls", e_cls, TOL_OUT)
+    gate("base_bert/sample", e_s, TOL_OUT)
     assert abs(hc.norm().item() - float(g["hidden_norm"])) <= 5e-3 * float(g["hidden_norm"])
 
 
@@ -112,7 +104,7 @@ def test_nlvr2_bert_features_reused_across_images():
     with torch.no_grad():
         pooled, logits = learner.forward_tensors("nlvr2", _encodings("nlvr2", batch, torch.device("cuda")))
     ref_p, ref_l = vo.viltbert_learner_forward(sd, TINY, TINY_BERT, "nlvr2", batch)
-    assert _rel(pooled, ref_p) <= TOL_OUT and _rel(logits, ref_l) <= TOL_OUT
+    check_outputs("viltbert_fresh", pooled, logits, 0.0, ref_p, ref_l, None)
 
 
 def test_attention_dropout_mask_statistics():

@@ -369,3 +369,88 @@ def test_ewc_realigns_saved_state_when_the_arena_layout_changes():
             assert torch.equal(new_t[o:o + k], arena.theta[o:o + k]) and bool((new_f[o:o + k] == 0).all()), n
     with pytest.raises(TypeError):
         ewc.compute_ewc_loss(types.SimpleNamespace(get_encoder=lambda: types.SimpleNamespace()))
+
+
+def _local_pretrained_dir(tmp_path):
+    """A local directory that ViltProcessor.from_pretrained / ViltConfig.from_pretrained resolve offline (what
+    `--pretrained_model_name dandelin/vilt-b32-mlm` resolves through the hub in a CLiMB run), at the tiny geometry."""
+    transformers = pytest.importorskip("transformers")
+    hub = str(tmp_path / "vilt-tiny-mlm")
+    transformers.ViltConfig(hidden_size=TINY.hidden_size, num_hidden_layers=TINY.num_hidden_layers,
+                            num_attention_heads=TINY.num_attention_heads, intermediate_size=TINY.intermediate_size,
+                            image_size=TINY.image_size, patch_size=TINY.patch_size, vocab_size=TINY.vocab_size,
+                            max_position_embeddings=TINY.max_position_embeddings).save_pretrained(hub)
+    tok = transformers.BertTokenizerFast(vocab_file=os.path.join(ROOT, "tests", "golden", "tokenizer_vocab.txt"))
+    image_cls = getattr(transformers, "ViltImageProcessor", None) or transformers.ViltFeatureExtractor
+    transformers.ViltProcessor(image_cls(size={"shortest_edge": 64}), tok).save_pretrained(hub)
+    return hub
+
+
+def test_load_encoder_map_entries_take_the_reference_call(tmp_path):
+    """train_language.py:278-279 / train_vision.py:310-311 call `load_encoder_map[name](args.checkpoint_name, device,
+    args.pretrained_model_name)` POSITIONALLY (reference signature vilt.py:481, viltbert.py:456): checkpoint = a file written
+    by torch.save(encoder.state_dict()) with `vilt.*` (and `bert.*`) keys; an NLVR2-trained checkpoint carries three modality
+    rows (vilt.py:98-109, 508-509)."""
+    import climb_b200.modeling as M
+    hub = _local_pretrained_dir(tmp_path)
+    dev = torch.device("cpu")
+    learner = _learner()                                         # task list contains nlvr2 -> 3 modality rows
+    learner.load_state_dict(vo.synth_state_dict(TINY, ALL_TASKS, seed=8), strict=False)
+    ckpt = str(tmp_path / "encoder_after_task_x")                # no 'nlvr2' in the name: the tensor's shape decides
+    torch.save(learner.get_encoder().state_dict(), ckpt)
+    enc = M.load_encoder_map["vilt-b200"](ckpt, dev, hub)
+    assert callable(enc.processor) and enc.processor.tokenizer is not None
+    assert enc.vilt.embeddings.token_type_embeddings.weight.shape[0] == 3
+    for k, v in learner.get_encoder().state_dict().items():
+        assert torch.equal(enc.state_dict()[k], v), k
+    # the text half of process_inputs works through the loaded processor (native tokenizer over its vocabulary)
+    ids = enc.tokenize(enc.processor.tokenizer, ["is the cat on the mat?", "two dogs"])["input_ids"]
+    assert ids.shape[0] == 2 and int(ids[0, 0]) == enc.processor.tokenizer.cls_token_id
+    # the tensor's own shape decides: a two-row checkpoint loads as two rows whatever its file name says (the reference
+    # expands on the NAME alone and then fails with a size mismatch)
+    two = _learner(tasks=["vqa"])
+    ckpt2 = str(tmp_path / "encoder_nlvr2_two_rows")
+    sd2 = two.get_encoder().state_dict()
+    assert sd2["vilt.embeddings.token_type_embeddings.weight"].shape[0] == 2
+    torch.save(sd2, ckpt2)
+    assert M.load_encoder_map["vilt-b200"](ckpt2, dev, hub).vilt.embeddings.token_type_embeddings.weight.shape[0] == 2
+    with pytest.raises(FileNotFoundError):
+        M.load_encoder_map["vilt-b200"](str(tmp_path / "missing"), dev, hub)
+    # ViLT-BERT: bert.* keys ride in the same checkpoint (viltbert.py:484-485)
+    bcfg = M.B200BertConfig(vocab_size=200, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                            max_position_embeddings=16)
+    vb = M.B200ViltBertEncoderWrapper(None, learner.get_encoder().vilt, M.B200BertModel(bcfg), dev)
+    ckpt3 = str(tmp_path / "viltbert_encoder")
+    torch.save(vb.state_dict(), ckpt3)
+    got = M.load_encoder_map["viltbert-b200"](ckpt3, dev, hub, bert_config=bcfg)
+    for k, v in vb.state_dict().items():
+        assert torch.equal(got.state_dict()[k], v), k
+    with pytest.raises(RuntimeError):                            # a ViLT-BERT checkpoint through the ViLT loader
+        M.load_encoder_map["vilt-b200"](ckpt3, dev, hub)
+    # create_continual_learner_map[...](model_name_or_path, ordered_cl_tasks, model_config, task_configs, device): config object
+    # in place of the hub name = random init offline
+    cl = M.create_continual_learner_map["vilt-b200"](learner.get_encoder().vilt.config, ["vqa"], M.model_configs["vilt-b200"],
+                                                     vo.TASK_SPECS, dev)
+    assert cl.get_encoder().vilt.grad_sync is None and cl.get_encoder().processor is None
+
+
+def test_prepare_grads_never_wipes_gradients_it_was_not_asked_about():
+    """ParamArena.prepare_grads: an empty `trainable` list (EWC's node when no Fisher-tracked parameter trains) is a no-op,
+    and a list that covers only part of the arena zeroes only its own fresh slices while other parameters already hold
+    accumulated arena gradients."""
+    learner = _learner()
+    arena = learner.vilt_encoder.vilt._arena
+    arena.sync(allow_cpu=True)
+    items = arena.named_items()
+    a_name, a_p = items[3]
+    b_name, b_p = items[10]
+    arena.grad.fill_(7.0)
+    arena.publish_grads([(a_name, a_p)])                 # a_p.grad is now the arena slice (value 7)
+    arena.prepare_grads([])
+    assert float(a_p.grad.flatten()[0]) == 7.0
+    arena.prepare_grads([(b_name, b_p)])                 # fresh for b only: a keeps its accumulated gradient
+    assert float(a_p.grad.flatten()[0]) == 7.0 and float(arena.grad_view(b_name).abs().max()) == 0.0
+    a_p.grad = None
+    arena.grad.fill_(7.0)
+    arena.prepare_grads([(b_name, b_p)])                 # nothing published anywhere: whole-arena memset
+    assert float(arena.grad.abs().max()) == 0.0

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import vilt_oracle as vo
-from tests.golden_util import (ALL_TASKS, BASE, BASE_HW, TINY, TINY_HW, TINY_T, compare_grads, load,
+from tests.golden_util import (ALL_TASKS, BASE, BASE_HW, TINY, TINY_HW, TINY_T, compare_grads, fixture_scales, load,
                                regen_batch)
 
 
@@ -24,11 +24,13 @@ def test_tiny_tasks_match_reference(task):
     seed = int(g["seed"])
     batch = regen_batch(g, task, TINY, TINY_T, TINY_HW, 3, seed, True)
     assert np.array_equal(g["in_pixel_values"], batch["pixel_values"].numpy())
-    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=seed)
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=seed, **fixture_scales(g))
     pooled, logits, loss, grads = _oracle_step(sd, TINY, task, batch)
     assert np.allclose(pooled.detach().numpy(), g["pooled"], atol=2e-6)
     assert np.allclose(logits.detach().numpy(), g["logits"], atol=5e-6)
     assert abs(loss.item() - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    if task == "vcr":
+        assert abs(float(g["loss"]) - np.log(4.0)) > 1e-2          # the multi-choice fixture is not the degenerate ln 4 one
     worst = compare_grads(g, grads, rtol_norm=1e-4, tol_elem=2e-4)
     print("worst grad", worst)
 
@@ -119,7 +121,7 @@ def test_tiny_viltbert_matches_reference(task, seed):
     """ViLT-BERT (src/modeling/viltbert.py): frozen BERT features -> ViltModel(inputs_embeds=...)."""
     g = load(f"tiny_viltbert_{task}")
     batch = regen_batch(g, task, TINY, TINY_T, TINY_HW, 3, seed, True)
-    sd = vo.synth_viltbert_state_dict(TINY, TINY_BERT, ALL_TASKS, seed=seed)
+    sd = vo.synth_viltbert_state_dict(TINY, TINY_BERT, ALL_TASKS, seed=seed, **fixture_scales(g))
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     pooled, logits = vo.viltbert_learner_forward(params, TINY, TINY_BERT, task, batch)
     loss = vo.task_loss(task, logits, batch["target"])
@@ -171,7 +173,7 @@ def test_tiny_padded_images_match_reference(tag, task, B, seed):
     batch = regen_batch(g, task, TINY, TINY_T, (64, 80), B, seed, True)
     assert "pixel_mask" in batch
     assert np.array_equal(g["in_pixel_values"], batch["pixel_values"].numpy())
-    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=seed)
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=seed, **fixture_scales(g))
     pooled, logits, loss, grads = _oracle_step(sd, TINY, task, batch)
     assert np.allclose(pooled.detach().numpy(), g["pooled"], atol=2e-6)
     assert np.allclose(logits.detach().numpy(), g["logits"], atol=5e-6)

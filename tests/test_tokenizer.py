@@ -152,6 +152,19 @@ def test_from_hf_and_encoder_wrapper_use_the_native_tokenizer():
         return {"input_ids": torch.zeros(len(text), 3, dtype=torch.long)}
     enc.native_tokenizer = True
     assert enc.tokenize(other, texts)["input_ids"].shape == (4, 3) and calls == [4]
+    # text PAIRS (the language-only multiple-choice path, convert_mc_batch_to_vilt_input_dict vilt.py:561-567) keep the
+    # processor's own tokenizer: second segment with token_type_ids 1, pair truncation
+    pairs = [["What color is the cat?", "black"], ["Is the man holding a Frisbee near the train station?", "he is riding a skateboard"]]
+    ref_p = hf(text=pairs, max_length=20, padding=True, truncation=True, return_tensors="pt")
+    got_p = enc.tokenize(hf, pairs)
+    for k in ("input_ids", "attention_mask", "token_type_ids"):
+        assert torch.equal(got_p[k], ref_p[k]), k
+    assert int(got_p["token_type_ids"].max()) == 1
+    # so does a tokenizer built with non-default normalisation
+    hf2 = tr.BertTokenizerFast(vocab=_vocab_dict(), strip_accents=False)
+    enc._native_tok = None
+    ref2 = hf2(text=["Café"], max_length=20, padding=True, truncation=True, return_tensors="pt")
+    assert torch.equal(enc.tokenize(hf2, ["Café"])["input_ids"], ref2["input_ids"]) and enc._native_tok is None
 
 
 def test_threads_edge_cases_and_errors():

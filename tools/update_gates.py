@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Regenerate tests/parity_gates.json from the `MEASURED <key> <error> gate <limit>` lines that the -m gpu parity
+tests print (run them with `-s` on a B200 and pass the log files here):
+
+    python tools/update_gates.py gpurun_out/parity.log gpurun_out/viltbert.log [...]
+
+gate = FACTOR x the measured error, rounded UP to two significant digits (FACTOR = 2: a kernel change that doubles
+the error of any fixture fails the suite). Keys measured more than once keep their largest measurement. Keys already
+in the table but absent from the logs are kept.
+"""
+import json
+import math
+import os
+import re
+import sys
+
+FACTOR = 2.0
+FLOOR = 1e-7          # fp32 noise level: errors that are exactly zero in one run still get a gate
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "tests", "parity_gates.json")
+LINE = re.compile(r"MEASURED (\S+) ([0-9.eE+-]+) gate")
+
+
+def round_up(x: float) -> float:
+    if x <= 0:
+        return FLOOR
+    e = math.floor(math.log10(x)) - 1
+    return math.ceil(x / 10 ** e) * 10 ** e
+
+
+def main(paths):
+    measured = {}
+    for p in paths:
+        for line in open(p, errors="replace"):
+            m = LINE.search(line)
+            if m:
+                measured[m.group(1)] = max(measured.get(m.group(1), 0.0), float(m.group(2)))
+    table = json.load(open(PATH)) if os.path.exists(PATH) else {}
+    for k, v in measured.items():
+        table[k] = float(f"{round_up(max(FACTOR * v, FLOOR)):.3g}")
+    json.dump(dict(sorted(table.items())), open(PATH, "w"), indent=1)
+    print(f"{len(measured)} measurements -> {PATH} ({len(table)} gates)")
+    json.dump(dict(sorted(measured.items())), open(os.path.join(ROOT, "profiles", "r2_parity_measured.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
