@@ -19,9 +19,12 @@ public API of this repo (B200ViltContinualLearner + ArenaAdamW). One JSON line g
              measured with CUDA events on the launch stream inside this process (climb_profile_*),
              against the measured sustained bf16 peak of MEASURED_PEAKS.json; plus the attention
              kernels against the measured HBM copy bandwidth
-  cpu_baseline  oracle/ (the CPU restatement of the reference arithmetic, pinned to the reference by
-             tests/golden) timed on this box's host cores on BASELINE config 1 (B=4) -- a reported
-             baseline, not the target
+  cpu_baseline  the UNMODIFIED reference (ViltContinualLearner + VQATrainer.train_step, imported from the archive that
+             oracle/stage_ref.py staged at build() time; kind "reference") timed on this box's host cores on
+             BASELINE config 1 (B=4) -- a reported baseline, not the target. Without a staged reference: the oracle
+             port (kind "port")
+  gpu_eager_baseline  the same unmodified reference module run eagerly on this GPU (fp32 and bf16 autocast) at the
+             same batch size: the like-for-like GPU number
 """
 from __future__ import annotations
 
@@ -103,11 +106,17 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference arithmetic on host cores
+# reference arm / cpu baseline: the UNMODIFIED reference on host cores (oracle/ref_runner.py over the archive that
+# oracle/stage_ref.py staged at build() time); the oracle port only if no reference was staged
 # ----------------------------------------------------------------------------------------------------
 def cpu_reference_steps(steps: int, warmup: int, batch: int = 4):
-    """BASELINE config 1: ViLT-base, seeded random init, VQA head, B=4 synthetic batch, fp32, all host
-    threads; one fwd + loss + bwd + AdamW step per iteration. Returns (samples/s, cores, seconds/step)."""
+    """BASELINE config 1: ViLT-base, seeded random init, VQA head, B=4 synthetic batch, fp32, all host threads; one
+    fwd + loss + bwd + AdamW step per iteration. Returns (samples/s, cores, seconds/step, kind, what ran)."""
+    from oracle import ref_runner
+    if ref_runner.available():
+        sps, cores, sec = ref_runner.cpu_reference(steps, warmup, batch)
+        return sps, cores, sec, "reference", ("the unmodified reference: ViltContinualLearner + VQATrainer.train_step + create_optimizer "
+                                              "(src/modeling/vilt.py, train_vqa.py:135-174) over the vendored transformers-4.17 ViltModel")
     from oracle import vilt_oracle as vo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -127,7 +136,7 @@ def cpu_reference_steps(steps: int, warmup: int, batch: int = 4):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = statistics.median(times)
-    return batch / sec, cores, sec
+    return batch / sec, cores, sec, "port", "oracle/vilt_oracle.py (CPU restatement pinned to the reference by tests/golden); no staged reference found"
 
 
 def workload_config(batch_per_gpu: int, world: int) -> dict:
@@ -139,26 +148,29 @@ def workload_config(batch_per_gpu: int, world: int) -> dict:
             "l2": "activation working set ~5 GB per step >> 126 MB L2; 4 rotating input batches"}
 
 
+REF_BATCH = 4       # BASELINE config 1: the reference's own CPU-runnable case = the bounded sample of the workload
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(1, args.warmup)
-    # each step is a bounded sample (B=4) of the workload; cap the run at a few minutes
-    steps = min(steps, 8)
-    warmup = min(warmup, 2)
-    sps, cores, sec = cpu_reference_steps(steps, warmup)
+    # --steps / --warmup are honoured; each step is a bounded sample (B = 4 sequences, ~1 s on 16 cores), so that the driver's
+    # K / W finish within a few minutes (the cap only guards against an accidental huge K)
+    steps, warmup = max(1, min(args.steps, 200)), max(0, min(args.warmup, 50))
+    sps, cores, sec, kind, what = cpu_reference_steps(steps, warmup, REF_BATCH)
+    cfg = workload_config(REF_BATCH, 1)
+    cfg["parallelism"] = "host cores (rank 0 only)"
+    cfg["l2"] = "n/a (CPU)"
+    cfg["sample"] = (f"each step = one B={REF_BATCH} batch of the same workload (BASELINE config 1: same model, sequence geometry, loss and "
+                     "optimizer as the B=64-per-GPU arm), fp32 on the host cores")
     line = {
-        "impl": "reference", "metric": "ViLT upstream-CL training throughput", "value": sps, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.batch, args.gpus),
-                       sample="each step = one B=4 batch of the workload (BASELINE config 1), fp32 on the host cores"),
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps of B=4 (BASELINE config 1) through oracle/vilt_oracle.py, "
-                                   "the CPU restatement pinned to the reference by tests/golden; the reference itself "
-                                   "is Python under /root/reference, which does not exist on the GPU box"},
-        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "ViLT upstream-CL training throughput", "value": round(sps, 3), "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} timed steps (median) of B={REF_BATCH}: {what}"},
+        "e2e": {"value": round(sps, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
@@ -357,12 +369,37 @@ def run_ours(args):
             attn_roof["bwd"]["traffic"] = at["bwd"]["dram_bytes_per_launch"]
             attn_roof["kernel"] = ("attn_tc_fwd2_kernel / attn_tc_bwd2_kernel (persistent, tcgen05 + TMEM); achieved = algorithmic bytes / time; "
                                    "the tensor pipe (operand fetch from shared memory + MMA) and the MUFU pipe bound these kernels before HBM does: DESIGN.md")
+        # the driver keeps `roofline` only: the attention kernels (the kernel BASELINE.json's metric names) ride inside it
+        roofline["kernels"] = [
+            {"name": "tcgen05 GEMMs (all launches)", "bound": "tensor", "achieved": roofline["achieved"], "peak": roofline["peak"],
+             "unit": "TFLOP/s", "frac": roofline["frac"], "ms_per_step": roofline["gemm_ms_per_step"]},
+            {"name": "attention forward (fused softmax(QK^T)V, per layer launch)", "bound": "hbm", "achieved": attn_roof["fwd"]["achieved"],
+             "peak": peaks["hbm"], "unit": "GB/s", "frac": attn_roof["fwd"]["frac"], "ms_per_step": attn_roof["fwd"]["ms_per_step"],
+             "algorithmic_bytes_per_launch": int(af_b / max(af_n, 1)), "traffic": attn_roof["fwd"].get("traffic")},
+            {"name": "attention backward (dQ, dK, dV, per layer launch)", "bound": "hbm", "achieved": attn_roof["bwd"]["achieved"],
+             "peak": peaks["hbm"], "unit": "GB/s", "frac": attn_roof["bwd"]["frac"], "ms_per_step": attn_roof["bwd"]["ms_per_step"],
+             "algorithmic_bytes_per_launch": int(ab_b / max(ab_n, 1)), "traffic": attn_roof["bwd"].get("traffic")}]
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sps, cores, sec = cpu_reference_steps(steps=5, warmup=1)
-        cpu_baseline = {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port",
-                        "sample": "5 steps (median) of B=4 fwd+loss+bwd+AdamW, BASELINE config 1, oracle/vilt_oracle.py fp32"}
+        sps, cores, sec, kind, what = cpu_reference_steps(steps=8, warmup=1)
+        cpu_baseline = {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": kind,
+                        "sample": f"8 timed steps (median) of B=4 fwd+loss+bwd+AdamW, BASELINE config 1, fp32: {what}"}
+
+    # like-for-like GPU baseline: the unmodified reference module as-is on this GPU (eager PyTorch), same step, same batch size
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            from oracle import ref_runner
+            if ref_runner.available():
+                resident.clear()
+                slots[:] = [None, None]
+                torch.cuda.empty_cache()
+                gpu_eager = ref_runner.gpu_eager(B)
+                gpu_eager["what"] = ("the UNMODIFIED reference (ViltContinualLearner + VQATrainer.train_step + torch AdamW over the vendored "
+                                     f"ViltModel) run eagerly on this GPU at B={B}; median of 3 steps after 2 warm-up steps")
+        except Exception as e:          # a baseline must never take the product's line down
+            gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         peaks = load_peaks()
@@ -380,10 +417,27 @@ def run_ours(args):
                     "last_loss": round(losses[-1], 4)},
             "gpu_launches": int(launches),
             "roofline": roofline, "attention_roofline": attn_roof, "cpu_baseline": cpu_baseline,
+            "gpu_eager_baseline": gpu_eager,
+            "precision": precision_note(),
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def precision_note():
+    """bf16 is the throughput mode; its measured error against the fp32 reference (tests/parity_gates.json holds 2 x these) and
+    the precise mode's (bf16x3 split operands, fp32 activations: climb_b200 `precision='bf16x3'`) are reported beside the number."""
+    p = os.path.join(ROOT, "profiles", "r2_parity_measured.json")
+    if not os.path.exists(p):
+        return None
+    m = json.load(open(p))
+    pick = lambda k: m.get(k)
+    return {"mode": "bf16 operands, fp32 accumulate / residual stream / statistics",
+            "measured_rel_error_vs_fp32_reference": {"bench_shape_b64_logits": pick("bench_shape_b64/logits"), "bench_shape_b64_pooled": pick("bench_shape_b64/pooled"),
+                                                     "bench_shape_b64_worst_grad": pick("bench_shape_b64/grad"), "base_vqa_logits": pick("base_vqa/logits")},
+            "precise_mode_rel_error": {"base_vqa_logits": pick("precise/base_vqa/logits"), "base_vqa_worst_grad": pick("precise/base_vqa/grad")},
+            "source": "profiles/r2_parity_measured.json (pytest -m gpu -s on a B200, tools/update_gates.py)"}
 
 
 _JSON_FD = None
@@ -409,6 +463,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU (the shipped scripts use 64)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-reference-on-this-GPU leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

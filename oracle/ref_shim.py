@@ -12,19 +12,49 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("CLIMB_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ARCHIVE = os.path.join(_HERE, "_ref", "climb_reference_src.zip")      # written by oracle/stage_ref.py at build() time
+
+
+def _mounted(root: str) -> bool:
+    return os.path.isdir(os.path.join(root, "src", "adapter-transformers", "src", "transformers"))
+
+
+def _unpack_staged() -> str:
+    """The GPU box has no /root/reference: unpack the archive that oracle/stage_ref.py staged (unmodified reference
+    packages, same directory layout) into a temporary directory, once per archive version."""
+    import tempfile
+    import zipfile
+    st = os.stat(STAGED_ARCHIVE)
+    dest = os.path.join(tempfile.gettempdir(), f"climb_b200_reference_{int(st.st_mtime)}_{st.st_size}")
+    marker = os.path.join(dest, ".complete")
+    if not os.path.exists(marker):
+        tmp = dest + f".{os.getpid()}"
+        with zipfile.ZipFile(STAGED_ARCHIVE) as z:
+            z.extractall(tmp)
+        try:
+            os.rename(tmp, dest)
+        except OSError:                      # another process won the race
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+        open(marker, "w").close()
+    return dest
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "adapter-transformers", "src", "transformers"))
+    return _mounted(REFERENCE_ROOT) or os.path.exists(STAGED_ARCHIVE)
 
 
 def install():
     """Make `import transformers` resolve to the vendored 4.17 fork and `modeling.*`,
     `cl_algorithms.*`, `configs.*` to CLiMB's own packages. Idempotent."""
+    global REFERENCE_ROOT
     if not reference_available():
-        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT} and no staged archive at {STAGED_ARCHIVE}")
     if getattr(install, "_done", False):
         return
+    if not _mounted(REFERENCE_ROOT):
+        REFERENCE_ROOT = _unpack_staged()
     sys.dont_write_bytecode = True           # the reference tree is read-only
     for name in list(sys.modules):
         if name == "transformers" or name.startswith("transformers."):

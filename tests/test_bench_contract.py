@@ -1,5 +1,6 @@
 """CPU: the parts of bench.py's contract that do not need a GPU -- the reference arm prints exactly ONE JSON line with the
-required keys (timing the oracle port on the host cores), other ranks of a torchrun launch stay silent and exit 0, and the
+required keys (timing the UNMODIFIED reference staged by oracle/stage_ref.py on the host cores; the oracle port only when
+nothing was staged), honours --steps / --warmup and prints its true batch size, other ranks of a torchrun launch stay silent and exit 0, and the
 product arm refuses to run without a CUDA device instead of falling back to anything."""
 import json
 import os
@@ -16,7 +17,7 @@ def _run(args, env=None):
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    r = _run(["--impl", "reference", "--steps", "2", "--warmup", "1"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
@@ -25,10 +26,14 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["value"] > 0 and abs(d["value"] - 4 / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
+    assert d["steps"] == 2 and d["warmup"] == 1                                   # the driver's K / W are honoured
+    assert d["value"] > 0 and abs(d["value"] - 4 / (d["ms_per_step"] / 1e3)) < 2e-2 * d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["batch_per_gpu"] == 4 and d["config"]["global_batch"] == 4 and "sample" in d["config"]   # its TRUE batch
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    from oracle import ref_runner
+    assert cb["kind"] == ("reference" if ref_runner.available() else "port")
+    assert cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

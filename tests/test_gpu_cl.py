@@ -196,7 +196,12 @@ def test_ewc_backward_leaves_frozen_parameters_and_published_gradients_alone():
     assert named[frozen].grad is None and float(arena.grad_view(frozen).abs().max()) == 0.0
     assert torch.allclose(named[live].grad, torch.full_like(named[live], 2 * 10.0 * 0.5 * -0.01), rtol=1e-3)
     # (a) adapters: the encoder publishes adapter gradients, then the EWC node runs with an empty trainable list
-    learner2 = _build(TINY, ALL_TASKS, sd, adapters={"vqa": ("houlsby", 4)})
+    from climb_b200.modeling import AdapterSpec
+    learner2 = _build(TINY, ALL_TASKS, sd)
+    spec = AdapterSpec.from_config("houlsby")
+    spec.reduction_factor = 4
+    learner2.add_adapter("vqa", spec)
+    learner2.to(dev)
     learner2.train_adapter("vqa")
     arena2 = learner2.vilt_encoder.vilt._arena
     arena2.sync(dev)

@@ -116,15 +116,15 @@ def _check_grads(g, learner, key, names=None, floor=0.02):
     grads = {n: p.grad for n, p in learner.named_parameters()}
     gscale = max(float(g[k]) for k in g.files if k.startswith("gnorm/"))
     report = []
-    for key in g.files:
-        if not key.startswith("gnorm/"):
+    for gk in g.files:
+        if not gk.startswith("gnorm/"):
             continue
-        name = key[len("gnorm/"):]
+        name = gk[len("gnorm/"):]
         if names is not None and name not in names:
             continue
         assert grads.get(name) is not None, f"no gradient for {name}"
         got = grads[name].detach().float().cpu()
-        ref_norm = float(g[key])
+        ref_norm = float(g[gk])
         if ref_norm < 1e-6 * gscale:
             assert got.norm().item() < 2e-3 * gscale, (name, got.norm().item(), gscale)
             continue
@@ -367,7 +367,7 @@ def test_bench_shape_step_vs_oracle():
     n0 = _lib.climb_launch_count()
     pooled, logits, loss = _step(learner, "vqa", batch, fused_loss=True)
     torch.cuda.synchronize()
-    assert _lib.climb_launch_count() - n0 > 300          # the engine's launch sequence ran (no fallback exists)
+    assert _lib.climb_launch_count() - n0 >= 250         # the engine's launch sequence ran (no fallback exists)
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     ref_p, ref_l = vo.learner_forward(params, BASE, "vqa", batch)
     ref_loss = vo.task_loss("vqa", ref_l, batch["target"])
