@@ -90,6 +90,8 @@ climb_layernorm_bwd_colsum = _sig(
     "climb_layernorm_bwd_colsum",
     [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P])
 climb_cast_f32_bf16 = _sig("climb_cast_f32_bf16", [_P, _P, c_int64, _P])
+climb_split_f32_bf16x2 = _sig("climb_split_f32_bf16x2", [_P, _P, _P, c_int64, _P])
+climb_error_flags = _sig("climb_error_flags", [], ctypes.c_uint32)
 climb_colsum = _sig("climb_colsum", [_P, c_int, c_int64, c_int, c_int, _P, _P])
 climb_bce_logits_loss = _sig(
     "climb_bce_logits_loss", [_P, c_int64, _P, c_int, c_int, c_float, c_float, _P, _P, _P, c_int64, _P])
@@ -107,7 +109,12 @@ climb_adamw_step = _sig(
 class ViltDimsC(Structure):
     _fields_ = [("hidden", c_int), ("layers", c_int), ("heads", c_int), ("ffn", c_int),
                 ("patch", c_int), ("channels", c_int), ("pos_grid", c_int), ("n_modality", c_int),
-                ("ln_eps", c_float)]
+                ("ln_eps", c_float), ("vocab_size", c_int), ("type_vocab_size", c_int), ("precision", c_int),
+                ("hidden_dropout", c_float), ("attn_dropout", c_float)]
+
+
+PREC_BF16, PREC_BF16X3 = 0, 1
+ERR_TOKEN_ID, ERR_TOKEN_TYPE, ERR_MODALITY = 1, 2, 4
 
 
 LAYER_FIELDS = ["qkv_w", "qkv_b", "o_w", "o_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
@@ -128,14 +135,15 @@ PARAM_FIELDS = ["cls_token", "pos_emb", "word_emb", "text_pos_emb", "text_type_e
 class ViltParamsC(Structure):
     _fields_ = [(n, c_int64) for n in PARAM_FIELDS] + [
         ("layer", POINTER(ViltLayerC)), ("adapter_r", c_int), ("adapter_act", c_int),
-        ("embed_flags", c_int32), ("tail_flags", c_int32)]
+        ("embed_flags", c_int32), ("tail_flags", c_int32), ("shadow_lo", c_void_p)]
 
 
 class ViltBatchC(Structure):
     _fields_ = [("B", c_int), ("T", c_int), ("H", c_int), ("W", c_int),
                 ("input_ids", c_void_p), ("inputs_embeds", c_void_p), ("token_type_ids", c_void_p),
                 ("attention_mask", c_void_p), ("pixel_values", c_void_p), ("image_type_idx", c_void_p),
-                ("image_type_idx_scalar", c_int), ("patch_geom", c_void_p), ("n_patch_slots", c_int)]
+                ("image_type_idx_scalar", c_int), ("patch_geom", c_void_p), ("n_patch_slots", c_int),
+                ("training", c_int), ("dropout_seed", ctypes.c_uint64)]
 
 
 class AdamWChunkC(Structure):
@@ -323,6 +331,24 @@ def layernorm_bwd(dy, x, gamma, beta, mean, rstd, *, rows=None, ldx=None, dres=N
 def cast_f32_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
     check(climb_cast_f32_bf16(ptr(src), ptr(dst), src.numel(), stream()))
+
+
+def split_f32_bf16x2(src: torch.Tensor, hi, lo) -> None:
+    """hi = bf16(src), lo = bf16(src - hi): the split operands of the bf16x3 precision mode (either may be None)."""
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    check(climb_split_f32_bf16x2(ptr(src), ptr(hi), ptr(lo), src.numel(), stream()))
+
+
+def raise_device_errors() -> None:
+    """Sticky device-side error flags -> Python exceptions (the reference's nn.Embedding raises IndexError for an
+    out-of-range id; our kernels clamp the id, raise a flag and keep going -- the flag of a kernel becomes visible once it
+    has run, so this reports at the next forward / at an explicit call)."""
+    bits = climb_error_flags()
+    if bits:
+        what = [n for b, n in ((ERR_TOKEN_ID, "input_ids outside the word-embedding table"),
+                               (ERR_TOKEN_TYPE, "token_type_ids outside the token-type table"),
+                               (ERR_MODALITY, "image_token_type_idx outside the modality-type table")) if bits & b]
+        raise IndexError("index out of range in an embedding lookup of an earlier climb_b200 forward: " + "; ".join(what))
 
 
 def colsum(src: torch.Tensor, out: torch.Tensor, rows=None, cols=None) -> None:

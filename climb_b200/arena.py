@@ -43,6 +43,8 @@ class ParamArena:
         self.with_grad = with_grad          # False: forward-only parameters (ViLT-BERT's frozen BERT), no gradient arena
         self.theta: Optional[torch.Tensor] = None
         self.shadow: Optional[torch.Tensor] = None
+        self.shadow_lo: Optional[torch.Tensor] = None     # bf16(theta - shadow): second half of the bf16x3 split operands
+        self._lo_version = None
         self.grad: Optional[torch.Tensor] = None
         self.offsets: Dict[str, int] = {}
         self.numels: Dict[str, int] = {}
@@ -105,6 +107,7 @@ class ParamArena:
                 p.data = view
         self.theta, self.offsets, self.numels, self.size = theta, offsets, numels, size
         self.shadow = torch.zeros(size, dtype=torch.bfloat16, device=device) if self.with_shadow else None
+        self.shadow_lo, self._lo_version = None, None
         self.grad = torch.zeros(size, dtype=torch.float32, device=device) if self.with_grad else None
         self._grad_views = {}
         for name, p in (items if self.with_grad else []):
@@ -130,6 +133,22 @@ class ParamArena:
             _lib.cast_f32_bf16(self.theta, self.shadow)
             self._shadow_version = v
             self.shadow_dirty = False
+
+    def refresh_shadow_lo(self) -> torch.Tensor:
+        """bf16x3 precision mode: (shadow, shadow_lo) = split of theta. Call after refresh_shadow(); recomputed whenever theta
+        may have changed since the last split (our own AdamW kernel refreshes only the hi half)."""
+        v = (self._version_sum, self.theta.data_ptr(), self._lo_epoch)
+        if self.shadow_lo is None or self._lo_version != v:
+            if self.shadow_lo is None:
+                self.shadow_lo = torch.empty_like(self.shadow)
+            _lib.split_f32_bf16x2(self.theta, self.shadow, self.shadow_lo)
+            self._lo_version = v
+        return self.shadow_lo
+
+    _lo_epoch = 0       # bumped by whoever edits theta behind torch's version counters (the AdamW kernel)
+
+    def touch(self) -> None:
+        self._lo_epoch += 1
 
     def grad_view(self, name: str) -> torch.Tensor:
         return self._grad_views[name]

@@ -21,6 +21,29 @@ void set_last_error(const char* fmt, ...) {
 
 unsigned long long g_launch_count = 0;
 
+// ---- sticky device-side error flags (climb_error_flags) -------------------------------------------
+static unsigned int* g_err_host = nullptr;
+static unsigned int* g_err_dev = nullptr;
+unsigned int* device_error_word() {
+    if (g_err_host == nullptr) {
+        unsigned int* h = nullptr;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        *h = 0u;
+        unsigned int* d = nullptr;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFreeHost(h);
+            return nullptr;
+        }
+        g_err_host = h;
+        g_err_dev = d;
+    }
+    return g_err_dev;
+}
+
 // ---- profiler ----------------------------------------------------------------------------------
 namespace {
 struct ProfRecord { cudaEvent_t a, b; int category; double work; };
@@ -74,6 +97,10 @@ const char* climb_last_error(void) { return g_last_error; }
 int climb_version(void) { return 100; }
 uint64_t climb_launch_count(void) { return g_launch_count; }
 int climb_gemm_pair_mode(int mode) { return climb::gemm_pair_mode(mode); }
+uint32_t climb_error_flags(void) {
+    if (g_err_host == nullptr) return 0u;
+    return __atomic_exchange_n(g_err_host, 0u, __ATOMIC_ACQ_REL);
+}
 
 int climb_profile_begin(void) {
     for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -140,6 +167,9 @@ int climb_layernorm_bwd_colsum(const float* dy_f32, const void* dy_bf16, const f
 
 int climb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
     return cast_f32_bf16(src, dst_bf16, n, S(stream));
+}
+int climb_split_f32_bf16x2(const float* src, void* hi_bf16, void* lo_bf16, int64_t n, void* stream) {
+    return split_f32_bf16x2(src, hi_bf16, lo_bf16, n, S(stream));
 }
 int climb_colsum(const void* src, int dtype, int64_t ld, int rows, int cols, float* out, void* stream) {
     return colsum(src, dtype, ld, rows, cols, out, S(stream));

@@ -9,21 +9,32 @@
 // float4 / uint4 accesses, one pass over the data.
 #include "common.cuh"
 #include "climb_b200.h"
+#include "internal.h"
 
 namespace climb {
 namespace {
 
+// ids outside their table are clamped to row 0 and reported through the sticky error word (climb_error_flags): nn.Embedding
+// raises IndexError in the reference; a silent out-of-bounds read (or, in the backward, a corrupting write) must not happen
+__device__ __forceinline__ long long checked_index(long long v, int n, unsigned int* err, unsigned int bit) {
+    if (n > 0 && (v < 0 || v >= n)) {
+        if (err != nullptr) atomicOr_system(err, bit);
+        return 0;
+    }
+    return v;
+}
+
 __global__ void text_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ inputs_embeds,
                                    const long long* __restrict__ tt, const float* __restrict__ word,
                                    const float* __restrict__ type_emb, const float* __restrict__ pos,
-                                   float* __restrict__ e, int rows, int T, int d4) {
+                                   float* __restrict__ e, int rows, int T, int d4, int vocab, int n_types, unsigned int* err) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(rows) * d4) return;
     const int r = static_cast<int>(i / d4), c = static_cast<int>(i - static_cast<long long>(r) * d4);
     const int t = r % T;
     const float4 w = inputs_embeds ? reinterpret_cast<const float4*>(inputs_embeds)[i]
-                                   : reinterpret_cast<const float4*>(word)[ids[r] * d4 + c];
-    const long long ty = tt ? tt[r] : 0;
+                                   : reinterpret_cast<const float4*>(word)[checked_index(ids[r], vocab, err, CLIMB_ERR_TOKEN_ID) * d4 + c];
+    const long long ty = tt ? checked_index(tt[r], n_types, err, CLIMB_ERR_TOKEN_TYPE) : 0;
     const float4 s = reinterpret_cast<const float4*>(type_emb)[ty * d4 + c];
     const float4 p = reinterpret_cast<const float4*>(pos)[static_cast<long long>(t) * d4 + c];
     reinterpret_cast<float4*>(e)[i] = make_float4(w.x + s.x + p.x, w.y + s.y + p.y, w.z + s.z + p.z, w.w + s.w + p.w);
@@ -83,7 +94,7 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
                                       const float* __restrict__ table, const float* __restrict__ cls,
                                       const float* __restrict__ pos_emb, const float* __restrict__ mod,
                                       const int* __restrict__ type_idx, int type_idx_scalar,
-                                      float* __restrict__ x, int B, int T, int Np, int d4) {
+                                      float* __restrict__ x, int B, int T, int Np, int d4, int n_mod, unsigned int* err) {
     const int L = T + 1 + Np;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * L * d4) return;
@@ -95,7 +106,7 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
         v = reinterpret_cast<const float4*>(text_ln)[(static_cast<long long>(b) * T + l) * d4 + c];
         m = reinterpret_cast<const float4*>(mod)[c];
     } else {
-        const int idx = type_idx ? type_idx[b] : type_idx_scalar;
+        const int idx = static_cast<int>(checked_index(type_idx ? type_idx[b] : type_idx_scalar, n_mod, err, CLIMB_ERR_MODALITY));
         m = reinterpret_cast<const float4*>(mod)[static_cast<long long>(idx) * d4 + c];
         if (l == T) {
             const float4 a = reinterpret_cast<const float4*>(cls)[c];
@@ -143,7 +154,7 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
                                              const int* __restrict__ geom, const float* __restrict__ cls,
                                              const float* __restrict__ pos_emb, const float* __restrict__ mod,
                                              const int* __restrict__ type_idx, int type_idx_scalar,
-                                             float* __restrict__ x, int B, int T, int Np, int G, int d4) {
+                                             float* __restrict__ x, int B, int T, int Np, int G, int d4, int n_mod, unsigned int* err) {
     const int L = T + 1 + Np;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * L * d4) return;
@@ -155,7 +166,7 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
         v = reinterpret_cast<const float4*>(text_ln)[(static_cast<long long>(b) * T + l) * d4 + c];
         m = reinterpret_cast<const float4*>(mod)[c];
     } else {
-        const int idx = type_idx ? type_idx[b] : type_idx_scalar;
+        const int idx = static_cast<int>(checked_index(type_idx ? type_idx[b] : type_idx_scalar, n_mod, err, CLIMB_ERR_MODALITY));
         m = reinterpret_cast<const float4*>(mod)[static_cast<long long>(idx) * d4 + c];
         if (l == T) {
             const float4 a = reinterpret_cast<const float4*>(cls)[c];
@@ -303,13 +314,15 @@ __global__ void embed_finalize_bwd_kernel(const float* __restrict__ S, float* __
 // de [B*T, d] -> word / segment / position embedding gradients (dense tables, atomics on collisions)
 __global__ void text_scatter_bwd_kernel(const float* __restrict__ de, const long long* __restrict__ ids,
                                         const long long* __restrict__ tt, float* __restrict__ d_word,
-                                        float* __restrict__ d_type, float* __restrict__ d_pos, int rows, int T, int d) {
+                                        float* __restrict__ d_type, float* __restrict__ d_pos, int rows, int T, int d,
+                                        int vocab, int n_types) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(rows) * d) return;
     const int r = static_cast<int>(i / d), c = static_cast<int>(i - static_cast<long long>(r) * d);
     const float g = de[i];
-    if (d_word && ids) atomicAdd(d_word + ids[r] * d + c, g);
-    if (d_type) atomicAdd(d_type + (tt ? tt[r] : 0) * d + c, g);
+    // (the forward already reported bad ids; here they only must not write outside the tables)
+    if (d_word && ids) atomicAdd(d_word + checked_index(ids[r], vocab, nullptr, 0u) * d + c, g);
+    if (d_type) atomicAdd(d_type + (tt ? checked_index(tt[r], n_types, nullptr, 0u) : 0) * d + c, g);
     if (d_pos) atomicAdd(d_pos + static_cast<long long>(r % T) * d + c, g);
 }
 
@@ -318,12 +331,13 @@ inline unsigned blocks_for(long long n, int threads) { return static_cast<unsign
 }  // namespace
 
 int text_gather(const long long* ids, const float* inputs_embeds, const long long* tt, const float* word,
-                const float* type_emb, const float* pos, float* e, int rows, int T, int d, cudaStream_t stream) {
+                const float* type_emb, const float* pos, float* e, int rows, int T, int d, cudaStream_t stream, int vocab,
+                int n_types) {
     CLIMB_REQUIRE((ids != nullptr) != (inputs_embeds != nullptr), "text_gather: exactly one of input_ids / inputs_embeds");
     CLIMB_REQUIRE(type_emb && pos && e && rows > 0 && d % 4 == 0, "text_gather: bad arguments");
     CLIMB_REQUIRE(ids == nullptr || word != nullptr, "text_gather: word table missing");
     text_gather_kernel<<<blocks_for(static_cast<long long>(rows) * (d / 4), 256), 256, 0, stream>>>(
-        ids, inputs_embeds, tt, word, type_emb, pos, e, rows, T, d / 4);
+        ids, inputs_embeds, tt, word, type_emb, pos, e, rows, T, d / 4, vocab, n_types, device_error_word());
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -349,11 +363,12 @@ int pos_interp(const float* pos_emb, float* table, int hp, int wp, int G, int d,
 
 int embed_assemble(const float* text_ln, const float* patch, const float* table, const float* cls,
                    const float* pos_emb, const float* mod, const int* type_idx, int type_idx_scalar, float* x,
-                   int B, int T, int Np, int d, cudaStream_t stream) {
+                   int B, int T, int Np, int d, cudaStream_t stream, int n_mod) {
     CLIMB_REQUIRE(text_ln && patch && table && cls && pos_emb && mod && x && d % 4 == 0, "embed_assemble: bad arguments");
     const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
     embed_assemble_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, table, cls, pos_emb, mod,
-                                                                     type_idx, type_idx_scalar, x, B, T, Np, d / 4);
+                                                                     type_idx, type_idx_scalar, x, B, T, Np, d / 4, n_mod,
+                                                                     device_error_word());
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -378,11 +393,11 @@ int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int
 
 int embed_assemble_ragged(const float* text_ln, const float* patch, const int* geom, const float* cls, const float* pos_emb,
                           const float* mod, const int* type_idx, int type_idx_scalar, float* x, int B, int T, int Np, int G,
-                          int d, cudaStream_t stream) {
+                          int d, cudaStream_t stream, int n_mod) {
     CLIMB_REQUIRE(text_ln && patch && geom && cls && pos_emb && mod && x && d % 4 == 0, "embed_assemble_ragged: bad arguments");
     const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
     embed_assemble_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, geom, cls, pos_emb, mod, type_idx,
-                                                                            type_idx_scalar, x, B, T, Np, G, d / 4);
+                                                                            type_idx_scalar, x, B, T, Np, G, d / 4, n_mod, device_error_word());
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -415,10 +430,10 @@ int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, 
 }
 
 int text_scatter_bwd(const float* de, const long long* ids, const long long* tt, float* d_word, float* d_type,
-                     float* d_pos, int rows, int T, int d, cudaStream_t stream) {
+                     float* d_pos, int rows, int T, int d, cudaStream_t stream, int vocab, int n_types) {
     CLIMB_REQUIRE(de && rows > 0, "text_scatter_bwd: bad arguments");
     text_scatter_bwd_kernel<<<blocks_for(static_cast<long long>(rows) * d, 256), 256, 0, stream>>>(
-        de, ids, tt, d_word, d_type, d_pos, rows, T, d);
+        de, ids, tt, d_word, d_type, d_pos, rows, T, d, vocab, n_types);
     CLIMB_LAUNCH_OK();
     return 0;
 }

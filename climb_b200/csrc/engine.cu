@@ -219,6 +219,7 @@ inline float* G(float* grad, long long off) { return off >= 0 ? grad + off : nul
 
 long long vilt_forward_workspace_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
                                        const climb_vilt_batch* batch, int save) {
+    if (dims && dims->precision == CLIMB_PREC_BF16X3) return vilt_forward_workspace_bytes_precise(dims, params, batch, save);
     Plan P;
     if (fill_plan(P, dims, params, batch, nullptr, save)) return -1;
     return P.bytes;
@@ -264,6 +265,7 @@ static void fill_scratch(BwdScratch& S, const Plan& P, void* base) {
 
 long long vilt_backward_scratch_bytes(const climb_vilt_dims* dims, const climb_vilt_params* params,
                                       const climb_vilt_batch* batch) {
+    if (dims && dims->precision == CLIMB_PREC_BF16X3) return vilt_backward_scratch_bytes_precise(dims, params, batch);
     Plan P;
     if (fill_plan(P, dims, params, batch, nullptr, 1)) return -1;
     BwdScratch S;
@@ -274,6 +276,8 @@ long long vilt_backward_scratch_bytes(const climb_vilt_dims* dims, const climb_v
 int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const climb_vilt_batch* bt,
                  const float* theta, const void* shadow, void* workspace, long long workspace_bytes, int save,
                  float* pooled_out, cudaStream_t s) {
+    if (dm && dm->precision == CLIMB_PREC_BF16X3)
+        return vilt_forward_precise(dm, pr, bt, theta, shadow, workspace, workspace_bytes, save, pooled_out, s);
     Plan P;
     TRY(fill_plan(P, dm, pr, bt, workspace, save));
     CLIMB_REQUIRE(theta && shadow && workspace && pooled_out, "vilt_forward: null buffer");
@@ -293,7 +297,8 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
     else CLIMB_CUDA_OK(cudaMemsetAsync(P.key_bias, 0, sizeof(float) * P.B * P.L, s));
     TRY(text_gather(reinterpret_cast<const long long*>(bt->input_ids), bt->inputs_embeds,
                     reinterpret_cast<const long long*>(bt->token_type_ids), F(theta, pr->word_emb),
-                    F(theta, pr->text_type_emb), F(theta, pr->text_pos_emb), P.text_e, BT, P.T, d, s));
+                    F(theta, pr->text_type_emb), F(theta, pr->text_pos_emb), P.text_e, BT, P.T, d, s, dm->vocab_size,
+                    dm->type_vocab_size));
     TRY(layernorm_fwd(P.text_e, d, F(theta, pr->text_ln_w), F(theta, pr->text_ln_b), dm->ln_eps, nullptr, P.text_ln,
                       P.text_mean, P.text_rstd, BT, d, CLIMB_EPI_NONE, s));
     if (P.geom) TRY(im2col_ragged(bt->pixel_values, P.geom, P.im2col, P.B, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s));
@@ -306,12 +311,12 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
     if (P.geom) {
         TRY(embed_assemble_ragged(P.text_ln, P.patch_out, P.geom, F(theta, pr->cls_token), F(theta, pr->pos_emb),
                                   F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B,
-                                  P.T, P.Np, dm->pos_grid, d, s));
+                                  P.T, P.Np, dm->pos_grid, d, s, dm->n_modality));
     } else {
         TRY(pos_interp(F(theta, pr->pos_emb), P.pos_table, P.hp, P.wp, dm->pos_grid, d, s));
         TRY(embed_assemble(P.text_ln, P.patch_out, P.pos_table, F(theta, pr->cls_token), F(theta, pr->pos_emb),
                            F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B, P.T,
-                           P.Np, d, s));
+                           P.Np, d, s, dm->n_modality));
     }
 
     // ---- encoder layers (modeling_vilt.py:503-525) ----
@@ -383,6 +388,9 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
                   const float* theta, const void* shadow, const void* workspace, long long workspace_bytes,
                   void* scratch, long long scratch_bytes, const float* dpooled, float* grad, int first_layer,
                   int last_layer, int parts, cudaStream_t s) {
+    if (dm && dm->precision == CLIMB_PREC_BF16X3)
+        return vilt_backward_precise(dm, pr, bt, theta, shadow, workspace, workspace_bytes, scratch, scratch_bytes, dpooled, grad,
+                                     first_layer, last_layer, parts, s);
     Plan P;
     TRY(fill_plan(P, dm, pr, bt, const_cast<void*>(workspace), 1));
     CLIMB_REQUIRE(theta && shadow && workspace && scratch && dpooled && grad, "vilt_backward: null buffer");
@@ -516,7 +524,7 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
         TRY(text_scatter_bwd(S.de_text, reinterpret_cast<const long long*>(bt->input_ids),
                              reinterpret_cast<const long long*>(bt->token_type_ids),
                              bt->input_ids ? G(grad, pr->word_emb) : nullptr, G(grad, pr->text_type_emb),
-                             G(grad, pr->text_pos_emb), BT, P.T, d, s));
+                             G(grad, pr->text_pos_emb), BT, P.T, d, s, dm->vocab_size, dm->type_vocab_size));
         TRY(run_wgrad(P.B * P.Np, d, P.Kp, S.dpatch, d, P.im2col, P.Kp, G(grad, pr->patch_w), s));
     }
     return 0;

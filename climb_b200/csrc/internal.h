@@ -5,6 +5,9 @@
 
 namespace climb {
 
+// capi.cu: device pointer of the sticky error word (host-mapped pinned memory), nullptr if it cannot be allocated
+unsigned int* device_error_word();
+
 int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream);
 int gemm_pair_mode(int mode);
 
@@ -47,12 +50,13 @@ int cross_entropy_loss(const float* logits, long long ld, const long long* targe
 
 // embed.cu
 int text_gather(const long long* ids, const float* inputs_embeds, const long long* tt, const float* word,
-                const float* type_emb, const float* pos, float* e, int rows, int T, int d, cudaStream_t stream);
+                const float* type_emb, const float* pos, float* e, int rows, int T, int d, cudaStream_t stream,
+                int vocab = 0, int n_types = 0);      // > 0: ids are range-checked (clamped + climb_error_flags)
 int im2col(const float* px, void* out, int B, int C, int H, int W, int P, cudaStream_t stream);
 int pos_interp(const float* pos_emb, float* table, int hp, int wp, int G, int d, cudaStream_t stream);
 int embed_assemble(const float* text_ln, const float* patch, const float* table, const float* cls,
                    const float* pos_emb, const float* mod, const int* type_idx, int type_idx_scalar, float* x,
-                   int B, int T, int Np, int d, cudaStream_t stream);
+                   int B, int T, int Np, int d, cudaStream_t stream, int n_mod = 0);
 int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T, int Np, int d, cudaStream_t stream);
 int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, float* S, float* d_cls,
                      float* d_pos, float* d_mod, float* d_patch_bias, int n_mod, int B, int T, int hp, int wp,
@@ -61,10 +65,10 @@ int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, 
 int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int H, int W, int P, int Np, cudaStream_t stream);
 int embed_assemble_ragged(const float* text_ln, const float* patch, const int* geom, const float* cls, const float* pos_emb,
                           const float* mod, const int* type_idx, int type_idx_scalar, float* x, int B, int T, int Np, int G,
-                          int d, cudaStream_t stream);
+                          int d, cudaStream_t stream, int n_mod = 0);
 int key_bias_ragged(const long long* mask, const int* geom, float* out, int B, int T, int L, cudaStream_t stream);
 int text_scatter_bwd(const float* de, const long long* ids, const long long* tt, float* d_word, float* d_type,
-                     float* d_pos, int rows, int T, int d, cudaStream_t stream);
+                     float* d_pos, int rows, int T, int d, cudaStream_t stream, int vocab = 0, int n_types = 0);
 
 // optim.cu
 int ewc_penalty(const float* theta, const float* theta_star, const float* fisher, long long n, float lambda,
@@ -100,5 +104,19 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
                   const float* theta, const void* shadow, const void* workspace, long long workspace_bytes,
                   void* scratch, long long scratch_bytes, const float* dpooled, float* grad, int first_layer,
                   int last_layer, int parts, cudaStream_t s);
+
+// precise.cu (CLIMB_PREC_BF16X3: split-operand contractions, fp32 activations and attention)
+long long vilt_forward_workspace_bytes_precise(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                                               const climb_vilt_batch* batch, int save);
+long long vilt_backward_scratch_bytes_precise(const climb_vilt_dims* dims, const climb_vilt_params* params,
+                                              const climb_vilt_batch* batch);
+int vilt_forward_precise(const climb_vilt_dims* dm, const climb_vilt_params* pr, const climb_vilt_batch* bt, const float* theta,
+                         const void* shadow, void* workspace, long long workspace_bytes, int save, float* pooled_out,
+                         cudaStream_t s);
+int vilt_backward_precise(const climb_vilt_dims* dm, const climb_vilt_params* pr, const climb_vilt_batch* bt, const float* theta,
+                          const void* shadow, const void* workspace, long long workspace_bytes, void* scratch,
+                          long long scratch_bytes, const float* dpooled, float* grad, int first_layer, int last_layer, int parts,
+                          cudaStream_t s);
+int split_f32_bf16x2(const float* src, void* hi, void* lo, long long n, cudaStream_t s);
 
 }  // namespace climb

@@ -237,9 +237,8 @@ class B200ViltModel(nn.Module):
         if c.hidden_size != c.num_attention_heads * 64 or c.hidden_size % 128:
             raise ValueError("climb_b200 kernels need head_dim 64 and hidden_size % 128 == 0 "
                              f"(got hidden={c.hidden_size}, heads={c.num_attention_heads})")
-        if c.hidden_dropout_prob != 0.0 or c.attention_probs_dropout_prob != 0.0:
-            raise NotImplementedError("dropout > 0 inside the encoder is not implemented yet (ViltConfig and every "
-                                      "CLiMB script use 0.0: configuration_vilt.py:112-113)")
+        if not (0.0 <= c.hidden_dropout_prob < 1.0 and 0.0 <= c.attention_probs_dropout_prob < 1.0):
+            raise ValueError("dropout probabilities must lie in [0, 1)")
         if c.hidden_act != "gelu":
             raise NotImplementedError("only hidden_act='gelu' (erf) is implemented")
         self.embeddings = _Embeddings(c)
@@ -368,6 +367,7 @@ class B200ViltModel(nn.Module):
             raise _lib.ClimbError("climb_b200 runs on CUDA tensors only (no CPU fallback)")
         arena = self._arena
         arena.sync(dev)
+        _lib.raise_device_errors()          # an out-of-range id of an EARLIER forward (clamped on the device) surfaces here
         B, C, H, W = pixel_values.shape
         T = (input_ids if input_ids is not None else inputs_embeds).shape[1]
         if C != c.num_channels or H % c.patch_size or W % c.patch_size:
@@ -420,6 +420,11 @@ class B200ViltModel(nn.Module):
         if geom is not None:
             keep.append(geom)
         b.patch_geom, b.n_patch_slots = _lib.ptr(geom), n_slots
+        b.training = int(self.training)
+        if self.training and (c.hidden_dropout_prob > 0.0 or c.attention_probs_dropout_prob > 0.0):
+            # Philox key of this forward's dropout masks, drawn from torch's CPU generator (seeded by the driver's set_seed,
+            # train_upstream_continual_learning.py:103); the backward regenerates the masks from the same key
+            b.dropout_seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
         call.batch = b
         call.trainable = st["trainable"]
         if emb is not None:      # with inputs_embeds the word table is not on the path (grad stays None)
@@ -461,7 +466,10 @@ class B200ViltModel(nn.Module):
         c = self.config
         items = arena.named_items()
         active = self._active_adapter
-        key = (id(arena.theta), active, tuple(p.requires_grad for _, p in items))
+        from .. import ops
+        precision = ops.get_precision()
+        key = (id(arena.theta), active, tuple(p.requires_grad for _, p in items), precision, c.hidden_dropout_prob,
+               c.attention_probs_dropout_prob)
         cached = getattr(self, "_static_cache", None)
         if cached is not None and cached["key"] == key:
             return cached
@@ -474,6 +482,10 @@ class B200ViltModel(nn.Module):
         d.patch, d.channels = c.patch_size, c.num_channels
         d.pos_grid = int(round(math.sqrt(self.embeddings.position_embeddings.shape[1] - 1)))
         d.n_modality, d.ln_eps = self.embeddings.token_type_embeddings.weight.shape[0], c.layer_norm_eps
+        d.vocab_size = self.embeddings.text_embeddings.word_embeddings.weight.shape[0]
+        d.type_vocab_size = self.embeddings.text_embeddings.token_type_embeddings.weight.shape[0]
+        d.precision = _lib.PREC_BF16X3 if precision == "bf16x3" else _lib.PREC_BF16
+        d.hidden_dropout, d.attn_dropout = float(c.hidden_dropout_prob), float(c.attention_probs_dropout_prob)
         layer_flags = [0] * d.layers
         for n in named:
             if n.startswith("encoder.layer.") and rg[n]:
@@ -530,6 +542,8 @@ class B200ViltModel(nn.Module):
     def _run_forward(self, call: _Call, save: bool) -> torch.Tensor:
         arena = self._arena
         arena.refresh_shadow()
+        if call.dims.precision == _lib.PREC_BF16X3:
+            call.params.shadow_lo = _lib.ptr(arena.refresh_shadow_lo())
         nbytes = _lib.climb_vilt_forward_workspace_bytes(ctypes.byref(call.dims), ctypes.byref(call.params),
                                                          ctypes.byref(call.batch), int(save))
         if nbytes < 0:
@@ -549,6 +563,8 @@ class B200ViltModel(nn.Module):
         arena = self._arena
         if call.arena_theta is not arena.theta:
             raise _lib.ClimbError("parameters were re-allocated between forward and backward")
+        if call.dims.precision == _lib.PREC_BF16X3:
+            call.params.shadow_lo = _lib.ptr(arena.refresh_shadow_lo())
         nbytes = _lib.climb_vilt_backward_scratch_bytes(ctypes.byref(call.dims), ctypes.byref(call.params),
                                                         ctypes.byref(call.batch))
         if self._scratch is None or self._scratch.numel() < nbytes or self._scratch.device != arena.theta.device:

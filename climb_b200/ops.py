@@ -14,6 +14,42 @@ import torch
 from . import _lib
 
 
+# ---- arithmetic mode (include/climb_b200.h: CLIMB_PREC_*) ---------------------------------------------------------------
+# "bf16"   : bf16 tensor-core operands, fp32 accumulation / residual stream / statistics: the throughput mode (default).
+# "bf16x3" : the parity gate -- every contraction as three accumulating tcgen05 launches over split operands
+#            (x = hi + lo, both bf16), fp32 activations in between, fp32 attention: logits within 1e-3 of the fp32
+#            reference (the north star's tolerance), about 5x slower. Process-wide switch, read at every forward.
+_PRECISION = "bf16"
+
+
+def set_precision(mode: str) -> str:
+    """Select the arithmetic of every climb_b200 forward / backward issued from now on; returns the previous mode."""
+    global _PRECISION
+    if mode not in ("bf16", "bf16x3"):
+        raise ValueError("precision must be 'bf16' (throughput) or 'bf16x3' (parity gate)")
+    old, _PRECISION = _PRECISION, mode
+    return old
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+class precision:
+    """with ops.precision('bf16x3'): ..."""
+
+    def __init__(self, mode: str):
+        self.mode = mode
+
+    def __enter__(self):
+        self.old = set_precision(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_precision(self.old)
+        return False
+
+
 def _bf16_padded(x: torch.Tensor, mult: int = 8) -> torch.Tensor:
     """bf16 copy of a 2-D fp32 tensor with the row stride padded to a multiple of 8 elements
     (TMA needs 16-byte row pitch); returns a [rows, cols] view of the padded buffer."""
@@ -71,7 +107,71 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+def _split_padded(x: torch.Tensor, mult: int = 8):
+    """(hi, lo) bf16 views [rows, cols] of a 2-D fp32 tensor, row stride padded to a multiple of 8 elements."""
+    rows, cols = x.shape
+    ld = (cols + mult - 1) // mult * mult
+    src = x.detach().float()
+    if ld != cols:
+        padded = torch.zeros(rows, ld, dtype=torch.float32, device=x.device)
+        padded[:, :cols].copy_(src)
+        src = padded
+    src = src.contiguous()
+    hi = torch.empty(rows, ld, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(rows, ld, dtype=torch.bfloat16, device=x.device)
+    _lib.split_f32_bf16x2(src, hi, lo)
+    return hi[:, :cols], lo[:, :cols]
+
+
+def _gemm3(a, b, out, **kw):
+    """out += Ahi Bhi^T + Alo Bhi^T + Ahi Blo^T: the split-operand contraction of the bf16x3 mode."""
+    (a_hi, a_lo), (b_hi, b_lo) = a, b
+    for x, y in ((a_hi, b_hi), (a_lo, b_hi), (a_hi, b_lo)):
+        _lib.gemm(x, y, out, accumulate=True, **kw)
+    return out
+
+
+class _Linear3Fn(torch.autograd.Function):
+    """_LinearFn in the bf16x3 precision mode (task heads, src/modeling/vilt.py:179-203)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        xs, ws = _split_padded(x2), _split_padded(weight)
+        N = weight.shape[0]
+        out = torch.zeros(x2.shape[0], N, dtype=torch.float32, device=x.device)
+        if bias is not None:
+            out += bias.detach()
+        _gemm3(xs, ws, out)
+        ctx.save_for_backward(*xs, *ws)
+        ctx.has_bias, ctx.lead = bias is not None, lead
+        return out.view(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_hi, x_lo, w_hi, w_lo = ctx.saved_tensors
+        N, K = w_hi.shape
+        dy2 = dy.reshape(-1, N).float().contiguous()
+        dys = _split_padded(dy2)
+        M = dy2.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.zeros(M, K, dtype=torch.float32, device=dy.device)
+            _gemm3(dys, (w_hi, w_lo), dx, b_mn_major=True, M=M, N=K, K=N)
+            dx = dx.view(*ctx.lead, K)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(N, K, dtype=torch.float32, device=dy.device)
+            _gemm3(dys, (x_hi, x_lo), dw, a_mn_major=True, b_mn_major=True, M=N, N=K, K=M)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(N, dtype=torch.float32, device=dy.device)
+            _lib.colsum(dy2, db)
+        return dx, dw, db
+
+
 def linear(x, weight, bias=None):
+    if _PRECISION == "bf16x3":
+        return _Linear3Fn.apply(x, weight, bias)
     return _LinearFn.apply(x, weight, bias)
 
 

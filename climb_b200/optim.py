@@ -118,6 +118,7 @@ class ArenaAdamW(torch.optim.Optimizer):
                                              n_groups, beta1, beta2, eps, st["step"], stream))
             if not coherent:
                 a.shadow_dirty = True
+            a.touch()           # theta changed behind torch's version counters: the bf16x3 lo half must be re-split
         for p, gi in loose:
             if not (p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32 and p.is_cuda):
                 raise _lib.ClimbError("ArenaAdamW handles contiguous fp32 CUDA parameters")

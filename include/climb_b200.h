@@ -147,6 +147,16 @@ int climb_layernorm_bwd_colsum(const float* dy_f32, const void* dy_bf16, const f
  * ------------------------------------------------------------------------------------------- */
 /* bf16 shadow of the fp32 master parameters (tensor-core operands); n elements, 16-byte aligned */
 int climb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* split operands of CLIMB_PREC_BF16X3: hi = bf16(x), lo = bf16(x - float(hi)); either output may be NULL */
+int climb_split_f32_bf16x2(const float* src, void* hi_bf16, void* lo_bf16, int64_t n, void* stream);
+
+/* Sticky device-side error flags (kernels clamp a bad index instead of faulting and raise a bit here; the word lives in
+ * host-mapped pinned memory, so reading it needs no synchronisation -- a kernel's bit becomes visible once that kernel has
+ * run). Returns the bits raised since the last call and clears them. */
+#define CLIMB_ERR_TOKEN_ID 1        /* input_ids outside [0, vocab_size)              (nn.Embedding: IndexError) */
+#define CLIMB_ERR_TOKEN_TYPE 2      /* token_type_ids outside [0, type_vocab_size) */
+#define CLIMB_ERR_MODALITY 4        /* image_token_type_idx outside the modality table */
+uint32_t climb_error_flags(void);
 /* out[c] += sum_r src[r*ld + c]  (bias gradients); dtype = CLIMB_BF16 / CLIMB_F32 */
 int climb_colsum(const void* src, int dtype, int64_t ld, int rows, int cols, float* out, void* stream);
 
@@ -208,7 +218,22 @@ typedef struct {
     int patch, channels, pos_grid;      /* pos_grid = image_size / patch_size of the position table */
     int n_modality;                     /* rows of token_type_embeddings (2, or 3 with NLVR2) */
     float ln_eps;
+    int vocab_size, type_vocab_size;    /* rows of the word / text token-type tables: ids are range-checked on the device
+                                           (nn.Embedding raises IndexError; here: clamped + climb_error_flags()); 0 = unchecked */
+    int precision;                      /* CLIMB_PREC_BF16 (throughput mode) or CLIMB_PREC_BF16X3 (parity gate, below) */
+    float hidden_dropout, attn_dropout; /* ViltConfig.hidden_dropout_prob / attention_probs_dropout_prob (modeling_vilt.py:303,
+                                           374,410,482), applied only when climb_vilt_batch.training != 0; defaults 0.0 */
 } climb_vilt_dims;
+
+/* Arithmetic of the engine.
+ *   CLIMB_PREC_BF16   : bf16 tensor-core operands, fp32 accumulation / residual stream / statistics. The throughput mode;
+ *                       2e-3 .. 6e-3 relative error on pooled / logits against the fp32 reference.
+ *   CLIMB_PREC_BF16X3 : the parity gate of the north star ("logits within 1e-3 rel"): every contraction runs as three
+ *                       accumulating tcgen05 launches over split operands  x = hi + lo (bf16 each):  A.W ~ Ahi.Whi + Alo.Whi
+ *                       + Ahi.Wlo  (error ~2^-16 per product instead of 2^-8), activations stay fp32 between the
+ *                       contractions and attention runs in an fp32 kernel. ~5x slower; same entry points, same gradients. */
+#define CLIMB_PREC_BF16 0
+#define CLIMB_PREC_BF16X3 1
 
 typedef struct {
     int64_t qkv_w, qkv_b, o_w, o_b, fc1_w, fc1_b, fc2_w, fc2_b;
@@ -230,6 +255,7 @@ typedef struct {
     int adapter_act;                    /* CLIMB_EPI_SWISH (houlsby) or CLIMB_EPI_RELU (pfeiffer) */
     int32_t embed_flags;                /* CLIMB_TRAIN_BASE if the embeddings need gradients */
     int32_t tail_flags;                 /* CLIMB_TRAIN_BASE if final LayerNorm + pooler need gradients */
+    const void* shadow_lo;              /* CLIMB_PREC_BF16X3 only: bf16(theta - float(shadow)), same offsets (climb_split_f32_bf16x2) */
 } climb_vilt_params;
 
 typedef struct {
@@ -248,6 +274,8 @@ typedef struct {
      * NULL / 0 = fixed resolution: every image fills the whole (H / patch) x (W / patch) grid. */
     const int32_t* patch_geom;
     int n_patch_slots;
+    int training;                       /* != 0: dims.hidden_dropout / attn_dropout are live (nn.Module.train()) */
+    uint64_t dropout_seed;              /* Philox key of this forward; the backward regenerates the masks from it */
 } climb_vilt_batch;
 
 /* bytes of the activation workspace a forward needs (save_for_backward = 1 keeps every layer's

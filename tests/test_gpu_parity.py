@@ -386,3 +386,25 @@ def test_bench_shape_step_vs_oracle():
     worst.sort(reverse=True)
     print("bench-shape worst gradient errors:", worst[:5])
     gate("bench_shape_b64/grad", worst[0][0], TOL_GRAD)
+
+
+def test_out_of_range_ids_are_reported_not_read_out_of_bounds():
+    """nn.Embedding raises IndexError for an id outside its table (the reference). The kernels clamp such an id, raise a
+    sticky device flag, and the next call into the encoder turns it into an IndexError -- nothing is read or (in the
+    backward) written outside the tables."""
+    from climb_b200 import _lib
+    torch.cuda.synchronize()
+    _lib.climb_error_flags()                      # clear anything an earlier test left
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=5)
+    learner = _build(TINY, ALL_TASKS, sd)
+    batch = vo.synth_batch("snli-ve", 3, TINY, T=TINY_T, image_hw=TINY_HW, seed=6)
+    bad = {k: v.clone() for k, v in batch.items()}
+    bad["input_ids"][1, 2] = TINY.vocab_size + 7
+    bad["token_type_ids"][0, 1] = 5
+    _step(learner, "snli-ve", bad)                # runs to completion, gradients included
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        _step(learner, "snli-ve", batch)
+    _step(learner, "snli-ve", batch)              # the flag was consumed: clean inputs run again
+    torch.cuda.synchronize()
+    assert _lib.climb_error_flags() == 0
