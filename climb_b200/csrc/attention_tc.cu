@@ -683,6 +683,668 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, persistent, probabilities in TENSOR MEMORY (round 2: the encoder's hot call)
+//
+// Same persistent structure as attn_tc_fwd2_kernel (one CTA per SM, both 128-row query tiles of a (b, h) item in flight,
+// two softmax groups of 8 warps, one MMA-issuing warp per tile), but P never touches shared memory:
+//   S_g = Q_g K^T          128 x 256 x 64 into TMEM columns [256 g, 256 g + 256)
+//   softmax                thread = (row, key HALF): half 0 owns keys 0..127 (S columns 0..127), half 1 keys 128..255. P is
+//                          written back as packed bf16 pairs (tcgen05.st) INTO THE S COLUMNS THE THREAD HAS ALREADY READ:
+//                          half 0 -> columns [0, 64), half 1 -> columns [128, 192) -- always behind its own read pointer, so
+//                          the two threads of a row never touch each other's unread scores
+//   O_g = P_g V            sixteen 128 x 64 x 16 instructions whose A operand is read from TMEM ([a_tmem] form of
+//                          tcgen05.mma: 128 lanes x 8 columns per instruction instead of a 4 KB shared-memory fetch),
+//                          accumulator = columns [192, 256) of the tile's region (S keys 192..255 have been consumed by then)
+// What this removes per tile and item: 64 KB of shared-memory stores of P, their proxy fences, the two-slot ring with its
+// eight barrier round trips, and 4 of the 6 KB every P.V instruction fetched from shared memory.
+// ------------------------------------------------------------------------------------------------
+struct Fwd3Smem {
+    static constexpr int kQ = 0;                    // [256 x 64] bf16: query tile g at g * 16 KB
+    static constexpr int kK = 32 * 1024;            // [256 x 64]
+    static constexpr int kV = 64 * 1024;            // 2 stages x [256 x 64]
+    static constexpr int kStage = 128 * 1024;       // 16 warps x 2 KB output staging
+    static constexpr int kBias = 160 * 1024;        // [2 groups][2 stages][256] floats
+    static constexpr int kXchg = 164 * 1024;        // [2 groups][max, sum][2 halves][128] floats
+    static constexpr int kFlag = 168 * 1024;        // [2 groups][2 stages][8] words: this 32-key chunk has a non-zero mask
+    static constexpr int kBar = 168 * 1024 + 128;
+    static constexpr int kTotal = 168 * 1024 + 256 + 1024;
+};
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (bf16, K-major: lane = row, one 32-bit column = two consecutive k) is
+// read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(kF2Threads, 1)
+attn_tc_fwd3_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias,
+                    __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int n_items, int L, int H, float scale_log2,
+                    long long* tl) {
+#if CLIMB_ATTN_TIMELINE
+#define TL(role, idx) do { if (tl != nullptr && blockIdx.x == 0 && it == 2) tl[(role) * 32 + (idx)] = clock64(); } while (0)
+#else
+#define TL(role, idx) do { } while (0)
+#endif
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Fwd3Smem::kBar);
+    uint64_t* qk_full = bars;            // [1]  tx
+    uint64_t* qk_free = bars + 1;        // [1]  n_groups commits
+    uint64_t* v_full = bars + 2;         // [2]  tx
+    uint64_t* v_free = bars + 4;         // [2]  n_groups commits
+    uint64_t* s_full = bars + 6;         // [2 groups] commit
+    uint64_t* s_free = bars + 8;         // [2 groups] 8 warp arrivals: O has been read out of TMEM
+    uint64_t* p_full = bars + 10;        // [2 groups] 8 warp arrivals: P of the tile is in TMEM
+    uint64_t* o_full = bars + 12;        // [2 groups] commit
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_groups = L > 128 ? 2 : 1;
+    const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == kF2ProducerWarp) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_qkv);
+            mbar_init(qk_full, 1);
+            mbar_init(qk_free, n_groups);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&v_full[s], 1);
+                mbar_init(&v_free[s], n_groups);
+                mbar_init(&s_full[s], 1);
+                mbar_init(&s_free[s], kF2GroupThreads / 32);
+                mbar_init(&p_full[s], kF2GroupThreads / 32);
+                mbar_init(&o_full[s], 1);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == kF2ProducerWarp) {
+        if (lane == 0) {
+            for (int it = 0; it < n_my; ++it) {
+                const int item = blockIdx.x + it * gridDim.x;
+                const int b = item / H, h = item - b * H;
+                if (it > 0) mbar_wait(qk_free, (it - 1) & 1);
+                mbar_arrive_expect_tx(qk_full, 2 * 256 * kRowB);
+                tma_load_3d(&map_qkv, qk_full, sm + Fwd3Smem::kQ, h * kDh, 0, b);
+                tma_load_3d(&map_qkv, qk_full, sm + Fwd3Smem::kK, (H + h) * kDh, 0, b);
+                const int s = it & 1, k = it >> 1;
+                if (k > 0) mbar_wait(&v_free[s], (k - 1) & 1);
+                mbar_arrive_expect_tx(&v_full[s], 256 * kRowB);
+                tma_load_3d(&map_qkv, &v_full[s], sm + Fwd3Smem::kV + s * (256 * kRowB), (2 * H + h) * kDh, 0, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kF2MmaWarp0) {
+        const int g = warp - kF2MmaWarp0;
+        if (lane == 0 && g < n_groups) {
+            const DescBase dQ(umma_smem_desc(smem_u32(sm + Fwd3Smem::kQ) + g * (128 * kRowB), 16, 1024));
+            const DescBase dK(umma_smem_desc(smem_u32(sm + Fwd3Smem::kK), 16, 1024));
+            const DescBase dV(umma_smem_desc(smem_u32(sm + Fwd3Smem::kV), 256 * kRowB, 1024));       // V in place as an MN-major B operand
+            const uint32_t t_acc = tmem + g * 256;
+            const uint32_t idesc_s = umma_instr_desc(128, 256, 0, 0);
+            const uint32_t idesc_o = umma_instr_desc(128, 64, 0, 1);
+            for (int it = 0; it < n_my; ++it) {
+                TL(g, 0);
+                mbar_wait(qk_full, it & 1);
+                TL(g, 1);
+                if (it > 0) mbar_wait(&s_free[g], (it - 1) & 1);
+                TL(g, 2);
+                tc_fence_after();
+#pragma unroll
+                for (uint32_t kk = 0; kk < 4; ++kk)
+                    umma_bf16_lohi(t_acc, dQ.lo + kk * 2, dQ.hi, dK.lo + kk * 2, dK.hi, idesc_s, kk > 0 ? 1u : 0u);
+                umma_commit(&s_full[g]);
+                umma_commit(qk_free);
+                TL(g, 3);
+                const int s = it & 1;
+                const uint32_t v_lo = dV.lo + s * ((256 * kRowB) >> 4);
+                mbar_wait(&v_full[s], (it >> 1) & 1);
+                mbar_wait(&p_full[g], it & 1);
+                TL(g, 4);
+                tc_fence_after();
+                // keys 0..127 sit in columns [0, 64) of the tile's region, keys 128..255 in [128, 192): 8 columns per instruction
+#pragma unroll
+                for (uint32_t ks = 0; ks < 16; ++ks)
+                    umma_bf16_ts(t_acc + 192, t_acc + (ks < 8 ? ks * 8 : 128 + (ks - 8) * 8), v_lo + ks * ((16 * kRowB) >> 4), dV.hi,
+                                 idesc_o, ks > 0 ? 1u : 0u);
+                umma_commit(&o_full[g]);
+                umma_commit(&v_free[s]);
+                TL(g, 5);
+            }
+        }
+        __syncwarp();
+    } else if ((warp >> 3) < n_groups) {
+        const int g = warp >> 3, wg = warp & 7;
+        const int lg = wg & 3, half = wg >> 2;               // TMEM lane group, key half (keys 128 * half ..)
+        const int row = lg * 32 + lane;
+        const int tg = threadIdx.x & (kF2GroupThreads - 1);
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16) + g * 256;
+        const uint32_t t_half = t_row + half * 128;          // this thread's scores; its probabilities go to t_half + [0, 64)
+        float* sBias = reinterpret_cast<float*>(sm + Fwd3Smem::kBias) + g * 512;                 // [2 stages][256]
+        float* sXmax = reinterpret_cast<float*>(sm + Fwd3Smem::kXchg) + g * 512;                 // [2][128]
+        float* sXsum = sXmax + 256;
+        uint8_t* stage = sm + Fwd3Smem::kStage + warp * 2048;
+        uint32_t* sFlag = reinterpret_cast<uint32_t*>(sm + Fwd3Smem::kFlag) + g * 16;          // [2 stages][8 x 32-key chunks]
+        auto load_bias = [&](int it) -> float {
+            if (tg >= L) return -INFINITY;
+            if (key_bias == nullptr) return 0.0f;
+            const int item = blockIdx.x + it * gridDim.x;
+            return __ldg(key_bias + static_cast<long long>(item / H) * L + tg);
+        };
+        auto store_bias = [&](int stg, float v) {        // thread tg holds key tg: warp wg covers the 32-key chunk wg
+            sBias[stg * 256 + tg] = v * kLog2e;
+            const uint32_t any = __ballot_sync(0xffffffffu, v != 0.0f);
+            if (lane == 0) sFlag[stg * 8 + wg] = any;
+        };
+        if (n_my > 0) store_bias(0, load_bias(0));
+        const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+        for (int it = 0; it < n_my; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int b = item / H, h = item - b * H;
+            const float bias_next = it + 1 < n_my ? load_bias(it + 1) : 0.0f;
+#define TLS(idx) do { if (wg == 0 && lane == 0) TL(2 + g, idx); } while (0)
+            TLS(0);
+            named_bar_sync<9>(g, kF2GroupThreads);       // bias row of this item visible; every warp is past its previous epilogue
+            TLS(1);
+            const float* bias = sBias + (it & 1) * 256 + half * 128;
+            const uint32_t* flag = sFlag + (it & 1) * 8 + half * 4;
+            mbar_wait(&s_full[g], it & 1);
+            TLS(2);
+            tc_fence_after();
+            // ---- pass 1: row max over this thread's 128 keys ----
+            float m = -INFINITY, m_raw = -INFINITY;
+            auto row_max = [&](const uint32_t (&r)[32], int c) {
+                if (flag[c] == 0u) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        m_raw = fmaxf(m_raw, fmaxf(fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                                   fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + j);
+                        m = fmaxf(m, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), scale_log2, b4.x), fmaf(__uint_as_float(r[j + 1]), scale_log2, b4.y)),
+                                           fmaxf(fmaf(__uint_as_float(r[j + 2]), scale_log2, b4.z), fmaf(__uint_as_float(r[j + 3]), scale_log2, b4.w))));
+                    }
+                }
+            };
+            uint32_t ra[16], rb[16];
+            {
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(t_half, r0);
+                tmem_ld_wait();
+                tmem_ld_32x32(t_half + 32, r1);
+                row_max(r0, 0);
+                tmem_ld_wait();
+                tmem_ld_32x32(t_half + 64, r0);
+                row_max(r1, 1);
+                tmem_ld_wait();
+                tmem_ld_32x32(t_half + 96, r1);
+                row_max(r0, 2);
+                tmem_ld_wait();
+                tmem_ld_32x16_a(t_half, ra);                  // pass 2's first 16 columns travel during the exchange below
+                row_max(r1, 3);
+            }
+            m = fmaxf(m, m_raw * scale_log2);                  // scale > 0
+            sXmax[half * 128 + row] = m;
+            named_bar_sync<1>(g * 4 + lg, 64);
+            m = fmaxf(m, sXmax[(half ^ 1) * 128 + row]);       // key 0 is always valid: m is finite
+            TLS(3);
+            // ---- pass 2: P = exp2(S * scale + mask - m), 32 keys at a time, packed to bf16 and stored over the scores already read ----
+            const uint64_t neg_m2 = pack_f32x2(-m, -m);
+            uint64_t sum2 = 0ull;
+            auto probs16 = [&](const uint32_t (&r)[16], float* p, bool masked, const float* bias16) {
+                if (!masked) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float x0, x1, x2, x3;
+                        unpack_f32x2(ffma2(pack_u32x2(r[j], r[j + 1]), scale2, neg_m2), x0, x1);
+                        unpack_f32x2(ffma2(pack_u32x2(r[j + 2], r[j + 3]), scale2, neg_m2), x2, x3);
+                        p[j] = ex2_ftz(x0);
+                        p[j + 1] = ex2_ftz(x1);
+                        if constexpr (POLY != 0) {
+                            exp2_poly2(x2, x3, p[j + 2], p[j + 3]);
+                        } else {
+                            p[j + 2] = ex2_ftz(x2);
+                            p[j + 3] = ex2_ftz(x3);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias16 + j);
+                        p[j] = ex2_ftz(fmaf(__uint_as_float(r[j]), scale_log2, b4.x - m));
+                        p[j + 1] = ex2_ftz(fmaf(__uint_as_float(r[j + 1]), scale_log2, b4.y - m));
+                        p[j + 2] = ex2_ftz(fmaf(__uint_as_float(r[j + 2]), scale_log2, b4.z - m));
+                        p[j + 3] = ex2_ftz(fmaf(__uint_as_float(r[j + 3]), scale_log2, b4.w - m));
+                    }
+                }
+            };
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool masked = flag[c] != 0u;
+                const float* bias32 = bias + c * 32;
+                float p[32];
+                tmem_ld_wait();
+                tmem_ld_32x16_a(t_half + c * 32 + 16, rb);
+                probs16(ra, p, masked, bias32);
+                tmem_ld_wait();
+                if (c < 3) tmem_ld_32x16_a(t_half + (c + 1) * 32, ra);
+                probs16(rb, p + 16, masked, bias32 + 16);
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    sum2 = fadd2(sum2, fadd2(pack_f32x2(p[j], p[j + 1]), pack_f32x2(p[j + 2], p[j + 3])));
+                    pk[j >> 1] = pack_bf16(p[j], p[j + 1]);
+                    pk[(j >> 1) + 1] = pack_bf16(p[j + 2], p[j + 3]);
+                }
+                // keys 32 c .. 32 c + 31 of this half -> 16 packed columns at [16 c, 16 c + 16) of the half's region: scores this
+                // thread read at chunk c / 2 or earlier
+                tmem_st_32x16(t_half + c * 16, pk);
+                TLS(4 + c);
+            }
+            tmem_st_wait();
+            warp_arrive(&p_full[g], lane);
+            TLS(8);
+            float sum, sum_hi;
+            unpack_f32x2(sum2, sum, sum_hi);
+            sum += sum_hi;
+            sXsum[half * 128 + row] = sum;
+            store_bias((it + 1) & 1, bias_next);
+            named_bar_sync<1>(g * 4 + lg, 64);
+            sum += sXsum[(half ^ 1) * 128 + row];
+            TLS(20);
+            mbar_wait(&o_full[g], it & 1);
+            TLS(21);
+            tc_fence_after();
+            uint32_t pk[16];
+            {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + 192 + half * 32, r);
+                tmem_ld_wait();
+                warp_arrive(&s_free[g], lane);         // the next item's S chain may overwrite the tile's region
+                const float inv = 1.0f / sum;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    pk[j] = pack_bf16(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+            }
+            const int qrow0 = g * 128 + lg * 32;
+            const int rows_valid = min(32, max(0, L - qrow0));
+            store_rows_32(stage, pk, ctx + (static_cast<long long>(b) * L + qrow0) * (H * kDh) + h * kDh + half * 32,
+                          static_cast<long long>(H) * kDh, rows_valid, lane);
+            if (half == 0 && g * 128 + row < L) lse[(static_cast<long long>(b) * H + h) * L + g * 128 + row] = (m + log2f(sum)) * kLn2;
+            TLS(22);
+        }
+    }
+#undef TLS
+#undef TL
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kF2ProducerWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, persistent, ONLINE softmax over 64-key blocks, four query tiles in flight (round 2, default)
+//
+// What bounds the two-pass kernels above is not the tensor pipe but the softmax side: TMEM is read at ~128 B per clock and
+// SM, the two-pass scheme reads every score twice (512 KB per item), and with two tiles in flight the chain S -> max ->
+// exp -> P.V -> drain of a tile is serial, so the TMEM port, the issue slots, the MUFU pipe and the tensor pipe take turns
+// instead of overlapping (their per-item times ADD UP to the measured item period). This kernel
+//   * reads S once: online softmax, thread = query row (no cross-thread exchange at all), 32 keys at a time; the running
+//     maximum is only raised when a chunk exceeds it by more than 2^8 (the probabilities then stay <= 256, exact in the
+//     fp32 sum and harmless in bf16), in which case the row's accumulator is rescaled in TMEM -- a path taken at most a few
+//     times per row;
+//   * keeps FOUR 128-row tiles in flight (slots): two consecutive (b, h) items x their two query tiles; a slot owns 128 TMEM
+//     columns: scores of one 64-key block in [0, 64), overwritten in place by the packed bf16 probabilities ([0, 32)), and
+//     the output accumulator in [64, 128). 4 softmax warps + 1 MMA-issuing warp per slot, one TMA producer warp;
+//   * P.V reads P from tensor memory ([a_tmem] operand), 32 keys (two instructions) per hand-over.
+// K / V of an item are loaded once (two stages: the items of slots 0-1 and 2-3), Q per slot.
+// ------------------------------------------------------------------------------------------------
+struct Fwd4Smem {
+    static constexpr int kK = 0;                    // 2 stages x [256 x 64] bf16
+    static constexpr int kV = 64 * 1024;            // 2 stages x [256 x 64]
+    static constexpr int kQ = 128 * 1024;           // 4 slots x [128 x 64]
+    static constexpr int kStage = 192 * 1024;       // 16 warps x 2 KB output staging
+    static constexpr int kBias = 224 * 1024;        // [2 pairs][256] bf16, log2 units
+    static constexpr int kFlag = 225 * 1024;        // [2 pairs][8] words: the 32-key chunk has a non-zero mask
+    static constexpr int kBar = 225 * 1024 + 64;
+    static constexpr int kTotal = 225 * 1024 + 64 + 48 * 8 + 1024;
+};
+static_assert(Fwd4Smem::kTotal <= 227 * 1024, "attention forward shared memory budget");
+constexpr int kF4SoftmaxWarps = 16;
+constexpr int kF4ProducerWarp = 16;
+constexpr int kF4MmaWarp0 = 17;                     // MMA warp of slot s = 17 + s
+constexpr int kF4Threads = 21 * 32;
+constexpr float kF4Tau = 8.0f;                      // log2 units: the running maximum may lag the true one by this much
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :
+        : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(kF4Threads, 1)
+attn_tc_fwd4_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
+                    const float* __restrict__ key_bias, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int n_items,
+                    int L, int H, float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Fwd4Smem::kBar);
+    uint64_t* q_full = bars;             // [4 slots] tx
+    uint64_t* q_free = bars + 4;         // [4] commit: the slot's last S chain has retired
+    uint64_t* k_full = bars + 8;         // [2 stages] tx
+    uint64_t* k_free = bars + 10;        // [2] n_tiles commits
+    uint64_t* v_full = bars + 12;        // [2] tx
+    uint64_t* v_free = bars + 14;        // [2] n_tiles commits
+    uint64_t* s_full = bars + 16;        // [4] commit: S of a 64-key block is in TMEM
+    uint64_t* s_free = bars + 20;        // [4] 4 warp arrivals: O has been read out, the slot may take its next tile
+    uint64_t* p_half = bars + 24;        // [4] 4 warp arrivals: P of 32 keys is in TMEM
+    uint64_t* pv_done = bars + 28;       // [4] commit: the P.V instructions issued so far have retired
+    uint64_t* o_full = bars + 32;        // [4] commit: O of the tile is complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = L > 128 ? 2 : 1;             // query tiles (slots per item) with real rows
+    const int n_kb = (L + 63) >> 6;                  // 64-key blocks with real keys
+    const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == kF4ProducerWarp) {
+        if (lane == 0) {
+            tma_prefetch_desc(&map_kv);
+            tma_prefetch_desc(&map_q);
+            for (int i = 0; i < 4; ++i) {
+                mbar_init(&q_full[i], 1);
+                mbar_init(&q_free[i], 1);
+                mbar_init(&s_full[i], 1);
+                mbar_init(&s_free[i], 4);
+                mbar_init(&p_half[i], 4);
+                mbar_init(&pv_done[i], 1);
+                mbar_init(&o_full[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&k_full[i], 1);
+                mbar_init(&k_free[i], n_tiles);
+                mbar_init(&v_full[i], 1);
+                mbar_init(&v_free[i], n_tiles);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == kF4ProducerWarp) {
+        if (lane == 0) {
+            for (int it = 0; it < n_my; ++it) {
+                const int item = blockIdx.x + it * gridDim.x;
+                const int b = item / H, h = item - b * H;
+                const int st = it & 1, u = it >> 1;                 // stage = item parity; u-th use of that stage
+                if (u > 0) mbar_wait(&k_free[st], (u - 1) & 1);
+                mbar_arrive_expect_tx(&k_full[st], 256 * kRowB);
+                tma_load_3d(&map_kv, &k_full[st], sm + Fwd4Smem::kK + st * (256 * kRowB), (H + h) * kDh, 0, b);
+                for (int g = 0; g < n_tiles; ++g) {
+                    const int slot = st * 2 + g;
+                    if (u > 0) mbar_wait(&q_free[slot], (u - 1) & 1);
+                    mbar_arrive_expect_tx(&q_full[slot], 128 * kRowB);
+                    tma_load_3d(&map_q, &q_full[slot], sm + Fwd4Smem::kQ + slot * (128 * kRowB), h * kDh, g * 128, b);
+                }
+                if (u > 0) mbar_wait(&v_free[st], (u - 1) & 1);
+                mbar_arrive_expect_tx(&v_full[st], 256 * kRowB);
+                tma_load_3d(&map_kv, &v_full[st], sm + Fwd4Smem::kV + st * (256 * kRowB), (2 * H + h) * kDh, 0, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kF4MmaWarp0) {
+        const int slot = warp - kF4MmaWarp0;
+        const int pair = slot >> 1, g = slot & 1;
+        if (lane == 0 && g < n_tiles) {
+            const int n_jobs = (n_my - pair + 1) >> 1;              // items pair, pair + 2, ...
+            const DescBase dQ(umma_smem_desc(smem_u32(sm + Fwd4Smem::kQ) + slot * (128 * kRowB), 16, 1024));
+            const DescBase dK(umma_smem_desc(smem_u32(sm + Fwd4Smem::kK) + pair * (256 * kRowB), 16, 1024));
+            const DescBase dV(umma_smem_desc(smem_u32(sm + Fwd4Smem::kV) + pair * (256 * kRowB), 256 * kRowB, 1024));   // MN-major B
+            const uint32_t t_slot = tmem + slot * 128;
+            const uint32_t idesc_s = umma_instr_desc(128, 64, 0, 0);
+            const uint32_t idesc_o = umma_instr_desc(128, 64, 0, 1);
+            uint32_t cnt_p = 0, cnt_pv = 0;
+            for (int u = 0; u < n_jobs; ++u) {
+                mbar_wait(&k_full[pair], u & 1);
+                mbar_wait(&q_full[slot], u & 1);
+                if (u > 0) mbar_wait(&s_free[slot], (u - 1) & 1);
+                tc_fence_after();
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    if (kb > 0) {                                   // the previous block's P (same columns) has been consumed
+                        mbar_wait(&pv_done[slot], (cnt_pv - 1) & 1);
+                        tc_fence_after();
+                    }
+#pragma unroll
+                    for (uint32_t kk = 0; kk < 4; ++kk)
+                        umma_bf16_lohi(t_slot, dQ.lo + kk * 2, dQ.hi, dK.lo + kb * ((64 * kRowB) >> 4) + kk * 2, dK.hi, idesc_s,
+                                       kk > 0 ? 1u : 0u);
+                    umma_commit(&s_full[slot]);
+                    if (kb == n_kb - 1) {
+                        umma_commit(&q_free[slot]);
+                        umma_commit(&k_free[pair]);
+                    }
+                    for (int hh = 0; hh < 2; ++hh) {
+                        mbar_wait(&p_half[slot], cnt_p & 1);
+                        ++cnt_p;
+                        if (kb == 0 && hh == 0) mbar_wait(&v_full[pair], u & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t ks = 0; ks < 2; ++ks)
+                            umma_bf16_ts(t_slot + 64, t_slot + hh * 16 + ks * 8,
+                                         dV.lo + (kb * 4 + hh * 2 + ks) * ((16 * kRowB) >> 4), dV.hi, idesc_o,
+                                         (kb > 0 || hh > 0 || ks > 0) ? 1u : 0u);
+                        umma_commit(&pv_done[slot]);
+                        ++cnt_pv;
+                    }
+                }
+                umma_commit(&o_full[slot]);
+                umma_commit(&v_free[pair]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int slot = warp >> 2, lg = warp & 3;
+        const int pair = slot >> 1, g = slot & 1;
+        if (g < n_tiles) {
+            const int n_jobs = (n_my - pair + 1) >> 1;
+            const int row = lg * 32 + lane;
+            const int tp = g * 128 + row;                           // the key whose mask this thread stages for its pair of slots
+            const uint32_t t_slot = tmem + (static_cast<uint32_t>(lg * 32) << 16) + slot * 128;
+            __nv_bfloat16* sBias = reinterpret_cast<__nv_bfloat16*>(sm + Fwd4Smem::kBias) + pair * 256;
+            uint32_t* sFlag = reinterpret_cast<uint32_t*>(sm + Fwd4Smem::kFlag) + pair * 8;
+            uint8_t* stage = sm + Fwd4Smem::kStage + warp * 2048;
+            const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+            uint32_t cnt_s = 0, cnt_c = 0;                          // S blocks waited for / 32-key chunks handed over (this slot)
+            for (int u = 0; u < n_jobs; ++u) {
+                const int it = pair + 2 * u;
+                const int item = blockIdx.x + it * gridDim.x;
+                const int b = item / H, h = item - b * H;
+                // additive key mask of this item, staged by the 2 x 128 threads that work on it
+                float kbias = -INFINITY;
+                if (tp < L) kbias = key_bias != nullptr ? __ldg(key_bias + static_cast<long long>(b) * L + tp) : 0.0f;
+                named_bar_sync<2>(pair, n_tiles * 128);             // everyone is done with the previous item's mask
+                sBias[tp] = __float2bfloat16_rn(kbias * kLog2e);
+                {
+                    const uint32_t any = __ballot_sync(0xffffffffu, kbias != 0.0f);
+                    if (lane == 0) sFlag[g * 4 + lg] = any;
+                }
+                named_bar_sync<2>(pair, n_tiles * 128);
+                float m = -INFINITY, l = 0.0f;
+                for (int c = 0; c < 2 * n_kb; ++c) {
+                    const int hh = c & 1;
+                    if (hh == 0) {
+                        mbar_wait(&s_full[slot], cnt_s & 1);
+                        ++cnt_s;
+                        tc_fence_after();
+                    }
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_slot + hh * 32, r);
+                    const bool masked = sFlag[c] != 0u;
+                    tmem_ld_wait();
+                    // x = S * scale + mask (log2 units), in place; mx = chunk maximum
+                    float mx = -INFINITY;
+                    if (!masked) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                                 fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))));
+                        mx *= scale_log2;                           // scale > 0
+                    } else {
+                        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(sBias + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float2 bb = __bfloat1622float2(b2[j >> 1]);
+                            const float x0 = fmaf(__uint_as_float(r[j]), scale_log2, bb.x);
+                            const float x1 = fmaf(__uint_as_float(r[j + 1]), scale_log2, bb.y);
+                            r[j] = __float_as_uint(x0);
+                            r[j + 1] = __float_as_uint(x1);
+                            mx = fmaxf(mx, fmaxf(x0, x1));
+                        }
+                    }
+                    if (c == 0) {
+                        m = mx;                                     // key 0 is always valid: finite
+                    } else if (__any_sync(0xffffffffu, mx > m + kF4Tau)) {
+                        // rare: raise the running maximum and rescale what has been accumulated for this row
+                        const float m_new = fmaxf(m, mx);
+                        const float f = ex2_ftz(m - m_new);
+                        mbar_wait(&pv_done[slot], (cnt_c - 1) & 1);  // every P.V issued for this slot has retired
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int q = 0; q < 2; ++q) {
+                            uint32_t o[32];
+                            tmem_ld_32x32(t_slot + 64 + q * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+                            tmem_st_32x32(t_slot + 64 + q * 32, o);
+                        }
+                        tmem_st_wait();
+                        l *= f;
+                        m = m_new;
+                    }
+                    uint32_t pk[16];
+                    uint64_t sum2 = 0ull;
+                    if (!masked) {
+                        const uint64_t neg_m2 = pack_f32x2(-m, -m);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float x0, x1, x2, x3, p0, p1, p2, p3;
+                            unpack_f32x2(ffma2(pack_u32x2(r[j], r[j + 1]), scale2, neg_m2), x0, x1);
+                            unpack_f32x2(ffma2(pack_u32x2(r[j + 2], r[j + 3]), scale2, neg_m2), x2, x3);
+                            p0 = ex2_ftz(x0);
+                            p1 = ex2_ftz(x1);
+                            if constexpr (POLY != 0) {
+                                exp2_poly2(x2, x3, p2, p3);
+                            } else {
+                                p2 = ex2_ftz(x2);
+                                p3 = ex2_ftz(x3);
+                            }
+                            sum2 = fadd2(sum2, fadd2(pack_f32x2(p0, p1), pack_f32x2(p2, p3)));
+                            pk[j >> 1] = pack_bf16(p0, p1);
+                            pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float p0 = ex2_ftz(__uint_as_float(r[j]) - m);
+                            const float p1 = ex2_ftz(__uint_as_float(r[j + 1]) - m);
+                            sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+                            pk[j >> 1] = pack_bf16(p0, p1);
+                        }
+                    }
+                    float s0, s1;
+                    unpack_f32x2(sum2, s0, s1);
+                    l += s0 + s1;
+                    // keys 32 c .. 32 c + 31 of the block -> 16 packed columns at [16 hh, 16 hh + 16): over scores already in registers
+                    tmem_st_32x16(t_slot + hh * 16, pk);
+                    tmem_st_wait();
+                    warp_arrive(&p_half[slot], lane);
+                    ++cnt_c;
+                }
+                // ---- epilogue: O / l -> bf16 -> staged, coalesced stores ----
+                mbar_wait(&o_full[slot], u & 1);
+                tc_fence_after();
+                const float inv = 1.0f / l;
+                const int qrow0 = g * 128 + lg * 32;
+                const int rows_valid = min(32, max(0, L - qrow0));
+                __nv_bfloat16* dst = ctx + (static_cast<long long>(b) * L + qrow0) * (H * kDh) + h * kDh;
+#pragma unroll 1
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t o[32], pk[16];
+                    tmem_ld_32x32(t_slot + 64 + q * 32, o);
+                    tmem_ld_wait();
+                    if (q == 1) warp_arrive(&s_free[slot], lane);      // the slot's columns may be overwritten by its next tile
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        pk[j] = pack_bf16(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv);
+                    store_rows_32(stage, pk, dst + q * 32, static_cast<long long>(H) * kDh, rows_valid, lane);
+                }
+                if (g * 128 + row < L) lse[(static_cast<long long>(b) * H + h) * L + g * 128 + row] = (m + log2f(l)) * kLn2;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kF4ProducerWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
 struct BwdSmem {
@@ -1550,8 +2212,41 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
         }
         tl = tl_buf;
 #endif
-        CLIMB_CUDA_OK(launch_pdl(attn_tc_fwd2_kernel, dim3(std::min(n_items, sm_count())), dim3(kF2Threads), Fwd2Smem::kTotal, stream,
-                                 mqkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, n_items, L, H, scale * kLog2e, env_flag("CLIMB_ATTN_STAGGER", 1), tl));
+        // CLIMB_ATTN_FWD = 3 (default): two-pass softmax, P in tensor memory, P.V with a TMEM A operand; 4: online softmax over
+        // 64-key blocks with four tiles in flight; 2: the round-1 kernel (P through a shared-memory ring). All three measure
+        // 40-42 us per launch at B = 64 ("what bounds the attention kernels"): the variants are kept for A/B runs.
+        static const int fwd_variant = env_flag("CLIMB_ATTN_FWD", 3);
+        const bool fwd3 = fwd_variant == 3;
+        if (fwd_variant != 2 && fwd_variant != 3) {
+            CUtensorMap mq128;
+            rc2 = make_map3(&mq128, qkv, B, L, 3LL * H * kDh, 128);
+            if (rc2) return rc2;
+            // CLIMB_ATTN_EXP=0: every exponential on the MUFU pipe (default: every other pair as a degree-4 polynomial on the FMA pipe)
+            static const bool poly = env_flag("CLIMB_ATTN_EXP", 1) != 0;
+            static bool attr4 = false;
+            if (!attr4) {
+                CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kTotal));
+                CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd4Smem::kTotal));
+                attr4 = true;
+            }
+            CLIMB_CUDA_OK(launch_pdl(poly ? attn_tc_fwd4_kernel<1> : attn_tc_fwd4_kernel<0>, dim3(std::min(n_items, sm_count())),
+                                     dim3(kF4Threads), Fwd4Smem::kTotal, stream, mqkv, mq128, key_bias, static_cast<__nv_bfloat16*>(ctx), lse,
+                                     n_items, L, H, scale * kLog2e));
+        } else if (fwd3) {
+            static const bool poly = env_flag("CLIMB_ATTN_EXP", 1) != 0;
+            static bool attr3 = false;
+            if (!attr3) {
+                CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd3Smem::kTotal));
+                CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd3Smem::kTotal));
+                attr3 = true;
+            }
+            CLIMB_CUDA_OK(launch_pdl(poly ? attn_tc_fwd3_kernel<1> : attn_tc_fwd3_kernel<0>, dim3(std::min(n_items, sm_count())),
+                                     dim3(kF2Threads), Fwd3Smem::kTotal, stream, mqkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, n_items,
+                                     L, H, scale * kLog2e, tl));
+        } else {
+            CLIMB_CUDA_OK(launch_pdl(attn_tc_fwd2_kernel, dim3(std::min(n_items, sm_count())), dim3(kF2Threads), Fwd2Smem::kTotal, stream,
+                                     mqkv, key_bias, static_cast<__nv_bfloat16*>(ctx), lse, n_items, L, H, scale * kLog2e, env_flag("CLIMB_ATTN_STAGGER", 1), tl));
+        }
         CLIMB_LAUNCH_OK();
 #if CLIMB_ATTN_TIMELINE
         if (tl != nullptr && ++tl_calls == 20) {
