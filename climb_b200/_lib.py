@@ -204,6 +204,9 @@ climb_bert_forward_workspace_bytes = _sig("climb_bert_forward_workspace_bytes", 
 climb_bert_forward = _sig("climb_bert_forward", [POINTER(BertDimsC), POINTER(BertParamsC), POINTER(BertBatchC), _P, _P, _P,
                                                  c_int64, c_float, c_float, ctypes.c_uint64, _P, _P])
 climb_dropout_add = _sig("climb_dropout_add", [_P, _P, _P, c_int64, c_float, ctypes.c_uint64, _P])
+climb_dropout_site_seed = _sig("climb_dropout_site_seed", [ctypes.c_uint64, c_int, c_int], ctypes.c_uint64)
+climb_dropout_keep_mask = _sig("climb_dropout_keep_mask", [_P, c_int64, c_float, ctypes.c_uint64, _P])
+climb_attention_dropout_keep_mask = _sig("climb_attention_dropout_keep_mask", [_P, c_int, c_int, c_int, c_float, ctypes.c_uint64, _P])
 
 
 def check(rc: int) -> None:

@@ -1387,7 +1387,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                    const float* __restrict__ key_bias, const __nv_bfloat16* __restrict__ ctx,
                    const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int L, int H, float scale_log2,
-                   float scale) {
+                   float scale, uint32_t drop_thresh, float inv_keep, unsigned long long seed) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
     float* sLse = reinterpret_cast<float*>(sm + BwdSmem::kLse);
@@ -1574,12 +1574,34 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
                     bias[e] = b4.x - lse_r; bias[e + 1] = b4.y - lse_r; bias[e + 2] = b4.z - lse_r; bias[e + 3] = b4.w - lse_r;
                 }
                 tmem_ld_wait();
+                if (drop_thresh == 0u) {
 #pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                    const float p0 = ex2_ftz(fmaf(__uint_as_float(rs[e]), scale_log2, bias[e]));
-                    const float p1 = ex2_ftz(fmaf(__uint_as_float(rs[e + 1]), scale_log2, bias[e + 1]));
-                    pp[hh][e >> 1] = pack_bf16(p0, p1);
-                    dd[hh][e >> 1] = pack_bf16(p0 * (__uint_as_float(rd[e]) - dl_r), p1 * (__uint_as_float(rd[e + 1]) - dl_r));
+                    for (int e = 0; e < 16; e += 2) {
+                        const float p0 = ex2_ftz(fmaf(__uint_as_float(rs[e]), scale_log2, bias[e]));
+                        const float p1 = ex2_ftz(fmaf(__uint_as_float(rs[e + 1]), scale_log2, bias[e + 1]));
+                        pp[hh][e >> 1] = pack_bf16(p0, p1);
+                        dd[hh][e >> 1] = pack_bf16(p0 * (__uint_as_float(rd[e]) - dl_r), p1 * (__uint_as_float(rd[e + 1]) - dl_r));
+                    }
+                } else {
+                    // dropout on the probabilities (modeling_vilt.py:374): the forward used Pd = P * keep / (1 - p) in O = Pd V, so
+                    //   dV = Pd^T dO,   dP = (dO V^T) * keep / (1 - p),   dS = P (dP - delta),  delta = rowsum(dO * O) = rowsum(Pd * dPd).
+                    // The mask is regenerated from the forward's counters: (b, h, query, key / 4) -> four keys per Philox call.
+                    const unsigned long long base = ((static_cast<unsigned long long>(b) * H + h) * L + (i * 128 + row)) * 64ull +
+                                                    static_cast<unsigned long long>((j * 128 + c * 32 + hh * 16) >> 2);
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        const uint4 rnd = philox4x32(seed, base + g4);
+                        const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; e2 += 2) {
+                            const int e = g4 * 4 + e2;
+                            const float k0 = dropout_scale(rr[e2], drop_thresh, inv_keep), k1 = dropout_scale(rr[e2 + 1], drop_thresh, inv_keep);
+                            const float p0 = ex2_ftz(fmaf(__uint_as_float(rs[e]), scale_log2, bias[e]));
+                            const float p1 = ex2_ftz(fmaf(__uint_as_float(rs[e + 1]), scale_log2, bias[e + 1]));
+                            pp[hh][e >> 1] = pack_bf16(p0 * k0, p1 * k1);
+                            dd[hh][e >> 1] = pack_bf16(p0 * (__uint_as_float(rd[e]) * k0 - dl_r), p1 * (__uint_as_float(rd[e + 1]) * k1 - dl_r));
+                        }
+                    }
                 }
             }
             // everything above overlapped the previous block's accumulation chains; they must have retired before
@@ -2283,9 +2305,11 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
 }
 
 int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
-                     void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream) {
+                     void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream, float p_drop,
+                     unsigned long long seed) {
     CLIMB_REQUIRE(L <= 256, "attention_tc_bwd: L=%d > 256", L);
-    if (L > 128 && H <= sm_count() && !attn_v1()) {
+    CLIMB_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "attention_tc_bwd: dropout p=%f outside [0, 1)", p_drop);
+    if (p_drop == 0.0f && L > 128 && H <= sm_count() && !attn_v1()) {
         CUtensorMap mqkv2, mdo2;
         int rc2 = make_map3(&mqkv2, qkv, B, L, 3LL * H * kDh, 128);
         if (rc2) return rc2;
@@ -2347,7 +2371,8 @@ int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, co
     dim3 grid(H, B);
     CLIMB_CUDA_OK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(kBwdThreads), BwdSmem::kTotal, stream, mqkv, mdo, key_bias,
                              static_cast<const __nv_bfloat16*>(ctx), static_cast<const __nv_bfloat16*>(dctx), lse,
-                             static_cast<__nv_bfloat16*>(dqkv), colsum, L, H, scale * kLog2e, scale));
+                             static_cast<__nv_bfloat16*>(dqkv), colsum, L, H, scale * kLog2e, scale,
+                             p_drop > 0.0f ? dropout_threshold(p_drop) : 0u, 1.0f / (1.0f - p_drop), seed));
     CLIMB_LAUNCH_OK();
     return 0;
 }

@@ -232,6 +232,13 @@ int climb_bert_forward(const climb_bert_dims* dims, const climb_bert_params* par
     return bert_forward(dims, params, batch, theta, shadow, workspace, workspace_bytes, hidden_dropout, attn_dropout, seed,
                         last_hidden_state, S(stream));
 }
+uint64_t climb_dropout_site_seed(uint64_t base, int layer, int site) { return dropout_site_seed(base, layer, site); }
+int climb_dropout_keep_mask(float* out, int64_t n, float p, uint64_t seed, void* stream) {
+    return dropout_mask_f32(nullptr, out, n, p, seed, S(stream));
+}
+int climb_attention_dropout_keep_mask(float* out, int B, int H, int L, float p, uint64_t seed, void* stream) {
+    return attn_dropout_mask(out, B, H, L, p, seed, S(stream));
+}
 int climb_dropout_add(const float* x, const float* res, float* y, int64_t n, float p, uint64_t seed, void* stream) {
     return dropout_add(x, res, y, n, p, seed, S(stream));
 }

@@ -94,7 +94,8 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
                                       const float* __restrict__ table, const float* __restrict__ cls,
                                       const float* __restrict__ pos_emb, const float* __restrict__ mod,
                                       const int* __restrict__ type_idx, int type_idx_scalar,
-                                      float* __restrict__ x, int B, int T, int Np, int d4, int n_mod, unsigned int* err) {
+                                      float* __restrict__ x, int B, int T, int Np, int d4, int n_mod, unsigned int* err,
+                                      uint32_t thresh, float inv_keep, unsigned long long seed) {
     const int L = T + 1 + Np;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * L * d4) return;
@@ -118,6 +119,13 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
             const float4 t = reinterpret_cast<const float4*>(table)[static_cast<long long>(p) * d4 + c];
             v = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
         }
+    }
+    if (thresh != 0u) {       // embedding dropout (modeling_vilt.py:201, :303): on the content rows, before the modality-type rows are added
+        const uint4 rnd = philox4x32(seed, static_cast<unsigned long long>(i));
+        v.x *= dropout_scale(rnd.x, thresh, inv_keep);
+        v.y *= dropout_scale(rnd.y, thresh, inv_keep);
+        v.z *= dropout_scale(rnd.z, thresh, inv_keep);
+        v.w *= dropout_scale(rnd.w, thresh, inv_keep);
     }
     reinterpret_cast<float4*>(x)[i] = make_float4(v.x + m.x, v.y + m.y, v.z + m.z, v.w + m.w);
 }
@@ -154,7 +162,8 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
                                              const int* __restrict__ geom, const float* __restrict__ cls,
                                              const float* __restrict__ pos_emb, const float* __restrict__ mod,
                                              const int* __restrict__ type_idx, int type_idx_scalar,
-                                             float* __restrict__ x, int B, int T, int Np, int G, int d4, int n_mod, unsigned int* err) {
+                                             float* __restrict__ x, int B, int T, int Np, int G, int d4, int n_mod, unsigned int* err,
+                                             uint32_t thresh, float inv_keep, unsigned long long seed) {
     const int L = T + 1 + Np;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * L * d4) return;
@@ -187,6 +196,13 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
                 v.w += t.w00 * q00.w + t.w01 * q01.w + t.w10 * q10.w + t.w11 * q11.w;
             }
         }
+    }
+    if (thresh != 0u) {       // embedding dropout (modeling_vilt.py:201, :303): on the content rows, before the modality-type rows are added
+        const uint4 rnd = philox4x32(seed, static_cast<unsigned long long>(i));
+        v.x *= dropout_scale(rnd.x, thresh, inv_keep);
+        v.y *= dropout_scale(rnd.y, thresh, inv_keep);
+        v.z *= dropout_scale(rnd.z, thresh, inv_keep);
+        v.w *= dropout_scale(rnd.w, thresh, inv_keep);
     }
     reinterpret_cast<float4*>(x)[i] = make_float4(v.x + m.x, v.y + m.y, v.z + m.z, v.w + m.w);
 }
@@ -363,12 +379,13 @@ int pos_interp(const float* pos_emb, float* table, int hp, int wp, int G, int d,
 
 int embed_assemble(const float* text_ln, const float* patch, const float* table, const float* cls,
                    const float* pos_emb, const float* mod, const int* type_idx, int type_idx_scalar, float* x,
-                   int B, int T, int Np, int d, cudaStream_t stream, int n_mod) {
+                   int B, int T, int Np, int d, cudaStream_t stream, int n_mod, float p_drop, unsigned long long seed) {
     CLIMB_REQUIRE(text_ln && patch && table && cls && pos_emb && mod && x && d % 4 == 0, "embed_assemble: bad arguments");
     const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
     embed_assemble_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, table, cls, pos_emb, mod,
                                                                      type_idx, type_idx_scalar, x, B, T, Np, d / 4, n_mod,
-                                                                     device_error_word());
+                                                                     device_error_word(), p_drop > 0.0f ? dropout_threshold(p_drop) : 0u,
+                                                                     1.0f / (1.0f - p_drop), seed);
     CLIMB_LAUNCH_OK();
     return 0;
 }
@@ -393,11 +410,13 @@ int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int
 
 int embed_assemble_ragged(const float* text_ln, const float* patch, const int* geom, const float* cls, const float* pos_emb,
                           const float* mod, const int* type_idx, int type_idx_scalar, float* x, int B, int T, int Np, int G,
-                          int d, cudaStream_t stream, int n_mod) {
+                          int d, cudaStream_t stream, int n_mod, float p_drop, unsigned long long seed) {
     CLIMB_REQUIRE(text_ln && patch && geom && cls && pos_emb && mod && x && d % 4 == 0, "embed_assemble_ragged: bad arguments");
     const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
     embed_assemble_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, geom, cls, pos_emb, mod, type_idx,
-                                                                            type_idx_scalar, x, B, T, Np, G, d / 4, n_mod, device_error_word());
+                                                                            type_idx_scalar, x, B, T, Np, G, d / 4, n_mod, device_error_word(),
+                                                                            p_drop > 0.0f ? dropout_threshold(p_drop) : 0u,
+                                                                            1.0f / (1.0f - p_drop), seed);
     CLIMB_LAUNCH_OK();
     return 0;
 }

@@ -71,6 +71,8 @@ struct Plan {
     bf16* cls_ln;       // [B, d]
     float *fmean, *frstd;
     float* pooled;      // [B, d]
+    float* drop_tmp;    // [M, d] dense output before dropout (hidden dropout p > 0 in train mode only)
+    bool drop_hidden;
     long long bytes;
 };
 
@@ -141,6 +143,8 @@ int fill_plan(Plan& P, const climb_vilt_dims* dm, const climb_vilt_params* pr, c
     P.fmean = b.take<float>(P.B);
     P.frstd = b.take<float>(P.B);
     P.pooled = b.take<float>(static_cast<long long>(P.B) * d);
+    P.drop_hidden = bt->training && dm->hidden_dropout > 0.0f;
+    P.drop_tmp = P.drop_hidden ? b.take<float>(M * d) : nullptr;
     P.bytes = (b.off + 255) & ~255LL;
     return 0;
 }
@@ -240,6 +244,8 @@ struct BwdScratch {
     float* S;                   // [2, L, d]
     bf16* dpool;                // [B, d]
     bf16* dcls;                 // [B, d]
+    bf16* dm_h;                 // [M, d]  gradient behind a hidden-dropout site (p > 0 only)
+    float* dxm;                 // [M, d]  embedding gradient behind the embedding dropout (p > 0 only)
     long long bytes;
 };
 
@@ -260,6 +266,8 @@ static void fill_scratch(BwdScratch& S, const Plan& P, void* base) {
     S.S = b.take<float>(2LL * P.L * d);
     S.dpool = b.take<bf16>(static_cast<long long>(P.B) * d);
     S.dcls = b.take<bf16>(static_cast<long long>(P.B) * d);
+    S.dm_h = P.drop_hidden ? b.take<bf16>(M * d) : nullptr;
+    S.dxm = P.drop_hidden ? b.take<float>(M * d) : nullptr;
     S.bytes = (b.off + 255) & ~255LL;
 }
 
@@ -290,6 +298,12 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
                   "vilt_forward: image_token_type_idx %d outside the %d-row modality table",
                   bt->image_type_idx_scalar, dm->n_modality);
     const int d = P.d, M = P.M, BT = P.B * P.T;
+    // dropout (train mode, ViltConfig.hidden_dropout_prob / attention_probs_dropout_prob > 0: csrc/dropout.cu)
+    const float p_h = bt->training ? dm->hidden_dropout : 0.0f, p_a = bt->training ? dm->attn_dropout : 0.0f;
+    CLIMB_REQUIRE(p_h >= 0.0f && p_h < 1.0f && p_a >= 0.0f && p_a < 1.0f, "vilt_forward: dropout probabilities must lie in [0, 1)");
+    CLIMB_REQUIRE(p_a == 0.0f || P.L <= 256, "vilt_forward: dropout on the attention probabilities is implemented for sequences of "
+                  "up to 256 tokens (L = %d)", P.L);
+    const unsigned long long dseed = bt->dropout_seed;
 
     // ---- embeddings (modeling_vilt.py:207-246) ----
     if (P.geom) TRY(key_bias_ragged(reinterpret_cast<const long long*>(bt->attention_mask), P.geom, P.key_bias, P.B, P.T, P.L, s));
@@ -311,12 +325,12 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
     if (P.geom) {
         TRY(embed_assemble_ragged(P.text_ln, P.patch_out, P.geom, F(theta, pr->cls_token), F(theta, pr->pos_emb),
                                   F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B,
-                                  P.T, P.Np, dm->pos_grid, d, s, dm->n_modality));
+                                  P.T, P.Np, dm->pos_grid, d, s, dm->n_modality, p_h, dropout_site_seed(dseed, -1, 1)));
     } else {
         TRY(pos_interp(F(theta, pr->pos_emb), P.pos_table, P.hp, P.wp, dm->pos_grid, d, s));
         TRY(embed_assemble(P.text_ln, P.patch_out, P.pos_table, F(theta, pr->cls_token), F(theta, pr->pos_emb),
                            F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B, P.T,
-                           P.Np, d, s, dm->n_modality));
+                           P.Np, d, s, dm->n_modality, p_h, dropout_site_seed(dseed, -1, 1)));
     }
 
     // ---- encoder layers (modeling_vilt.py:503-525) ----
@@ -334,8 +348,16 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
             l.bias = F(theta, w.qkv_b); l.C = a.qkv;
             TRY(run_linear(l, s));
         }
-        TRY(attention_fwd(a.qkv, P.key_bias, a.ctx, a.lse, P.B, P.L, P.heads, scale, s));
-        {
+        if (p_a > 0.0f) TRY(attention_tc_fwd(a.qkv, P.key_bias, a.ctx, a.lse, P.B, P.L, P.heads, scale, s, p_a, dropout_site_seed(dseed, li, 0)));
+        else TRY(attention_fwd(a.qkv, P.key_bias, a.ctx, a.lse, P.B, P.L, P.heads, scale, s));
+        if (p_h > 0.0f) {
+            // ViltSelfOutput: dropout(dense(ctx)) before the adapter / residual (modeling_vilt.py:407-414)
+            Lin l{M, d, d, a.ctx, d, H(shadow, w.o_w)};
+            l.bias = F(theta, w.o_b); l.C = P.drop_tmp; l.c_dtype = CLIMB_F32;
+            TRY(run_linear(l, s));
+            TRY(dropout_res(P.drop_tmp, a.x_in, a.x1, mh_ad ? a.mh_in : nullptr, nullptr, static_cast<long long>(M) * d, p_h,
+                            dropout_site_seed(dseed, li, 1), s));
+        } else {
             Lin l{M, d, d, a.ctx, d, H(shadow, w.o_w)};
             l.bias = F(theta, w.o_b); l.C = a.x1; l.c_dtype = CLIMB_F32; l.residual = a.x_in;
             if (mh_ad) l.aux = a.mh_in;                       // adapter sees O(ctx)+b before the residual
@@ -356,7 +378,14 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
             l.bias = F(theta, w.fc1_b); l.C = a.inter; l.epi = CLIMB_EPI_GELU_SAVE_GRAD; l.aux = a.u;   // u <- gelu'(pre)
             TRY(run_linear(l, s));
         }
-        {
+        if (p_h > 0.0f) {
+            // ViltOutput: dropout(dense(inter)) + residual (modeling_vilt.py:480-484)
+            Lin l{M, d, P.ff, a.inter, P.ff, H(shadow, w.fc2_w)};
+            l.bias = F(theta, w.fc2_b); l.C = P.drop_tmp; l.c_dtype = CLIMB_F32;
+            TRY(run_linear(l, s));
+            TRY(dropout_res(P.drop_tmp, a.x1, x_out, nullptr, out_ad ? a.out_in : nullptr, static_cast<long long>(M) * d, p_h,
+                            dropout_site_seed(dseed, li, 2), s));
+        } else {
             Lin l{M, d, P.ff, a.inter, P.ff, H(shadow, w.fc2_w)};
             l.bias = F(theta, w.fc2_b); l.C = x_out; l.c_dtype = CLIMB_F32; l.residual = a.x1;
             if (out_ad) l.c2 = a.out_in;                      // adapter sees FC2 + residual
@@ -400,6 +429,8 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
     CLIMB_REQUIRE(scratch_bytes >= S.bytes, "vilt_backward: scratch %lld < required %lld", scratch_bytes, S.bytes);
     const int d = P.d, M = P.M, ff = P.ff, r = P.r, BT = P.B * P.T;
     const int dact = pr->adapter_act == CLIMB_EPI_RELU ? CLIMB_EPI_DRELU : CLIMB_EPI_DSWISH;
+    const float p_h = bt->training ? dm->hidden_dropout : 0.0f, p_a = bt->training ? dm->attn_dropout : 0.0f;
+    const unsigned long long dseed = bt->dropout_seed;
 
     // lowest layer that still needs a gradient (everything below is skipped)
     int lowest = P.layers;
@@ -466,11 +497,16 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
         // the K = 768 epilogue the FC1 sums cost 57 us per launch, a third of that kernel's instructions; issued as
         // INDEPENDENT background launches beside the dgrad GEMMs they measured 2 % slower on the whole step than as
         // ordinary 8-13 us passes: the co-resident CTAs take issue slots and L2 bandwidth from an epilogue-bound GEMM.)
-        TRY(run_dgrad(M, d, ff, dx_h, H(shadow, w.fc2_w), S.du, CLIMB_BF16, CLIMB_EPI_MUL_AUX, a.u, ff, nullptr, nullptr, s,
+        const bf16* dy_h = dx_h;               // gradient at the FC2 output: behind the hidden dropout when it is on
+        if (p_h > 0.0f) {
+            TRY(dropout_mask_bf16(dx_h, S.dm_h, static_cast<long long>(M) * d, p_h, dropout_site_seed(dseed, li, 2), s));
+            dy_h = S.dm_h;
+        }
+        TRY(run_dgrad(M, d, ff, dy_h, H(shadow, w.fc2_w), S.du, CLIMB_BF16, CLIMB_EPI_MUL_AUX, a.u, ff, nullptr, nullptr, s,
                       nullptr));
         if (base) {
-            TRY(run_wgrad(M, d, ff, dx_h, d, a.inter, ff, G(grad, w.fc2_w), s));
-            TRY(colsum(dx_h, CLIMB_BF16, d, M, d, G(grad, w.fc2_b), s));
+            TRY(run_wgrad(M, d, ff, dy_h, d, a.inter, ff, G(grad, w.fc2_w), s));
+            TRY(colsum(dy_h, CLIMB_BF16, d, M, d, G(grad, w.fc2_b), s));
             TRY(run_wgrad(M, ff, d, S.du, ff, a.h2, d, G(grad, w.fc1_w), s));
             TRY(colsum(S.du, CLIMB_BF16, ff, M, ff, G(grad, w.fc1_b), s));
         }
@@ -494,10 +530,22 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             TRY(run_dgrad(M, r, d, S.dz, H(shadow, w.mh_down_w), S.dmh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, dn, nullptr, s));
             dho = S.dmh;
         }
+        if (p_h > 0.0f) {                       // behind ViltSelfOutput's dropout
+            TRY(dropout_mask_bf16(dho, S.dm_h, static_cast<long long>(M) * d, p_h, dropout_site_seed(dseed, li, 1), s));
+            dho = S.dm_h;
+        }
         TRY(run_dgrad(M, d, d, dho, H(shadow, w.o_w), S.dh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, nullptr, nullptr, s));   // dctx
+        if (p_a > 0.0f) {
+            // dropout on the probabilities: mask regenerated inside the kernel; its analytic v-bias shortcut (rows of P sum to
+            // one) does not hold for the dropped probabilities, so the q | k | v bias gradients are plain column sums of dqkv
+            TRY(attention_tc_bwd(a.qkv, P.key_bias, a.ctx, S.dh, a.lse, S.dqkv, nullptr, P.B, P.L, P.heads, 0.125f, s, p_a,
+                                 dropout_site_seed(dseed, li, 0)));
+            if (base) TRY(colsum(S.dqkv, CLIMB_BF16, 3 * d, M, 3 * d, G(grad, w.qkv_b), s));
+        } else {
         // the q/k/v bias gradient (column sums of dqkv) comes out of the attention backward's epilogue
         TRY(attention_bwd(a.qkv, P.key_bias, a.ctx, S.dh, a.lse, S.delta, S.dqkv, base ? G(grad, w.qkv_b) : nullptr, P.B,
                           P.L, P.heads, 0.125f, s));
+        }
         if (base) {
             // dW_o = dho^T ctx depends on nothing the attention backward writes: issued right behind it as an
             // INDEPENDENT launch, its CTAs fill the SMs that kernel's last partial wave leaves idle
@@ -514,10 +562,18 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
 
     // ---- embeddings ----
     if ((parts & CLIMB_BWD_EMBED) && (pr->embed_flags & CLIMB_TRAIN_BASE)) {
-        TRY(embed_split_bwd(dx, S.dy_text, S.dpatch, P.B, P.T, P.Np, d, s));
-        TRY(embed_reduce_bwd(dx, bt->image_type_idx, bt->image_type_idx_scalar, S.S, G(grad, pr->cls_token),
-                             G(grad, pr->pos_emb), G(grad, pr->mod_emb), G(grad, pr->patch_b), dm->n_modality, P.B, P.T,
-                             P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0));
+        const float* dxe = dx;                  // gradient of the content rows: behind the embedding dropout when it is on
+        if (p_h > 0.0f) {
+            TRY(dropout_mask_f32(dx, S.dxm, static_cast<long long>(M) * d, p_h, dropout_site_seed(dseed, -1, 1), s));
+            dxe = S.dxm;
+            // the modality-type rows are added AFTER the dropout: their gradient is the unmasked one
+            TRY(embed_reduce_bwd(dx, bt->image_type_idx, bt->image_type_idx_scalar, S.S, nullptr, nullptr, G(grad, pr->mod_emb),
+                                 nullptr, dm->n_modality, P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0));
+        }
+        TRY(embed_split_bwd(dxe, S.dy_text, S.dpatch, P.B, P.T, P.Np, d, s));
+        TRY(embed_reduce_bwd(dxe, bt->image_type_idx, bt->image_type_idx_scalar, S.S, G(grad, pr->cls_token),
+                             G(grad, pr->pos_emb), p_h > 0.0f ? nullptr : G(grad, pr->mod_emb), G(grad, pr->patch_b), dm->n_modality,
+                             P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0));
         TRY(layernorm_bwd(S.dy_text, nullptr, P.text_e, d, F(theta, pr->text_ln_w), F(theta, pr->text_ln_b), P.text_mean,
                           P.text_rstd, nullptr, S.de_text, nullptr, G(grad, pr->text_ln_w), G(grad, pr->text_ln_b), BT, d,
                           CLIMB_EPI_NONE, s));

@@ -34,7 +34,8 @@ int encode_tmap_bf16(void* map_out, const void* ptr, int rank, const long long* 
 int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H, float scale,
                      cudaStream_t stream, float p_drop = 0.0f, unsigned long long seed = 0);
 int attention_tc_bwd(const void* qkv, const float* key_bias, const void* ctx, const void* dctx, const float* lse,
-                     void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream);
+                     void* dqkv, float* colsum, int B, int L, int H, float scale, cudaStream_t stream, float p_drop = 0.0f,
+                     unsigned long long seed = 0);
 
 // elementwise.cu
 int cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
@@ -56,7 +57,8 @@ int im2col(const float* px, void* out, int B, int C, int H, int W, int P, cudaSt
 int pos_interp(const float* pos_emb, float* table, int hp, int wp, int G, int d, cudaStream_t stream);
 int embed_assemble(const float* text_ln, const float* patch, const float* table, const float* cls,
                    const float* pos_emb, const float* mod, const int* type_idx, int type_idx_scalar, float* x,
-                   int B, int T, int Np, int d, cudaStream_t stream, int n_mod = 0);
+                   int B, int T, int Np, int d, cudaStream_t stream, int n_mod = 0, float p_drop = 0.0f,
+                   unsigned long long seed = 0);
 int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T, int Np, int d, cudaStream_t stream);
 int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, float* S, float* d_cls,
                      float* d_pos, float* d_mod, float* d_patch_bias, int n_mod, int B, int T, int hp, int wp,
@@ -65,7 +67,7 @@ int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, 
 int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int H, int W, int P, int Np, cudaStream_t stream);
 int embed_assemble_ragged(const float* text_ln, const float* patch, const int* geom, const float* cls, const float* pos_emb,
                           const float* mod, const int* type_idx, int type_idx_scalar, float* x, int B, int T, int Np, int G,
-                          int d, cudaStream_t stream, int n_mod = 0);
+                          int d, cudaStream_t stream, int n_mod = 0, float p_drop = 0.0f, unsigned long long seed = 0);
 int key_bias_ragged(const long long* mask, const int* geom, float* out, int B, int T, int L, cudaStream_t stream);
 int text_scatter_bwd(const float* de, const long long* ids, const long long* tt, float* d_word, float* d_type,
                      float* d_pos, int rows, int T, int d, cudaStream_t stream, int vocab = 0, int n_types = 0);
@@ -104,6 +106,14 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
                   const float* theta, const void* shadow, const void* workspace, long long workspace_bytes,
                   void* scratch, long long scratch_bytes, const float* dpooled, float* grad, int first_layer,
                   int last_layer, int parts, cudaStream_t s);
+
+// dropout.cu (ViLT encoder dropout p > 0: hidden-state sites, mask export for the tests)
+unsigned long long dropout_site_seed(unsigned long long base, int layer, int site);
+int dropout_res(const float* x, const float* res, float* y, void* pre_bf16, void* post_bf16, long long n, float p,
+                unsigned long long seed, cudaStream_t s);
+int dropout_mask_bf16(const void* src, void* dst, long long n, float p, unsigned long long seed, cudaStream_t s);
+int dropout_mask_f32(const float* src, float* dst, long long n, float p, unsigned long long seed, cudaStream_t s);
+int attn_dropout_mask(float* out, int B, int H, int L, float p, unsigned long long seed, cudaStream_t s);
 
 // precise.cu (CLIMB_PREC_BF16X3: split-operand contractions, fp32 activations and attention)
 long long vilt_forward_workspace_bytes_precise(const climb_vilt_dims* dims, const climb_vilt_params* params,

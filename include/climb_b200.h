@@ -350,6 +350,17 @@ int climb_bert_forward(const climb_bert_dims* dims, const climb_bert_params* par
  * Element i of stream `seed` is kept iff philox(seed, i) >= p: the mask is a pure function of (seed, i). */
 int climb_dropout_add(const float* x, const float* res, float* y, int64_t n, float p, uint64_t seed, void* stream);
 
+/* Dropout inside the ViLT encoder (dims.hidden_dropout / attn_dropout > 0 with batch.training != 0; modeling_vilt.py:201,303,374,
+ * 410,482). Every mask is a pure function of (site seed, element index); the backward regenerates it. These entry points expose
+ * the masks so that a test can hand the SAME masks to the CPU oracle:
+ *   climb_dropout_site_seed(batch.dropout_seed, layer, site): layer -1 / site 1 = embeddings ([B, L, hidden] rows after assembly,
+ *       before the modality-type rows are added); layer l / site 0 = attention probabilities, 1 = self-output dense, 2 = output dense
+ *   climb_dropout_keep_mask          : out[i] = 0 or 1 / (1 - p) for the n elements of a hidden-state site (n % 4 == 0)
+ *   climb_attention_dropout_keep_mask: out[b, h, q, k] likewise for the probabilities, fp32 [B, H, L, L] */
+uint64_t climb_dropout_site_seed(uint64_t base_seed, int layer, int site);
+int climb_dropout_keep_mask(float* out, int64_t n, float p, uint64_t seed, void* stream);
+int climb_attention_dropout_keep_mask(float* out, int B, int H, int L, float p, uint64_t seed, void* stream);
+
 /* ---- image side of the input pipeline ------------------------------------------------------
  * Replaces ViltFeatureExtractor.__call__ (adapter-transformers/src/transformers/models/vilt/feature_extraction_vilt.py:
  * 253-292, called from ViltEncoderWrapper.process_inputs, src/modeling/vilt.py:83-96): Pillow BICUBIC resize of uint8 RGB

@@ -247,15 +247,22 @@ def visual_embed_ragged(sd, pixel_values: Tensor, pixel_mask: Tensor, dims: Vilt
 
 
 def embeddings(sd, dims: ViltDims, input_ids, attention_mask, token_type_ids, pixel_values,
-               image_token_type_idx: int = 1, inputs_embeds=None, pixel_mask=None) -> Tuple[Tensor, Tensor]:
-    """ViltEmbeddings.forward, modeling_vilt.py:207-246: text || image with modality-type rows."""
+               image_token_type_idx: int = 1, inputs_embeds=None, pixel_mask=None, masks=None) -> Tuple[Tensor, Tensor]:
+    """ViltEmbeddings.forward, modeling_vilt.py:207-246: text || image with modality-type rows.
+    masks["embed"] ([B, L, d] keep factors 0 or 1 / (1 - p)) = the two embedding dropouts (:303 on the text LayerNorm output,
+    :201 on patches + position embeddings), both applied BEFORE the modality-type rows are added (:231-241)."""
     tt = sd[ENC + "embeddings.token_type_embeddings.weight"]
-    text = text_embeddings(sd, input_ids, token_type_ids, dims, inputs_embeds) + tt[0]
+    text = text_embeddings(sd, input_ids, token_type_ids, dims, inputs_embeds)
     if pixel_mask is not None and not bool((pixel_mask != 0).all()):
         image, image_mask = visual_embed_ragged(sd, pixel_values, pixel_mask, dims)
     else:
         image = visual_embed_fixed(sd, pixel_values, dims)
         image_mask = torch.ones(image.shape[:2], dtype=text.dtype)
+    if masks is not None and "embed" in masks:
+        T = text.shape[1]
+        text = text * masks["embed"][:, :T]
+        image = image * masks["embed"][:, T:]
+    text = text + tt[0]
     image = image + tt[image_token_type_idx]
     masks = torch.cat([attention_mask.to(text.dtype), image_mask.to(text.dtype)], dim=1)
     return torch.cat([text, image], dim=1), masks
@@ -284,8 +291,11 @@ class AdapterSpec:
 
 
 def vilt_layer(sd, i: int, x: Tensor, ext_mask: Tensor, dims: ViltDims,
-               adapter: Optional[AdapterSpec] = None) -> Tensor:
-    """ViltLayer.forward, modeling_vilt.py:503-525 (pre-LN block)."""
+               adapter: Optional[AdapterSpec] = None, masks=None) -> Tensor:
+    """ViltLayer.forward, modeling_vilt.py:503-525 (pre-LN block). masks (optional, keep factors 0 or 1 / (1 - p)):
+    ("attn", i) [B, H, L, L] on the probabilities (:374), ("self_out", i) [B, L, d] on dense(ctx) (:410),
+    ("out", i) [B, L, d] on dense(inter) (:482) -- dropout with EXPLICIT masks, so that a test can feed the CUDA path's."""
+    masks = masks or {}
     l = f"{ENC}encoder.layer.{i}."
     d, H = dims.hidden_size, dims.num_attention_heads
     dh = d // H
@@ -298,15 +308,22 @@ def vilt_layer(sd, i: int, x: Tensor, ext_mask: Tensor, dims: ViltDims,
     k = heads(F.linear(h1, sd[l + "attention.attention.key.weight"], sd[l + "attention.attention.key.bias"]))
     v = heads(F.linear(h1, sd[l + "attention.attention.value.weight"], sd[l + "attention.attention.value.bias"]))
     scores = q @ k.transpose(-1, -2) / math.sqrt(dh) + ext_mask       # :363-368
-    probs = torch.softmax(scores, dim=-1)                              # :371 (dropout p = 0, :375)
+    probs = torch.softmax(scores, dim=-1)                              # :371
+    if ("attn", i) in masks:
+        probs = probs * masks[("attn", i)]                             # :374-375
     ctx = (probs @ v).permute(0, 2, 1, 3).reshape(B, L, d)             # :381-384
     a = F.linear(ctx, sd[l + "attention.output.dense.weight"], sd[l + "attention.output.dense.bias"])   # :409
+    if ("self_out", i) in masks:
+        a = a * masks[("self_out", i)]                                 # :410
     if adapter is not None and "mh" in adapter.sites:
         a = adapter_bottleneck(sd, l + f"attention.output.adapters.{adapter.name}.", a, adapter.non_linearity, adapter.scaling)
     x = a + x                                                          # :514
     h2 = F.layer_norm(x, (d,), sd[l + "layernorm_after.weight"], sd[l + "layernorm_after.bias"], dims.layer_norm_eps)
     inter = F.gelu(F.linear(h2, sd[l + "intermediate.dense.weight"], sd[l + "intermediate.dense.bias"]))  # :461-466
-    o = F.linear(inter, sd[l + "output.dense.weight"], sd[l + "output.dense.bias"]) + x                   # :480-484
+    o = F.linear(inter, sd[l + "output.dense.weight"], sd[l + "output.dense.bias"])                       # :481
+    if ("out", i) in masks:
+        o = o * masks[("out", i)]                                      # :482
+    o = o + x                                                          # :484
     if adapter is not None and "output" in adapter.sites:
         o = adapter_bottleneck(sd, l + f"output.adapters.{adapter.name}.", o, adapter.non_linearity, adapter.scaling)
     return o
@@ -314,13 +331,13 @@ def vilt_layer(sd, i: int, x: Tensor, ext_mask: Tensor, dims: ViltDims,
 
 def vilt_forward(sd, dims: ViltDims, input_ids, attention_mask, token_type_ids, pixel_values,
                  image_token_type_idx: int = 1, inputs_embeds=None,
-                 adapter: Optional[AdapterSpec] = None, return_hidden: bool = False, pixel_mask=None):
+                 adapter: Optional[AdapterSpec] = None, return_hidden: bool = False, pixel_mask=None, dropout_masks=None):
     """ViltModel.forward -> pooler_output, modeling_vilt.py:777-884, 887-899."""
     x, masks = embeddings(sd, dims, input_ids, attention_mask, token_type_ids, pixel_values,
-                          image_token_type_idx, inputs_embeds, pixel_mask)
+                          image_token_type_idx, inputs_embeds, pixel_mask, masks=dropout_masks)
     ext = (1.0 - masks)[:, None, None, :] * -10000.0                   # modeling_utils.py:299-311
     for i in range(dims.num_hidden_layers):
-        x = vilt_layer(sd, i, x, ext, dims, adapter)
+        x = vilt_layer(sd, i, x, ext, dims, adapter, masks=dropout_masks)
     x = F.layer_norm(x, (dims.hidden_size,), sd[ENC + "layernorm.weight"], sd[ENC + "layernorm.bias"], dims.layer_norm_eps)
     pooled = torch.tanh(F.linear(x[:, 0], sd[ENC + "pooler.dense.weight"], sd[ENC + "pooler.dense.bias"]))
     return (pooled, x) if return_hidden else pooled
@@ -341,7 +358,7 @@ def task_head(sd, task: str, pooled: Tensor, spec: Optional[Dict] = None, train:
 
 
 def learner_forward(sd, dims: ViltDims, task: str, batch: Dict[str, Tensor],
-                    adapter: Optional[AdapterSpec] = None, spec: Optional[Dict] = None):
+                    adapter: Optional[AdapterSpec] = None, spec: Optional[Dict] = None, dropout_masks=None):
     """ViltContinualLearner.forward on tensor inputs (src/modeling/vilt.py:218-350):
     single image (:241-261), NLVR2 two passes with image_token_type_idx 1, 2 (:291-304), VCR four
     text choices over the same pixels (:334-349). Returns (pooled, logits)."""
@@ -353,7 +370,7 @@ def learner_forward(sd, dims: ViltDims, task: str, batch: Dict[str, Tensor],
                 for c in range(spec["num_choices"])]
         pooled = torch.stack(outs, dim=0).transpose(0, 1)
     elif spec["num_images"] == 1:
-        pooled = vilt_forward(sd, dims, ids, am, tt, px, 1, adapter=adapter, pixel_mask=pm)
+        pooled = vilt_forward(sd, dims, ids, am, tt, px, 1, adapter=adapter, pixel_mask=pm, dropout_masks=dropout_masks)
     else:
         outs = [vilt_forward(sd, dims, ids, am, tt, px[:, i], i + 1, adapter=adapter,
                              pixel_mask=None if pm is None else pm[:, i])
