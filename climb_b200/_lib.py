@@ -74,6 +74,7 @@ climb_wordpiece_encode = _sig("climb_wordpiece_encode", [c_void_p, c_char_p, c_v
 climb_profile_begin = _sig("climb_profile_begin", [])
 climb_profile_end = _sig("climb_profile_end", [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64), c_int])
 climb_gemm_bf16 = _sig("climb_gemm_bf16", [POINTER(GemmDesc), _P])
+climb_adapter_fused = _sig("climb_adapter_fused", [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P])
 climb_attention_fwd = _sig("climb_attention_fwd", [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P])
 climb_attention_fwd_dropout = _sig("climb_attention_fwd_dropout",
                                    [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, ctypes.c_uint64, _P])

@@ -129,6 +129,13 @@ int climb_profile_end(double* ms, double* work, int64_t* launches, int n_categor
 
 int climb_gemm_bf16(const climb_gemm_desc* desc, void* stream) { return gemm_bf16(desc, S(stream)); }
 
+int climb_adapter_fused(int backward, int M, int d, int r, int act, const void* a_bf16, const void* w_down_bf16, const void* w_up_bf16,
+                        const float* b_down, const float* b_up, void* pre_bf16, void* z_bf16, const float* c_in, float* c_out,
+                        void* c2_bf16, float* colsum_z, void* stream) {
+    return adapter_fused(backward, M, d, r, act, a_bf16, w_down_bf16, w_up_bf16, b_down, b_up, pre_bf16, z_bf16, c_in, c_out, c2_bf16,
+                         colsum_z, S(stream));
+}
+
 int climb_attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L,
                         int H, float scale, void* stream) {
     return attention_fwd(qkv, key_bias, ctx, lse, B, L, H, scale, S(stream));

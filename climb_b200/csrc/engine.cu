@@ -335,6 +335,7 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
 
     // ---- encoder layers (modeling_vilt.py:503-525) ----
     const float scale = 0.125f;   // 1 / sqrt(64)
+    const bool fused_ad = P.r > 0 && adapter_fused_ok(d, P.r);      // one-launch bottleneck (gemm_tcgen05.cu: adapter_fused_kernel)
     for (int li = 0; li < P.layers; ++li) {
         const climb_vilt_layer& w = pr->layer[li];
         LayerAct& a = P.act[li];
@@ -363,7 +364,11 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
             if (mh_ad) l.aux = a.mh_in;                       // adapter sees O(ctx)+b before the residual
             TRY(run_linear(l, s));
         }
-        if (mh_ad) {
+        if (mh_ad && fused_ad) {
+            // x1 (= x_in + h) += W_u act(W_d h + b_d) + b_u in ONE launch: the r-wide intermediate stays on the SM
+            TRY(adapter_fused(0, M, d, P.r, pr->adapter_act, a.mh_in, H(shadow, w.mh_down_w), H(shadow, w.mh_up_w), F(theta, w.mh_down_b),
+                              F(theta, w.mh_up_b), a.mh_pre, a.mh_z, a.x1, a.x1, nullptr, nullptr, s));
+        } else if (mh_ad) {
             Lin dn{M, P.r, d, a.mh_in, d, H(shadow, w.mh_down_w)};
             dn.bias = F(theta, w.mh_down_b); dn.C = a.mh_z; dn.epi = pr->adapter_act; dn.aux = a.mh_pre;
             TRY(run_linear(dn, s));
@@ -391,7 +396,10 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
             if (out_ad) l.c2 = a.out_in;                      // adapter sees FC2 + residual
             TRY(run_linear(l, s));
         }
-        if (out_ad) {
+        if (out_ad && fused_ad) {
+            TRY(adapter_fused(0, M, d, P.r, pr->adapter_act, a.out_in, H(shadow, w.out_down_w), H(shadow, w.out_up_w), F(theta, w.out_down_b),
+                              F(theta, w.out_up_b), a.out_pre, a.out_z, x_out, x_out, nullptr, nullptr, s));
+        } else if (out_ad) {
             Lin dn{M, P.r, d, a.out_in, d, H(shadow, w.out_down_w)};
             dn.bias = F(theta, w.out_down_b); dn.C = a.out_z; dn.epi = pr->adapter_act; dn.aux = a.out_pre;
             TRY(run_linear(dn, s));
@@ -431,6 +439,7 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
     const int dact = pr->adapter_act == CLIMB_EPI_RELU ? CLIMB_EPI_DRELU : CLIMB_EPI_DSWISH;
     const float p_h = bt->training ? dm->hidden_dropout : 0.0f, p_a = bt->training ? dm->attn_dropout : 0.0f;
     const unsigned long long dseed = bt->dropout_seed;
+    const bool fused_ad = r > 0 && adapter_fused_ok(d, r);
 
     // lowest layer that still needs a gradient (everything below is skipped)
     int lowest = P.layers;
@@ -481,7 +490,17 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
         const bool out_ad = r > 0 && w.out_down_w >= 0;
 
         // ---- output adapter: out = y + up(act(down(y))) ----
-        if (out_ad) {
+        if (out_ad && fused_ad) {
+            // the up-projection's gradients need dx_h as it is NOW (the fused launch refreshes it in place)
+            if (adp) {
+                TRY(run_wgrad(M, d, r, dx_h, d, a.out_z, r, G(grad, w.out_up_w), s));
+                TRY(colsum(dx_h, CLIMB_BF16, d, M, d, G(grad, w.out_up_b), s));
+            }
+            // dpre = (dx W_u) * act'(pre) -> S.dz (+ its column sums = the down-bias gradient); dx += dpre W_d in place, dx_h refreshed
+            TRY(adapter_fused(1, M, d, r, pr->adapter_act, dx_h, H(shadow, w.out_down_w), H(shadow, w.out_up_w), nullptr, nullptr,
+                              a.out_pre, S.dz, dx, dx, dx_h, adp ? G(grad, w.out_down_b) : nullptr, s));
+            if (adp) TRY(run_wgrad(M, r, d, S.dz, r, a.out_in, d, G(grad, w.out_down_w), s));
+        } else if (out_ad) {
             TRY(run_dgrad(M, d, r, dx_h, H(shadow, w.out_up_w), S.dz, CLIMB_BF16, dact, a.out_pre, r, nullptr, nullptr, s));
             if (adp) {
                 TRY(run_wgrad(M, d, r, dx_h, d, a.out_z, r, G(grad, w.out_up_w), s));
@@ -519,7 +538,17 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
         // now dn / dn_h = dx1
         // ---- attention block: x1 = x + A, A = h (+ adapter), h = O(ctx) + b ----
         const bf16* dho = dn_h;            // gradient at the O-proj output
-        if (mh_ad) {
+        if (mh_ad && fused_ad) {
+            if (adp) {
+                TRY(run_wgrad(M, d, r, dn_h, d, a.mh_z, r, G(grad, w.mh_up_w), s));
+                TRY(colsum(dn_h, CLIMB_BF16, d, M, d, G(grad, w.mh_up_b), s));
+            }
+            // gradient at the O-proj output: dmh (bf16) = dn + ((dn W_u) * act'(pre)) W_d; dn itself (the residual path) is untouched
+            TRY(adapter_fused(1, M, d, r, pr->adapter_act, dn_h, H(shadow, w.mh_down_w), H(shadow, w.mh_up_w), nullptr, nullptr,
+                              a.mh_pre, S.dz, dn, nullptr, S.dmh, adp ? G(grad, w.mh_down_b) : nullptr, s));
+            if (adp) TRY(run_wgrad(M, r, d, S.dz, r, a.mh_in, d, G(grad, w.mh_down_w), s));
+            dho = S.dmh;
+        } else if (mh_ad) {
             TRY(run_dgrad(M, d, r, dn_h, H(shadow, w.mh_up_w), S.dz, CLIMB_BF16, dact, a.mh_pre, r, nullptr, nullptr, s));
             if (adp) {
                 TRY(run_wgrad(M, d, r, dn_h, d, a.mh_z, r, G(grad, w.mh_up_w), s));

@@ -1368,6 +1368,306 @@ gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused adapter bottleneck (adapters/modeling.py:160-179 as ViLT wires it, mixins/vilt.py:23-125):
+//     forward   out = y + W_u act(W_d y + b_d) + b_u                 y = the site's input (bf16 copy) / residual stream (fp32)
+//     backward  dy  = dout + (dout W_u * act'(pre)) W_d              (+ dpre for the two weight gradients, + its column sums)
+// ONE launch per site and direction instead of two generic GEMM launches on ragged widths: a CTA owns 128 rows and runs
+//     stage 1   T[128, r] = A[128, d] B1          12 k-blocks of A through a 4-stage TMA ring, accumulator = 64 TMEM columns
+//     stage 2   forward: z = act(T + b_d)   backward: dpre = T * act'(pre)      thread = row; the bf16 result goes to global
+//               memory (kept for the weight gradients) AND, as a K-major A operand tile, to shared memory -- the r-wide
+//               intermediate never round-trips through HBM between the two projections
+//     stage 3   C[128, d] (fp32 residual stream, in place) += Z[128, r] B2 (+ b_u) in six 128-column chunks through two TMEM
+//               accumulators, the chunk's residual read and its result written by the epilogue warps in coalesced 64 B units
+// B1 / B2 are the adapter's two weight matrices read in place: forward W_d, W_u K-major; backward W_u, W_d MN-major.
+// r <= 64 (CLiMB: reduction factor 16 -> r = 48), r % 16 == 0, d % 128 == 0.
+// ------------------------------------------------------------------------------------------
+struct AdapterArgs {
+    int M, d, r;
+    int backward;               // 0 forward, 1 backward
+    int act;                    // CLIMB_EPI_SWISH / CLIMB_EPI_RELU
+    const float* bias1;         // forward: b_d [r]
+    const float* bias2;         // forward: b_u [d]
+    __nv_bfloat16* pre;         // [M, r]  forward: written (pre-activation), backward: read
+    __nv_bfloat16* z;           // [M, r]  forward: written act(pre), backward: written dpre
+    const float* c_in;          // fp32 [M, d] residual input
+    float* c_out;               // fp32 [M, d] result (may alias c_in) or null
+    __nv_bfloat16* c2;          // optional bf16 copy of the result [M, d]
+    float* colsum_z;            // backward, optional [r]: += column sums of dpre (the down-projection's bias gradient)
+    int n_tiles;
+};
+constexpr int kAdStages = 4;
+constexpr int kAdStageBytes = 16384 + 8192;      // A k-block [128 x 64] + B1 k-block [64 x 64]
+constexpr int kAdZ = kAdStages * kAdStageBytes;                 // Z tile [128 x 64] bf16
+constexpr int kAdB2 = kAdZ + 16384;                             // 2 x 16 KB ring of B2 chunks
+constexpr int kAdStg = kAdB2 + 2 * 16384;                       // 8 warps x 2 KB staging
+constexpr int kAdBar = kAdStg + 8 * 2048;
+constexpr int kAdSmemBytes = kAdBar + 256 + 1024;
+constexpr int kAdThreads = 64 + 8 * 32;
+
+__global__ void __launch_bounds__(kAdThreads, 1)
+adapter_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b1,
+                     const __grid_constant__ CUtensorMap map_b2, const AdapterArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAdBar);
+    uint64_t* full1 = bars;              // [4] tx
+    uint64_t* empty1 = bars + 4;         // [4] commit
+    uint64_t* full2 = bars + 8;          // [2] tx
+    uint64_t* empty2 = bars + 10;        // [2] commit
+    uint64_t* t_full = bars + 12;        // stage-1 accumulator complete
+    uint64_t* t_empty = bars + 13;       // ... and read out (4 warp arrivals)
+    uint64_t* z_full = bars + 14;        // Z tile is in shared memory (4 warp arrivals)
+    uint64_t* acc_full = bars + 15;      // [2]
+    uint64_t* acc_empty = bars + 17;     // [2] 8 warp arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_n = p.d / kBlockK, ch_n = p.d / 128, ks_n = p.r / 16;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b1);
+        tma_prefetch_desc(&map_b2);
+        for (int s = 0; s < kAdStages; ++s) { mbar_init(&full1[s], 1); mbar_init(&empty1[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full2[s], 1); mbar_init(&empty2[s], 1);
+            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8);
+        }
+        mbar_init(t_full, 1); mbar_init(t_empty, 4); mbar_init(z_full, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s1 = 0, s2 = 0;
+            uint32_t ph1 = 0, ph2 = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < kb_n; ++kb) {
+                    mbar_wait(&empty1[s1], ph1 ^ 1u);
+                    uint8_t* sa = smem + s1 * kAdStageBytes;
+                    mbar_arrive_expect_tx(&full1[s1], kAdStageBytes);
+                    tma_load_2d(&map_a, &full1[s1], sa, kb * kBlockK, tile * kBlockM);
+                    if (!p.backward) tma_load_2d(&map_b1, &full1[s1], sa + 16384, kb * kBlockK, 0);      // W_d [r, d]: rows past r are zero fill
+                    else             tma_load_2d(&map_b1, &full1[s1], sa + 16384, 0, kb * kBlockK);      // W_u [d, r]: columns past r are zero fill
+                    if (++s1 == kAdStages) { s1 = 0; ph1 ^= 1u; }
+                }
+                for (int c = 0; c < ch_n; ++c) {
+                    mbar_wait(&empty2[s2], ph2 ^ 1u);
+                    uint8_t* sb = smem + kAdB2 + s2 * 16384;
+                    mbar_arrive_expect_tx(&full2[s2], 16384);
+                    if (!p.backward) {
+                        tma_load_2d(&map_b2, &full2[s2], sb, 0, c * 128);                               // W_u [d, r]: 128 rows (n) x 64 (k, zero fill past r)
+                    } else {
+                        tma_load_2d(&map_b2, &full2[s2], sb, c * 128, 0);                               // W_d [r, d]: 64 (k rows, zero fill past r) x 64 n
+                        tma_load_2d(&map_b2, &full2[s2], sb + 8192, c * 128 + 64, 0);
+                    }
+                    if (++s2 == 2) { s2 = 0; ph2 ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc1 = make_instr_desc(kBlockM, 64, 0, p.backward);
+            const uint32_t idesc2 = make_instr_desc(kBlockM, 128, 0, p.backward);
+            const uint32_t b1_lbo = p.backward ? kBlockK * 128 : 16, b1_kstep = p.backward ? 16 * 128 : 32;
+            const uint32_t b2_lbo = p.backward ? 64 * 128 : 16, b2_kstep = p.backward ? 16 * 128 : 32;
+            int s1 = 0, s2 = 0, it = 0;
+            uint32_t ph1 = 0, ph2 = 0, acc_n = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                if (it > 0) mbar_wait(t_empty, (it - 1) & 1);
+                tc_fence_after();
+                for (int kb = 0; kb < kb_n; ++kb) {
+                    mbar_wait(&full1[s1], ph1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s1 * kAdStageBytes), sb = sa + 16384;
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / 16; ++kk)
+                        umma_bf16(tmem, make_smem_desc(sa + kk * 32, 16, 1024), make_smem_desc(sb + kk * b1_kstep, b1_lbo, 1024), idesc1,
+                                  (kb > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&empty1[s1]);
+                    if (++s1 == kAdStages) { s1 = 0; ph1 ^= 1u; }
+                }
+                umma_commit(t_full);
+                mbar_wait(z_full, it & 1);
+                tc_fence_after();
+                const uint32_t sz = smem_u32(smem + kAdZ);
+                for (int c = 0; c < ch_n; ++c, ++acc_n) {
+                    const uint32_t ab = acc_n & 1u;
+                    mbar_wait(&full2[s2], ph2);
+                    if (acc_n >= 2) mbar_wait(&acc_empty[ab], ((acc_n >> 1) - 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + kAdB2 + s2 * 16384);
+                    for (int kk = 0; kk < ks_n; ++kk)
+                        umma_bf16(tmem + 128 + ab * 128, make_smem_desc(sz + kk * 32, 16, 1024),
+                                  make_smem_desc(sb + kk * b2_kstep, b2_lbo, 1024), idesc2, kk > 0 ? 1u : 0u);
+                    umma_commit(&empty2[s2]);
+                    umma_commit(&acc_full[ab]);
+                    if (++s2 == 2) { s2 = 0; ph2 ^= 1u; }
+                }
+            }
+        }
+    } else {
+        const int ew = warp - 2, lg = warp & 3, sub = ew >> 2;       // TMEM lane group (warp % 4), which half of a chunk's units
+        uint8_t* stg = smem + kAdStg + ew * 2048;
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(lg * 32) << 16);
+        const int rsub = lane >> 2, gj = lane & 3;
+        int it = 0;
+        uint32_t acc_n = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int row0 = tile * kBlockM + lg * 32;
+            const int rows_valid = min(32, max(0, p.M - row0));
+            // the residual of the first chunk travels while stages 1 and 2 run
+            const uint8_t* in_base = reinterpret_cast<const uint8_t*>(p.c_in) + (static_cast<long long>(row0) + rsub) * (p.d * 4LL) + gj * 16;
+            uint8_t* out_base = p.c_out ? reinterpret_cast<uint8_t*>(p.c_out) + (static_cast<long long>(row0) + rsub) * (p.d * 4LL) + gj * 16 : nullptr;
+            const long long pitch8 = 8LL * p.d * 4;
+            uint4 pf[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) load_unit(pf[q], in_base + static_cast<long long>((sub * 4 + q) * 16) * 4, pitch8, rows_valid, lane);
+            // ---- stage 2 (one warp per lane group): the r-wide intermediate ----
+            if (sub == 0) {
+                mbar_wait(t_full, it & 1);
+                tc_fence_after();
+                const int row = row0 + lane;
+                const bool valid = lane < rows_valid;
+                uint8_t* zrow = smem + kAdZ + (lg * 32 + lane) * 128;
+#pragma unroll 1
+                for (int u = 0; u < 4; ++u) {                 // 16 columns at a time
+                    uint32_t zp[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    if (u * 16 < p.r) {
+                        uint32_t t[16];
+                        tmem_ld_32x16(t_row + u * 16, t);
+                        float v[16];
+                        uint32_t prev[8];
+                        if (p.backward) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) prev[j] = 0u;
+                            if (valid) {
+                                const uint4* src = reinterpret_cast<const uint4*>(p.pre + static_cast<long long>(row) * p.r + u * 16);
+                                const uint4 a = src[0], b = src[1];
+                                prev[0] = a.x; prev[1] = a.y; prev[2] = a.z; prev[3] = a.w;
+                                prev[4] = b.x; prev[5] = b.y; prev[6] = b.z; prev[7] = b.w;
+                            }
+                        }
+                        tmem_ld_wait_regs16(t);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(t[j]);
+                        if (!p.backward) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias1 + u * 16 + j);
+                            uint32_t pp[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) pp[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                            if (valid) {
+                                uint4* dst = reinterpret_cast<uint4*>(p.pre + static_cast<long long>(row) * p.r + u * 16);
+                                dst[0] = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+                                dst[1] = make_uint4(pp[4], pp[5], pp[6], pp[7]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = p.act == CLIMB_EPI_RELU ? fmaxf(v[j], 0.0f) : swish_f(v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 a = unpack_bf16(prev[j]);
+                                if (p.act == CLIMB_EPI_RELU) {
+                                    v[2 * j] = a.x > 0.0f ? v[2 * j] : 0.0f;
+                                    v[2 * j + 1] = a.y > 0.0f ? v[2 * j + 1] : 0.0f;
+                                } else {
+                                    v[2 * j] *= dswish_f(a.x);
+                                    v[2 * j + 1] *= dswish_f(a.y);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) zp[j] = valid ? pack_bf16(v[2 * j], v[2 * j + 1]) : 0u;
+                        if (valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(p.z + static_cast<long long>(row) * p.r + u * 16);
+                            dst[0] = make_uint4(zp[0], zp[1], zp[2], zp[3]);
+                            dst[1] = make_uint4(zp[4], zp[5], zp[6], zp[7]);
+                        }
+                        if (p.backward && p.colsum_z != nullptr) {
+                            // column sums of the bf16-rounded dpre over the warp's 32 rows, one atomic per column
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float2 f = unpack_bf16(zp[j]);
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    f.x += __shfl_xor_sync(0xffffffffu, f.x, o);
+                                    f.y += __shfl_xor_sync(0xffffffffu, f.y, o);
+                                }
+                                if (lane == 0) {
+                                    atomicAdd(p.colsum_z + u * 16 + 2 * j, f.x);
+                                    atomicAdd(p.colsum_z + u * 16 + 2 * j + 1, f.y);
+                                }
+                            }
+                        }
+                    }
+                    // granules 2u, 2u + 1 of the row in the K-major, 128B-swizzled Z tile (columns past r are zeros)
+                    const uint32_t rr = static_cast<uint32_t>(lg * 32 + lane) & 7u;
+                    *reinterpret_cast<uint4*>(zrow + (((2 * u) ^ rr) << 4)) = make_uint4(zp[0], zp[1], zp[2], zp[3]);
+                    *reinterpret_cast<uint4*>(zrow + (((2 * u + 1) ^ rr) << 4)) = make_uint4(zp[4], zp[5], zp[6], zp[7]);
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(t_empty);
+                    mbar_arrive(z_full);
+                }
+            }
+            // ---- stage 3: residual stream += Z B2, 16-column units; warp `sub` takes units sub * 4 .. sub * 4 + 3 of each chunk.
+            //      The residual of a whole chunk (4 units = 8 KB per warp, 64 KB per SM) is in flight at any time: every unit's
+            //      registers are refilled with the NEXT chunk's data as soon as they have been consumed ----
+            for (int c = 0; c < ch_n; ++c, ++acc_n) {
+                const uint32_t ab = acc_n & 1u;
+                mbar_wait(&acc_full[ab], (acc_n >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = c * 128 + (sub * 4 + q) * 16;
+                    uint32_t a[16], res[16];
+                    tmem_ld_32x16(t_row + 128 + ab * 128 + (sub * 4 + q) * 16, a);
+                    transpose_unit_in(stg, pf[q], res, lane);
+                    if (c + 1 < ch_n) load_unit(pf[q], in_base + static_cast<long long>(col + 128) * 4, pitch8, rows_valid, lane);
+                    tmem_ld_wait_regs16(a);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v = __uint_as_float(a[j]) + __uint_as_float(res[j]);
+                        if (p.bias2 != nullptr) v += __ldg(p.bias2 + col + j);
+                        a[j] = __float_as_uint(v);
+                    }
+                    if (p.c2 != nullptr) {
+                        uint32_t hw[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hw[j] = pack_bf16(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
+                        uint8_t* c2_lane = reinterpret_cast<uint8_t*>(p.c2) + (static_cast<long long>(row0) + (lane >> 1)) * (p.d * 2LL) +
+                                           static_cast<long long>(col) * 2 + (lane & 1) * 16;
+                        store_unit_half(stg, hw, c2_lane, 16LL * p.d * 2, rows_valid, lane);
+                    }
+                    if (out_base != nullptr) store_unit(stg, a, out_base + static_cast<long long>(col) * 4, pitch8, rows_valid, lane);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ab]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -1748,6 +2048,52 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
         case 64: return launch_gemm<64>(d, a, stream);
         default: CLIMB_REQUIRE(false, "gemm: block_n must be 0, 64, 128 or 256 (got %d)", bn);
     }
+    return 0;
+}
+
+// Fused adapter bottleneck (see adapter_fused_kernel). A [M, d] bf16: the site's input (forward) or the gradient at its output
+// (backward); w_down [r, d], w_up [d, r] bf16 (the shadow arena); c_in / c_out fp32 [M, d] (may alias); c2 optional bf16 copy.
+bool adapter_fused_ok(int d, int r) {
+    static const bool on = [] { const char* e = getenv("CLIMB_ADAPTER_FUSED"); return !(e && e[0] == '0'); }();
+    return on && r > 0 && r <= 64 && r % 16 == 0 && d % 128 == 0 && d >= 128;
+}
+
+int adapter_fused(int backward, int M, int d, int r, int act, const void* A, const void* w_down, const void* w_up, const float* b_down,
+                  const float* b_up, void* pre, void* z, const float* c_in, float* c_out, void* c2, float* colsum_z,
+                  cudaStream_t stream) {
+    CLIMB_REQUIRE(adapter_fused_ok(d, r), "adapter_fused: unsupported shape d=%d r=%d", d, r);
+    CLIMB_REQUIRE(A && w_down && w_up && pre && z && c_in && M > 0, "adapter_fused: null operand");
+    CLIMB_REQUIRE(act == CLIMB_EPI_SWISH || act == CLIMB_EPI_RELU, "adapter_fused: activation must be swish or relu");
+    CUtensorMap ma, mb1, mb2;
+    int rc = make_tmap_2d(&ma, A, d, M, d, kBlockK, kBlockM);
+    if (rc) return rc;
+    if (!backward) {
+        rc = make_tmap_2d(&mb1, w_down, d, r, d, 64, 64);          // W_d [r, d]: K-major B1, 64 (k) x 64 rows (n, zero fill past r)
+        if (rc) return rc;
+        rc = make_tmap_2d(&mb2, w_up, r, d, r, 64, 128);           // W_u [d, r]: K-major B2, 64 (k, zero fill past r) x 128 rows (n)
+    } else {
+        rc = make_tmap_2d(&mb1, w_up, r, d, r, 64, 64);            // W_u [d, r]: MN-major B1, 64 (n, zero fill past r) x 64 k-rows
+        if (rc) return rc;
+        rc = make_tmap_2d(&mb2, w_down, d, r, d, 64, 64);          // W_d [r, d]: MN-major B2, 64 (n) x 64 k-rows (zero fill past r)
+    }
+    if (rc) return rc;
+    AdapterArgs a{};
+    a.M = M; a.d = d; a.r = r; a.backward = backward ? 1 : 0; a.act = act;
+    a.bias1 = backward ? nullptr : b_down;
+    a.bias2 = backward ? nullptr : b_up;
+    a.pre = static_cast<__nv_bfloat16*>(pre); a.z = static_cast<__nv_bfloat16*>(z);
+    a.c_in = c_in; a.c_out = c_out; a.c2 = static_cast<__nv_bfloat16*>(c2);
+    a.colsum_z = backward ? colsum_z : nullptr;
+    a.n_tiles = (M + kBlockM - 1) / kBlockM;
+    CLIMB_REQUIRE(backward || b_down != nullptr, "adapter_fused: forward needs the down-projection bias");
+    static bool attr_set = false;
+    if (!attr_set) {
+        CLIMB_CUDA_OK(cudaFuncSetAttribute(adapter_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAdSmemBytes));
+        attr_set = true;
+    }
+    const int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
+    CLIMB_CUDA_OK(launch_pdl(adapter_fused_kernel, dim3(grid), dim3(kAdThreads), kAdSmemBytes, stream, ma, mb1, mb2, a));
+    CLIMB_LAUNCH_OK();
     return 0;
 }
 

@@ -10,6 +10,11 @@ unsigned int* device_error_word();
 
 int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream);
 int gemm_pair_mode(int mode);
+// fused adapter bottleneck (gemm_tcgen05.cu): down -> activation -> up -> residual in one launch, forward and backward
+bool adapter_fused_ok(int d, int r);
+int adapter_fused(int backward, int M, int d, int r, int act, const void* A, const void* w_down, const void* w_up, const float* b_down,
+                  const float* b_up, void* pre, void* z, const float* c_in, float* c_out, void* c2, float* colsum_z,
+                  cudaStream_t stream);
 
 int attention_fwd(const void* qkv, const float* key_bias, void* ctx, float* lse, int B, int L, int H,
                   float scale, cudaStream_t stream);

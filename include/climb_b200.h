@@ -98,6 +98,20 @@ typedef struct {
 int climb_gemm_bf16(const climb_gemm_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused adapter bottleneck (Adapter.forward as ViLT wires it: adapters/modeling.py:160-179, mixins/vilt.py:23-125), one launch
+ * per site and direction; the r-wide intermediate never round-trips through HBM between the two projections.
+ *   backward = 0:  pre = A W_d^T + b_d ;  z = act(pre) ;  c_out = c_in + z W_u^T + b_u                 (A = the site's input)
+ *   backward = 1:  z   = (A W_u) * act'(pre)  (= dpre) ;  c_out = c_in + z W_d ;  colsum_z += column sums of z
+ *                  (A = gradient at the site's output; dpre and A then feed the two weight gradients)
+ * A bf16 [M, d]; W_d bf16 [r, d]; W_u bf16 [d, r]; pre, z bf16 [M, r]; c_in / c_out fp32 [M, d] (may alias; c_out may be NULL);
+ * c2 optional bf16 copy of the result [M, d]. act = CLIMB_EPI_SWISH or CLIMB_EPI_RELU. r <= 64, r % 16 == 0, d % 128 == 0
+ * (CLiMB's reduction factor 16 on ViLT-base: d = 768, r = 48); other widths run as two climb_gemm_bf16 launches in the engine.
+ * ------------------------------------------------------------------------------------------- */
+int climb_adapter_fused(int backward, int M, int d, int r, int act, const void* a_bf16, const void* w_down_bf16, const void* w_up_bf16,
+                        const float* b_down, const float* b_up, void* pre_bf16, void* z_bf16, const float* c_in, float* c_out,
+                        void* c2_bf16, float* colsum_z, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused multi-head self-attention, head dim 64 (ViltSelfAttention, modeling_vilt.py:355-388):
  *   ctx = softmax(Q K^T / 8 + key_bias) V, key_bias = (1 - mask) * -10000 (modeling_utils.py:299-311)
  * qkv  bf16 [B, L, 3*H*64] (q | k | v, head-major inside each third)

@@ -412,3 +412,53 @@ def test_layernorm_strided_cls_rows():
     yb, yf, mean, rstd = L.layernorm_fwd(x, g, b, 1e-12, rows=B, ldx=L_ * d, out_f32=True)
     ref = torch.nn.functional.layer_norm(x[:, 0], (d,), g, b, 1e-12)
     assert _max_err(yf, ref) < 2e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,d,r,act", [(15168, 768, 48, "swish"), (300, 768, 48, "relu"), (77, 128, 64, "swish"), (129, 256, 16, "relu")])
+def test_adapter_fused_bottleneck_fwd_bwd(M, d, r, act):
+    """climb_adapter_fused (down -> act -> up -> residual in one launch) against fp32 torch on the bf16-rounded operands:
+    ViLT-base with CLiMB's reduction factor 16 (d = 768, r = 48) at the benchmark's row count, ragged row counts, r = 64 / 16."""
+    import torch.nn.functional as F
+    from climb_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(M + r)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).to(dev)
+    A = rnd(M, d).bfloat16()
+    wd, wu = rnd(r, d, scale=0.05).bfloat16(), rnd(d, r, scale=0.05).bfloat16()
+    bd, bu = rnd(r, scale=0.1), rnd(d, scale=0.1)
+    c_in = rnd(M, d)
+    act_id = _lib.EPI_SWISH if act == "swish" else _lib.EPI_RELU
+    f = F.silu if act == "swish" else F.relu
+    # ---- forward ----
+    pre = torch.empty(M, r, dtype=torch.bfloat16, device=dev)
+    z = torch.empty_like(pre)
+    out = c_in.clone()
+    c2 = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
+    _lib.check(_lib.climb_adapter_fused(0, M, d, r, act_id, _lib.ptr(A), _lib.ptr(wd), _lib.ptr(wu), _lib.ptr(bd), _lib.ptr(bu),
+                                        _lib.ptr(pre), _lib.ptr(z), _lib.ptr(out), _lib.ptr(out), _lib.ptr(c2), None, _lib.stream()))
+    ref_pre = A.float() @ wd.float().t() + bd
+    ref_z = f(ref_pre)
+    ref_out = c_in + ref_z.bfloat16().float() @ wu.float().t() + bu
+    assert _rel_err(pre.float(), ref_pre) < 4e-3 and _rel_err(z.float(), ref_z) < 6e-3
+    assert _rel_err(out, ref_out) < 2e-3 and _rel_err(c2.float(), ref_out) < 5e-3
+    # ---- backward: A = dout (bf16), c_in = dout (fp32) ----
+    dout = rnd(M, d)
+    dout_h = dout.bfloat16()
+    dpre = torch.empty_like(pre)
+    dx = dout.clone()
+    dx_h = dout_h.clone()
+    cs = torch.zeros(r, dtype=torch.float32, device=dev)
+    _lib.check(_lib.climb_adapter_fused(1, M, d, r, act_id, _lib.ptr(dx_h), _lib.ptr(wd), _lib.ptr(wu), None, None, _lib.ptr(pre),
+                                        _lib.ptr(dpre), _lib.ptr(dx), _lib.ptr(dx), _lib.ptr(dx_h), _lib.ptr(cs), _lib.stream()))
+    p32 = pre.float().requires_grad_(True)
+    (f(p32)).backward(dout_h.float() @ wu.float())
+    ref_dpre = p32.grad
+    ref_dx = dout + ref_dpre.bfloat16().float() @ wd.float()
+    assert _rel_err(dpre.float(), ref_dpre) < 6e-3
+    assert _rel_err(dx, ref_dx) < 2e-3 and _rel_err(dx_h.float(), ref_dx) < 5e-3
+    assert _rel_err(cs, dpre.float().sum(0)) < 2e-3
+    # bf16-only output (the mh site's backward): c_out = NULL
+    dmh = torch.empty_like(dx_h)
+    _lib.check(_lib.climb_adapter_fused(1, M, d, r, act_id, _lib.ptr(dout_h), _lib.ptr(wd), _lib.ptr(wu), None, None, _lib.ptr(pre),
+                                        _lib.ptr(dpre), _lib.ptr(dout), None, _lib.ptr(dmh), None, _lib.stream()))
+    assert _rel_err(dmh.float(), ref_dx) < 5e-3
