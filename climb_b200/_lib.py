@@ -52,6 +52,7 @@ class GemmDesc(Structure):
         ("split_k", c_int),
         ("block_n", c_int),
         ("independent", c_int),
+        ("colsum_a", c_void_p),
     ]
 
 
@@ -67,6 +68,7 @@ climb_last_error = _sig("climb_last_error", [], c_char_p)
 climb_version = _sig("climb_version", [])
 climb_launch_count = _sig("climb_launch_count", [], ctypes.c_uint64)
 climb_gemm_pair_mode = _sig("climb_gemm_pair_mode", [ctypes.c_int])
+climb_set_sm_reserve = _sig("climb_set_sm_reserve", [ctypes.c_int])
 climb_wordpiece_create = _sig("climb_wordpiece_create", [c_char_p, ctypes.c_int64, c_int, c_int], c_void_p)
 climb_wordpiece_destroy = _sig("climb_wordpiece_destroy", [c_void_p], None)
 climb_wordpiece_encode = _sig("climb_wordpiece_encode", [c_void_p, c_char_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -234,7 +236,7 @@ def stream() -> int:
 # -------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=False, b_mn_major=False,
          bias=None, residual=None, epilogue=EPI_NONE, aux=None, c2=None, colsum=None, alpha=1.0, accumulate=False,
-         split_k=0, block_n=0, M=None, N=None, K=None) -> torch.Tensor:
+         split_k=0, block_n=0, M=None, N=None, K=None, colsum_a=None) -> torch.Tensor:
     """out[M,N] = epi(alpha * A B^T + bias) + residual. A, B bf16 2-D (possibly row-strided views)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and out.dim() == 2
@@ -275,6 +277,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
     d.accumulate = int(accumulate)
     d.split_k = split_k
     d.block_n = block_n
+    d.colsum_a = ptr(colsum_a)
+    if colsum_a is not None:
+        assert colsum_a.dtype == torch.float32 and colsum_a.numel() >= M
     check(climb_gemm_bf16(ctypes.byref(d), stream()))
     return out
 

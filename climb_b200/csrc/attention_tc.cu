@@ -2199,14 +2199,7 @@ int env_flag(const char* name, int dflt) {
     return e != nullptr && e[0] != 0 ? std::atoi(e) : dflt;
 }
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+int sm_count() { return climb::num_sms(); }      // gemm_tcgen05.cu: device SM count minus the data-parallel reserve
 
 }  // namespace
 

@@ -97,6 +97,7 @@ const char* climb_last_error(void) { return g_last_error; }
 int climb_version(void) { return 100; }
 uint64_t climb_launch_count(void) { return g_launch_count; }
 int climb_gemm_pair_mode(int mode) { return climb::gemm_pair_mode(mode); }
+int climb_set_sm_reserve(int n) { return climb::sm_reserve(n); }
 uint32_t climb_error_flags(void) {
     if (g_err_host == nullptr) return 0u;
     return __atomic_exchange_n(g_err_host, 0u, __ATOMIC_ACQ_REL);

@@ -195,7 +195,7 @@ int run_dgrad(int M, int N, int K, const bf16* dY, const bf16* W, void* dX, int 
 
 // dW[N, K] += dY[M, N]^T * X[M, K]; both operands read in place (MN-major), split over tokens
 int run_wgrad(int M, int N, int K, const bf16* dY, long long lddy, const bf16* X, long long ldx, float* dW,
-              cudaStream_t s, int independent = 0) {
+              cudaStream_t s, int independent = 0, float* dbias = nullptr) {
     climb_gemm_desc g;
     std::memset(&g, 0, sizeof(g));
     g.M = N; g.N = K; g.K = M;
@@ -204,6 +204,7 @@ int run_wgrad(int M, int N, int K, const bf16* dY, long long lddy, const bf16* X
     g.C = dW; g.ldc = K; g.c_dtype = CLIMB_F32;
     g.alpha = 1.0f; g.accumulate = 1; g.split_k = 0;
     g.independent = independent;
+    g.colsum_a = dbias;           // the Linear's bias gradient = column sums of dY, summed inside the weight-gradient kernel
     return gemm_bf16(&g, s);
 }
 
@@ -524,10 +525,10 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
         TRY(run_dgrad(M, d, ff, dy_h, H(shadow, w.fc2_w), S.du, CLIMB_BF16, CLIMB_EPI_MUL_AUX, a.u, ff, nullptr, nullptr, s,
                       nullptr));
         if (base) {
-            TRY(run_wgrad(M, d, ff, dy_h, d, a.inter, ff, G(grad, w.fc2_w), s));
-            TRY(colsum(dy_h, CLIMB_BF16, d, M, d, G(grad, w.fc2_b), s));
-            TRY(run_wgrad(M, ff, d, S.du, ff, a.h2, d, G(grad, w.fc1_w), s));
-            TRY(colsum(S.du, CLIMB_BF16, ff, M, ff, G(grad, w.fc1_b), s));
+            // the two bias gradients (column sums of dy / du) ride inside the weight-gradient kernels: one more MMA per
+            // k-step against a tile of ones instead of two streaming passes (gemm_pair_wgrad_kernel, colsum_a)
+            TRY(run_wgrad(M, d, ff, dy_h, d, a.inter, ff, G(grad, w.fc2_w), s, 0, G(grad, w.fc2_b)));
+            TRY(run_wgrad(M, ff, d, S.du, ff, a.h2, d, G(grad, w.fc1_w), s, 0, G(grad, w.fc1_b)));
         }
         TRY(run_dgrad(M, ff, d, S.du, H(shadow, w.fc1_w), S.dh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, nullptr, nullptr, s));
         // dx1 = dx + LN2'(dh2)
@@ -578,8 +579,7 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
         if (base) {
             // dW_o = dho^T ctx depends on nothing the attention backward writes: issued right behind it as an
             // INDEPENDENT launch, its CTAs fill the SMs that kernel's last partial wave leaves idle
-            TRY(run_wgrad(M, d, d, dho, d, a.ctx, d, G(grad, w.o_w), s, /*independent=*/1));
-            TRY(colsum(dho, CLIMB_BF16, d, M, d, G(grad, w.o_b), s));
+            TRY(run_wgrad(M, d, d, dho, d, a.ctx, d, G(grad, w.o_w), s, /*independent=*/1, G(grad, w.o_b)));
         }
         if (base) TRY(run_wgrad(M, 3 * d, d, S.dqkv, 3 * d, a.h1, d, G(grad, w.qkv_w), s));
         TRY(run_dgrad(M, 3 * d, d, S.dqkv, H(shadow, w.qkv_w), S.dh, CLIMB_BF16, CLIMB_EPI_NONE, nullptr, 0, nullptr, nullptr, s));  // dh1

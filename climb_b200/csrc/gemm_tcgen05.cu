@@ -22,6 +22,8 @@
 
 namespace climb {
 
+int colsum(const void* src, int dtype, long long ld, int rows, int cols, float* out, cudaStream_t stream);      // elementwise.cu
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -46,6 +48,7 @@ struct GemmDeviceArgs {
     void* c2;                     // optional bf16 copy of the final value [M, ldc2]
     long long ldc2;
     float* colsum;                // optional [N] += column sums of the (bf16) C tile
+    float* colsum_a;              // pair wgrad kernel only, optional [M] += sum over k of A[k, m] (the bias gradient next to dW)
     float alpha;
     int accumulate;
     int split_k;
@@ -87,6 +90,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= 1ull << 46;     // descriptor version (Blackwell)
     d |= 2ull << 61;     // SWIZZLE_128B
     return d;
+}
+
+// un-swizzled (interleaved) layout: 8-row x 16-byte core matrices, LBO = next core matrix along K, SBO = next 8 rows
+__device__ __forceinline__ uint64_t make_smem_desc_noswizzle(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;     // descriptor version (Blackwell); layout type 0 = no swizzle
+    return d;
+}
+
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 
 __device__ __forceinline__ uint32_t make_instr_desc(int umma_m, int umma_n, int a_mn, int b_mn) {
@@ -1234,6 +1251,7 @@ gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     uint64_t* acc_full = empty_bar + 8;
     uint64_t* acc_empty = acc_full + kAccStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+    uint8_t* ones = bar_base + 256;                // 768 B of bf16 1.0: the B operand of the column-sum MMAs (p.colsum_a)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -1258,6 +1276,10 @@ gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         tmem_alloc_pair(tmem_slot, kTmemCols);
         tmem_relinquish_pair();
     }
+    if (warp == 2 && p.colsum_a != nullptr) {
+        for (int i = lane; i < 768 / 4; i += 32) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+        fence_proxy_async();                       // read by the tensor core (async proxy) of the leader CTA
+    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -1267,6 +1289,13 @@ gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const int tiles_mn = p.m_tiles * p.n_tiles;
     const int total_tiles = tiles_mn * p.split_k;
     constexpr int kBox = kBlockK * 128;            // one 64 (mn) x 64 (k) box
+    // Bias gradient next to the weight gradient (p.colsum_a, host: only when every pair owns at most ONE tile, so the second
+    // accumulator stage is free): colsum_a[m] += sum_k A[k, m] is one more MMA per k-step, D2[256, 16] += A^T[256, 16k] ONES[16k, 16]
+    // into TMEM columns [256, 272) -- every column of D2 holds the sums. The tiles of one m-block share the work: the tile
+    // with n-block j takes the k-blocks kb % n_tiles == j (each k-block exactly once per m-block and split), and every one
+    // adds its partial sums with 128 atomics per CTA. Cost: 8 KB of operand fetch per k-step on 1 / n_tiles of the k-blocks,
+    // instead of a separate streaming pass over dY (13 us for the FC1 bias at B = 64).
+    constexpr uint32_t kCsCol = kFastBlockN;       // first column of the second accumulator stage
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1298,17 +1327,23 @@ gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             const uint32_t idesc = make_instr_desc(kPairTileM, kFastBlockN, 1, 1);
+            const uint32_t idesc_cs = make_instr_desc(kPairTileM, 16, 1, 0);
+            // ONES as a K-major, un-swizzled B operand: 8 rows (n) x 16 k per CTA = two 128-byte core matrices (LBO apart)
+            const uint64_t d_ones = make_smem_desc_noswizzle(smem_u32(ones), 128, 256);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = pair; tile < total_tiles; tile += n_pairs) {
                 const int split = tile / tiles_mn;
+                const int n_blk = (tile - split * tiles_mn) % p.n_tiles;
                 const int kb0 = split * p.k_blocks_per_split;
                 const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kFastBlockN);
+                int cs_next = p.colsum_a != nullptr ? kb0 + (n_blk - kb0 % p.n_tiles + p.n_tiles) % p.n_tiles : kb1;
+                uint32_t cs_acc = 0u;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -1319,6 +1354,14 @@ gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         const uint64_t da = make_smem_desc(sa + kk * (16 * 128), kBox, 1024);
                         const uint64_t db = make_smem_desc(sb + kk * (16 * 128), kBox, 1024);
                         umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                    }
+                    if (kb == cs_next) {
+#pragma unroll
+                        for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                            umma_bf16_pair(tmem_base + kCsCol, make_smem_desc(sa + kk * (16 * 128), kBox, 1024), d_ones, idesc_cs, cs_acc);
+                            cs_acc = 1u;
+                        }
+                        cs_next += p.n_tiles;
                     }
                     umma_commit_pair(&empty_bar[stage]);
                     if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
@@ -1352,6 +1395,16 @@ gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 tmem_ld_wait();
                 store_rows<8>(scratch, r, reinterpret_cast<uint8_t*>(p.C) + (static_cast<long long>(row0) * p.ldc + n0) * 4,
                               p.ldc * 4, 32, lane, true);
+            }
+            if (p.colsum_a != nullptr && col_half == 0) {
+                const int kb0 = split * p.k_blocks_per_split;
+                const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+                if (kb0 + (n_blk - kb0 % p.n_tiles + p.n_tiles) % p.n_tiles < kb1) {      // this tile issued column-sum MMAs
+                    uint32_t v;
+                    tmem_ld_32x1(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + kCsCol, v);
+                    tmem_ld_wait();
+                    atomicAdd(p.colsum_a + row0 + lane, __uint_as_float(v));
+                }
             }
             tc_fence_before();
             mbar_arrive_cluster(acc_empty_leader + static_cast<uint32_t>(acc) * 8u);
@@ -1710,6 +1763,17 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, long long inner, long long o
     return 0;
 }
 
+}  // namespace
+
+// SMs the persistent kernels may fill: the device's count minus a reserve the data-parallel layer sets while NCCL's
+// reduction kernels are resident (climb_set_sm_reserve): a persistent grid of 148 CTAs next to k foreign CTAs runs its
+// last k CTAs as a second round -- up to twice the kernel time -- while a grid of 148 - k runs one round at (148 - k) / 148 speed.
+static int g_sm_reserve = 0;
+int sm_reserve(int n) {
+    const int old = g_sm_reserve;
+    if (n >= 0) g_sm_reserve = n;
+    return old;
+}
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -1718,8 +1782,12 @@ int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    int avail = n - g_sm_reserve;
+    avail &= ~1;                       // CTA pairs
+    return avail < 8 ? 8 : avail;
 }
+
+namespace {
 
 template <int BLOCK_N, bool HAS_INPUT>
 int launch_gemm_t(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t stream) {
@@ -1860,7 +1928,10 @@ inline bool aligned16(const void* p, long long pitch_bytes) {
 
 // is this the weight-gradient form the pair wgrad kernel covers?
 bool pair_wgrad_ok(const climb_gemm_desc* d) {
-    return d->accumulate && d->c_dtype == CLIMB_F32 && d->a_mn_major && d->b_mn_major && !d->independent &&
+    // independent launches (the attention-output wgrad behind the attention backward): CLIMB_WGRAD_INDEP_PAIR=1 lets them take
+    // the pair kernel too (A/B switch)
+    static const bool indep_pair = [] { const char* e = getenv("CLIMB_WGRAD_INDEP_PAIR"); return e && e[0] == '1'; }();
+    return d->accumulate && d->c_dtype == CLIMB_F32 && d->a_mn_major && d->b_mn_major && (!d->independent || indep_pair) &&
            d->M % kPairTileM == 0 && d->N % kFastBlockN == 0 && d->K >= 16 * kBlockK && d->split_k <= 0 &&
            (d->block_n == 0 || d->block_n == kFastBlockN) && d->bias == nullptr && d->residual == nullptr && d->aux == nullptr &&
            d->c2 == nullptr && d->colsum == nullptr && d->epilogue == CLIMB_EPI_NONE && (d->alpha == 0.0f || d->alpha == 1.0f) &&
@@ -1898,6 +1969,14 @@ int launch_pair_wgrad(const climb_gemm_desc* d, GemmDeviceArgs& a, cudaStream_t 
     }
     const int total = tiles * a.split_k;
     const int pairs = total < pairs_max ? total : pairs_max;
+    // the fused bias-gradient sums live in the second accumulator stage: only when no pair owns more than one tile
+    // (every FC1 / FC2 / O weight gradient of ViLT-base); otherwise they are an ordinary streaming pass over dY
+    static const bool fuse_cs = [] { const char* e = getenv("CLIMB_WGRAD_COLSUM"); return !(e && e[0] == '0'); }();
+    if (d->colsum_a != nullptr && !(fuse_cs && total <= pairs_max)) {
+        rc = colsum(d->A, CLIMB_BF16, d->lda, d->K, d->M, d->colsum_a, stream);
+        if (rc) return rc;
+        a.colsum_a = nullptr;
+    }
     ProfScope prof(PROF_GEMM, 2.0 * d->M * static_cast<double>(d->N) * d->K, stream);
     CLIMB_CUDA_OK(launch_pdl_cluster(gemm_pair_wgrad_kernel, dim3(2 * pairs), dim3(kNumThreads), kWgradSmemBytes, stream, 2u, ta, tb, a));
     CLIMB_LAUNCH_OK();
@@ -1990,12 +2069,20 @@ int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream) {
     a.epilogue = d->epilogue; a.aux = d->aux; a.ldaux = d->ldaux;
     a.c2 = d->c2; a.ldc2 = d->ldc2;
     a.colsum = d->colsum;
+    a.colsum_a = d->colsum_a;
     a.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
     a.accumulate = d->accumulate ? 1 : 0;
     static const bool indep_ok = [] { const char* e = getenv("CLIMB_NO_INDEPENDENT"); return !(e && e[0] == '1'); }();   // dev A/B switch
     a.skip_pdl_wait = (d->independent && pdl_enabled() && indep_ok) ? 1 : 0;
 
+    if (d->colsum_a != nullptr)
+        CLIMB_REQUIRE(d->a_mn_major && d->accumulate, "gemm: colsum_a belongs to the weight-gradient form (A MN-major, accumulate)");
     if (!g_disable_fast && g_pair_wgrad && pair_wgrad_ok(d)) return launch_pair_wgrad(d, a, stream);
+    if (d->colsum_a != nullptr) {       // every other kernel: the bias gradient is a streaming pass over A = dY [K rows, M columns]
+        const int rc_cs = colsum(d->A, CLIMB_BF16, d->lda, d->K, d->M, d->colsum_a, stream);
+        if (rc_cs) return rc_cs;
+        a.colsum_a = nullptr;
+    }
     if (!g_disable_fast) {
         const int kind = fast_kind(d);
         // CTA-pair kernels (cta_group::2): K-major A, at least one 256-row tile per pair of SMs

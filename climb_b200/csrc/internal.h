@@ -10,6 +10,8 @@ unsigned int* device_error_word();
 
 int gemm_bf16(const climb_gemm_desc* d, cudaStream_t stream);
 int gemm_pair_mode(int mode);
+int num_sms();                  // SMs the persistent kernels may fill (device count minus sm_reserve)
+int sm_reserve(int n);          // n >= 0 sets the reserve, n < 0 queries; returns the previous value
 // fused adapter bottleneck (gemm_tcgen05.cu): down -> activation -> up -> residual in one launch, forward and backward
 bool adapter_fused_ok(int d, int r);
 int adapter_fused(int backward, int M, int d, int r, int act, const void* A, const void* w_down, const void* w_up, const float* b_down,

@@ -50,6 +50,12 @@ uint64_t climb_launch_count(void);
  * The environment variable CLIMB_GEMM_PAIR (0 / 1) sets the initial mode. */
 int climb_gemm_pair_mode(int mode);
 
+/* SMs left free by the persistent kernels (GEMMs, attention): their grids are sized to (SM count - n). The data-parallel
+ * layer (climb_b200/distributed.py) sets n = the number of CTAs NCCL's reduction kernels occupy while a gradient all-reduce is
+ * in flight and 0 afterwards, so that a persistent grid never has to run its last CTAs as a second round behind them.
+ * n >= 0 sets, n < 0 only queries; returns the previous value. */
+int climb_set_sm_reserve(int n);
+
 /* Device-time profiler used by bench.py's roofline: between begin and end every GEMM / attention
  * launcher is bracketed by two CUDA events ON ITS LAUNCH STREAM. climb_profile_end synchronises and
  * returns per category (0 = tcgen05 GEMM, 1 = attention fwd, 2 = attention bwd [3 kernels], 3 = unused)
@@ -93,6 +99,11 @@ typedef struct {
      * leaves idle; the launch AFTER it is then issued as a full stream barrier. The engine uses it for the
      * attention-output wgrad, which follows the attention backward (768 CTAs = 5.19 waves) without depending on it. */
     int independent;
+    /* Weight-gradient form only (a_mn_major = 1, accumulate = 1: A = dY [K tokens, M], C = dW): optional [M],
+     * colsum_a[m] += sum_k A[k, m] -- the bias gradient that belongs to dW (nn.Linear's backward produces both from the
+     * same dY). Inside the CTA-pair weight-gradient kernel these are one extra tcgen05.mma per k-step against a tile of
+     * ones (no second pass over dY); on every other kernel a streaming column-sum launch issued by climb_gemm_bf16. */
+    float* colsum_a;
 } climb_gemm_desc;
 
 int climb_gemm_bf16(const climb_gemm_desc* desc, void* stream);

@@ -111,6 +111,28 @@ def test_gemm_wgrad_layer_shapes(tokens, n_out, k_in, pair_mode):
     assert _rel_err(dw, 2 * ref - 0.5) < 1e-5
 
 
+@pytest.mark.parametrize("tokens,n_out,k_in", [(15168, 3072, 768), (15168, 768, 3072), (15168, 768, 768), (15168, 2304, 768),
+                                               (3001, 768, 768), (30336, 768, 3072), (1100, 200, 512)])
+def test_gemm_wgrad_with_bias_gradient(tokens, n_out, k_in, pair_mode):
+    """colsum_a: the bias gradient (column sums of dY) produced next to dW. Inside the CTA-pair weight-gradient kernel it is
+    one more MMA per k-step against a tile of ones when no pair owns more than one tile (FC1 / FC2 / O shapes at B = 64);
+    multi-round shapes, ragged shapes and the one-CTA kernels fall back to the streaming pass. Both accumulate."""
+    L = _lib()
+    torch.manual_seed(tokens + k_in)
+    dy = (torch.randn(tokens, n_out, device="cuda") * 0.5 + 0.1).bfloat16()
+    x = torch.randn(tokens, k_in, device="cuda").bfloat16()
+    dw = torch.full((n_out, k_in), 0.5, device="cuda", dtype=torch.float32)
+    db = torch.full((n_out,), 0.25, device="cuda", dtype=torch.float32)
+    L.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, accumulate=True, colsum_a=db)
+    ref = 0.5 + dy.float().t() @ x.float()
+    ref_b = 0.25 + dy.double().sum(0).float()
+    assert _rel_err(dw, ref) < 3e-5, _rel_err(dw, ref)          # fp32 split-K atomics over up to 30 336 tokens
+    assert _rel_err(db, ref_b) < 2e-6, _rel_err(db, ref_b)
+    L.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, accumulate=True, colsum_a=db)          # accumulates on top
+    assert _rel_err(dw, 2 * ref - 0.5) < 3e-5
+    assert _rel_err(db, 2 * ref_b - 0.25) < 2e-6
+
+
 @pytest.mark.parametrize("M,K,N", [(2500, 768, 2304), (15168, 768, 2304), (2400, 200, 2304), (2433, 3072, 2304),
                                    # N = 768 at the bench's M: 357 tiles = 2 rounds + 61 -> the last 61 run as 122 half-width tiles
                                    (15168, 768, 768), (15168, 3072, 768), (15104, 768, 1024), (9600, 256, 512)])
