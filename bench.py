@@ -214,6 +214,10 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import datetime
+        if args.nccl_ctas > 0:
+            # NCCL's reduction kernels share the SMs with the persistent GEMM / attention grids: cap their CTAs (read by NCCL when
+            # the communicator is created) and size the persistent grids to the SMs that are left while a reduction is in flight
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
@@ -228,7 +232,10 @@ def run_ours(args):
                                        task_specs).to(dev)
     learner.train()
     if world > 1:
-        cdist.attach(learner)                   # gradient all-reduce over NCCL after every backward
+        # gradient all-reduce over NCCL from inside the chunked backward; the optimizer waits span by span (the plain training
+        # step reads no gradient between backward() and step(): train_vqa.py:168-172)
+        cdist.attach(learner, sm_reserve=int(os.environ.get("NCCL_MAX_CTAS", "0") or 0) if args.sm_reserve < 0 else args.sm_reserve,
+                     defer_to_optimizer=bool(args.defer_optimizer), layers_per_chunk=args.layers_per_chunk, bucket_mb=args.bucket_mb)
     opt = learner.create_optimizer({"lr": 1e-4, "weight_decay": 1e-2, "adam_epsilon": 1e-8})
     total_steps = args.warmup * 2 + args.steps * 2 + 8
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: min(1.0, (s + 1) / 10.0) * max(0.0, 1.0 - s / (10.0 * total_steps)))
@@ -462,6 +469,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU (the shipped scripts use 64)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nccl-ctas", type=int, default=0, help="N > 1 GPUs: cap on NCCL's CTAs (NCCL_MAX_CTAS, unless already set); 0 = NCCL's default")
+    ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the persistent kernels leave free during a reduction; -1 = the NCCL CTA cap")
+    ap.add_argument("--defer-optimizer", type=int, default=1, help="1: AdamW waits for the gradient all-reduce span by span (overlap); 0: after all of it")
+    ap.add_argument("--layers-per-chunk", type=int, default=3)
+    ap.add_argument("--bucket-mb", type=float, default=64.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-reference-on-this-GPU leg")
     args = ap.parse_args()

@@ -163,6 +163,9 @@ class ParamArena:
         trainable = list(trainable)
         if not trainable:
             return          # nothing of this arena is written: gradients other nodes already published stay as they are
+        if getattr(self, "_pending_reductions", None) is not None:      # a deferred exchange no optimizer step consumed
+            from .distributed import wait_pending
+            wait_pending(self)
         fresh = [(n, p) for n, p in trainable if not self._is_arena_grad(n, p)]
         if len(fresh) == len(trainable) and not self._any_published():
             self.grad.zero_()           # fresh step, nothing accumulated anywhere in the arena: one memset

@@ -73,30 +73,94 @@ class GradSync:
     its backward in chunks of that many layers and calls begin / reduce_range / finish so that each
     chunk's gradient span is all-reduced while the layers below it are still computing."""
 
-    def __init__(self, learner, bucket_mb: float = 64.0, group=None, layers_per_chunk: int = 3):
+    def __init__(self, learner, bucket_mb: float = 64.0, group=None, layers_per_chunk: int = 3, sm_reserve=None,
+                 defer_to_optimizer: bool = False):
+        """sm_reserve: SMs the persistent kernels leave to NCCL's reduction CTAs while an all-reduce is in flight
+        (climb_set_sm_reserve); default = $NCCL_MAX_CTAS when that cap is set, else 0 (grids keep every SM).
+        defer_to_optimizer: finish() does not make the compute stream wait for the reductions; ArenaAdamW.step() waits span
+        by span instead, so the update of the top layers runs while the bottom spans are still on the wire. Only valid when
+        NOTHING reads the encoder's gradients between backward() and optimizer.step() (no clipping, no EWC/Fisher pass over
+        .grad) -- which is the reference's plain training step (train_vqa.py:168-172)."""
         self.learner = learner
         self.group = group
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.layers_per_chunk = layers_per_chunk
+        if sm_reserve is None:
+            import os
+            sm_reserve = int(os.environ.get("CLIMB_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "0")) or 0)
+        self.sm_reserve = max(0, int(sm_reserve))
+        self.defer_to_optimizer = bool(defer_to_optimizer)
         self._cache = None
         self._hooks = []
         self._works = []
+        self._ranges = []
+        self._reserved = False
+        self._loose = []            # task-head parameters whose gradient autograd has produced in this backward
+        self._loose_works = []
+        self._callback_queued = False
         vilt = learner.get_encoder().vilt
         vilt.grad_sync = self
         for n, p in learner.named_parameters():
             if not n.startswith(("vilt_encoder.", "viltbert_encoder.")):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._sync_loose))
 
+    # ---- task heads (ordinary autograd tensors outside the arena) -----------------------------------
     def _sync_loose(self, p: torch.Tensor) -> None:
-        if p.grad is not None:
-            w = shard_weight()
-            if w != 1.0:
-                p.grad.mul_(w)
-            if p.grad.is_cuda:
-                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
-            else:       # gloo (CPU tests) has no AVG
-                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
-                p.grad.div_(dist.get_world_size(self.group))
+        """post-accumulate-grad hook: remember the parameter. The heads sit between the loss and the encoder, so all of them
+        are done when the encoder's backward node starts: begin() sends them as ONE grouped all-reduce that travels under
+        the encoder backward. Whatever is left when autograd finishes (encoder frozen / not in the graph) goes out from an
+        end-of-backward callback."""
+        if p.grad is None:
+            return
+        self._loose.append(p)
+        if not self._callback_queued:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(self._end_of_backward)
+                self._callback_queued = True
+            except RuntimeError:        # not inside a backward pass (a hook fired by hand)
+                self._flush_loose()
+                self._wait_loose()
+
+    def _allreduce_views(self, views):
+        """Asynchronous mean all-reduce of several gradient views as one NCCL group (one launch instead of one per tensor:
+        the host cost of ~50 small collectives per step is what made the adapter configuration launch-bound on 2 GPUs)."""
+        if not views:
+            return None
+        if not views[0].is_cuda:        # gloo (CPU tests) has no AVG and no grouped launch
+            return _Several([_SumThenDivide(v, self.group) for v in views])
+        if len(views) == 1:
+            return dist.all_reduce(views[0], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        with dist._coalescing_manager(self.group, async_ops=True) as cm:
+            for v in views:
+                dist.all_reduce(v, op=dist.ReduceOp.AVG, group=self.group)
+        return cm
+
+    def _flush_loose(self) -> None:
+        if not self._loose:
+            return
+        seen, grads = set(), []
+        for p in self._loose:
+            if id(p) not in seen and p.grad is not None:
+                seen.add(id(p))
+                grads.append(p.grad)
+        self._loose = []
+        w = shard_weight()
+        if w != 1.0:
+            for g in grads:
+                g.mul_(w)
+        work = self._allreduce_views(grads)
+        if work is not None:
+            self._loose_works.append(work)
+
+    def _wait_loose(self) -> None:
+        for w in self._loose_works:
+            w.wait()
+        self._loose_works = []
+
+    def _end_of_backward(self) -> None:
+        self._callback_queued = False
+        self._flush_loose()
+        self._wait_loose()
 
     # ---- overlapped path -------------------------------------------------------------------------
     def _spans(self, arena):
@@ -109,28 +173,77 @@ class GradSync:
             self._cache = (key, bucketize(spans, self.bucket_elems), spans)
         return self._cache[2]
 
+    def layer_chunks(self, n_layers: int):
+        """(first, last) layer ranges of the chunked backward, top down: `layers_per_chunk` layers each, except that the
+        bottom chunk is cut once more (its upper layers / the lowest layer): what is still on the wire when the backward
+        ends is the only part of the exchange nothing overlaps, so the last spans are kept small."""
+        c = self.layers_per_chunk
+        out, first = [], n_layers - 1
+        while first >= 0:
+            last = max(0, first - c + 1)
+            if last == 0 and first - last >= 1:
+                out.append((first, 1))
+                out.append((0, 0))
+            else:
+                out.append((first, last))
+            first = last - 1
+        return out
+
+    def _reserve(self, on: bool) -> None:
+        if self.sm_reserve <= 0 or on == self._reserved:
+            return
+        from . import _lib
+        _lib.climb_set_sm_reserve(self.sm_reserve if on else 0)
+        self._reserved = on
+
     def begin(self, arena) -> None:
+        wait_pending(arena)         # a deferred exchange nobody consumed (optimizer step skipped)
         self._works = []
+        self._ranges = []
+        if dist.get_world_size(self.group) > 1:
+            self._flush_loose()     # the task heads' gradients are complete: they travel under the encoder backward
 
     def reduce_range(self, arena, lo: int, hi: int) -> None:
         """All-reduce (mean) the trainable spans inside [lo, hi) of the gradient arena, asynchronously:
         NCCL's stream waits for the kernels enqueued so far, not for the ones that follow."""
         if dist.get_world_size(self.group) == 1:
             return
+        ranges = []
         for s, e in self._spans(arena):
             s2, e2 = max(s, lo), min(e, hi)
             if e2 > s2:
-                w = shard_weight()
-                for bs, be in bucketize([(s2, e2)], self.bucket_elems):
-                    if w != 1.0:
-                        arena.grad[bs:be].mul_(w)
-                    self._works.append(dist.all_reduce(arena.grad[bs:be], op=dist.ReduceOp.AVG, group=self.group,
-                                                       async_op=True))
+                ranges.extend(bucketize([(s2, e2)], self.bucket_elems))
+        if not ranges:
+            return
+        w = shard_weight()
+        if w != 1.0:
+            for bs, be in ranges:
+                arena.grad[bs:be].mul_(w)
+        self._reserve(True)     # from here on NCCL's CTAs sit on some SMs: the persistent grids leave them room
+        # large buckets go out one by one (they complete one by one: the deferred optimizer starts on the first while the
+        # others travel); a run of small spans (adapters: two per layer) goes out as ONE grouped launch
+        small = [(bs, be) for bs, be in ranges if be - bs < self.bucket_elems // 8]
+        for bs, be in ranges:
+            if (bs, be) not in small or len(small) == 1:
+                self._works.append(self._allreduce_views([arena.grad[bs:be]]))
+                self._ranges.append((bs, be))
+        if len(small) > 1:
+            work = self._allreduce_views([arena.grad[bs:be] for bs, be in small])
+            for r in small:
+                self._works.append(work)
+                self._ranges.append(r)
 
     def finish(self, arena) -> None:
-        for w in self._works:
-            w.wait()            # stream-level wait: the optimizer kernels queue behind the reductions
-        self._works = []
+        self._wait_loose()          # issued before the first span: long complete
+        if self.defer_to_optimizer:
+            # ArenaAdamW.step() consumes these span by span (optim.py); anything else that touches the gradients first
+            # calls wait_pending(arena)
+            arena._pending_reductions = (list(zip(self._ranges, self._works)), self)
+        else:
+            for w in self._works:
+                w.wait()            # stream-level wait: the optimizer kernels queue behind the reductions
+            self._reserve(False)
+        self._works, self._ranges = [], []
 
     # ---- one-shot path (layers_per_chunk = 0) ------------------------------------------------------
     def __call__(self, arena) -> None:
@@ -145,7 +258,9 @@ class GradSync:
         if w != 1.0:
             for s, e in self._cache[1]:
                 arena.grad[s:e].mul_(w)
+        self._flush_loose()
         allreduce_mean_(arena.grad, self._cache[1], self.group)
+        self._wait_loose()
 
     def detach(self):
         self.learner.get_encoder().vilt.grad_sync = None
@@ -154,12 +269,67 @@ class GradSync:
         self._hooks = []
 
 
-def attach(learner, bucket_mb: float = 64.0, group=None, layers_per_chunk: int = 3) -> GradSync:
+class _SumThenDivide:
+    """gloo stand-in for an async AVG all-reduce (CPU tests): wait() finishes the SUM and divides by the world size."""
+
+    def __init__(self, view, group):
+        self.view, self.world = view, dist.get_world_size(group)
+        self.work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def wait(self):
+        self.work.wait()
+        self.view.div_(self.world)
+
+
+class _Several:
+    def __init__(self, works):
+        self.works = works
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+
+
+def wait_pending(arena) -> None:
+    """Make the current stream wait for a deferred gradient exchange of `arena` (GradSync(defer_to_optimizer=True)) and
+    clear it. Called by everything that reads or rewrites the gradient arena outside ArenaAdamW.step()."""
+    pend = getattr(arena, "_pending_reductions", None)
+    if pend is None:
+        return
+    for _, w in pend[0]:
+        w.wait()
+    pend[1]._reserve(False)
+    arena._pending_reductions = None
+
+
+def pending_segments(chunks, ranges):
+    """For ArenaAdamW: chunks = [(start, length, group)], ranges = [(lo, hi)] in the order their all-reduces were ISSUED
+    (NCCL completes them in that order). Returns (order, bounds): `order` = chunk indices sorted by the index of the LAST
+    issued range each chunk overlaps (-1 = none: its gradient is local and final), `bounds[k]` = how many of the sorted
+    chunks may be updated once range k has completed (bounds[-1] of the un-ranged prefix is returned as bounds[0] start)."""
+    seg = []
+    for s, l, _ in chunks:
+        k = -1
+        for i, (lo, hi) in enumerate(ranges):
+            if s < hi and s + l > lo:
+                k = i
+        seg.append(k)
+    order = sorted(range(len(chunks)), key=lambda i: (seg[i], chunks[i][0]))
+    n_free = sum(1 for k in seg if k < 0)
+    bounds, done = [], n_free
+    for i in range(len(ranges)):
+        done += sum(1 for k in seg if k == i)
+        bounds.append(done)
+    return order, n_free, bounds
+
+
+def attach(learner, bucket_mb: float = 64.0, group=None, layers_per_chunk: int = 3, sm_reserve=None,
+           defer_to_optimizer: bool = False) -> GradSync:
     """Make every backward of `learner` end with its gradients averaged over the ranks. Parameters must
     already be identical on all ranks (same seed / same checkpoint), as in any data-parallel run."""
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
-    return GradSync(learner, bucket_mb, group, layers_per_chunk)
+    return GradSync(learner, bucket_mb, group, layers_per_chunk, sm_reserve, defer_to_optimizer)
 
 
 def attach_if_distributed(learner, **kw):

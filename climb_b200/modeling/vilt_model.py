@@ -591,15 +591,14 @@ class B200ViltModel(nn.Module):
             # while the next chunk computes
             off = arena.offsets
             hi_elem = arena.size
-            first = n_layers - 1
             sync.begin(arena)
-            while first >= 0:
-                last = max(0, first - chunk + 1)
+            chunks = sync.layer_chunks(n_layers) if hasattr(sync, "layer_chunks") else \
+                [(f, max(0, f - chunk + 1)) for f in range(n_layers - 1, -1, -chunk)]
+            for first, last in chunks:
                 run(first, last, _lib.BWD_TAIL if first == n_layers - 1 else 0)
                 lo_elem = off[f"encoder.layer.{last}.attention.attention.query.weight"]
                 sync.reduce_range(arena, lo_elem, hi_elem)
                 hi_elem = lo_elem
-                first = last - 1
             # the embeddings go last and alone: their all-reduce (the 94 MB word table dominates) is the only one
             # with nothing left to hide behind, so the bottom layers' spans are already in flight when it starts
             run(-1, 0, _lib.BWD_EMBED)

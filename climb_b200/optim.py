@@ -44,6 +44,32 @@ class ArenaAdamW(torch.optim.Optimizer):
         self._arena_state: Dict[int, Dict] = {}
         self._table_cache = None
 
+    def _deferred_plan(self, aid, a, sig, pending):
+        """Chunk table of arena `a` re-sorted by the completion order of the pending all-reduces, and the launch plan
+        [(first chunk, end chunk, works to wait for first)]. Cached per (parameter set, range layout)."""
+        from .distributed import pending_segments
+        ranges = tuple(r for r, _ in pending)
+        key = (sig, aid, ranges)
+        cache = getattr(self, "_deferred_cache", None)
+        if cache is None or cache[0] != key:
+            chunks = self._chunk_lists[aid]
+            order, n_free, bounds = pending_segments(chunks, ranges)
+            table = _upload_chunks([chunks[i] for i in order], a.theta.device)
+            # merge the per-range bounds into at most ~6 launches: tiny launches cannot fill the machine
+            plan, start, waits, min_chunks = [], 0, [], max(1, len(chunks) // 6)
+            if n_free:
+                plan.append((0, n_free, []))
+                start = n_free
+            for k, b in enumerate(bounds):
+                waits.append(k)
+                if b - start >= min_chunks or k == len(bounds) - 1:
+                    plan.append((start, b, list(waits)))
+                    start, waits = b, []
+            cache = (key, table, plan)
+            self._deferred_cache = cache
+        works = [w for _, w in pending]
+        return cache[1], [(c0, c1, [works[k] for k in ks]) for c0, c1, ks in cache[2]]
+
     def _arena_of(self, p: torch.Tensor):
         for a in self.arenas:
             if a.theta is None:
@@ -90,7 +116,14 @@ class ArenaAdamW(torch.optim.Optimizer):
                     lst.append((start + o, min(_CHUNK, n - o), gi))
             self._table_cache = (sig, {aid: (a, _upload_chunks(ch, a.theta.device), len(ch))
                                        for aid, (a, ch) in per_arena.items()})
+            self._chunk_lists = {aid: ch for aid, (a, ch) in per_arena.items()}
+            self._deferred_cache = None
         for aid, (a, table, n_chunks) in self._table_cache[1].items():
+            pend = getattr(a, "_pending_reductions", None)
+            if pend is not None:
+                table, launches = self._deferred_plan(aid, a, sig, pend[0])
+            else:
+                launches = [(0, n_chunks, None)]
             st = self._arena_state.get(aid)
             if st is None or st["theta_ptr"] != a.theta.data_ptr():
                 new = dict(exp_avg=torch.zeros_like(a.theta), exp_avg_sq=torch.zeros_like(a.theta),
@@ -112,10 +145,20 @@ class ArenaAdamW(torch.optim.Optimizer):
             # the kernel also refreshes the bf16 shadow of everything it updates; parameters it skipped
             # (grad None) did not change, so the shadow stays coherent if it was coherent before
             coherent = a.shadow is not None and not a.shadow_dirty and a._shadow_version == a._version_sum
-            _lib.check(_lib.climb_adamw_step(_lib.ptr(a.theta), _lib.ptr(a.grad), _lib.ptr(st["exp_avg"]),
-                                             _lib.ptr(st["exp_avg_sq"]), _lib.ptr(a.shadow) if coherent else None,
-                                             _lib.ptr(table), n_chunks, lr_arr, wd_arr,
-                                             n_groups, beta1, beta2, eps, st["step"], stream))
+            # one launch per arena -- or, behind a deferred gradient exchange (GradSync(defer_to_optimizer=True)), one launch
+            # per group of chunks whose all-reduce has completed: the update of the top layers runs while the bottom spans
+            # are still on the wire (the chunk table is sorted by completion order; a launch takes a slice of it)
+            for c0, c1, works in launches:
+                for w in works or ():
+                    w.wait()                    # stream-level wait for the reductions this slice depends on
+                if c1 > c0:
+                    _lib.check(_lib.climb_adamw_step(_lib.ptr(a.theta), _lib.ptr(a.grad), _lib.ptr(st["exp_avg"]),
+                                                     _lib.ptr(st["exp_avg_sq"]), _lib.ptr(a.shadow) if coherent else None,
+                                                     _lib.ptr(table) + c0 * ctypes.sizeof(_lib.AdamWChunkC), c1 - c0, lr_arr, wd_arr,
+                                                     n_groups, beta1, beta2, eps, st["step"], stream))
+            if pend is not None:
+                pend[1]._reserve(False)         # NCCL's CTAs are gone: the persistent kernels take every SM again
+                a._pending_reductions = None
             if not coherent:
                 a.shadow_dirty = True
             a.touch()           # theta changed behind torch's version counters: the bf16x3 lo half must be re-split

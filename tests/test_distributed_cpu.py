@@ -22,6 +22,28 @@ def test_spans_and_buckets():
     assert bucketize([(0, 956), (1024, 1034)], 400) == [(0, 400), (400, 800), (800, 956), (1024, 1034)]
 
 
+def test_layer_chunks_and_deferred_optimizer_plan():
+    """Host logic of the overlapped exchange: the bottom chunk of the chunked backward is cut once more, and ArenaAdamW's
+    chunk table is re-sorted by the completion order of the pending all-reduces."""
+    from climb_b200 import distributed as cdist
+    sync = cdist.GradSync.__new__(cdist.GradSync)
+    sync.layers_per_chunk = 3
+    assert sync.layer_chunks(12) == [(11, 9), (8, 6), (5, 3), (2, 1), (0, 0)]
+    sync.layers_per_chunk = 2
+    assert sync.layer_chunks(4) == [(3, 2), (1, 1), (0, 0)]
+    sync.layers_per_chunk = 1
+    assert sync.layer_chunks(3) == [(2, 2), (1, 1), (0, 0)]
+    # chunks (start, length, group); ranges in ISSUE order: top span first (two buckets), then the bottom span
+    chunks = [(0, 100, 0), (100, 100, 1), (200, 100, 0), (300, 100, 0), (400, 50, 1), (1000, 10, 0)]
+    ranges = [(250, 350), (350, 450), (0, 250)]
+    order, n_free, bounds = cdist.pending_segments(chunks, ranges)
+    assert n_free == 1 and order[0] == 5                      # the chunk no range covers goes first, without waiting
+    # chunk 3 (300..400) straddles buckets 0 and 1 -> ready after bucket 1; chunk 2 (200..300) straddles bucket 0 and the
+    # bottom span -> ready after the bottom span
+    assert [chunks[i][0] for i in order] == [1000, 300, 400, 0, 100, 200]
+    assert bounds == [1, 3, 6]
+
+
 def test_shard_batch_keeps_groups_together():
     batch = {"x": torch.arange(16), "names": list("abcdefghijklmnop"), "k": "vcr"}
     parts = [shard_batch(batch, r, 2, group_size=4) for r in range(2)]

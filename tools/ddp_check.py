@@ -72,6 +72,44 @@ def main():
         if rank == 0:
             print(f"{task}: world {world}, worst relative gradient difference vs whole-batch {worst:.3e}, ranks identical: {same}", flush=True)
         ok = ok and worst < 2e-2 and same
+    # ---- deferred exchange: ArenaAdamW waits span by span (GradSync(defer_to_optimizer=True)) + SM reserve: two training
+    #      steps must leave every rank with bit-identical parameters (a span consumed before its all-reduce completed would
+    #      hold this rank's own gradient) and agree with the plain finish()-waits-for-everything path up to the run-to-run
+    #      noise of the fp32 atomics in the weight gradients ----
+    import copy
+    sd0 = copy.deepcopy(learner.state_dict())
+    ids = torch.randint(1000, 30000, (4, 40), generator=torch.Generator().manual_seed(100 + rank))
+    enc = {"input_ids": ids.to(dev), "attention_mask": torch.ones(4, 40, dtype=torch.int64, device=dev),
+           "token_type_ids": torch.zeros(4, 40, dtype=torch.int64, device=dev),
+           "pixel_values": (torch.rand(4, 3, 384, 384, generator=torch.Generator().manual_seed(200 + rank)) * 2 - 1).to(dev)}
+    tgt = torch.zeros(4, 3129, device=dev)
+    tgt[torch.arange(4), torch.arange(4) * 7 + rank] = 1.0
+    finals = []
+    for defer, reserve in ((False, 0), (True, 8)):
+        learner.load_state_dict(sd0)
+        learner.zero_grad(set_to_none=True)
+        sync = cdist.attach(learner, layers_per_chunk=2, bucket_mb=8.0, defer_to_optimizer=defer, sm_reserve=reserve)
+        opt = learner.create_optimizer({"lr": 1e-3, "weight_decay": 1e-2, "adam_epsilon": 1e-8})
+        for _ in range(2):
+            _, logits = learner.forward_tensors("vqa", enc)
+            ops.vqa_loss(logits, tgt).backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        sync.detach()
+        finals.append(torch.cat([p.detach().flatten() for p in learner.parameters()]).clone())
+    from climb_b200 import _lib
+    p0 = torch.cat([sd0[n].flatten().float() for n, _ in learner.named_parameters()])
+    upd = (finals[0] - p0).norm().item()
+    diff = (finals[1] - finals[0]).norm().item() / max(upd, 1e-30)
+    other = finals[1].clone()
+    dist.broadcast(other, src=0)
+    ranks_same = bool(torch.equal(other, finals[1]))
+    reserve_reset = _lib.climb_set_sm_reserve(-1) == 0
+    if rank == 0:
+        print(f"deferred per-span optimizer + SM reserve: ranks bit-identical after 2 steps: {ranks_same}; difference to the plain path "
+              f"/ size of the update: {diff:.3e}; reserve released: {reserve_reset}", flush=True)
+    ok = ok and ranks_same and diff < 2e-2 and reserve_reset
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
