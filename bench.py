@@ -218,7 +218,12 @@ def run_ours(args):
             # NCCL's reduction kernels share the SMs with the persistent GEMM / attention grids: cap their CTAs (read by NCCL when
             # the communicator is created) and size the persistent grids to the SMs that are left while a reduction is in flight
             os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        kw = {}
+        if args.nccl_high_priority:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            kw["pg_options"] = opts
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180), **kw)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
     B = args.batch
@@ -473,6 +478,7 @@ def main():
     ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the persistent kernels leave free during a reduction; -1 = the NCCL CTA cap")
     ap.add_argument("--defer-optimizer", type=int, default=1, help="1: AdamW waits for the gradient all-reduce span by span (overlap); 0: after all of it")
     ap.add_argument("--layers-per-chunk", type=int, default=3)
+    ap.add_argument("--nccl-high-priority", type=int, default=0, help="1: NCCL's kernels on a high-priority stream")
     ap.add_argument("--bucket-mb", type=float, default=64.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager-reference-on-this-GPU leg")

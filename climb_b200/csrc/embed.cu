@@ -95,7 +95,7 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
                                       const float* __restrict__ pos_emb, const float* __restrict__ mod,
                                       const int* __restrict__ type_idx, int type_idx_scalar,
                                       float* __restrict__ x, int B, int T, int Np, int d4, int n_mod, unsigned int* err,
-                                      uint32_t thresh, float inv_keep, unsigned long long seed) {
+                                      uint32_t thresh, float inv_keep, unsigned long long seed, int rep) {
     const int L = T + 1 + Np;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * L * d4) return;
@@ -115,7 +115,7 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
             v = make_float4(a.x + p0.x, a.y + p0.y, a.z + p0.z, a.w + p0.w);
         } else {
             const int p = l - T - 1;
-            const float4 a = reinterpret_cast<const float4*>(patch)[(static_cast<long long>(b) * Np + p) * d4 + c];
+            const float4 a = reinterpret_cast<const float4*>(patch)[(static_cast<long long>(b / rep) * Np + p) * d4 + c];   // image b / rep
             const float4 t = reinterpret_cast<const float4*>(table)[static_cast<long long>(p) * d4 + c];
             v = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
         }
@@ -136,7 +136,7 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
 // are padding: zero pixels, no position embedding, masked out as attention keys. (The reference fills them with
 // randomly chosen masked patches and permutes the valid ones: every output CLiMB consumes is invariant to both.)
 __global__ void im2col_ragged_kernel(const float* __restrict__ px, const int* __restrict__ geom,
-                                     __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int Np) {
+                                     __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int Np, int rep) {
     const int K = C * P * P;
     const int k8 = K / 8;
     const long long total = static_cast<long long>(B) * Np * k8;
@@ -145,7 +145,7 @@ __global__ void im2col_ragged_kernel(const float* __restrict__ px, const int* __
     const long long m = i / k8;
     const int k0 = static_cast<int>(i - m * k8) * 8;
     const int b = static_cast<int>(m / Np), slot = static_cast<int>(m - static_cast<long long>(b) * Np);
-    const int hb = geom[2 * b], wb = geom[2 * b + 1];
+    const int hb = geom[2 * b * rep], wb = geom[2 * b * rep + 1];       // geom is per sequence; image b serves sequences b * rep ..
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (slot < hb * wb) {
         const int py = slot / wb, pxi = slot - py * wb;
@@ -163,7 +163,7 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
                                              const float* __restrict__ pos_emb, const float* __restrict__ mod,
                                              const int* __restrict__ type_idx, int type_idx_scalar,
                                              float* __restrict__ x, int B, int T, int Np, int G, int d4, int n_mod, unsigned int* err,
-                                             uint32_t thresh, float inv_keep, unsigned long long seed) {
+                                             uint32_t thresh, float inv_keep, unsigned long long seed, int rep) {
     const int L = T + 1 + Np;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * L * d4) return;
@@ -183,7 +183,7 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
             v = make_float4(a.x + p0.x, a.y + p0.y, a.z + p0.z, a.w + p0.w);
         } else {
             const int slot = l - T - 1;
-            v = reinterpret_cast<const float4*>(patch)[(static_cast<long long>(b) * Np + slot) * d4 + c];
+            v = reinterpret_cast<const float4*>(patch)[(static_cast<long long>(b / rep) * Np + slot) * d4 + c];
             const int hb = geom[2 * b], wb = geom[2 * b + 1];
             if (slot < hb * wb) {
                 const Taps t = bilinear_taps(slot / wb, slot % wb, hb, wb, G);
@@ -259,6 +259,27 @@ __global__ void embed_split_bwd_kernel(const float* __restrict__ dx, float* __re
         o.y = pack_bf16(v.z, v.w);
         reinterpret_cast<uint2*>(dpatch)[(static_cast<long long>(b) * Np + (l - T - 1)) * d4 + c] = o;
     }
+}
+
+// dpatch[i, p, :] = sum over the `rep` sequences that share image i of dx[i * rep + j, T + 1 + p, :]  (VCR: one image, four
+// answer choices -- vilt.py:334-347 -- the patch projection runs once per image and its gradient collects all four)
+__global__ void embed_patch_sum_bwd_kernel(const float* __restrict__ dx, __nv_bfloat16* __restrict__ dpatch, int Bi, int rep,
+                                           int T, int Np, int d4) {
+    const int L = T + 1 + Np;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(Bi) * Np * d4) return;
+    const long long row = i / d4;
+    const int c = static_cast<int>(i - row * d4);
+    const int img = static_cast<int>(row / Np), p = static_cast<int>(row - static_cast<long long>(img) * Np);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < rep; ++j) {
+        const float4 v = reinterpret_cast<const float4*>(dx)[((static_cast<long long>(img) * rep + j) * L + T + 1 + p) * d4 + c];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    uint2 o;
+    o.x = pack_bf16(a.x, a.y);
+    o.y = pack_bf16(a.z, a.w);
+    reinterpret_cast<uint2*>(dpatch)[i] = o;
 }
 
 // S[k][l, c] = sum over the sequences b whose image type index is k+1 of dx[b, l, c]  (k = 0, 1).
@@ -379,44 +400,49 @@ int pos_interp(const float* pos_emb, float* table, int hp, int wp, int G, int d,
 
 int embed_assemble(const float* text_ln, const float* patch, const float* table, const float* cls,
                    const float* pos_emb, const float* mod, const int* type_idx, int type_idx_scalar, float* x,
-                   int B, int T, int Np, int d, cudaStream_t stream, int n_mod, float p_drop, unsigned long long seed) {
-    CLIMB_REQUIRE(text_ln && patch && table && cls && pos_emb && mod && x && d % 4 == 0, "embed_assemble: bad arguments");
+                   int B, int T, int Np, int d, cudaStream_t stream, int n_mod, float p_drop, unsigned long long seed, int rep) {
+    CLIMB_REQUIRE(text_ln && patch && table && cls && pos_emb && mod && x && d % 4 == 0 && rep >= 1, "embed_assemble: bad arguments");
     const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
     embed_assemble_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, table, cls, pos_emb, mod,
                                                                      type_idx, type_idx_scalar, x, B, T, Np, d / 4, n_mod,
                                                                      device_error_word(), p_drop > 0.0f ? dropout_threshold(p_drop) : 0u,
-                                                                     1.0f / (1.0f - p_drop), seed);
+                                                                     1.0f / (1.0f - p_drop), seed, rep);
     CLIMB_LAUNCH_OK();
     return 0;
 }
 
-int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T, int Np, int d, cudaStream_t stream) {
-    CLIMB_REQUIRE(dx && d % 4 == 0, "embed_split_bwd: bad arguments");
+int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T, int Np, int d, cudaStream_t stream, int rep) {
+    CLIMB_REQUIRE(dx && d % 4 == 0 && rep >= 1 && B % rep == 0, "embed_split_bwd: bad arguments");
     const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
-    embed_split_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(dx, dy_text, static_cast<__nv_bfloat16*>(dpatch), B, T, Np, d / 4);
+    embed_split_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(dx, dy_text, rep > 1 ? nullptr : static_cast<__nv_bfloat16*>(dpatch), B, T, Np, d / 4);
     CLIMB_LAUNCH_OK();
+    if (rep > 1 && dpatch != nullptr) {
+        const long long tp = static_cast<long long>(B / rep) * Np * (d / 4);
+        embed_patch_sum_bwd_kernel<<<blocks_for(tp, 256), 256, 0, stream>>>(dx, static_cast<__nv_bfloat16*>(dpatch), B / rep, rep, T, Np, d / 4);
+        CLIMB_LAUNCH_OK();
+    }
     return 0;
 }
 
-int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int H, int W, int P, int Np, cudaStream_t stream) {
+int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int H, int W, int P, int Np, cudaStream_t stream, int rep) {
     CLIMB_REQUIRE(px && geom && out && B > 0 && Np > 0, "im2col_ragged: bad arguments");
     CLIMB_REQUIRE(P % 8 == 0 && H % P == 0 && W % P == 0, "im2col_ragged: H, W must be multiples of the patch size (%d x %d, P=%d)", H, W, P);
     CLIMB_REQUIRE((reinterpret_cast<uintptr_t>(px) & 15) == 0 && W % 4 == 0, "im2col_ragged: pixel rows must be 16-byte aligned");
     const long long total = static_cast<long long>(B) * Np * (C * P * P / 8);
-    im2col_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, geom, static_cast<__nv_bfloat16*>(out), B, C, H, W, P, Np);
+    im2col_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, geom, static_cast<__nv_bfloat16*>(out), B, C, H, W, P, Np, rep);
     CLIMB_LAUNCH_OK();
     return 0;
 }
 
 int embed_assemble_ragged(const float* text_ln, const float* patch, const int* geom, const float* cls, const float* pos_emb,
                           const float* mod, const int* type_idx, int type_idx_scalar, float* x, int B, int T, int Np, int G,
-                          int d, cudaStream_t stream, int n_mod, float p_drop, unsigned long long seed) {
-    CLIMB_REQUIRE(text_ln && patch && geom && cls && pos_emb && mod && x && d % 4 == 0, "embed_assemble_ragged: bad arguments");
+                          int d, cudaStream_t stream, int n_mod, float p_drop, unsigned long long seed, int rep) {
+    CLIMB_REQUIRE(text_ln && patch && geom && cls && pos_emb && mod && x && d % 4 == 0 && rep >= 1, "embed_assemble_ragged: bad arguments");
     const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
     embed_assemble_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, geom, cls, pos_emb, mod, type_idx,
                                                                             type_idx_scalar, x, B, T, Np, G, d / 4, n_mod, device_error_word(),
                                                                             p_drop > 0.0f ? dropout_threshold(p_drop) : 0u,
-                                                                            1.0f / (1.0f - p_drop), seed);
+                                                                            1.0f / (1.0f - p_drop), seed, rep);
     CLIMB_LAUNCH_OK();
     return 0;
 }

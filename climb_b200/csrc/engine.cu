@@ -57,6 +57,7 @@ struct LayerAct {
 
 struct Plan {
     int B, T, Hh, Ww, hp, wp, Np, L, M, d, ff, heads, layers, Kp, r;
+    int rep, Bi;        // climb_vilt_batch.image_repeat: Bi = B / rep images, each shared by rep consecutive sequences
     const int* geom;    // [B, 2] valid patch rows / cols per image (padded batches) or null
     // embeddings
     float* key_bias;    // [B, L]
@@ -88,6 +89,9 @@ int fill_plan(Plan& P, const climb_vilt_dims* dm, const climb_vilt_params* pr, c
                   "engine: image %dx%d is not a multiple of the patch size %d (fixed-resolution path)",
                   bt->H, bt->W, dm->patch);
     P.B = bt->B; P.T = bt->T; P.Hh = bt->H; P.Ww = bt->W;
+    P.rep = bt->image_repeat > 1 ? bt->image_repeat : 1;
+    CLIMB_REQUIRE(P.B % P.rep == 0, "engine: image_repeat=%d does not divide the %d sequences", P.rep, P.B);
+    P.Bi = P.B / P.rep;
     P.hp = bt->H / dm->patch; P.wp = bt->W / dm->patch; P.Np = P.hp * P.wp;
     P.geom = bt->patch_geom;
     if (P.geom != nullptr) {
@@ -316,22 +320,23 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
                     dm->type_vocab_size));
     TRY(layernorm_fwd(P.text_e, d, F(theta, pr->text_ln_w), F(theta, pr->text_ln_b), dm->ln_eps, nullptr, P.text_ln,
                       P.text_mean, P.text_rstd, BT, d, CLIMB_EPI_NONE, s));
-    if (P.geom) TRY(im2col_ragged(bt->pixel_values, P.geom, P.im2col, P.B, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s));
-    else TRY(im2col(bt->pixel_values, P.im2col, P.B, dm->channels, P.Hh, P.Ww, dm->patch, s));
+    // image_repeat > 1 (VCR: four answer choices per image, vilt.py:334-347): the patch projection runs once per image
+    if (P.geom) TRY(im2col_ragged(bt->pixel_values, P.geom, P.im2col, P.Bi, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s, P.rep));
+    else TRY(im2col(bt->pixel_values, P.im2col, P.Bi, dm->channels, P.Hh, P.Ww, dm->patch, s));
     {
-        Lin l{P.B * P.Np, d, P.Kp, P.im2col, P.Kp, H(shadow, pr->patch_w)};
+        Lin l{P.Bi * P.Np, d, P.Kp, P.im2col, P.Kp, H(shadow, pr->patch_w)};
         l.bias = F(theta, pr->patch_b); l.C = P.patch_out; l.c_dtype = CLIMB_F32;
         TRY(run_linear(l, s));
     }
     if (P.geom) {
         TRY(embed_assemble_ragged(P.text_ln, P.patch_out, P.geom, F(theta, pr->cls_token), F(theta, pr->pos_emb),
                                   F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B,
-                                  P.T, P.Np, dm->pos_grid, d, s, dm->n_modality, p_h, dropout_site_seed(dseed, -1, 1)));
+                                  P.T, P.Np, dm->pos_grid, d, s, dm->n_modality, p_h, dropout_site_seed(dseed, -1, 1), P.rep));
     } else {
         TRY(pos_interp(F(theta, pr->pos_emb), P.pos_table, P.hp, P.wp, dm->pos_grid, d, s));
         TRY(embed_assemble(P.text_ln, P.patch_out, P.pos_table, F(theta, pr->cls_token), F(theta, pr->pos_emb),
                            F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B, P.T,
-                           P.Np, d, s, dm->n_modality, p_h, dropout_site_seed(dseed, -1, 1)));
+                           P.Np, d, s, dm->n_modality, p_h, dropout_site_seed(dseed, -1, 1), P.rep));
     }
 
     // ---- encoder layers (modeling_vilt.py:503-525) ----
@@ -599,7 +604,7 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             TRY(embed_reduce_bwd(dx, bt->image_type_idx, bt->image_type_idx_scalar, S.S, nullptr, nullptr, G(grad, pr->mod_emb),
                                  nullptr, dm->n_modality, P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0));
         }
-        TRY(embed_split_bwd(dxe, S.dy_text, S.dpatch, P.B, P.T, P.Np, d, s));
+        TRY(embed_split_bwd(dxe, S.dy_text, S.dpatch, P.B, P.T, P.Np, d, s, P.rep));
         TRY(embed_reduce_bwd(dxe, bt->image_type_idx, bt->image_type_idx_scalar, S.S, G(grad, pr->cls_token),
                              G(grad, pr->pos_emb), p_h > 0.0f ? nullptr : G(grad, pr->mod_emb), G(grad, pr->patch_b), dm->n_modality,
                              P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0));
@@ -610,7 +615,7 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
                              reinterpret_cast<const long long*>(bt->token_type_ids),
                              bt->input_ids ? G(grad, pr->word_emb) : nullptr, G(grad, pr->text_type_emb),
                              G(grad, pr->text_pos_emb), BT, P.T, d, s, dm->vocab_size, dm->type_vocab_size));
-        TRY(run_wgrad(P.B * P.Np, d, P.Kp, S.dpatch, d, P.im2col, P.Kp, G(grad, pr->patch_w), s));
+        TRY(run_wgrad(P.Bi * P.Np, d, P.Kp, S.dpatch, d, P.im2col, P.Kp, G(grad, pr->patch_w), s));
     }
     return 0;
 }

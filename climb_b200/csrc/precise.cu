@@ -427,6 +427,7 @@ int fill_plan(Plan& P, const climb_vilt_dims* dm, const climb_vilt_params* pr, c
     CLIMB_REQUIRE(bt->B > 0 && bt->T > 0, "engine: empty batch (B=%d, T=%d)", bt->B, bt->T);
     CLIMB_REQUIRE(bt->H > 0 && bt->W > 0 && bt->H % dm->patch == 0 && bt->W % dm->patch == 0,
                   "engine: image %dx%d is not a multiple of the patch size %d", bt->H, bt->W, dm->patch);
+    CLIMB_REQUIRE(bt->image_repeat <= 1, "engine (bf16x3): image_repeat=%d is implemented by the bf16 engine only", bt->image_repeat);
     P.B = bt->B; P.T = bt->T; P.Hh = bt->H; P.Ww = bt->W;
     P.hp = bt->H / dm->patch; P.wp = bt->W / dm->patch; P.Np = P.hp * P.wp;
     P.geom = bt->patch_geom;

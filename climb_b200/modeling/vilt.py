@@ -250,10 +250,11 @@ class B200ViltContinualLearner(ContinualLearner):
         px = encodings['pixel_values']
         bs = px.shape[0]
         pm = self._enc(encodings, 'pixel_mask')
+        # the reference feeds the same pixels once per choice (vilt.py:334-347); here every image is embedded once and its
+        # patch rows are shared by its num_choices sequences (climb_vilt_batch.image_repeat)
         pooled = self.vilt_encoder(input_ids=encodings['input_ids'], attention_mask=encodings['attention_mask'],
-                                   token_type_ids=encodings['token_type_ids'],
-                                   pixel_values=px.repeat_interleave(num_choices, dim=0),
-                                   pixel_mask=None if pm is None else pm.repeat_interleave(num_choices, dim=0))
+                                   token_type_ids=encodings['token_type_ids'], pixel_values=px, pixel_mask=pm,
+                                   image_repeat=num_choices)
         pooled = pooled.view(bs, num_choices, -1)                     # == stack(dim=0).transpose(0, 1)
         logits = self.task_layer[task_key](pooled).squeeze()
         return pooled, logits

@@ -340,9 +340,11 @@ class B200ViltModel(nn.Module):
     # -- forward -----------------------------------------------------------------------------------
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, pixel_values=None, pixel_mask=None,
                 head_mask=None, inputs_embeds=None, image_embeds=None, image_token_type_idx=None,
-                output_attentions=None, output_hidden_states=None, return_dict=None):
-        """ViltModel.forward (modeling_vilt.py:777-884) on the fixed-resolution path. image_token_type_idx may
-        be an int (as in the reference) or an int tensor [B] (batched NLVR2 passes)."""
+                output_attentions=None, output_hidden_states=None, return_dict=None, image_repeat: int = 1):
+        """ViltModel.forward (modeling_vilt.py:777-884). image_token_type_idx may be an int (as in the reference) or an
+        int tensor [B] (batched NLVR2 passes). image_repeat = r > 1 (extension): pixel_values / pixel_mask hold B / r images,
+        image i belongs to the r consecutive text rows i * r ... (VCR's four answer choices over one image,
+        src/modeling/vilt.py:334-347): same result as pixel_values.repeat_interleave(r, 0), patch projection once per image."""
         if head_mask is not None or image_embeds is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("head_mask / image_embeds / output_attentions / output_hidden_states are outside "
                                       "CLiMB's hot path and not implemented in climb_b200")
@@ -351,7 +353,7 @@ class B200ViltModel(nn.Module):
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")
         call = self._prepare_call(input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, inputs_embeds,
-                                  image_token_type_idx)
+                                  image_token_type_idx, int(image_repeat))
         if torch.is_grad_enabled() and call.trainable:
             anchor = torch.zeros((), device=pixel_values.device, requires_grad=True)
             pooled = _EncoderFn.apply(anchor, self, call)
@@ -360,7 +362,7 @@ class B200ViltModel(nn.Module):
         return ViltOutput(pooler_output=pooled)
 
     def _prepare_call(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, inputs_embeds,
-                      image_token_type_idx) -> _Call:
+                      image_token_type_idx, image_repeat: int = 1) -> _Call:
         c = self.config
         dev = pixel_values.device
         if dev.type != "cuda":
@@ -368,15 +370,29 @@ class B200ViltModel(nn.Module):
         arena = self._arena
         arena.sync(dev)
         _lib.raise_device_errors()          # an out-of-range id of an EARLIER forward (clamped on the device) surfaces here
-        B, C, H, W = pixel_values.shape
-        T = (input_ids if input_ids is not None else inputs_embeds).shape[1]
+        Bi, C, H, W = pixel_values.shape
+        text = input_ids if input_ids is not None else inputs_embeds
+        T = text.shape[1]
+        if image_repeat < 1:
+            raise ValueError(f"image_repeat must be >= 1 (got {image_repeat})")
+        from .. import ops as _ops
+        if image_repeat > 1 and _ops.get_precision() == "bf16x3":
+            # the precise (bf16x3) engine keeps one image per sequence
+            pixel_values = pixel_values.repeat_interleave(image_repeat, dim=0)
+            pixel_mask = None if pixel_mask is None else pixel_mask.repeat_interleave(image_repeat, dim=0)
+            Bi, image_repeat = Bi * image_repeat, 1
+        B = Bi * image_repeat
+        if text.shape[0] != B:
+            raise ValueError(f"{text.shape[0]} text rows for {Bi} images x image_repeat {image_repeat}")
         if C != c.num_channels or H % c.patch_size or W % c.patch_size:
             raise NotImplementedError(f"pixel_values {tuple(pixel_values.shape)}: the fixed-resolution path needs "
                                       f"{c.num_channels} channels and H, W multiples of {c.patch_size}")
         if c.max_image_length is not None and c.max_image_length > 0 and c.max_image_length < (H // c.patch_size) * (W // c.patch_size):
             raise NotImplementedError("config.max_image_length > 0 makes the reference drop random patches of large images "
                                       "(modeling_vilt.py:171-187); climb_b200 implements the default max_image_length = -1")
-        geom, n_slots = self._patch_geometry(pixel_mask, B, H, W, dev)
+        geom, n_slots = self._patch_geometry(pixel_mask, Bi, H, W, dev)
+        if geom is not None and image_repeat > 1:
+            geom = geom.repeat_interleave(image_repeat, dim=0).contiguous()       # the engine reads the geometry per sequence
         pos_rows = self.embeddings.text_embeddings.position_embeddings.weight.shape[0]
         if T > pos_rows:
             raise ValueError(f"text length {T} exceeds the {pos_rows} text position embeddings")
@@ -420,6 +436,7 @@ class B200ViltModel(nn.Module):
         if geom is not None:
             keep.append(geom)
         b.patch_geom, b.n_patch_slots = _lib.ptr(geom), n_slots
+        b.image_repeat = image_repeat
         b.training = int(self.training)
         if self.training and (c.hidden_dropout_prob > 0.0 or c.attention_probs_dropout_prob > 0.0):
             # Philox key of this forward's dropout masks, drawn from torch's CPU generator (seeded by the driver's set_seed,

@@ -301,6 +301,11 @@ typedef struct {
     int n_patch_slots;
     int training;                       /* != 0: dims.hidden_dropout / attn_dropout are live (nn.Module.train()) */
     uint64_t dropout_seed;              /* Philox key of this forward; the backward regenerates the masks from it */
+    /* > 1: pixel_values holds B / image_repeat images, image i belongs to the image_repeat consecutive sequences
+     * i * image_repeat ... (VCR: one image, four answer choices, src/modeling/vilt.py:334-347 feeds the same pixels four
+     * times): im2col + patch projection run once per image, the embedding assembly broadcasts the rows, the backward sums
+     * the patch gradients of the sequences that share an image. patch_geom stays per sequence. 0 / 1 = one image per sequence. */
+    int image_repeat;
 } climb_vilt_batch;
 
 /* bytes of the activation workspace a forward needs (save_for_backward = 1 keeps every layer's

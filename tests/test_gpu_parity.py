@@ -254,6 +254,44 @@ def test_base_padded_images_vs_reference_golden():
     _check_grads(g, learner, "base_ragged_vqa")
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+def test_vcr_shared_image_equals_repeated_pixels(ragged):
+    """SURVEY 8 f-2, second clause: VCR feeds the same pixels once per answer choice (src/modeling/vilt.py:334-347). With
+    image_repeat = 4 the patch projection runs once per image and its rows are shared; outputs and every gradient
+    (the patch projection's collects all four sequences) must equal the repeat_interleave'd call."""
+    dev = torch.device("cuda")
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=77)
+    batch = vo.synth_batch("vcr", 3, TINY, T=TINY_T, image_hw=(64, 80) if ragged else TINY_HW, seed=78, masked=True)
+    enc = _encodings("vcr", batch, dev)
+    if ragged:
+        # make the images ragged by hand: valid rectangles of different sizes, zero padding
+        pm = torch.zeros_like(enc["pixel_mask"])
+        for i, (h, w) in enumerate([(32, 64), (64, 32), (64, 64)][: pm.shape[0]]):
+            pm[i, :h, :w] = 1
+        enc["pixel_mask"] = pm
+        enc["pixel_values"] = enc["pixel_values"] * pm[:, None].float()
+    results = []
+    for shared in (True, False):
+        learner = _build(TINY, ALL_TASKS, sd)
+        learner.train()
+        learner.task_layer["vcr"][0].eval()
+        vilt = learner.get_encoder()
+        if shared:
+            pooled = vilt(input_ids=enc["input_ids"], attention_mask=enc["attention_mask"], token_type_ids=enc["token_type_ids"],
+                          pixel_values=enc["pixel_values"], pixel_mask=enc["pixel_mask"], image_repeat=4)
+        else:
+            pooled = vilt(input_ids=enc["input_ids"], attention_mask=enc["attention_mask"], token_type_ids=enc["token_type_ids"],
+                          pixel_values=enc["pixel_values"].repeat_interleave(4, 0), pixel_mask=enc["pixel_mask"].repeat_interleave(4, 0))
+        (pooled * torch.linspace(-1, 1, pooled.numel(), device=dev).view_as(pooled)).sum().backward()
+        results.append((pooled.detach().clone(), {n: p.grad.detach().clone() for n, p in learner.named_parameters() if p.grad is not None}))
+    (p_s, g_s), (p_r, g_r) = results
+    assert torch.equal(p_s, p_r)                  # identical arithmetic: the same patch rows, read from one place instead of four
+    assert set(g_s) == set(g_r)
+    for n in g_r:
+        tol = 2e-3 if "patch_embeddings.projection.weight" in n else 1e-5      # sum of 4 fp32 rows then bf16 vs 4 bf16 rows in the GEMM
+        assert _rel(g_s[n], g_r[n]) <= tol, (n, _rel(g_s[n], g_r[n]))
+
+
 def test_all_ones_pixel_mask_takes_the_same_path_as_no_mask():
     sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=3)
     learner = _build(TINY, ALL_TASKS, sd).eval()
