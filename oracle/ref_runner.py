@@ -69,11 +69,18 @@ class ReferenceStepper:
     def step(self, batch, autocast: bool = False):
         """One VQATrainer.train_step (the reference's own method) on `batch`."""
         self.learner.vilt_encoder.process_inputs = lambda images, texts: batch["_enc"]
-        if autocast:
-            with torch.autocast(self.device.type, dtype=torch.bfloat16):
+        # The vendored visual_embed builds its patch-index grid with bare torch.arange / torch.meshgrid (modeling_vilt.py:151-153)
+        # and indexes it with indices taken from the pixel mask: on a GPU that mixes a CPU tensor with CUDA indices, which the
+        # torch of this image rejects. Running the UNCHANGED code under a default-device context puts those factory calls on
+        # the model's device -- the reference itself is not edited.
+        import contextlib
+        ctx = torch.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+        with ctx:
+            if autocast:
+                with torch.autocast(self.device.type, dtype=torch.bfloat16):
+                    out = self.trainer.train_step(self.learner, batch, self.optimizer)
+            else:
                 out = self.trainer.train_step(self.learner, batch, self.optimizer)
-        else:
-            out = self.trainer.train_step(self.learner, batch, self.optimizer)
         return out[0]
 
     def time_steps(self, B: int, steps: int, warmup: int, autocast: bool = False):
