@@ -379,8 +379,8 @@ def run_ours(args):
             at = json.load(open(ap_))
             attn_roof["fwd"]["traffic"] = at["fwd"]["dram_bytes_per_launch"]
             attn_roof["bwd"]["traffic"] = at["bwd"]["dram_bytes_per_launch"]
-            attn_roof["kernel"] = ("attn_tc_fwd2_kernel / attn_tc_bwd2_kernel (persistent, tcgen05 + TMEM); achieved = algorithmic bytes / time; "
-                                   "the tensor pipe (operand fetch from shared memory + MMA) and the MUFU pipe bound these kernels before HBM does: DESIGN.md")
+            attn_roof["kernel"] = ("attn_tc_fwd3_kernel (P in tensor memory) / attn_tc_bwd2_kernel (persistent, tcgen05 + TMEM); achieved = algorithmic bytes / time; "
+                                   "the instruction stream of the softmax / elementwise warps bounds these kernels before HBM does: DESIGN.md section 3")
         # the driver keeps `roofline` only: the attention kernels (the kernel BASELINE.json's metric names) ride inside it
         roofline["kernels"] = [
             {"name": "tcgen05 GEMMs (all launches)", "bound": "tensor", "achieved": roofline["achieved"], "peak": roofline["peak"],
@@ -419,7 +419,9 @@ def run_ours(args):
             "metric": "ViLT upstream-CL training throughput", "value": round(value, 1), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(B, world),
+            "config": dict(workload_config(B, world), **({"ddp": f"gradient all-reduce (NCCL AVG, {args.bucket_mb:g} MB buckets) from inside the "
+                           f"backward, issued in chunks of {args.layers_per_chunk} layers; AdamW "
+                           + ("deferred span by span behind the in-flight reductions" if args.defer_optimizer else "after all of them")} if world > 1 else {})),
             "samples_per_s_per_gpu": round(value / world, 1),
             "model_tflops_per_gpu": round(value / world * FLOPS_PER_SAMPLE_STEP / 1e12, 1),
             "step_frac_of_tensor_roofline": round(value / world * FLOPS_PER_SAMPLE_STEP / 1e12 / peaks["tf_sustained"], 4),
