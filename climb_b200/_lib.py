@@ -146,7 +146,7 @@ class ViltBatchC(Structure):
                 ("input_ids", c_void_p), ("inputs_embeds", c_void_p), ("token_type_ids", c_void_p),
                 ("attention_mask", c_void_p), ("pixel_values", c_void_p), ("image_type_idx", c_void_p),
                 ("image_type_idx_scalar", c_int), ("patch_geom", c_void_p), ("n_patch_slots", c_int),
-                ("training", c_int), ("dropout_seed", ctypes.c_uint64), ("image_repeat", c_int)]
+                ("training", c_int), ("dropout_seed", ctypes.c_uint64), ("image_repeat", c_int), ("patch_select", c_void_p)]
 
 
 class AdamWChunkC(Structure):

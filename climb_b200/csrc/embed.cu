@@ -135,8 +135,17 @@ __global__ void embed_assemble_kernel(const float* __restrict__ text_ln, const f
 // valid patches occupy slots s = py * w_b + px < h_b * w_b of its Np slots in raster order; the remaining slots
 // are padding: zero pixels, no position embedding, masked out as attention keys. (The reference fills them with
 // randomly chosen masked patches and permutes the valid ones: every output CLiMB consumes is invariant to both.)
+// Which patch of image b's own h_b x w_b grid sits in sequence slot `slot` (raster index, -1 = padding slot).
+// sel == nullptr: slots 0 .. h_b w_b - 1 hold the valid patches in raster order. sel [B, Np] (config.max_image_length > 0,
+// modeling_vilt.py:163-189): the host drew which valid patches each image keeps, exactly as the reference does.
+__device__ __forceinline__ int slot_patch(const int* __restrict__ sel, int b, int Np, int slot, int hb, int wb) {
+    if (sel != nullptr) return sel[static_cast<long long>(b) * Np + slot];
+    return slot < hb * wb ? slot : -1;
+}
+
 __global__ void im2col_ragged_kernel(const float* __restrict__ px, const int* __restrict__ geom,
-                                     __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int Np, int rep) {
+                                     __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int Np, int rep,
+                                     const int* __restrict__ sel) {
     const int K = C * P * P;
     const int k8 = K / 8;
     const long long total = static_cast<long long>(B) * Np * k8;
@@ -147,8 +156,9 @@ __global__ void im2col_ragged_kernel(const float* __restrict__ px, const int* __
     const int b = static_cast<int>(m / Np), slot = static_cast<int>(m - static_cast<long long>(b) * Np);
     const int hb = geom[2 * b * rep], wb = geom[2 * b * rep + 1];       // geom is per sequence; image b serves sequences b * rep ..
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (slot < hb * wb) {
-        const int py = slot / wb, pxi = slot - py * wb;
+    const int pj = slot_patch(sel, b * rep, Np, slot, hb, wb);
+    if (pj >= 0) {
+        const int py = pj / wb, pxi = pj - py * wb;
         const int c = k0 / (P * P), rem = k0 - c * P * P, ky = rem / P, kx = rem - ky * P;
         const float* src = px + ((static_cast<long long>(b) * C + c) * H + (py * P + ky)) * W + pxi * P + kx;
         const float4 a = *reinterpret_cast<const float4*>(src);
@@ -163,7 +173,8 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
                                              const float* __restrict__ pos_emb, const float* __restrict__ mod,
                                              const int* __restrict__ type_idx, int type_idx_scalar,
                                              float* __restrict__ x, int B, int T, int Np, int G, int d4, int n_mod, unsigned int* err,
-                                             uint32_t thresh, float inv_keep, unsigned long long seed, int rep) {
+                                             uint32_t thresh, float inv_keep, unsigned long long seed, int rep,
+                                             const int* __restrict__ sel) {
     const int L = T + 1 + Np;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * L * d4) return;
@@ -185,8 +196,9 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
             const int slot = l - T - 1;
             v = reinterpret_cast<const float4*>(patch)[(static_cast<long long>(b / rep) * Np + slot) * d4 + c];
             const int hb = geom[2 * b], wb = geom[2 * b + 1];
-            if (slot < hb * wb) {
-                const Taps t = bilinear_taps(slot / wb, slot % wb, hb, wb, G);
+            const int pj = slot_patch(sel, b, Np, slot, hb, wb);
+            if (pj >= 0) {
+                const Taps t = bilinear_taps(pj / wb, pj % wb, hb, wb, G);
                 const float4* g = reinterpret_cast<const float4*>(pos_emb) + d4;      // skip row 0 (the [cls] position)
                 const float4 q00 = g[static_cast<long long>(t.i00) * d4 + c], q01 = g[static_cast<long long>(t.i01) * d4 + c];
                 const float4 q10 = g[static_cast<long long>(t.i10) * d4 + c], q11 = g[static_cast<long long>(t.i11) * d4 + c];
@@ -209,7 +221,8 @@ __global__ void embed_assemble_ragged_kernel(const float* __restrict__ text_ln, 
 
 // d_pos[1 + g, :] += sum over images / valid slots of the transposed bilinear taps (per-image grids: no batch pre-sum)
 __global__ void pos_scatter_ragged_bwd_kernel(const float* __restrict__ dx, const int* __restrict__ geom,
-                                              float* __restrict__ d_pos, int B, int T, int Np, int G, int d) {
+                                              float* __restrict__ d_pos, int B, int T, int Np, int G, int d,
+                                              const int* __restrict__ sel) {
     const int L = T + 1 + Np;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * Np * d) return;
@@ -217,9 +230,10 @@ __global__ void pos_scatter_ragged_bwd_kernel(const float* __restrict__ dx, cons
     const int c = static_cast<int>(i - m * d);
     const int b = static_cast<int>(m / Np), slot = static_cast<int>(m - static_cast<long long>(b) * Np);
     const int hb = geom[2 * b], wb = geom[2 * b + 1];
-    if (slot >= hb * wb) return;
+    const int pj = slot_patch(sel, b, Np, slot, hb, wb);
+    if (pj < 0) return;
     const float g = dx[(static_cast<long long>(b) * L + T + 1 + slot) * d + c];
-    const Taps t = bilinear_taps(slot / wb, slot % wb, hb, wb, G);
+    const Taps t = bilinear_taps(pj / wb, pj % wb, hb, wb, G);
     float* dp = d_pos + d;
     if (t.w00 != 0.0f) atomicAdd(dp + static_cast<long long>(t.i00) * d + c, t.w00 * g);
     if (t.w01 != 0.0f) atomicAdd(dp + static_cast<long long>(t.i01) * d + c, t.w01 * g);
@@ -229,13 +243,13 @@ __global__ void pos_scatter_ragged_bwd_kernel(const float* __restrict__ dx, cons
 
 // key_bias for padded images: text mask | 0 for [cls] | 0 for valid slots, -10000 for padding slots
 __global__ void key_bias_ragged_kernel(const long long* __restrict__ mask, const int* __restrict__ geom,
-                                       float* __restrict__ out, int B, int T, int L) {
+                                       float* __restrict__ out, int B, int T, int L, const int* __restrict__ sel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * L) return;
     const int b = i / L, j = i - b * L;
     float v = 0.0f;
     if (j < T) v = mask ? (1.0f - static_cast<float>(mask[static_cast<long long>(b) * T + j])) * -10000.0f : 0.0f;
-    else if (j > T) v = (j - T - 1) < geom[2 * b] * geom[2 * b + 1] ? 0.0f : -10000.0f;
+    else if (j > T) v = slot_patch(sel, b, L - T - 1, j - T - 1, geom[2 * b], geom[2 * b + 1]) >= 0 ? 0.0f : -10000.0f;
     out[i] = v;
 }
 
@@ -424,39 +438,40 @@ int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T,
     return 0;
 }
 
-int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int H, int W, int P, int Np, cudaStream_t stream, int rep) {
+int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int H, int W, int P, int Np, cudaStream_t stream, int rep,
+                  const int* sel) {
     CLIMB_REQUIRE(px && geom && out && B > 0 && Np > 0, "im2col_ragged: bad arguments");
     CLIMB_REQUIRE(P % 8 == 0 && H % P == 0 && W % P == 0, "im2col_ragged: H, W must be multiples of the patch size (%d x %d, P=%d)", H, W, P);
     CLIMB_REQUIRE((reinterpret_cast<uintptr_t>(px) & 15) == 0 && W % 4 == 0, "im2col_ragged: pixel rows must be 16-byte aligned");
     const long long total = static_cast<long long>(B) * Np * (C * P * P / 8);
-    im2col_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, geom, static_cast<__nv_bfloat16*>(out), B, C, H, W, P, Np, rep);
+    im2col_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(px, geom, static_cast<__nv_bfloat16*>(out), B, C, H, W, P, Np, rep, sel);
     CLIMB_LAUNCH_OK();
     return 0;
 }
 
 int embed_assemble_ragged(const float* text_ln, const float* patch, const int* geom, const float* cls, const float* pos_emb,
                           const float* mod, const int* type_idx, int type_idx_scalar, float* x, int B, int T, int Np, int G,
-                          int d, cudaStream_t stream, int n_mod, float p_drop, unsigned long long seed, int rep) {
+                          int d, cudaStream_t stream, int n_mod, float p_drop, unsigned long long seed, int rep, const int* sel) {
     CLIMB_REQUIRE(text_ln && patch && geom && cls && pos_emb && mod && x && d % 4 == 0 && rep >= 1, "embed_assemble_ragged: bad arguments");
     const long long total = static_cast<long long>(B) * (T + 1 + Np) * (d / 4);
     embed_assemble_ragged_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(text_ln, patch, geom, cls, pos_emb, mod, type_idx,
                                                                             type_idx_scalar, x, B, T, Np, G, d / 4, n_mod, device_error_word(),
                                                                             p_drop > 0.0f ? dropout_threshold(p_drop) : 0u,
-                                                                            1.0f / (1.0f - p_drop), seed, rep);
+                                                                            1.0f / (1.0f - p_drop), seed, rep, sel);
     CLIMB_LAUNCH_OK();
     return 0;
 }
 
-int key_bias_ragged(const long long* mask, const int* geom, float* out, int B, int T, int L, cudaStream_t stream) {
+int key_bias_ragged(const long long* mask, const int* geom, float* out, int B, int T, int L, cudaStream_t stream, const int* sel) {
     CLIMB_REQUIRE(geom && out && B > 0 && T > 0 && L > T, "key_bias_ragged: bad arguments");
-    key_bias_ragged_kernel<<<(B * L + 255) / 256, 256, 0, stream>>>(mask, geom, out, B, T, L);
+    key_bias_ragged_kernel<<<(B * L + 255) / 256, 256, 0, stream>>>(mask, geom, out, B, T, L, sel);
     CLIMB_LAUNCH_OK();
     return 0;
 }
 
 int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, float* S, float* d_cls,
                      float* d_pos, float* d_mod, float* d_patch_bias, int n_mod, int B, int T, int hp, int wp,
-                     int G, int d, cudaStream_t stream, const int* geom, int ragged_np) {
+                     int G, int d, cudaStream_t stream, const int* geom, int ragged_np, const int* sel) {
     CLIMB_REQUIRE(dx && S && d % 4 == 0, "embed_reduce_bwd: bad arguments");
     if (geom == nullptr) ragged_np = 0;
     const int L = T + 1 + (ragged_np > 0 ? ragged_np : hp * wp);
@@ -468,7 +483,7 @@ int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, 
     CLIMB_LAUNCH_OK();
     if (ragged_np > 0 && d_pos != nullptr) {
         pos_scatter_ragged_bwd_kernel<<<blocks_for(static_cast<long long>(B) * ragged_np * d, 256), 256, 0, stream>>>(
-            dx, geom, d_pos, B, T, ragged_np, G, d);
+            dx, geom, d_pos, B, T, ragged_np, G, d, sel);
         CLIMB_LAUNCH_OK();
     }
     return 0;

@@ -99,6 +99,8 @@ int fill_plan(Plan& P, const climb_vilt_dims* dm, const climb_vilt_params* pr, c
                       "engine: n_patch_slots=%d outside (0, %d] for the padded %d x %d patch grid", bt->n_patch_slots, P.Np, P.hp, P.wp);
         P.Np = bt->n_patch_slots;
     }
+    CLIMB_REQUIRE(bt->patch_select == nullptr || (P.geom != nullptr && P.rep == 1),
+                  "engine: patch_select needs patch_geom and one image per sequence (image_repeat <= 1)");
     P.L = P.T + 1 + P.Np; P.M = P.B * P.L;
     P.d = dm->hidden; P.ff = dm->ffn; P.heads = dm->heads; P.layers = dm->layers;
     P.Kp = dm->channels * dm->patch * dm->patch;
@@ -311,7 +313,7 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
     const unsigned long long dseed = bt->dropout_seed;
 
     // ---- embeddings (modeling_vilt.py:207-246) ----
-    if (P.geom) TRY(key_bias_ragged(reinterpret_cast<const long long*>(bt->attention_mask), P.geom, P.key_bias, P.B, P.T, P.L, s));
+    if (P.geom) TRY(key_bias_ragged(reinterpret_cast<const long long*>(bt->attention_mask), P.geom, P.key_bias, P.B, P.T, P.L, s, bt->patch_select));
     else if (bt->attention_mask) TRY(key_bias(reinterpret_cast<const long long*>(bt->attention_mask), P.key_bias, P.B, P.T, P.L, s));
     else CLIMB_CUDA_OK(cudaMemsetAsync(P.key_bias, 0, sizeof(float) * P.B * P.L, s));
     TRY(text_gather(reinterpret_cast<const long long*>(bt->input_ids), bt->inputs_embeds,
@@ -321,7 +323,7 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
     TRY(layernorm_fwd(P.text_e, d, F(theta, pr->text_ln_w), F(theta, pr->text_ln_b), dm->ln_eps, nullptr, P.text_ln,
                       P.text_mean, P.text_rstd, BT, d, CLIMB_EPI_NONE, s));
     // image_repeat > 1 (VCR: four answer choices per image, vilt.py:334-347): the patch projection runs once per image
-    if (P.geom) TRY(im2col_ragged(bt->pixel_values, P.geom, P.im2col, P.Bi, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s, P.rep));
+    if (P.geom) TRY(im2col_ragged(bt->pixel_values, P.geom, P.im2col, P.Bi, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s, P.rep, bt->patch_select));
     else TRY(im2col(bt->pixel_values, P.im2col, P.Bi, dm->channels, P.Hh, P.Ww, dm->patch, s));
     {
         Lin l{P.Bi * P.Np, d, P.Kp, P.im2col, P.Kp, H(shadow, pr->patch_w)};
@@ -331,7 +333,7 @@ int vilt_forward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const c
     if (P.geom) {
         TRY(embed_assemble_ragged(P.text_ln, P.patch_out, P.geom, F(theta, pr->cls_token), F(theta, pr->pos_emb),
                                   F(theta, pr->mod_emb), bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B,
-                                  P.T, P.Np, dm->pos_grid, d, s, dm->n_modality, p_h, dropout_site_seed(dseed, -1, 1), P.rep));
+                                  P.T, P.Np, dm->pos_grid, d, s, dm->n_modality, p_h, dropout_site_seed(dseed, -1, 1), P.rep, bt->patch_select));
     } else {
         TRY(pos_interp(F(theta, pr->pos_emb), P.pos_table, P.hp, P.wp, dm->pos_grid, d, s));
         TRY(embed_assemble(P.text_ln, P.patch_out, P.pos_table, F(theta, pr->cls_token), F(theta, pr->pos_emb),
@@ -602,12 +604,12 @@ int vilt_backward(const climb_vilt_dims* dm, const climb_vilt_params* pr, const 
             dxe = S.dxm;
             // the modality-type rows are added AFTER the dropout: their gradient is the unmasked one
             TRY(embed_reduce_bwd(dx, bt->image_type_idx, bt->image_type_idx_scalar, S.S, nullptr, nullptr, G(grad, pr->mod_emb),
-                                 nullptr, dm->n_modality, P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0));
+                                 nullptr, dm->n_modality, P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0, bt->patch_select));
         }
         TRY(embed_split_bwd(dxe, S.dy_text, S.dpatch, P.B, P.T, P.Np, d, s, P.rep));
         TRY(embed_reduce_bwd(dxe, bt->image_type_idx, bt->image_type_idx_scalar, S.S, G(grad, pr->cls_token),
                              G(grad, pr->pos_emb), p_h > 0.0f ? nullptr : G(grad, pr->mod_emb), G(grad, pr->patch_b), dm->n_modality,
-                             P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0));
+                             P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s, P.geom, P.geom ? P.Np : 0, bt->patch_select));
         TRY(layernorm_bwd(S.dy_text, nullptr, P.text_e, d, F(theta, pr->text_ln_w), F(theta, pr->text_ln_b), P.text_mean,
                           P.text_rstd, nullptr, S.de_text, nullptr, G(grad, pr->text_ln_w), G(grad, pr->text_ln_b), BT, d,
                           CLIMB_EPI_NONE, s));

@@ -70,14 +70,16 @@ int embed_assemble(const float* text_ln, const float* patch, const float* table,
 int embed_split_bwd(const float* dx, float* dy_text, void* dpatch, int B, int T, int Np, int d, cudaStream_t stream, int rep = 1);
 int embed_reduce_bwd(const float* dx, const int* type_idx, int type_idx_scalar, float* S, float* d_cls,
                      float* d_pos, float* d_mod, float* d_patch_bias, int n_mod, int B, int T, int hp, int wp,
-                     int G, int d, cudaStream_t stream, const int* geom = nullptr, int ragged_np = 0);
+                     int G, int d, cudaStream_t stream, const int* geom = nullptr, int ragged_np = 0, const int* sel = nullptr);
 // variable-resolution (padded images): geom = [B, 2] valid patch rows / cols per image, Np patch slots per sequence
+// sel (optional, [B, Np] int32): raster index of the patch in every slot or -1 (climb_vilt_batch.patch_select)
 int im2col_ragged(const float* px, const int* geom, void* out, int B, int C, int H, int W, int P, int Np, cudaStream_t stream,
-                  int rep = 1);
+                  int rep = 1, const int* sel = nullptr);
 int embed_assemble_ragged(const float* text_ln, const float* patch, const int* geom, const float* cls, const float* pos_emb,
                           const float* mod, const int* type_idx, int type_idx_scalar, float* x, int B, int T, int Np, int G,
-                          int d, cudaStream_t stream, int n_mod = 0, float p_drop = 0.0f, unsigned long long seed = 0, int rep = 1);
-int key_bias_ragged(const long long* mask, const int* geom, float* out, int B, int T, int L, cudaStream_t stream);
+                          int d, cudaStream_t stream, int n_mod = 0, float p_drop = 0.0f, unsigned long long seed = 0, int rep = 1,
+                          const int* sel = nullptr);
+int key_bias_ragged(const long long* mask, const int* geom, float* out, int B, int T, int L, cudaStream_t stream, const int* sel = nullptr);
 int text_scatter_bwd(const float* de, const long long* ids, const long long* tt, float* d_word, float* d_type,
                      float* d_pos, int rows, int T, int d, cudaStream_t stream, int vocab = 0, int n_types = 0);
 

@@ -588,7 +588,7 @@ int vilt_forward_precise(const climb_vilt_dims* dm, const climb_vilt_params* pr,
     Ctx c{static_cast<const bf16*>(shadow), static_cast<const bf16*>(pr->shadow_lo), P.a_hi, P.a_lo, nullptr, nullptr, s};
 
     // ---- embeddings (modeling_vilt.py:207-246) ----
-    if (P.geom) TRY(key_bias_ragged(reinterpret_cast<const long long*>(bt->attention_mask), P.geom, P.key_bias, P.B, P.T, P.L, s));
+    if (P.geom) TRY(key_bias_ragged(reinterpret_cast<const long long*>(bt->attention_mask), P.geom, P.key_bias, P.B, P.T, P.L, s, bt->patch_select));
     else if (bt->attention_mask) TRY(key_bias(reinterpret_cast<const long long*>(bt->attention_mask), P.key_bias, P.B, P.T, P.L, s));
     else CLIMB_CUDA_OK(cudaMemsetAsync(P.key_bias, 0, sizeof(float) * P.B * P.L, s));
     TRY(text_gather(reinterpret_cast<const long long*>(bt->input_ids), bt->inputs_embeds,
@@ -601,8 +601,8 @@ int vilt_forward_precise(const climb_vilt_dims* dm, const climb_vilt_params* pr,
         residual_pixels_kernel<<<blocks_for(npx, 256), 256, 0, s>>>(bt->pixel_values, P.px_lo, npx);
         CLIMB_LAUNCH_OK();
         if (P.geom) {
-            TRY(im2col_ragged(bt->pixel_values, P.geom, P.im2col_hi, P.B, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s));
-            TRY(im2col_ragged(P.px_lo, P.geom, P.im2col_lo, P.B, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s));
+            TRY(im2col_ragged(bt->pixel_values, P.geom, P.im2col_hi, P.B, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s, 1, bt->patch_select));
+            TRY(im2col_ragged(P.px_lo, P.geom, P.im2col_lo, P.B, dm->channels, P.Hh, P.Ww, dm->patch, P.Np, s, 1, bt->patch_select));
         } else {
             TRY(im2col(bt->pixel_values, P.im2col_hi, P.B, dm->channels, P.Hh, P.Ww, dm->patch, s));
             TRY(im2col(P.px_lo, P.im2col_lo, P.B, dm->channels, P.Hh, P.Ww, dm->patch, s));
@@ -616,7 +616,7 @@ int vilt_forward_precise(const climb_vilt_dims* dm, const climb_vilt_params* pr,
     if (P.geom) {
         TRY(embed_assemble_ragged(P.text_ln, P.patch_out, P.geom, F(theta, pr->cls_token), F(theta, pr->pos_emb), F(theta, pr->mod_emb),
                                   bt->image_type_idx, bt->image_type_idx_scalar, P.act[0].x_in, P.B, P.T, P.Np, dm->pos_grid, d, s,
-                                  dm->n_modality));
+                                  dm->n_modality, 0.0f, 0, 1, bt->patch_select));
     } else {
         TRY(pos_interp(F(theta, pr->pos_emb), P.pos_table, P.hp, P.wp, dm->pos_grid, d, s));
         TRY(embed_assemble(P.text_ln, P.patch_out, P.pos_table, F(theta, pr->cls_token), F(theta, pr->pos_emb), F(theta, pr->mod_emb),
@@ -778,7 +778,7 @@ int vilt_backward_precise(const climb_vilt_dims* dm, const climb_vilt_params* pr
         CLIMB_LAUNCH_OK();
         TRY(embed_reduce_bwd(dx, bt->image_type_idx, bt->image_type_idx_scalar, S.S, G(grad, pr->cls_token), G(grad, pr->pos_emb),
                              G(grad, pr->mod_emb), G(grad, pr->patch_b), dm->n_modality, P.B, P.T, P.hp, P.wp, dm->pos_grid, d, s,
-                             P.geom, P.geom ? P.Np : 0));
+                             P.geom, P.geom ? P.Np : 0, bt->patch_select));
         TRY(layernorm_bwd(S.dy_text, nullptr, P.text_e, d, F(theta, pr->text_ln_w), F(theta, pr->text_ln_b), P.text_mean, P.text_rstd,
                           nullptr, S.de_text, nullptr, G(grad, pr->text_ln_w), G(grad, pr->text_ln_b), BT, d, CLIMB_EPI_NONE, s));
         TRY(text_scatter_bwd(S.de_text, reinterpret_cast<const long long*>(bt->input_ids),

@@ -241,7 +241,9 @@ class B200ViltContinualLearner(ContinualLearner):
         type_idx = (torch.arange(num_images, device=px.device, dtype=torch.int32) + 1).repeat(bs)
         pooled = self.vilt_encoder(input_ids=rep(ids), attention_mask=rep(am), token_type_ids=rep(tt),
                                    pixel_values=px, pixel_mask=self._enc(encodings, 'pixel_mask'),
-                                   image_token_type_idx=type_idx)
+                                   image_token_type_idx=type_idx,
+                                   # the reference runs image 0 of every sample, then image 1 (vilt.py:291-304)
+                                   patch_draw_order=[b * num_images + i for i in range(num_images) for b in range(bs)])
         pooled = pooled.view(bs, num_images * pooled.shape[-1])       # == torch.cat(pooler_outputs, dim=-1)
         return pooled, self.task_layer[task_key](pooled)
 
@@ -254,7 +256,9 @@ class B200ViltContinualLearner(ContinualLearner):
         # patch rows are shared by its num_choices sequences (climb_vilt_batch.image_repeat)
         pooled = self.vilt_encoder(input_ids=encodings['input_ids'], attention_mask=encodings['attention_mask'],
                                    token_type_ids=encodings['token_type_ids'], pixel_values=px, pixel_mask=pm,
-                                   image_repeat=num_choices)
+                                   image_repeat=num_choices,
+                                   # the reference runs choice 0 of every sample, then choice 1 ... (vilt.py:334-347)
+                                   patch_draw_order=[b * num_choices + c for c in range(num_choices) for b in range(bs)])
         pooled = pooled.view(bs, num_choices, -1)                     # == stack(dim=0).transpose(0, 1)
         logits = self.task_layer[task_key](pooled).squeeze()
         return pooled, logits

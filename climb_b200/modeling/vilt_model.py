@@ -340,11 +340,15 @@ class B200ViltModel(nn.Module):
     # -- forward -----------------------------------------------------------------------------------
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, pixel_values=None, pixel_mask=None,
                 head_mask=None, inputs_embeds=None, image_embeds=None, image_token_type_idx=None,
-                output_attentions=None, output_hidden_states=None, return_dict=None, image_repeat: int = 1):
+                output_attentions=None, output_hidden_states=None, return_dict=None, image_repeat: int = 1,
+                patch_draw_order=None):
         """ViltModel.forward (modeling_vilt.py:777-884). image_token_type_idx may be an int (as in the reference) or an
         int tensor [B] (batched NLVR2 passes). image_repeat = r > 1 (extension): pixel_values / pixel_mask hold B / r images,
         image i belongs to the r consecutive text rows i * r ... (VCR's four answer choices over one image,
-        src/modeling/vilt.py:334-347): same result as pixel_values.repeat_interleave(r, 0), patch projection once per image."""
+        src/modeling/vilt.py:334-347): same result as pixel_values.repeat_interleave(r, 0), patch projection once per image.
+        patch_draw_order (extension, only read when config.max_image_length > 0 drops patches): the order in which the
+        sequences of this batched call would have drawn their random patch subsets in the reference's separate encoder
+        passes (NLVR2: image 0 of every sample, then image 1; VCR: choice 0 of every sample, then choice 1 ...)."""
         if head_mask is not None or image_embeds is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("head_mask / image_embeds / output_attentions / output_hidden_states are outside "
                                       "CLiMB's hot path and not implemented in climb_b200")
@@ -353,7 +357,7 @@ class B200ViltModel(nn.Module):
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")
         call = self._prepare_call(input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, inputs_embeds,
-                                  image_token_type_idx, int(image_repeat))
+                                  image_token_type_idx, int(image_repeat), patch_draw_order)
         if torch.is_grad_enabled() and call.trainable:
             anchor = torch.zeros((), device=pixel_values.device, requires_grad=True)
             pooled = _EncoderFn.apply(anchor, self, call)
@@ -362,7 +366,7 @@ class B200ViltModel(nn.Module):
         return ViltOutput(pooler_output=pooled)
 
     def _prepare_call(self, input_ids, attention_mask, token_type_ids, pixel_values, pixel_mask, inputs_embeds,
-                      image_token_type_idx, image_repeat: int = 1) -> _Call:
+                      image_token_type_idx, image_repeat: int = 1, draw_order=None) -> _Call:
         c = self.config
         dev = pixel_values.device
         if dev.type != "cuda":
@@ -387,10 +391,17 @@ class B200ViltModel(nn.Module):
         if C != c.num_channels or H % c.patch_size or W % c.patch_size:
             raise NotImplementedError(f"pixel_values {tuple(pixel_values.shape)}: the fixed-resolution path needs "
                                       f"{c.num_channels} channels and H, W multiples of {c.patch_size}")
-        if c.max_image_length is not None and c.max_image_length > 0 and c.max_image_length < (H // c.patch_size) * (W // c.patch_size):
-            raise NotImplementedError("config.max_image_length > 0 makes the reference drop random patches of large images "
-                                      "(modeling_vilt.py:171-187); climb_b200 implements the default max_image_length = -1")
-        geom, n_slots = self._patch_geometry(pixel_mask, Bi, H, W, dev)
+        sel = None
+        if isinstance(c.max_image_length, int) and 0 < c.max_image_length < (H // c.patch_size) * (W // c.patch_size):
+            # the cap may bite (modeling_vilt.py:163-189). Every encoder call of the reference draws its own subset, so images
+            # shared by several sequences (VCR) are expanded first
+            if image_repeat > 1:
+                pixel_values = pixel_values.repeat_interleave(image_repeat, dim=0)
+                pixel_mask = None if pixel_mask is None else pixel_mask.repeat_interleave(image_repeat, dim=0)
+                Bi, image_repeat = Bi * image_repeat, 1
+            geom, n_slots, sel = self._patch_selection(pixel_mask, Bi, H, W, dev, c.max_image_length, draw_order)
+        else:
+            geom, n_slots = self._patch_geometry(pixel_mask, Bi, H, W, dev)
         if geom is not None and image_repeat > 1:
             geom = geom.repeat_interleave(image_repeat, dim=0).contiguous()       # the engine reads the geometry per sequence
         pos_rows = self.embeddings.text_embeddings.position_embeddings.weight.shape[0]
@@ -436,6 +447,9 @@ class B200ViltModel(nn.Module):
         if geom is not None:
             keep.append(geom)
         b.patch_geom, b.n_patch_slots = _lib.ptr(geom), n_slots
+        if sel is not None:
+            keep.append(sel)
+            b.patch_select = _lib.ptr(sel)
         b.image_repeat = image_repeat
         b.training = int(self.training)
         if self.training and (c.hidden_dropout_prob > 0.0 or c.attention_probs_dropout_prob > 0.0):
@@ -475,6 +489,50 @@ class B200ViltModel(nn.Module):
                 raise ValueError("pixel_mask marks an image as entirely padding")
             return geom.to(dev).contiguous(), n
         return geom.contiguous(), full
+
+    def _patch_selection(self, pixel_mask, B, H, W, dev, max_image_length: int, draw_order=None):
+        """config.max_image_length > 0, modeling_vilt.py:163-189: the sequence gets min(max_b h_b w_b, max_image_length) patch
+        rows; an image with at least that many valid patches keeps a RANDOM subset of them, a smaller image keeps all of its
+        patches and is padded with masked rows. The subset is drawn here, on the host, with the reference's own calls in the
+        reference's order -- torch.multinomial(torch.ones(v).float(), n) per image on torch's CPU generator (the reference
+        builds the weights on the CPU whatever device the model is on), including the draw it spends on choosing padding rows
+        -- so that a seeded run keeps exactly the patches the reference keeps. Reading the mask costs one device-to-host
+        copy when it lives on the GPU. Returns (geom [B, 2] int32, n_slots, select [B, n_slots] int32: raster index of the
+        kept patch in the image's own grid, -1 = padding); select is None when the cap drops nothing."""
+        P = self.config.patch_size
+        hp, wp = H // P, W // P
+        if pixel_mask is None:
+            h = torch.full((B,), hp, dtype=torch.int64)
+            w = torch.full((B,), wp, dtype=torch.int64)
+        else:
+            if tuple(pixel_mask.shape) != (B, H, W):
+                raise ValueError(f"pixel_mask shape {tuple(pixel_mask.shape)} does not match pixel_values ({B}, {H}, {W})")
+            xm = pixel_mask[:, ::P, ::P].cpu()
+            h = (xm[:, :, 0] != 0).sum(dim=1)
+            w = (xm[:, 0, :] != 0).sum(dim=1)
+        eff = h * w
+        if int(eff.min()) <= 0:
+            raise ValueError("pixel_mask marks an image as entirely padding")
+        n = min(int(eff.max()), int(max_image_length))
+        geom = torch.stack([h, w], dim=1).to(torch.int32)
+        if n == int(eff.max()):
+            # nothing is dropped: images at the maximum are permuted (outputs invariant), smaller ones padded = the default path
+            if int(eff.min()) == hp * wp:
+                return None, 0, None
+            return geom.to(dev).contiguous(), n, None
+        sel = torch.full((B, n), -1, dtype=torch.int32)
+        order = list(range(B)) if draw_order is None else [int(i) for i in draw_order]
+        if sorted(order) != list(range(B)):
+            raise ValueError("patch_draw_order must be a permutation of the sequences of the call")
+        for i in order:
+            v = int(eff[i])
+            pad = n - v
+            if pad <= 0:
+                sel[i] = torch.multinomial(torch.ones(v).float(), n).to(torch.int32)          # :177-178
+            else:
+                torch.multinomial(torch.ones(hp * wp - v).float(), pad, replacement=True)      # :180, keeps the generator in step
+                sel[i, :v] = torch.arange(v, dtype=torch.int32)
+        return geom.to(dev).contiguous(), n, sel.to(dev).contiguous()
 
     def _static_tables(self):
         """C structs that only change when the arena is rebuilt, the active adapter changes or a

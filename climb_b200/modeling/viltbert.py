@@ -91,7 +91,8 @@ class B200ViltBertContinualLearner(B200ViltContinualLearner):
         pooled = self.viltbert_encoder(input_ids=None, inputs_embeds=rep(feats), attention_mask=rep(am),
                                        token_type_ids=rep(tt), pixel_values=px,
                                        pixel_mask=self._enc(encodings, 'pixel_mask'),
-                                       image_token_type_idx=type_idx)
+                                       image_token_type_idx=type_idx,
+                                       patch_draw_order=[b * num_images + i for i in range(num_images) for b in range(bs)])
         pooled = pooled.view(bs, num_images * pooled.shape[-1])
         return pooled, self.task_layer[task_key](pooled)
 

@@ -306,6 +306,12 @@ typedef struct {
      * times): im2col + patch projection run once per image, the embedding assembly broadcasts the rows, the backward sums
      * the patch gradients of the sequences that share an image. patch_geom stays per sequence. 0 / 1 = one image per sequence. */
     int image_repeat;
+    /* config.max_image_length > 0 (modeling_vilt.py:163-189: an image with more valid patches than the cap keeps a random
+     * subset, drawn with torch.multinomial): patch_select [B, n_patch_slots] int32 = raster index (in the image's own
+     * h_b x w_b grid) of the patch in every sequence slot, -1 = padding slot. The HOST draws the subset with the same torch
+     * calls in the same order as the reference (climb_b200/modeling/vilt_model.py), so a seeded run keeps the same patches.
+     * Needs patch_geom; NULL = slots 0 .. h_b w_b - 1 hold all valid patches in raster order. */
+    const int32_t* patch_select;
 } climb_vilt_batch;
 
 /* bytes of the activation workspace a forward needs (save_for_backward = 1 keeps every layer's

@@ -55,7 +55,7 @@ def build_reference_learner(dims: ViltDims, tasks, sd):
     cfg = ViltConfig(hidden_size=dims.hidden_size, num_hidden_layers=dims.num_hidden_layers,
                      num_attention_heads=dims.num_attention_heads, intermediate_size=dims.intermediate_size,
                      image_size=dims.image_size, patch_size=dims.patch_size, vocab_size=dims.vocab_size,
-                     max_position_embeddings=dims.max_position_embeddings)
+                     max_position_embeddings=dims.max_position_embeddings, max_image_length=dims.max_image_length)
     enc = ViltEncoderWrapper(ref_shim.StubProcessor(), ViltModel(cfg), torch.device("cpu"))
     learner = ViltContinualLearner(list(tasks), enc, dims.hidden_size, task_configs)
     missing, unexpected = learner.load_state_dict(sd, strict=False)
@@ -134,8 +134,11 @@ def scales_for(task):
     return VCR_SCALES if task == "vcr" else dict(layer_scale=1.0, head_scale=1.0)
 
 
-def run_task(dims, hw, T, task, B, seed, tag, masked, full_grads, image_sizes=None):
+def run_task(dims, hw, T, task, B, seed, tag, masked, full_grads, image_sizes=None, max_image_length=-1):
     tasks = ALL_TASKS
+    if max_image_length > 0:        # ViltConfig.max_image_length: random patch dropping (modeling_vilt.py:163-189)
+        import dataclasses
+        dims = dataclasses.replace(dims, max_image_length=max_image_length)
     sc = scales_for(task)
     sd = synth_state_dict(dims, tasks, seed=seed, **sc)
     learner = build_reference_learner(dims, tasks, sd)
@@ -155,6 +158,8 @@ def run_task(dims, hw, T, task, B, seed, tag, masked, full_grads, image_sizes=No
                head_scale=np.float32(sc["head_scale"]))
     if image_sizes is not None:
         out["image_sizes"] = np.array(image_sizes)
+    if max_image_length > 0:
+        out["max_image_length"] = np.int64(max_image_length)
     for n, p in learner.named_parameters():
         g = p.grad
         if g is None:
@@ -356,10 +361,23 @@ def main():
     ap.add_argument("--only-viltbert", action="store_true", help="regenerate the ViLT-BERT fixtures only")
     ap.add_argument("--only-ragged", action="store_true", help="regenerate the padded-image (pixel_mask) fixtures only")
     ap.add_argument("--only-vcr", action="store_true", help="regenerate the three VCR (multi-choice) fixtures only")
+    ap.add_argument("--only-maxlen", action="store_true", help="regenerate the max_image_length (patch dropping) fixtures only")
     a = ap.parse_args()
     ref_shim.install()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    # config.max_image_length > 0: 4 x 5 patch grid capped at 9 rows -- larger images keep a random subset (the seed set in
+    # run_task fixes it), smaller ones are padded; single image, image pair (two encoder passes = two rounds of draws) and
+    # four choices (four passes over the same pixels, each with its own subset); one batch without any pixel_mask padding
+    run_task(TINY, (64, 80), TINY_T, "snli-ve", B=4, seed=600, tag="tiny_maxlen_snli-ve", masked=True, full_grads=True,
+             image_sizes=[(64, 80), (48, 64), (32, 64), (64, 32)], max_image_length=9)
+    run_task(TINY, (64, 80), TINY_T, "nlvr2", B=3, seed=601, tag="tiny_maxlen_nlvr2", masked=True, full_grads=True,
+             image_sizes=[(64, 80), (48, 48), (32, 64), (64, 48), (16, 80), (48, 80)], max_image_length=9)
+    run_task(TINY, (64, 80), TINY_T, "vcr", B=3, seed=602, tag="tiny_maxlen_vcr", masked=True, full_grads=True,
+             image_sizes=[(48, 80), (64, 64), (32, 48)], max_image_length=9)
+    run_task(TINY, TINY_HW, TINY_T, "vqa", B=3, seed=603, tag="tiny_maxlen_full_vqa", masked=True, full_grads=True, max_image_length=7)
+    if a.only_maxlen:
+        return
     if a.only_vcr:
         run_task(TINY, (64, 80), TINY_T, "vcr", B=3, seed=502, tag="tiny_ragged_vcr", masked=True, full_grads=True,
                  image_sizes=[(48, 80), (64, 64), (32, 48)])

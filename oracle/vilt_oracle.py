@@ -45,6 +45,7 @@ class ViltDims:
     type_vocab_size: int = 2
     modality_type_vocab_size: int = 2
     layer_norm_eps: float = 1e-12
+    max_image_length: int = -1          # ViltConfig.max_image_length (configuration_vilt.py): > 0 caps the patch rows per image
 
     @property
     def patch_dim(self) -> int:
@@ -221,6 +222,25 @@ def patch_geometry(pixel_mask: Tensor, patch_size: int) -> Tuple[Tensor, Tensor]
     return (xm[:, :, 0] != 0).sum(dim=1), (xm[:, 0, :] != 0).sum(dim=1)
 
 
+def select_patches(hs: Tensor, ws: Tensor, grid: int, max_image_length: int):
+    """modeling_vilt.py:163-189 with max_image_length > 0: n = min(max_b h_b w_b, max_image_length) rows per image; an image
+    with v >= n valid patches keeps torch.multinomial(torch.ones(v).float(), n) of them (:177-178, indices into its valid
+    patches in raster order), a smaller one keeps all and is padded with n - v masked rows chosen by a second multinomial
+    (:180) whose values do not matter but whose draw advances the generator. Same calls, same order as the reference, so
+    the same seed gives the same subset. Returns (n, [LongTensor of kept raster indices per image])."""
+    eff = hs * ws
+    n = min(int(eff.max()), int(max_image_length))
+    keep = []
+    for b in range(len(hs)):
+        v = int(eff[b])
+        if n - v <= 0:
+            keep.append(torch.multinomial(torch.ones(v).float(), n))
+        else:
+            torch.multinomial(torch.ones(grid - v).float(), n - v, replacement=True)
+            keep.append(torch.arange(v))
+    return n, keep
+
+
 def visual_embed_ragged(sd, pixel_values: Tensor, pixel_mask: Tensor, dims: ViltDims) -> Tuple[Tensor, Tensor]:
     """ViltEmbeddings.visual_embed for a batch padded to a common H x W (modeling_vilt.py:121-205, default
     max_image_length = -1): every image keeps ALL its valid patches with the position table interpolated to
@@ -234,13 +254,18 @@ def visual_embed_ragged(sd, pixel_values: Tensor, pixel_mask: Tensor, dims: Vilt
     B, d = x.shape[:2]
     hs, ws = patch_geometry(pixel_mask, dims.patch_size)
     n = int((hs * ws).max())
+    keep = None
+    if isinstance(dims.max_image_length, int) and 0 < dims.max_image_length < n:
+        n, keep = select_patches(hs, ws, x.shape[2] * x.shape[3], dims.max_image_length)
     rows, masks = [], []
     for b in range(B):
         h, w = int(hs[b]), int(ws[b])
         v = x[b, :, :h, :w].flatten(1).transpose(0, 1) + interpolated_position_table(sd, dims, h, w)     # [h*w, d]
-        pad = n - h * w
+        if keep is not None:
+            v = v[keep[b]]
+        pad = n - v.shape[0]
         rows.append(torch.cat([v, v.new_zeros(pad, d)], dim=0))
-        masks.append(torch.cat([torch.ones(h * w), torch.zeros(pad)]))
+        masks.append(torch.cat([torch.ones(v.shape[0]), torch.zeros(pad)]))
     x = torch.stack(rows, dim=0)
     cls = sd[e + "cls_token"].expand(B, -1, -1) + sd[e + "position_embeddings"][:, :1, :]
     return torch.cat([cls, x], dim=1), torch.cat([torch.ones(B, 1), torch.stack(masks, dim=0)], dim=1)
@@ -253,7 +278,11 @@ def embeddings(sd, dims: ViltDims, input_ids, attention_mask, token_type_ids, pi
     :201 on patches + position embeddings), both applied BEFORE the modality-type rows are added (:231-241)."""
     tt = sd[ENC + "embeddings.token_type_embeddings.weight"]
     text = text_embeddings(sd, input_ids, token_type_ids, dims, inputs_embeds)
-    if pixel_mask is not None and not bool((pixel_mask != 0).all()):
+    grid = (pixel_values.shape[-2] // dims.patch_size) * (pixel_values.shape[-1] // dims.patch_size)
+    capped = isinstance(dims.max_image_length, int) and 0 < dims.max_image_length < grid
+    if capped and pixel_mask is None:
+        pixel_mask = torch.ones(pixel_values.shape[0], pixel_values.shape[-2], pixel_values.shape[-1], dtype=torch.long)
+    if pixel_mask is not None and (capped or not bool((pixel_mask != 0).all())):
         image, image_mask = visual_embed_ragged(sd, pixel_values, pixel_mask, dims)
     else:
         image = visual_embed_fixed(sd, pixel_values, dims)

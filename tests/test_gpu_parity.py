@@ -55,7 +55,7 @@ def _build(dims, tasks, sd, adapters=None):
     cfg = B200ViltConfig(hidden_size=dims.hidden_size, num_hidden_layers=dims.num_hidden_layers,
                          num_attention_heads=dims.num_attention_heads, intermediate_size=dims.intermediate_size,
                          image_size=dims.image_size, patch_size=dims.patch_size, vocab_size=dims.vocab_size,
-                         max_position_embeddings=dims.max_position_embeddings)
+                         max_position_embeddings=dims.max_position_embeddings, max_image_length=dims.max_image_length)
     dev = torch.device("cuda")
     enc = B200ViltEncoderWrapper(None, B200ViltModel(cfg), dev)
     learner = B200ViltContinualLearner(list(tasks), enc, dims.hidden_size, vo.TASK_SPECS)
@@ -243,6 +243,26 @@ def test_tiny_padded_images_vs_reference_golden(tag, task, B, seed, host_mask):
     key = f"{tag}/{'host' if host_mask else 'dev'}_mask"
     check_outputs(key, pooled, logits, loss.item(), g["pooled"], g["logits"], g["loss"])
     _check_grads(g, learner, key)
+
+
+@pytest.mark.parametrize("tag,task,B,seed,hw", [("tiny_maxlen_snli-ve", "snli-ve", 4, 600, (64, 80)), ("tiny_maxlen_nlvr2", "nlvr2", 3, 601, (64, 80)),
+                                                 ("tiny_maxlen_vcr", "vcr", 3, 602, (64, 80)), ("tiny_maxlen_full_vqa", "vqa", 3, 603, None)])
+def test_tiny_max_image_length_vs_reference_golden(tag, task, B, seed, hw):
+    """config.max_image_length > 0 (random patch dropping, modeling_vilt.py:163-189): the host draws the kept patches with
+    the reference's own torch.multinomial calls in the reference's order (per encoder pass for NLVR2 / VCR), the engine
+    gathers them (climb_vilt_batch.patch_select). Same seed => same patches => the unmodified reference's outputs and
+    gradients."""
+    import dataclasses
+    from tests.golden_util import TINY_HW
+    g = load(tag)
+    batch = regen_batch(g, task, TINY, TINY_T, hw or TINY_HW, B, seed, True)
+    dims = dataclasses.replace(TINY, max_image_length=int(g["max_image_length"]))
+    learner = _build(dims, ALL_TASKS, vo.synth_state_dict(TINY, ALL_TASKS, seed=seed, **fixture_scales(g)))
+    assert learner.get_encoder().vilt.config.max_image_length == int(g["max_image_length"])
+    torch.manual_seed(seed)
+    pooled, logits, loss = _step(learner, task, batch, host_mask=True)
+    check_outputs(tag, pooled, logits, loss.item(), g["pooled"], g["logits"], g["loss"])
+    _check_grads(g, learner, tag)
 
 
 def test_base_padded_images_vs_reference_golden():

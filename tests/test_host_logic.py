@@ -42,7 +42,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.AdamWChunkC) == 16
     assert ctypes.sizeof(_lib.ViltDimsC) == 14 * 4          # ..., vocab_size, type_vocab_size, precision, hidden_dropout, attn_dropout
     assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0
-    assert ctypes.sizeof(_lib.ViltBatchC) == 4 * 4 + 6 * 8 + 8 + 8 + 8 + 8 + 8  # ..., image_type_idx_scalar(+pad), patch_geom, n_patch_slots + training, dropout_seed, image_repeat(+pad)
+    assert ctypes.sizeof(_lib.ViltBatchC) == 4 * 4 + 6 * 8 + 8 + 8 + 8 + 8 + 8 + 8  # ..., image_type_idx_scalar(+pad), patch_geom, n_patch_slots + training, dropout_seed, image_repeat(+pad), patch_select
     assert ctypes.sizeof(_lib.ViltParamsC) == 14 * 8 + 8 + 4 * 4 + 8              # offsets, layer*, adapter_r/act + flags, shadow_lo
     assert ctypes.sizeof(_lib.BertDimsC) == 5 * 4
     assert ctypes.sizeof(_lib.BertLayerC) == 12 * 8
