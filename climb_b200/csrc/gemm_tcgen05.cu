@@ -1205,6 +1205,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tmem_relinquish_pair();
     }
     tc_fence_before();
+    __syncthreads();                           // the TMEM address in shared memory (racecheck does not take barrier.cluster as CTA-level ordering)
     cluster_sync_all();                        // barriers of BOTH CTAs are initialised before any remote arrival
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -1275,12 +1276,13 @@ gemm_pair_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (warp == 1) {
         tmem_alloc_pair(tmem_slot, kTmemCols);
         tmem_relinquish_pair();
-    }
-    if (warp == 2 && p.colsum_a != nullptr) {
-        for (int i = lane; i < 768 / 4; i += 32) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
-        fence_proxy_async();                       // read by the tensor core (async proxy) of the leader CTA
+        if (p.colsum_a != nullptr) {               // (same warp as the allocation: racecheck orders the two shared-memory writers)
+            for (int i = lane; i < 768 / 4; i += 32) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+            fence_proxy_async();                   // read by the tensor core (async proxy) of the leader CTA
+        }
     }
     tc_fence_before();
+    __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;

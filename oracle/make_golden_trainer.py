@@ -33,7 +33,7 @@ from oracle.vilt_oracle import synth_state_dict  # noqa: E402
 PARAM_FULL_MAX = 4096
 
 
-def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algorithm, replay_frequency, record):
+def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algorithm, replay_frequency, record, device="cpu"):
     from modeling.vilt import convert_batch_to_vilt_input_dict
     if task == "vqa":
         from train.visionlanguage_tasks.train_vqa import VQATrainer as cls
@@ -46,7 +46,7 @@ def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algor
     t = cls.__new__(cls)
     torch.nn.Module.__init__(t)                      # TaskTrainer is an nn.Module (task_trainer.py:5-9)
     t.args = types.SimpleNamespace(cl_algorithm=cl_algorithm, replay_frequency=replay_frequency)
-    t.device = torch.device("cpu")
+    t.device = torch.device(device)
     t.batch2inputs_converter = convert_batch_to_vilt_input_dict
     for k, v in loaders.items():
         setattr(t, k, v)
@@ -66,7 +66,7 @@ def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algor
     def forward_pass(model, batch, do_eval=False):
         out = ref_forward(t, model, batch, do_eval)
         if do_eval:
-            record["_eval_tmp"].append(out[1].detach().clone())
+            record["_eval_tmp"].append(out[1].detach().clone().cpu())
         return out
 
     def eval_(model):
@@ -80,7 +80,10 @@ def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algor
     return t
 
 
-def run(tag):
+def run_reference_scenario(tag, learner, device="cpu"):
+    """Drive `learner` -- the reference's own ViltContinualLearner when the golden trajectories are written, the CUDA learner in
+    tests/test_gpu_zzz_reference_trainer.py -- through scenario `tag` with the UNMODIFIED reference trainers and the UNMODIFIED
+    ExperienceReplayMemory. Returns (record in oracle.trainer_oracle.run_scenario's format, extras)."""
     from cl_algorithms.experience_replay import ExperienceReplayMemory
     import cl_algorithms.experience_replay as er_mod
     import train.visionlanguage_tasks.train_vqa as tv
@@ -88,28 +91,26 @@ def run(tag):
     tv.tqdm = tn.tqdm = lambda it, **k: it
     sc = to.SCENARIOS[tag]
     dims = TINY
-    sd = synth_state_dict(dims, ALL_TASKS, seed=sc["seed"])
-    learner = build_reference_learner(dims, ALL_TASKS, sd)
     pools, train_dl, val_dl, replay_dl = to.build_data(sc, dims, TINY_T, TINY_HW)
-    proc = to.PoolProcessor(pools, torch.device("cpu"))
+    proc = to.PoolProcessor(pools, torch.device(device))
     learner.vilt_encoder.process_inputs = proc
     record = {"loss": [], "lr": [], "replay": [], "eval_score": [], "eval_logits": []}
     cl = "experience_replay" if sc["replay"] else "sequential_ft"
     replay_memory = None
+    memory_idxs, sampled = [], []
     random.seed(sc["seed"])
     torch.manual_seed(sc["seed"])                    # visual_embed's multinomial permutation
+    ref_sample = er_mod.TaskMemoryBuffer.sample_replay_batch
     if sc["replay"]:
         r = sc["replay"]
         prev_rec = {"loss": [], "lr": [], "eval_score": [], "eval_logits": []}
-        prev = make_reference_trainer(r["task"], replay_dl, replay_dl, r["hparams"], 1, cl, 0, prev_rec)
+        prev = make_reference_trainer(r["task"], replay_dl, replay_dl, r["hparams"], 1, cl, 0, prev_rec, device)
         replay_memory = ExperienceReplayMemory()
         replay_memory.add_task_memory_buffer(args=types.SimpleNamespace(batch_size=sc["batch_size"]), task_key=r["task"],
                                              task_config={"task_name": r["task"]}, task_trainer=prev,
                                              memory_percentage=r["memory_percentage"], sampling_strategy="random")
         memory_idxs = list(replay_memory.memory_buffers[r["task"]].memory_idxs)
         ref_replay = ExperienceReplayMemory.run_replay_step
-        sampled = []
-        ref_sample = er_mod.TaskMemoryBuffer.sample_replay_batch
 
         def sample_replay_batch(self):
             b = ref_sample(self)
@@ -125,8 +126,23 @@ def run(tag):
 
         replay_memory.run_replay_step = run_replay_step
     trainer = make_reference_trainer(sc["task"], train_dl, val_dl, sc["hparams"], sc["num_epochs"], cl,
-                                     sc["replay"]["replay_frequency"] if sc["replay"] else 100, record)
-    best_score, best_model = trainer.train(learner, replay_memory=replay_memory)
+                                     sc["replay"]["replay_frequency"] if sc["replay"] else 100, record, device)
+    try:
+        best_score, best_model = trainer.train(learner, replay_memory=replay_memory)
+    finally:
+        er_mod.TaskMemoryBuffer.sample_replay_batch = ref_sample
+    rec = dict(record)
+    rec["best_score"], rec["best_epoch"], rec["best_model"], rec["trainer"] = best_score, best_model["epoch"], best_model["model"], trainer
+    return rec, dict(proc=proc, memory_idxs=memory_idxs, sampled=sampled, sc=sc)
+
+
+def run(tag):
+    sc = to.SCENARIOS[tag]
+    sd = synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"])
+    learner = build_reference_learner(TINY, ALL_TASKS, sd)
+    record, extra = run_reference_scenario(tag, learner)
+    proc, memory_idxs, sampled = extra["proc"], extra["memory_idxs"], extra["sampled"]
+    best_score, best_model = record["best_score"], {"epoch": record["best_epoch"], "model": record["best_model"]}
     out = {"loss": np.array(record["loss"], np.float64), "lr": np.array(record["lr"], np.float64),
            "eval_score": np.array(record["eval_score"], np.float64), "best_score": np.float64(best_score),
            "best_epoch": np.int64(best_model["epoch"]), "seed": np.int64(sc["seed"]),
