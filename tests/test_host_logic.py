@@ -455,3 +455,42 @@ def test_prepare_grads_never_wipes_gradients_it_was_not_asked_about():
     arena.grad.fill_(7.0)
     arena.prepare_grads([(b_name, b_p)])                 # nothing published anywhere: whole-arena memset
     assert float(arena.grad.abs().max()) == 0.0
+
+
+def test_max_image_length_draws_the_reference_subsets_on_the_host():
+    """B200ViltModel._patch_selection (config.max_image_length > 0, modeling_vilt.py:163-189) against the oracle's restatement
+    select_patches, which tests/test_oracle_golden.py pins to the unmodified reference: same seed -> same kept patches, in
+    sequence order and in the reference's per-pass order (patch_draw_order); a cap that drops nothing takes the default path."""
+    vilt = _learner().get_encoder().vilt
+    P = vilt.config.patch_size                      # 16
+    H, W = 64, 80                                   # 4 x 5 patch grid
+    sizes = [(64, 80), (48, 64), (32, 64), (64, 32), (16, 80), (48, 80)]
+    pm = torch.zeros(len(sizes), H, W, dtype=torch.long)
+    for k, (h, w) in enumerate(sizes):
+        pm[k, :h, :w] = 1
+    hs, ws = vo.patch_geometry(pm, P)
+    dev = torch.device("cpu")
+    for order in (None, [0, 2, 4, 1, 3, 5]):
+        torch.manual_seed(7)
+        geom, n, sel = vilt._patch_selection(pm, len(sizes), H, W, dev, 9, order)
+        torch.manual_seed(7)
+        idx = list(range(len(sizes))) if order is None else order
+        n_ref, keep = vo.select_patches(hs[idx], ws[idx], (H // P) * (W // P), 9)
+        assert n == n_ref == 9 and tuple(sel.shape) == (len(sizes), 9)
+        assert geom.tolist() == [[h // P, w // P] for h, w in sizes]
+        for j, i in enumerate(idx):
+            got = [int(x) for x in sel[i] if x >= 0]
+            assert got == keep[j].tolist(), (order, i, got, keep[j].tolist())
+            v = (sizes[i][0] // P) * (sizes[i][1] // P)
+            assert len(got) == min(v, 9) and all(0 <= x < v for x in got) and len(set(got)) == len(got)
+    # a cap at or above the largest image drops nothing: no selection, the default geometry path
+    geom, n, sel = vilt._patch_selection(pm, len(sizes), H, W, dev, 20)
+    assert sel is None and n == 20
+    geom, n, sel = vilt._patch_selection(None, 3, H, W, dev, 20)
+    assert geom is None and sel is None
+    # no pixel mask at all, cap below the grid: every image draws a subset of the full grid
+    torch.manual_seed(3)
+    geom, n, sel = vilt._patch_selection(None, 3, H, W, dev, 7)
+    assert n == 7 and geom.tolist() == [[4, 5]] * 3 and all(len(set(r.tolist())) == 7 and 0 <= int(r.min()) and int(r.max()) < 20 for r in sel)
+    with pytest.raises(ValueError):
+        vilt._patch_selection(pm, len(sizes), H, W, dev, 9, [0, 0, 1, 2, 3, 4])
