@@ -52,7 +52,10 @@ def main(paths):
         table[k] = float(f"{round_up(max(FACTOR * v, class_floor(k), FLOOR)):.3g}")
     json.dump(dict(sorted(table.items())), open(PATH, "w"), indent=1)
     print(f"{len(measured)} measurements -> {PATH} ({len(table)} gates)")
-    json.dump(dict(sorted(measured.items())), open(os.path.join(ROOT, "profiles", "r2_parity_measured.json"), "w"), indent=1)
+    mp = os.path.join(ROOT, "profiles", "r2_parity_measured.json")
+    merged = json.load(open(mp)) if os.path.exists(mp) else {}           # keys absent from these logs keep their last measurement
+    merged.update(measured)
+    json.dump(dict(sorted(merged.items())), open(mp, "w"), indent=1)
 
 
 if __name__ == "__main__":
