@@ -368,7 +368,9 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": "gemm_pair_kernel<KIND> / gemm_pair_wgrad_kernel (cta_group::2) + gemm_fast_kernel<KIND> + gemm_bf16_tcgen05_kernel (all tcgen05 GEMM launches of the step)",
                     "achieved": round(achieved, 1),
                     "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4),
-                    "traffic": traffic, "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+                    "traffic": traffic, "traffic_note": "mean DRAM bytes (ncu, read + write) over the nine hot GEMM launches of one layer, forward and "
+                    "backward; per launch and per shape in profiles/gemm_traffic.json (measured <= algorithmic for every one of them)",
+                    "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
                     "launches_per_step": g_n // 2, "gemm_ms_per_step": round(g_ms / 2, 3),
                     "gemm_share_of_step": round((g_ms / 2) / (ms_total / args.steps), 3),
                     "note": "per-launch CUDA events serialise the stream, so these two profiling steps run without the "
