@@ -31,6 +31,7 @@ from oracle.make_golden import ALL_TASKS, GOLDEN_DIR, TINY, TINY_HW, TINY_T, bui
 from oracle.vilt_oracle import synth_state_dict  # noqa: E402
 
 PARAM_FULL_MAX = 4096
+ALL_SCENARIOS = dict(to.SCENARIOS, **to.REFERENCE_SCENARIOS)
 
 
 def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algorithm, replay_frequency, record, device="cpu"):
@@ -39,6 +40,14 @@ def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algor
         from train.visionlanguage_tasks.train_vqa import VQATrainer as cls
         loaders = dict(vqa_train_dataloader=train_dl, vqa_val_dataloader=val_dl)
         crit = torch.nn.BCEWithLogitsLoss(reduction="mean")
+    elif task == "snli-ve":
+        from train.visionlanguage_tasks.train_snli_ve import SNLIVETrainer as cls
+        loaders = dict(snli_ve_train_dataloader=train_dl, snli_ve_dev_dataloader=val_dl)
+        crit = torch.nn.CrossEntropyLoss()
+    elif task == "vcr":
+        from train.visionlanguage_tasks.train_vcr import VCRTrainer as cls
+        loaders = dict(vcr_train_dataloader=train_dl, vcr_val_dataloader=val_dl)
+        crit = torch.nn.CrossEntropyLoss()
     else:
         from train.visionlanguage_tasks.train_nlvr2 import NLVR2Trainer as cls
         loaders = dict(nlvr_train_dataloader=train_dl, nlvr_val_dataloader=val_dl)
@@ -88,9 +97,13 @@ def run_reference_scenario(tag, learner, device="cpu"):
     import cl_algorithms.experience_replay as er_mod
     import train.visionlanguage_tasks.train_vqa as tv
     import train.visionlanguage_tasks.train_nlvr2 as tn
-    tv.tqdm = tn.tqdm = lambda it, **k: it
-    sc = to.SCENARIOS[tag]
+    import train.visionlanguage_tasks.train_snli_ve as ts
+    import train.visionlanguage_tasks.train_vcr as tc
+    tv.tqdm = tn.tqdm = ts.tqdm = tc.tqdm = lambda it, **k: it
+    sc = ALL_SCENARIOS[tag]
     dims = TINY
+    if "vcr" in learner.task_layer:
+        learner.task_layer["vcr"][0].p = 0.0         # the head's Dropout(0.1): see trainer_oracle.REFERENCE_SCENARIOS
     pools, train_dl, val_dl, replay_dl = to.build_data(sc, dims, TINY_T, TINY_HW)
     proc = to.PoolProcessor(pools, torch.device(device))
     learner.vilt_encoder.process_inputs = proc
@@ -137,8 +150,8 @@ def run_reference_scenario(tag, learner, device="cpu"):
 
 
 def run(tag):
-    sc = to.SCENARIOS[tag]
-    sd = synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"])
+    sc = ALL_SCENARIOS[tag]
+    sd = synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"], **sc.get("scales", {}))
     learner = build_reference_learner(TINY, ALL_TASKS, sd)
     record, extra = run_reference_scenario(tag, learner)
     proc, memory_idxs, sampled = extra["proc"], extra["memory_idxs"], extra["sampled"]
@@ -169,8 +182,10 @@ def run(tag):
 def main():
     ref_shim.install()
     torch.set_num_threads(os.cpu_count() or 1)
-    for tag in to.SCENARIOS:
-        run(tag)
+    only = sys.argv[1:]
+    for tag in ALL_SCENARIOS:
+        if not only or tag in only:
+            run(tag)
 
 
 if __name__ == "__main__":

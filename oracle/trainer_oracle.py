@@ -69,7 +69,9 @@ class TaskPool:
         out = []
         for i in range(lo, hi):
             imgs = [(self.task, i, j) for j in range(self.pixel_values.shape[1])]
-            item = {"image": imgs[0] if len(imgs) == 1 else imgs, "text": (self.task, i)}
+            # VCR: one text handle per answer choice (forward_multi_choice flattens the list of lists, vilt.py:326-327)
+            text = (self.task, i) if self.input_ids.dim() == 2 else [(self.task, i, c) for c in range(self.input_ids.shape[1])]
+            item = {"image": imgs[0] if len(imgs) == 1 else imgs, "text": text}
             if self.task == "vqa":
                 item["target_scores"] = self.target[i]
             else:
@@ -113,10 +115,11 @@ class PoolProcessor:
     def __call__(self, images, texts):
         self.calls += 1
         P = self.pools
+        pick = lambda field, h: getattr(P[h[0]], field)[h[1]] if len(h) == 2 else getattr(P[h[0]], field)[h[1], h[2]]
         enc = {
-            "input_ids": torch.stack([P[t].input_ids[i] for t, i in texts]),
-            "attention_mask": torch.stack([P[t].attention_mask[i] for t, i in texts]),
-            "token_type_ids": torch.stack([P[t].token_type_ids[i] for t, i in texts]),
+            "input_ids": torch.stack([pick("input_ids", h) for h in texts]),
+            "attention_mask": torch.stack([pick("attention_mask", h) for h in texts]),
+            "token_type_ids": torch.stack([pick("token_type_ids", h) for h in texts]),
             "pixel_values": torch.stack([P[t].pixel_values[i, j] for t, i, j in images]),
         }
         enc["pixel_mask"] = torch.ones(enc["pixel_values"].shape[0], *enc["pixel_values"].shape[-2:], dtype=torch.long)
@@ -310,6 +313,21 @@ SCENARIOS = {
     # NLVR2 (two images per sample) trained for 3 epochs x 3 steps, sequential fine-tuning
     "trainer_nlvr2": dict(task="nlvr2", n_train=12, n_val=12, batch_size=4, num_epochs=3, seed=701,
                           hparams={"lr": 2e-3, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None),
+}
+
+
+# Scenarios that exist only as trajectories of the UNMODIFIED reference trainers (oracle/make_golden_trainer.py) and are replayed
+# by the reference's own trainer code on the CUDA learner (tests/test_gpu_zzz_reference_trainer.py): the two remaining task
+# trainers, SNLIVETrainer (train_snli_ve.py) and VCRTrainer (train_vcr.py: four text choices per image). The VCR head's
+# Dropout(0.1) (src/modeling/vilt.py:199-202) is set to p = 0 on both sides: it draws from different generators on CPU and GPU.
+REFERENCE_SCENARIOS = {
+    "trainer_snli_ve": dict(task="snli-ve", n_train=12, n_val=12, batch_size=4, num_epochs=2, seed=702,
+                            hparams={"lr": 2e-3, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None),
+    # weights scaled as in the single-step VCR fixtures (vilt_oracle.synth_state_dict: without it the four choices of a sample
+    # tie at random init and the loss sits at ln 4 whatever the model does)
+    "trainer_vcr": dict(task="vcr", n_train=8, n_val=8, batch_size=4, num_epochs=2, seed=703,
+                        hparams={"lr": 5e-4, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None,      # (2e-3: bf16 moves the 4th loss by 5 %)
+                        scales=dict(layer_scale=6.0, head_scale=20.0)),      # = make_golden.VCR_SCALES
 }
 
 

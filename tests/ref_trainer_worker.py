@@ -23,8 +23,8 @@ def main(tag):
     from climb_b200 import _lib
     from climb_b200.optim import ArenaAdamW
 
-    sc = to.SCENARIOS[tag]
-    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"])
+    sc = dict(to.SCENARIOS, **to.REFERENCE_SCENARIOS)[tag]
+    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"], **sc.get("scales", {}))
     learner = _build(TINY, ALL_TASKS, sd)
     assert isinstance(learner.create_optimizer(sc["hparams"]), ArenaAdamW)
     launches0 = _lib.climb_launch_count()

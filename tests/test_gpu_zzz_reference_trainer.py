@@ -1,6 +1,7 @@
 """GPU: the reference's REAL trainer code drives the CUDA learner. tests/test_gpu_zz_trainer.py replays the trainer loops through
 their restatement (oracle/trainer_oracle.py); here nothing is restated: the unmodified `VQATrainer.train()` /
-`NLVR2Trainer.train()` (train_vqa.py:176-244, train_nlvr2.py) with their own `train_step`, `forward_pass`, `eval`,
+`NLVR2Trainer.train()` / `SNLIVETrainer.train()` / `VCRTrainer.train()` (train_vqa.py:176-244, train_nlvr2.py, train_snli_ve.py,
+train_vcr.py: all four task trainers) with their own `train_step`, `forward_pass`, `eval`,
 `copy.deepcopy(model)` snapshots and polynomial-decay schedule, and the unmodified `ExperienceReplayMemory.run_replay_step`,
 imported from the archive `build()` staged from /root/reference (oracle/_ref/, travels to the GPU box), call
 `model(task_key=..., images=..., texts=...)`, `model.create_optimizer(...)` on B200ViltContinualLearner -- the drop-in claim of
@@ -19,7 +20,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("tag", list(to.SCENARIOS))
+@pytest.mark.parametrize("tag", list(to.SCENARIOS) + list(to.REFERENCE_SCENARIOS))
 def test_unmodified_reference_trainers_drive_the_cuda_learner(tag):
     from oracle import ref_shim
     if not ref_shim.reference_available():
