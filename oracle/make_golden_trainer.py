@@ -89,7 +89,35 @@ def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algor
     return t
 
 
-def run_reference_scenario(tag, learner, device="cpu"):
+def scenario_state_dict(sc):
+    """Seeded weights of a scenario: (base state dict, full state dict incl. the adapters' weights when the scenario has any)."""
+    kw = dict(sc.get("scales", {}))
+    base = synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"], **kw)
+    if not sc.get("adapters"):
+        return base, base
+    a = sc["adapters"]
+    r = TINY.hidden_size // a["reduction_factor"]
+    sites = ("mh", "output") if a["config"] == "houlsby" else ("output",)
+    full = synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"], adapters={t: r for t in a["tasks"]}, adapter_sites=sites, **kw)
+    return {k: v for k, v in full.items() if ".adapters." not in k}, full
+
+
+def prepare_adapters(sc, learner, handler_cls):
+    """What the driver does before a task with --cl_algorithm adapter (train_upstream_continual_learning.py:155-160,195-197):
+    handler.add_adapters_to_model(model), then activate_adapter_for_training(task, model) -- with the seeded adapter weights
+    loaded in between so that the reference model and the CUDA model start from the same bottlenecks."""
+    a = sc["adapters"]
+    handler = handler_cls("vanilla", types.SimpleNamespace(adapter_config=a["config"], adapter_reduction_factor=a["reduction_factor"],
+                                                           ordered_cl_tasks=a["tasks"]))
+    handler.add_adapters_to_model(learner)
+    _, full = scenario_state_dict(sc)
+    missing, unexpected = learner.load_state_dict(full, strict=False)
+    assert not unexpected, unexpected
+    handler.activate_adapter_for_training(sc["task"], learner)
+    return handler
+
+
+def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None):
     """Drive `learner` -- the reference's own ViltContinualLearner when the golden trajectories are written, the CUDA learner in
     tests/test_gpu_zzz_reference_trainer.py -- through scenario `tag` with the UNMODIFIED reference trainers and the UNMODIFIED
     ExperienceReplayMemory. Returns (record in oracle.trainer_oracle.run_scenario's format, extras)."""
@@ -107,9 +135,10 @@ def run_reference_scenario(tag, learner, device="cpu"):
     pools, train_dl, val_dl, replay_dl = to.build_data(sc, dims, TINY_T, TINY_HW)
     proc = to.PoolProcessor(pools, torch.device(device))
     learner.vilt_encoder.process_inputs = proc
-    record = {"loss": [], "lr": [], "replay": [], "eval_score": [], "eval_logits": []}
-    cl = "experience_replay" if sc["replay"] else "sequential_ft"
+    record = {"loss": [], "lr": [], "replay": [], "eval_score": [], "eval_logits": [], "ewc": []}
+    cl = "experience_replay" if sc["replay"] else ("ewc" if sc.get("ewc") else "sequential_ft")
     replay_memory = None
+    ewc = None
     memory_idxs, sampled = [], []
     random.seed(sc["seed"])
     torch.manual_seed(sc["seed"])                    # visual_embed's multinomial permutation
@@ -138,10 +167,28 @@ def run_reference_scenario(tag, learner, device="cpu"):
             return loss
 
         replay_memory.run_replay_step = run_replay_step
+    if sc.get("ewc"):
+        e = sc["ewc"]
+        if ewc_cls is None:
+            from cl_algorithms.ewc import EWC as ewc_cls          # the reference's own
+            import cl_algorithms.ewc as ewc_mod
+            ewc_mod.tqdm = lambda it, **k: it
+        prev_rec = {"loss": [], "lr": [], "eval_score": [], "eval_logits": []}
+        prev = make_reference_trainer(e["task"], replay_dl, replay_dl, e["hparams"], 1, cl, 0, prev_rec, device)
+        ewc = ewc_cls(types.SimpleNamespace(ewc_fisher_sample_percentage=e["fisher_sample_percentage"], ewc_loss_weight=e["loss_weight"]))
+        ewc.save_task_parameters(task_key=e["task"], model=learner, task_trainer=prev, device=torch.device(device))
+        ref_penalty = ewc.compute_ewc_loss
+
+        def compute_ewc_loss(model):
+            task, loss = ref_penalty(model)
+            record["ewc"].append((task, float(loss)))
+            return task, loss
+
+        ewc.compute_ewc_loss = compute_ewc_loss
     trainer = make_reference_trainer(sc["task"], train_dl, val_dl, sc["hparams"], sc["num_epochs"], cl,
                                      sc["replay"]["replay_frequency"] if sc["replay"] else 100, record, device)
     try:
-        best_score, best_model = trainer.train(learner, replay_memory=replay_memory)
+        best_score, best_model = trainer.train(learner, replay_memory=replay_memory, ewc=ewc)
     finally:
         er_mod.TaskMemoryBuffer.sample_replay_batch = ref_sample
     rec = dict(record)
@@ -151,8 +198,11 @@ def run_reference_scenario(tag, learner, device="cpu"):
 
 def run(tag):
     sc = ALL_SCENARIOS[tag]
-    sd = synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"], **sc.get("scales", {}))
+    sd, _ = scenario_state_dict(sc)
     learner = build_reference_learner(TINY, ALL_TASKS, sd)
+    if sc.get("adapters"):
+        from cl_algorithms.adapters import AdapterHandler         # the reference's own
+        prepare_adapters(sc, learner, AdapterHandler)
     record, extra = run_reference_scenario(tag, learner)
     proc, memory_idxs, sampled = extra["proc"], extra["memory_idxs"], extra["sampled"]
     best_score, best_model = record["best_score"], {"epoch": record["best_epoch"], "model": record["best_model"]}
@@ -160,8 +210,13 @@ def run(tag):
            "eval_score": np.array(record["eval_score"], np.float64), "best_score": np.float64(best_score),
            "best_epoch": np.int64(best_model["epoch"]), "seed": np.int64(sc["seed"]),
            "process_inputs_calls": np.int64(proc.calls)}
+    if sc.get("adapters"):
+        out["trainable"] = np.array(sorted(n for n, p in learner.named_parameters() if p.requires_grad))
     for e, lg in enumerate(record["eval_logits"]):
         out[f"eval_logits/{e}"] = lg.numpy()
+    if sc.get("ewc"):
+        out["ewc_loss"] = np.array([l for _, l in record["ewc"]], np.float64)
+        out["ewc_task"] = np.array([t for t, _ in record["ewc"]])
     if sc["replay"]:
         out["replay_loss"] = np.array([l for _, l in record["replay"]], np.float64)
         out["replay_task"] = np.array([t for t, _ in record["replay"]])

@@ -325,6 +325,21 @@ REFERENCE_SCENARIOS = {
                             hparams={"lr": 2e-3, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None),
     # weights scaled as in the single-step VCR fixtures (vilt_oracle.synth_state_dict: without it the four choices of a sample
     # tie at random init and the loss sits at ln 4 whatever the model does)
+    # EWC at trainer level: Fisher information of a VQA "previous task" (EWC.save_task_parameters: the loop with un-zeroed
+    # cumulative gradients, ewc.py:55-71), then SNLI-VE trained with the penalty added in SNLIVETrainer.train_step
+    # (train_snli_ve.py:142-145). The fixture is written with the reference's EWC class on the reference learner; on the GPU the
+    # same unmodified trainer runs with climb_b200.cl_algorithms.EWC (device-resident theta*, F) on the CUDA learner.
+    "trainer_snli_ve_ewc": dict(task="snli-ve", n_train=12, n_val=8, batch_size=4, num_epochs=2, seed=704,
+                                hparams={"lr": 1e-3, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None,
+                                ewc=dict(task="vqa", n_train=8, fisher_sample_percentage=1.0, loss_weight=50.0,
+                                         hparams={"lr": 1e-3, "weight_decay": 1e-2, "adam_epsilon": 1e-8})),
+    # Adapters at trainer level: AdapterHandler.add_adapters_to_model / activate_adapter_for_training (adapters.py:52-61, as
+    # train_upstream_continual_learning.py:155-160,195-197 calls them) put a Houlsby adapter per task into the model and freeze
+    # the ViltModel; NLVR2Trainer.train() then trains the adapter + heads. Reduction factor 4 on the tiny model = bottleneck
+    # width 32: on the CUDA learner every site runs through the fused adapter kernel.
+    "trainer_nlvr2_adapters": dict(task="nlvr2", n_train=12, n_val=12, batch_size=4, num_epochs=2, seed=705,
+                                   hparams={"lr": 5e-4, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None,   # (2e-3: bf16 moves a loss by 2.7 %)
+                                   adapters=dict(config="houlsby", reduction_factor=4, tasks=["vqa", "nlvr2"])),
     "trainer_vcr": dict(task="vcr", n_train=8, n_val=8, batch_size=4, num_epochs=2, seed=703,
                         hparams={"lr": 5e-4, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None,      # (2e-3: bf16 moves the 4th loss by 5 %)
                         scales=dict(layer_scale=6.0, head_scale=20.0)),      # = make_golden.VCR_SCALES
@@ -339,10 +354,10 @@ def build_data(sc: Dict, dims: vo.ViltDims, T: int, hw):
     train_dl = Batches(items[:sc["n_train"]], sc["batch_size"])
     val_dl = Batches(items[sc["n_train"]:], sc["batch_size"])
     replay_dl = None
-    if sc["replay"]:
-        r = sc["replay"]
-        pools[r["task"]] = TaskPool(r["task"], r["n_train"], dims, T, hw, sc["seed"] + 50)
-        replay_dl = Batches(pools[r["task"]].items(0, r["n_train"]), sc["batch_size"])
+    prev = sc["replay"] or sc.get("ewc")           # the previous task's loader: replay memory or EWC's Fisher loop
+    if prev:
+        pools[prev["task"]] = TaskPool(prev["task"], prev["n_train"], dims, T, hw, sc["seed"] + 50)
+        replay_dl = Batches(pools[prev["task"]].items(0, prev["n_train"]), sc["batch_size"])
     return pools, train_dl, val_dl, replay_dl
 
 

@@ -16,7 +16,7 @@ def main(tag):
     ref_shim.install()
     from oracle import trainer_oracle as to
     from oracle import vilt_oracle as vo
-    from oracle.make_golden_trainer import run_reference_scenario
+    from oracle.make_golden_trainer import prepare_adapters, run_reference_scenario, scenario_state_dict
     from tests.golden_util import ALL_TASKS, TINY, load
     from tests.test_gpu_parity import _build
     from tests.trainer_util import check_trajectory
@@ -24,11 +24,20 @@ def main(tag):
     from climb_b200.optim import ArenaAdamW
 
     sc = dict(to.SCENARIOS, **to.REFERENCE_SCENARIOS)[tag]
-    sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"], **sc.get("scales", {}))
+    sd, sd_full = scenario_state_dict(sc)
     learner = _build(TINY, ALL_TASKS, sd)
+    if sc.get("adapters"):
+        from climb_b200.cl_algorithms import AdapterHandler       # this repo's handler behind the reference's call surface
+        prepare_adapters(sc, learner, AdapterHandler)
+        sd = sd_full
+        g0 = load(tag)
+        assert sorted(n for n, p in learner.named_parameters() if p.requires_grad) == list(g0["trainable"])
     assert isinstance(learner.create_optimizer(sc["hparams"]), ArenaAdamW)
     launches0 = _lib.climb_launch_count()
-    rec, extra = run_reference_scenario(tag, learner, "cuda")
+    ewc_cls = None
+    if sc.get("ewc"):
+        from climb_b200.cl_algorithms import EWC as ewc_cls        # device-resident theta*, F behind the reference's hook surface
+    rec, extra = run_reference_scenario(tag, learner, "cuda", ewc_cls=ewc_cls)
     assert _lib.climb_launch_count() - launches0 > 100, "the trajectory did not run on the CUDA kernels"
     import train.visionlanguage_tasks.train_vqa as tv
     assert "reference" in tv.__file__ or "climb_b200_reference" in tv.__file__, tv.__file__      # the reference's own module ran
@@ -38,6 +47,17 @@ def main(tag):
         # python's RNG drives the memory contents and the sampled replay batches: identical to the reference run
         assert extra["memory_idxs"] == list(g["memory_idxs"])
         assert extra["sampled"] == g["replay_samples"].tolist()
+    if sc.get("ewc"):
+        import numpy as np
+        got = np.array([l for _, l in rec["ewc"]])
+        assert [t for t, _ in rec["ewc"]] == list(g["ewc_task"])
+        ref = g["ewc_loss"]
+        assert got.shape == ref.shape and got[0] == 0.0 and ref[0] == 0.0          # first step: theta == theta*
+        # the penalty is lambda * sum F (theta - theta*)^2 after a few Adam steps: quadratic in parameter differences that
+        # bf16 gradients move by a few percent -- a looser bound than the task loss, same reasoning as the replay losses
+        rel = np.abs(got[1:] - ref[1:]) / np.abs(ref[1:])
+        print("EWC penalties", got.round(4).tolist(), "reference", ref.round(4).tolist(), "rel", rel.round(3).tolist())
+        assert rel.max() <= 0.03, rel          # measured on a B200: 5e-3
     worst = check_trajectory(tag, rec, tol_loss=2e-2, tol_logits=5e-2, tol_update=1.5, tol_update_median=0.3,
                              named_final=dict(learner.named_parameters()), named_init=sd, named_best=None,
                              replay_lr=sc["replay"]["hparams"]["lr"] if sc["replay"] else 0.0)

@@ -5,7 +5,9 @@ train_vcr.py: all four task trainers) with their own `train_step`, `forward_pass
 `copy.deepcopy(model)` snapshots and polynomial-decay schedule, and the unmodified `ExperienceReplayMemory.run_replay_step`,
 imported from the archive `build()` staged from /root/reference (oracle/_ref/, travels to the GPU box), call
 `model(task_key=..., images=..., texts=...)`, `model.create_optimizer(...)` on B200ViltContinualLearner -- the drop-in claim of
-INTEGRATION.md exercised by the harness's own code. Each scenario runs in its own process (tests/ref_trainer_worker.py):
+INTEGRATION.md exercised by the harness's own code. Scenarios: sequential FT on NLVR2 / SNLI-VE / VCR, VQA with experience replay,
+SNLI-VE with EWC (this repo's EWC class under the unmodified trainer; fixture from the reference's EWC) and NLVR2 with adapters (this
+repo's AdapterHandler; fixture from the reference's handler + adapter-transformers). Each scenario runs in its own process (tests/ref_trainer_worker.py):
 importing the reference puts its vendored transformers fork in front of the stock package.
 Skipped when no reference is available (no /root/reference and no staged archive)."""
 import os
