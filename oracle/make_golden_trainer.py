@@ -27,8 +27,9 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_shim  # noqa: E402
 from oracle import trainer_oracle as to  # noqa: E402
-from oracle.make_golden import ALL_TASKS, GOLDEN_DIR, TINY, TINY_HW, TINY_T, build_reference_learner, grad_sample_index  # noqa: E402
-from oracle.vilt_oracle import synth_state_dict  # noqa: E402
+from oracle.make_golden import (ALL_TASKS, GOLDEN_DIR, TINY, TINY_BERT, TINY_HW, TINY_T, build_reference_learner,  # noqa: E402
+                                build_reference_viltbert, grad_sample_index)
+from oracle.vilt_oracle import synth_state_dict, synth_viltbert_state_dict  # noqa: E402
 
 PARAM_FULL_MAX = 4096
 ALL_SCENARIOS = dict(to.SCENARIOS, **to.REFERENCE_SCENARIOS)
@@ -92,6 +93,9 @@ def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algor
 def scenario_state_dict(sc):
     """Seeded weights of a scenario: (base state dict, full state dict incl. the adapters' weights when the scenario has any)."""
     kw = dict(sc.get("scales", {}))
+    if sc.get("encoder") == "viltbert":
+        base = synth_viltbert_state_dict(TINY, TINY_BERT, ALL_TASKS, seed=sc["seed"], **kw)
+        return base, base
     base = synth_state_dict(TINY, ALL_TASKS, seed=sc["seed"], **kw)
     if not sc.get("adapters"):
         return base, base
@@ -134,7 +138,7 @@ def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None):
         learner.task_layer["vcr"][0].p = 0.0         # the head's Dropout(0.1): see trainer_oracle.REFERENCE_SCENARIOS
     pools, train_dl, val_dl, replay_dl = to.build_data(sc, dims, TINY_T, TINY_HW)
     proc = to.PoolProcessor(pools, torch.device(device))
-    learner.vilt_encoder.process_inputs = proc
+    learner.get_encoder().process_inputs = proc
     record = {"loss": [], "lr": [], "replay": [], "eval_score": [], "eval_logits": [], "ewc": []}
     cl = "experience_replay" if sc["replay"] else ("ewc" if sc.get("ewc") else "sequential_ft")
     replay_memory = None
@@ -199,7 +203,8 @@ def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None):
 def run(tag):
     sc = ALL_SCENARIOS[tag]
     sd, _ = scenario_state_dict(sc)
-    learner = build_reference_learner(TINY, ALL_TASKS, sd)
+    learner = build_reference_viltbert(TINY, TINY_BERT, ALL_TASKS, sd) if sc.get("encoder") == "viltbert" else \
+        build_reference_learner(TINY, ALL_TASKS, sd)
     if sc.get("adapters"):
         from cl_algorithms.adapters import AdapterHandler         # the reference's own
         prepare_adapters(sc, learner, AdapterHandler)

@@ -340,6 +340,9 @@ REFERENCE_SCENARIOS = {
     "trainer_nlvr2_adapters": dict(task="nlvr2", n_train=12, n_val=12, batch_size=4, num_epochs=2, seed=705,
                                    hparams={"lr": 5e-4, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None,   # (2e-3: bf16 moves a loss by 2.7 %)
                                    adapters=dict(config="houlsby", reduction_factor=4, tasks=["vqa", "nlvr2"])),
+    # (No ViLT-BERT scenario: the reference's ViltBertContinualLearner has no create_optimizer -- viltbert.py defines it on the
+    # encoder wrapper only, SURVEY appendix C10 -- so its own trainers cannot run that learner; ViLT-BERT is pinned by the
+    # single-step fixtures tiny_viltbert_* instead.)
     "trainer_vcr": dict(task="vcr", n_train=8, n_val=8, batch_size=4, num_epochs=2, seed=703,
                         hparams={"lr": 5e-4, "weight_decay": 1e-2, "adam_epsilon": 1e-8}, replay=None,      # (2e-3: bf16 moves the 4th loss by 5 %)
                         scales=dict(layer_scale=6.0, head_scale=20.0)),      # = make_golden.VCR_SCALES

@@ -25,7 +25,12 @@ def main(tag):
 
     sc = dict(to.SCENARIOS, **to.REFERENCE_SCENARIOS)[tag]
     sd, sd_full = scenario_state_dict(sc)
-    learner = _build(TINY, ALL_TASKS, sd)
+    if sc.get("encoder") == "viltbert":
+        from oracle.make_golden import TINY_BERT
+        from tests.test_gpu_viltbert import _build as _build_viltbert
+        learner = _build_viltbert(TINY, TINY_BERT, ALL_TASKS, sd)
+    else:
+        learner = _build(TINY, ALL_TASKS, sd)
     if sc.get("adapters"):
         from climb_b200.cl_algorithms import AdapterHandler       # this repo's handler behind the reference's call surface
         prepare_adapters(sc, learner, AdapterHandler)
