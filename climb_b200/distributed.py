@@ -340,22 +340,78 @@ def attach(learner, bucket_mb: float = 64.0, group=None, layers_per_chunk: int =
 
 def attach_if_distributed(learner, **kw):
     """What create_*_continual_learner_model calls: under a multi-rank torch.distributed launch (torchrun + the
-    unchanged CLiMB driver) attach the gradient synchronisation and make rank 0 the only writer of
-    checkpoints; a single process gets the learner back untouched."""
+    unchanged CLiMB driver) attach the gradient synchronisation, make the learner's training forward work on
+    this rank's rows (sharded_forward below) and make rank 0 the only writer of checkpoints; a single process gets the
+    learner back untouched."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return None
     sync = GradSync(learner, **kw)
+    learner._ddp_forward_shard = True
     rank_zero_only_io()
     return sync
 
 
-# ---- the unchanged harness under torchrun ---------------------------------------------------------------------------
-# The trainers build plain (unsharded) loaders (vqa_dataset.py:262-268), so every rank draws the SAME batch (same seed,
-# train_upstream_continual_learning.py:103). The registry's batch2inputs_converter is the one hook between the loader and
-# the model: forward_pass calls it on the batch dict and afterwards reads the labels from the SAME dict
-# (train_vqa.py:127,156) -- so slicing the dict IN PLACE to this rank's rows shards inputs and labels consistently.
-# Evaluation stays replicated (the trainers divide by the full dataset length, train_vqa.py:263): the slice is applied in
-# training mode only, which the learner announces through set_training_mode() from its train() / eval().
+# ---- the unchanged harness under torchrun: rows sharded INSIDE the learner's forward ------------------------------------------
+# The trainers build plain (unsharded) loaders (vqa_dataset.py:262-268), so under torchrun every rank draws the SAME batch
+# (same seed, train_upstream_continual_learning.py:103), and they read the labels from the batch dict themselves --
+# NLVR2Trainer.train_step even BEFORE it calls the model (train_nlvr2.py:128-131), so nothing that edits the batch on the way
+# into the model can keep inputs and labels consistent for every trainer. Instead the learner's training forward
+#   * runs the encoder on this rank's contiguous rows only (NLVR2 image pairs / VCR four-choice tuples are single list entries
+#     and stay together),
+#   * all-gathers pooled outputs and logits, and returns them for the WHOLE batch -- so the trainer's loss, whatever it does
+#     with its labels, is the whole-batch loss on every rank (the logged losses are identical across ranks),
+#   * in the backward hands back the gradient of its own rows times the world size: after GradSync's mean over ranks every
+#     rank holds exactly the whole-batch gradient, also when the rows do not divide evenly; terms that are identical on all
+#     ranks (the EWC penalty) pass through the mean unchanged.
+# Evaluation stays replicated (the trainers divide by the full dataset length, train_vqa.py:263).
+def rank_rows(n: int, rank: int = None, world: int = None, group=None):
+    world = dist.get_world_size(group) if world is None else world
+    rank = dist.get_rank(group) if rank is None else rank
+    per = (n + world - 1) // world
+    return min(n, rank * per), min(n, (rank + 1) * per), per
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, local, n, group):
+        world = dist.get_world_size(group)
+        lo, hi, per = rank_rows(n, group=group)
+        pad = local.new_zeros((per,) + tuple(local.shape[1:]))
+        pad[: hi - lo] = local
+        if local.is_cuda:
+            out = local.new_empty((world * per,) + tuple(local.shape[1:]))
+            dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+            parts = [out[r * per: (r + 1) * per] for r in range(world)]
+        else:
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad.contiguous(), group=group)
+        rows = [rank_rows(n, r, world)[:2] for r in range(world)]
+        ctx.lo, ctx.hi, ctx.world = lo, hi, world
+        return torch.cat([p[: b - a] for p, (a, b) in zip(parts, rows)], dim=0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.lo: ctx.hi] * ctx.world, None, None
+
+
+def sharded_forward(forward_fn, images, texts, group=None):
+    """forward_fn(images, texts) -> (pooled [rows, ...], logits [rows, C]) on this rank's rows of the batch; returns both for
+    the whole batch (see the block comment above)."""
+    n = len(texts)
+    lo, hi, _ = rank_rows(n, group=group)
+    if hi <= lo:
+        raise RuntimeError(f"batch of {n} samples leaves rank {dist.get_rank(group)} of {dist.get_world_size(group)} without rows: "
+                           "use a batch size >= the number of ranks")
+    pooled, logits = forward_fn(images[lo:hi], texts[lo:hi])
+    logits = logits.reshape(hi - lo, -1)            # (the multi-choice head's .squeeze() drops the batch dimension of a 1-row shard)
+    return _GatherRows.apply(pooled, n, group), _GatherRows.apply(logits, n, group)
+
+
+# ---- batch-dict sharding helpers ---------------------------------------------------------------------------------------
+# shard_batch_inplace / sharding(converter) cut a collated batch dict to this rank's rows on its way into the model. They
+# serve harnesses that read their labels AFTER the conversion (VQATrainer, train_vqa.py:127,156); the registry does NOT
+# use them, because NLVR2Trainer reads its labels before (train_nlvr2.py:128-131) -- see sharded_forward below for what
+# the unchanged harness gets instead. The learner's train() / eval() announce the mode through set_training_mode().
 _training_mode = True
 _last_shard = None          # (rows on this rank, rows of the whole batch) of the most recent sharded batch
 _SHARD_MARK = "_b200_rank_slice"

@@ -3,7 +3,6 @@
 A CLiMB checkout gains the B200 encoder by merging these two dicts into its own maps and the
 model_configs entry below into src/configs/model_configs.py (INTEGRATION.md shows the three-line patch).
 """
-from ..distributed import sharding
 from .continual_learner import ContinualLearner, EncoderWrapper
 from .vilt import (B200ViltContinualLearner, B200ViltEncoderWrapper, convert_batch_to_vilt_input_dict,
                    create_vilt_continual_learner_model, load_vilt_encoder)
@@ -29,7 +28,7 @@ vilt_b200_config = {
     'encoder_dim': 768,
     'visual_input_type': 'pil-image',
     'encoder_class': B200ViltEncoderWrapper,
-    'batch2inputs_converter': sharding(convert_batch_to_vilt_input_dict),     # + this rank's rows under torchrun (distributed.py)
+    'batch2inputs_converter': convert_batch_to_vilt_input_dict,     # (rank sharding under torchrun happens inside the learner's forward: distributed.py)
     'encoder_name': 'ViLT-B200',
 }
 # src/configs/model_configs.py:36-42
@@ -37,7 +36,7 @@ viltbert_b200_config = {
     'encoder_dim': 768,
     'visual_input_type': 'pil-image',
     'encoder_class': B200ViltBertEncoderWrapper,
-    'batch2inputs_converter': sharding(convert_batch_to_viltbert_input_dict),
+    'batch2inputs_converter': convert_batch_to_viltbert_input_dict,
     'encoder_name': 'ViLT-BERT-B200',
 }
 model_configs = {'vilt-b200': vilt_b200_config, 'viltbert-b200': viltbert_b200_config}

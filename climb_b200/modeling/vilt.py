@@ -194,7 +194,7 @@ class B200ViltContinualLearner(ContinualLearner):
                           arenas=[self.vilt_encoder.vilt._arena])
 
     def train(self, mode: bool = True):
-        """nn.Module.train / eval, plus: tell the rank-slicing batch converter (climb_b200.distributed.sharding) whether
+        """nn.Module.train / eval, plus: tell the optional rank-slicing batch converter (climb_b200.distributed.sharding) whether
         the harness is training (batches are cut to this rank's rows) or evaluating (replicated, train_vqa.py:246-282)."""
         from ..distributed import set_training_mode
         set_training_mode(mode)
@@ -202,6 +202,14 @@ class B200ViltContinualLearner(ContinualLearner):
 
     # ---- forward ------------------------------------------------------------------------------
     def forward(self, task_key: str, images: List, texts: List[str]):
+        if getattr(self, "_ddp_forward_shard", False) and self.training:
+            # the unchanged harness under torchrun (climb_b200.distributed.attach_if_distributed): this rank's rows only,
+            # outputs all-gathered to the whole batch
+            from ..distributed import sharded_forward
+            return sharded_forward(lambda im, tx: self._forward_rows(task_key, im, tx), images, texts)
+        return self._forward_rows(task_key, images, texts)
+
+    def _forward_rows(self, task_key: str, images: List, texts: List[str]):
         task_config = self.task_configs[task_key]
         if task_config['model_type'] == 'multi-choice':
             texts = list(itertools.chain(*texts))

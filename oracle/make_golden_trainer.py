@@ -35,8 +35,11 @@ PARAM_FULL_MAX = 4096
 ALL_SCENARIOS = dict(to.SCENARIOS, **to.REFERENCE_SCENARIOS)
 
 
-def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algorithm, replay_frequency, record, device="cpu"):
+def make_reference_trainer(task, train_dl, val_dl, hparams, num_epochs, cl_algorithm, replay_frequency, record, device="cpu",
+                           converter=None):
     from modeling.vilt import convert_batch_to_vilt_input_dict
+    if converter is not None:       # what TaskTrainer.__init__ reads from model_configs[args.encoder_name]['batch2inputs_converter']
+        convert_batch_to_vilt_input_dict = converter
     if task == "vqa":
         from train.visionlanguage_tasks.train_vqa import VQATrainer as cls
         loaders = dict(vqa_train_dataloader=train_dl, vqa_val_dataloader=val_dl)
@@ -121,7 +124,7 @@ def prepare_adapters(sc, learner, handler_cls):
     return handler
 
 
-def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None):
+def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None, converter=None):
     """Drive `learner` -- the reference's own ViltContinualLearner when the golden trajectories are written, the CUDA learner in
     tests/test_gpu_zzz_reference_trainer.py -- through scenario `tag` with the UNMODIFIED reference trainers and the UNMODIFIED
     ExperienceReplayMemory. Returns (record in oracle.trainer_oracle.run_scenario's format, extras)."""
@@ -134,11 +137,14 @@ def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None):
     tv.tqdm = tn.tqdm = ts.tqdm = tc.tqdm = lambda it, **k: it
     sc = ALL_SCENARIOS[tag]
     dims = TINY
-    if "vcr" in learner.task_layer:
+    if "vcr" in getattr(learner, "task_layer", {}):
         learner.task_layer["vcr"][0].p = 0.0         # the head's Dropout(0.1): see trainer_oracle.REFERENCE_SCENARIOS
     pools, train_dl, val_dl, replay_dl = to.build_data(sc, dims, TINY_T, TINY_HW)
     proc = to.PoolProcessor(pools, torch.device(device))
-    learner.get_encoder().process_inputs = proc
+    if hasattr(learner, "processor"):            # oracle.trainer_oracle.OracleLearner (CPU debugging of the harness logic)
+        learner.processor = proc
+    else:
+        learner.get_encoder().process_inputs = proc
     record = {"loss": [], "lr": [], "replay": [], "eval_score": [], "eval_logits": [], "ewc": []}
     cl = "experience_replay" if sc["replay"] else ("ewc" if sc.get("ewc") else "sequential_ft")
     replay_memory = None
@@ -150,7 +156,7 @@ def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None):
     if sc["replay"]:
         r = sc["replay"]
         prev_rec = {"loss": [], "lr": [], "eval_score": [], "eval_logits": []}
-        prev = make_reference_trainer(r["task"], replay_dl, replay_dl, r["hparams"], 1, cl, 0, prev_rec, device)
+        prev = make_reference_trainer(r["task"], replay_dl, replay_dl, r["hparams"], 1, cl, 0, prev_rec, device, converter)
         replay_memory = ExperienceReplayMemory()
         replay_memory.add_task_memory_buffer(args=types.SimpleNamespace(batch_size=sc["batch_size"]), task_key=r["task"],
                                              task_config={"task_name": r["task"]}, task_trainer=prev,
@@ -178,7 +184,7 @@ def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None):
             import cl_algorithms.ewc as ewc_mod
             ewc_mod.tqdm = lambda it, **k: it
         prev_rec = {"loss": [], "lr": [], "eval_score": [], "eval_logits": []}
-        prev = make_reference_trainer(e["task"], replay_dl, replay_dl, e["hparams"], 1, cl, 0, prev_rec, device)
+        prev = make_reference_trainer(e["task"], replay_dl, replay_dl, e["hparams"], 1, cl, 0, prev_rec, device, converter)
         ewc = ewc_cls(types.SimpleNamespace(ewc_fisher_sample_percentage=e["fisher_sample_percentage"], ewc_loss_weight=e["loss_weight"]))
         ewc.save_task_parameters(task_key=e["task"], model=learner, task_trainer=prev, device=torch.device(device))
         ref_penalty = ewc.compute_ewc_loss
@@ -190,7 +196,7 @@ def run_reference_scenario(tag, learner, device="cpu", ewc_cls=None):
 
         ewc.compute_ewc_loss = compute_ewc_loss
     trainer = make_reference_trainer(sc["task"], train_dl, val_dl, sc["hparams"], sc["num_epochs"], cl,
-                                     sc["replay"]["replay_frequency"] if sc["replay"] else 100, record, device)
+                                     sc["replay"]["replay_frequency"] if sc["replay"] else 100, record, device, converter)
     try:
         best_score, best_model = trainer.train(learner, replay_memory=replay_memory, ewc=ewc)
     finally:

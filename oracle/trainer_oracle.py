@@ -290,11 +290,16 @@ class OracleLearner:
         spec = vo.TASK_SPECS[task_key]
         n_img = spec["num_images"]
         flat = [h for hs in images for h in hs] if n_img > 1 else images          # vilt.py:280
-        enc = self.process_inputs(flat, texts)
+        n_choices = spec.get("num_choices", 1) if spec["model_type"] == "multi-choice" else 1
+        flat_texts = [h for hs in texts for h in hs] if n_choices > 1 else texts   # vilt.py:326-327
+        enc = self.process_inputs(flat, flat_texts)
         batch = dict(enc)
         if n_img > 1:
             px = enc["pixel_values"]
             batch["pixel_values"] = px.view(len(texts), n_img, *px.shape[-3:])     # vilt.py:287
+        if n_choices > 1:                                                          # vilt.py:329-331
+            for k in ("input_ids", "attention_mask", "token_type_ids"):
+                batch[k] = enc[k].view(len(texts), n_choices, -1)
         batch.pop("pixel_mask", None)
         return vo.learner_forward(self.params, self.dims, task_key, batch)
 

@@ -182,15 +182,15 @@ def test_chunked_backward_overlapped_allreduce_world2_gloo(mode):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# the UNCHANGED harness under torchrun: the registry's batch2inputs_converter cuts the batch dict to this rank's rows
+# the UNCHANGED harness under torchrun: the learner's training forward works on this rank's rows and returns the gathered outputs
 # ---------------------------------------------------------------------------------------------------------
 def _harness_worker(rank, world, port, out):
-    """The restated VQATrainer.train_step (oracle/trainer_oracle.py, train_vqa.py:134-174) over the CPU oracle learner,
-    with the REGISTRY's converter (model_configs['vilt-b200']['batch2inputs_converter']). Every rank is handed the SAME
-    5-sample batch dict (plain loaders, same seed); after the rank-weighted gradient mean each rank must hold the
-    gradient of the WHOLE batch."""
+    """climb_b200.distributed.sharded_forward (what B200ViltContinualLearner.forward does in training mode once
+    attach_if_distributed ran) around the CPU oracle learner, driven by the restated trainers' train_step. Every rank is handed
+    the SAME 5-sample batch (plain loaders, same seed) -- an uneven split, 3 + 2 rows. The trainer must see whole-batch logits
+    and compute the whole-batch loss on every rank (whatever it does with its labels: NLVR2Trainer reads them BEFORE it calls
+    the model, train_nlvr2.py:128-131), and after the plain mean over ranks every rank must hold the whole-batch gradient."""
     from climb_b200 import distributed as cdist
-    from climb_b200.modeling import model_configs
     from oracle import trainer_oracle as to
     from oracle import vilt_oracle as vo
     from tests.golden_util import ALL_TASKS, TINY, TINY_HW, TINY_T
@@ -198,47 +198,64 @@ def _harness_worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(2)
-        pool = to.TaskPool("vqa", 5, TINY, TINY_T, TINY_HW, seed=900)
-        items = pool.items(0, 5)
-        sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=900)
-        proc = to.PoolProcessor({"vqa": pool}, torch.device("cpu"))
+        ok, worst_all = True, 0.0
+        for task in ("vqa", "nlvr2", "vcr"):
+            pool = to.TaskPool(task, 5, TINY, TINY_T, TINY_HW, seed=900)
+            items = pool.items(0, 5)
+            sd = vo.synth_state_dict(TINY, ALL_TASKS, seed=900, **(dict(layer_scale=6.0, head_scale=20.0) if task == "vcr" else {}))
+            proc = to.PoolProcessor({task: pool}, torch.device("cpu"))
+            calls = []
 
-        def grads_of(sharded: bool):
-            model = to.OracleLearner(TINY, ALL_TASKS, sd, proc)
-            trainer = to.TrainerOracle("vqa", to.Batches(items, 5), to.Batches(items, 5), {"lr": 1e-3}, 1, torch.device("cpu"))
-            if sharded:
-                trainer.batch2inputs_converter = model_configs["vilt-b200"]["batch2inputs_converter"]
-            batch = to.collate(items)
-            loss, output, _, _ = trainer.train_step(model, batch)
-            return model, batch, output, {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+            def step(sharded: bool):
+                model = to.OracleLearner(TINY, ALL_TASKS, sd, proc)
+                inner = model.__call__
 
-        cdist.set_training_mode(False)                    # evaluation: replicated, the dict is left alone
-        _, batch_eval, out_eval, g_full = grads_of(sharded=True)
-        ok = len(batch_eval["raw_texts"]) == 5 and out_eval[1].shape[0] == 5 and cdist._SHARD_MARK not in batch_eval
-        cdist.set_training_mode(True)
-        _, batch, output, g_rank = grads_of(sharded=True)
-        rows = 3 if rank == 0 else 2                      # ceil(5 / 2) rows on rank 0, the rest on rank 1
-        ok = ok and len(batch["raw_texts"]) == rows and len(batch["images"]) == rows and batch["target_scores"].shape[0] == rows
-        ok = ok and output[1].shape[0] == rows
-        ok = ok and torch.equal(batch["target_scores"], to.collate(items)["target_scores"][0 if rank == 0 else 3: 3 if rank == 0 else 5])
-        ok = ok and abs(cdist.shard_weight() - rows * world / 5.0) < 1e-12
-        worst = 0.0
-        gscale = max(g.norm().item() for g in g_full.values())     # (the key-bias gradients are analytically zero: fp32 noise)
-        for n, g in g_rank.items():
-            flat = g.clone().flatten() * cdist.shard_weight()
-            cdist.allreduce_mean_(flat, [(0, flat.numel())])
-            ref = g_full[n].flatten()
-            worst = max(worst, (flat - ref).norm().item() / max(ref.norm().item(), 1e-3 * gscale))
-        ok = ok and worst < 2e-5
-        # a second conversion of the same dict (EWC's Fisher loop, replay) must not cut it again
-        model_configs["vilt-b200"]["batch2inputs_converter"](batch)
-        ok = ok and len(batch["raw_texts"]) == rows
-        out[rank] = (bool(ok), worst)
+                class Sharded:                       # the learner's forward under attach_if_distributed
+                    def __call__(self, task_key, images, texts):
+                        calls.append(len(texts))
+                        if not sharded:
+                            return inner(task_key, images, texts)
+                        return cdist.sharded_forward(lambda im, tx: inner(task_key, im, tx), images, texts)
+
+                    def __getattr__(self, name):
+                        return getattr(model, name)
+
+                batch = to.collate(items)
+                logits_fn = Sharded()
+                pooled, logits = logits_fn(task, batch["images"], batch["raw_texts"])
+                target = batch["target_scores"] if task == "vqa" else batch["labels"]
+                loss = vo.task_loss(task, logits, target)          # the WHOLE batch's labels, untouched
+                loss.backward()
+                return loss, logits, {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+
+            loss_full, logits_full, g_full = step(False)
+            loss_rank, logits_rank, g_rank = step(True)
+            ok = ok and logits_rank.shape == logits_full.shape and torch.allclose(logits_rank, logits_full, atol=1e-6)
+            ok = ok and abs(loss_rank.item() - loss_full.item()) < 1e-6 * max(1.0, abs(loss_full.item()))
+            worst = 0.0
+            gscale = max(g.norm().item() for g in g_full.values())     # (the key-bias gradients are analytically zero: fp32 noise)
+            ok = ok and set(g_rank) == set(g_full)
+            for n, g in g_rank.items():
+                flat = g.clone().flatten()
+                cdist.allreduce_mean_(flat, [(0, flat.numel())])        # GradSync's plain mean over ranks
+                ref = g_full[n].flatten()
+                worst = max(worst, (flat - ref).norm().item() / max(ref.norm().item(), 1e-3 * gscale))
+            ok = ok and worst < 2e-5
+            worst_all = max(worst_all, worst)
+        # a batch smaller than the world leaves a rank without rows: loud error, not a hang
+        try:
+            cdist.sharded_forward(lambda im, tx: None, [0], ["a"])
+            ok = ok and rank == 0 and False
+        except RuntimeError:
+            ok = ok and rank == 1
+        except Exception:
+            ok = ok and rank == 0          # rank 0 has the row and fails later on the dummy forward
+        out[rank] = (bool(ok), worst_all)
     finally:
         dist.destroy_process_group()
 
 
-def test_registry_converter_shards_the_unchanged_harness_world2_gloo():
+def test_sharded_forward_gives_the_unchanged_harness_whole_batch_outputs_and_gradients_world2_gloo():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -258,6 +275,6 @@ def test_learner_train_eval_drive_the_sharding_mode_and_single_process_is_untouc
     learner.train()
     assert cdist._training_mode is True
     batch = {"images": [1, 2, 3], "raw_texts": ["a", "b", "c"], "labels": torch.arange(3)}
-    inputs = model_configs["vilt-b200"]["batch2inputs_converter"](batch)       # no process group: nothing is cut
+    inputs = model_configs["vilt-b200"]["batch2inputs_converter"](batch)       # the reference's converter: the batch dict is never edited
     assert inputs == {"images": [1, 2, 3], "texts": ["a", "b", "c"]} and len(batch["labels"]) == 3
-    assert cdist.attach_if_distributed(learner) is None
+    assert cdist.attach_if_distributed(learner) is None and not getattr(learner, "_ddp_forward_shard", False)
