@@ -37,14 +37,23 @@ def main():
     from climb_b200.modeling import model_configs
 
     ok = True
-    for tag in ("trainer_vqa_er", "trainer_nlvr2", "trainer_snli_ve"):
+    from oracle.make_golden_trainer import prepare_adapters
+    for tag in ("trainer_vqa_er", "trainer_nlvr2", "trainer_snli_ve", "trainer_snli_ve_ewc", "trainer_nlvr2_adapters"):
         sc = dict(to.SCENARIOS, **to.REFERENCE_SCENARIOS)[tag]
         assert sc["batch_size"] % world == 0
-        sd, _ = scenario_state_dict(sc)
+        sd, sd_full = scenario_state_dict(sc)
         learner = _build(TINY, ALL_TASKS, sd)
+        ewc_cls = None
+        if sc.get("adapters"):                                    # AdapterHandler, as the driver calls it before the task
+            from climb_b200.cl_algorithms import AdapterHandler
+            prepare_adapters(sc, learner, AdapterHandler)
+            sd = sd_full
+        if sc.get("ewc"):
+            from climb_b200.cl_algorithms import EWC as ewc_cls
         sync = cdist.attach_if_distributed(learner)               # what create_*_continual_learner_model does
         assert sync is not None
-        rec, extra = run_reference_scenario(tag, learner, str(dev), converter=model_configs["vilt-b200"]["batch2inputs_converter"])
+        rec, extra = run_reference_scenario(tag, learner, str(dev), ewc_cls=ewc_cls,
+                                            converter=model_configs["vilt-b200"]["batch2inputs_converter"])
         # (every rank computed the WHOLE batch's loss from the gathered logits: the recorded losses are already the golden's)
         t = torch.tensor(rec["loss"], dtype=torch.float64, device=dev)
         t0 = t.clone()
