@@ -93,6 +93,21 @@ def test_padded_images_within_1e3_of_the_reference():
     _grads(g, learner, "precise/tiny_ragged_nlvr2")
 
 
+@pytest.mark.parametrize("tag,task,B,seed,hw", [("tiny_maxlen_snli-ve", "snli-ve", 4, 600, (64, 80)), ("tiny_maxlen_vcr", "vcr", 3, 602, (64, 80))])
+def test_max_image_length_within_1e3_of_the_reference(tag, task, B, seed, hw):
+    """config.max_image_length > 0 in the precision mode: the same host-drawn patch subsets (patch_select) through the bf16x3
+    engine; VCR's shared image is expanded for it (one subset per encoder pass of the reference)."""
+    import dataclasses
+    g = load(tag)
+    batch = regen_batch(g, task, TINY, TINY_T, hw, B, seed, True)
+    dims = dataclasses.replace(TINY, max_image_length=int(g["max_image_length"]))
+    learner = _build(dims, ALL_TASKS, vo.synth_state_dict(TINY, ALL_TASKS, seed=seed, **fixture_scales(g)))
+    torch.manual_seed(seed)
+    pooled, logits, loss = _step(learner, task, batch, host_mask=True)
+    _outputs(f"precise/{tag}", pooled, logits, loss.item(), g["pooled"], g["logits"], g["loss"])
+    _grads(g, learner, f"precise/{tag}")
+
+
 def test_bench_geometry_step_within_1e3_of_the_oracle():
     """One ViLT-base VQA step on B = 16 sequences of 40 + 197 tokens (the benchmark's geometry) against the CPU oracle."""
     import os
