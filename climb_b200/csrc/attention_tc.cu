@@ -2248,7 +2248,10 @@ int attention_tc_fwd(const void* qkv, const float* key_bias, void* ctx, float* l
                                      dim3(kF4Threads), Fwd4Smem::kTotal, stream, mqkv, mq128, key_bias, static_cast<__nv_bfloat16*>(ctx), lse,
                                      n_items, L, H, scale * kLog2e));
         } else if (fwd3) {
-            static const bool poly = env_flag("CLIMB_ATTN_EXP", 1) != 0;
+            // every exponential on the MUFU pipe by default (CLIMB_ATTN_EXP=1: every other pair as a polynomial on the FMA pipe):
+            // with P in tensor memory the kernel is bound by issue slots, not by MUFU (21 % busy), and the polynomial costs
+            // 6.5 issue slots per element against 1 -- measured 41.6 vs 42.7 us per launch at B = 64
+            static const bool poly = env_flag("CLIMB_ATTN_EXP", 0) != 0;
             static bool attr3 = false;
             if (!attr3) {
                 CLIMB_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd3Smem::kTotal));
