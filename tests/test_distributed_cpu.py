@@ -104,7 +104,8 @@ def _chunked_worker(rank, world, port, out, mode):
         arena.sync(allow_cpu=True)
         off, num = arena.offsets, arena.numels
         n_layers = len(vilt.encoder.layer)
-        sync = cdist.attach(learner, bucket_mb=0.05, layers_per_chunk=1)        # small buckets: several per chunk
+        deferred = mode == "deferred"
+        sync = cdist.attach(learner, bucket_mb=0.05, layers_per_chunk=1, defer_to_optimizer=deferred)   # small buckets: several per chunk
         calls, reduced = [], [0]
         pattern = torch.arange(arena.size, dtype=torch.float32) % 97 + 1
 
@@ -143,9 +144,25 @@ def _chunked_worker(rank, world, port, out, mode):
         call.dims, call.params, call.layers, call.batch = st["dims"], st["params"], st["layers"], _lib.ViltBatchC()
         call.trainable, call.workspace, call.ws_bytes, call.arena_theta, call.keep = st["trainable"], None, 0, arena.theta, []
         vilt._run_backward(call, torch.zeros(2, vilt.config.hidden_size))
+        if deferred:
+            # finish() handed the in-flight reductions to the optimizer instead of waiting: ranges in issue order (top layer
+            # first), each with its work; with gloo's SUM-then-divide stand-in the division is still pending
+            pend = arena._pending_reductions
+            ok_def = pend is not None and len(pend[0]) > n_layers and all(hi > lo for (lo, hi), _ in pend[0])
+            starts = [lo for (lo, hi), _ in pend[0]]
+            ok_def = ok_def and starts[0] > starts[-1]                       # top of the arena first, embeddings last
+            covered = sum(hi - lo for (lo, hi), _ in pend[0])
+            from climb_b200.distributed import pending_segments
+            chunks = [(off[n], num[n], 0) for n, p in arena.named_items() if p.requires_grad]
+            order, n_free, bounds = pending_segments(chunks, [r for r, _ in pend[0]])
+            ok_def = ok_def and n_free == 0 and bounds[-1] == len(chunks) and sorted(order) == list(range(len(chunks)))
+            cdist.wait_pending(arena)                                        # what ArenaAdamW.step / prepare_grads / EWC do
+            ok_def = ok_def and arena._pending_reductions is None and covered >= sum(num[n] for n, p in arena.named_items() if p.requires_grad)
+        else:
+            ok_def = getattr(arena, "_pending_reductions", None) is None
         # every chunk top-down, one layer each, tail with the first chunk, embeddings last and alone
         want = [(l, l, _lib.BWD_TAIL if l == n_layers - 1 else 0) for l in range(n_layers - 1, -1, -1)] + [(-1, 0, _lib.BWD_EMBED)]
-        ok = calls == want
+        ok = calls == want and ok_def
         mean = (1 + world) / 2.0
         n_trainable = 0
         for n, p in arena.named_items():
@@ -170,7 +187,7 @@ def _chunked_worker(rank, world, port, out, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["full", "frozen_bottom", "adapters"])
+@pytest.mark.parametrize("mode", ["full", "frozen_bottom", "adapters", "deferred"])
 def test_chunked_backward_overlapped_allreduce_world2_gloo(mode):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
